@@ -1,0 +1,902 @@
+/*
+ * od_oracle.c -- CPU restatement of the OptaDOS spectral-integration hot path.
+ * TEST INFRASTRUCTURE ONLY (see od_oracle.h).  Every routine cites the reference
+ * lines it follows (paths relative to optados/src/ in the reference tree).
+ * Loops are kept DENSE exactly like the reference (no windowing), so that this
+ * file also serves as the timed "restated reference loop" CPU baseline.
+ */
+#include "od_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- column-major index helpers (0-based) ---- */
+#define BE(s, ib, is, ik) ((s)->band_energy[(size_t)(ib) + (size_t)(s)->nb * ((size_t)(is) + (size_t)(s)->ns * (size_t)(ik))])
+#define BG(s, ib, i, ik, is) \
+  ((s)->band_gradient[(size_t)(ib) + (size_t)(s)->nb * ((size_t)(i) + 3 * ((size_t)(ik) + (size_t)(s)->nk * (size_t)(is)))])
+#define RL(r, i, j) ((r)[(i) + 3 * (j)])
+
+/* algorithms.f90:73-91 */
+double odo_gaussian(double m, double w, double x) {
+  double t = (x - m) / w;
+  if (0.5 * (t * t) > 30.0) return 0.0;
+  return ODO_INV_SQRT_TWO_PI * exp(-0.5 * (t * t)) / w;
+}
+
+/* algorithms.f90:252-306 (NSWC erf) */
+double odo_erf(double x) {
+  static const double C = 0.564189583547756;
+  static const double A[5] = {0.771058495001320E-04, -0.133733772997339E-02, 0.323076579225834E-01,
+                              0.479137145607681E-01, 0.128379167095513E+00};
+  static const double B[3] = {0.301048631703895E-02, 0.538971687740286E-01, 0.375795757275549E+00};
+  static const double P[8] = {-1.36864857382717E-07, 5.64195517478974E-01, 7.21175825088309E+00,
+                              4.31622272220567E+01,  1.52989285046940E+02, 3.39320816734344E+02,
+                              4.51918953711873E+02,  3.00459261020162E+02};
+  static const double Q[8] = {1.00000000000000E+00, 1.27827273196294E+01, 7.70001529352295E+01,
+                              2.77585444743988E+02, 6.38980264465631E+02, 9.31354094850610E+02,
+                              7.90950925327898E+02, 3.00459260956983E+02};
+  static const double R[5] = {2.10144126479064E+00, 2.62370141675169E+01, 2.13688200555087E+01,
+                              4.65807828718470E+00, 2.82094791773523E-01};
+  static const double S[4] = {9.41537750555460E+01, 1.87114811799590E+02, 9.90191814623914E+01,
+                              1.80124575948747E+01};
+  double ax = fabs(x), t, top, bot, x2, r;
+  if (ax <= 0.5) {
+    t = x * x;
+    top = ((((A[0] * t + A[1]) * t + A[2]) * t + A[3]) * t + A[4]) + 1.0;
+    bot = ((B[0] * t + B[1]) * t + B[2]) * t + 1.0;
+    return x * (top / bot);
+  } else if (ax <= 4.0) {
+    top = ((((((P[0] * ax + P[1]) * ax + P[2]) * ax + P[3]) * ax + P[4]) * ax + P[5]) * ax + P[6]) * ax + P[7];
+    bot = ((((((Q[0] * ax + Q[1]) * ax + Q[2]) * ax + Q[3]) * ax + Q[4]) * ax + Q[5]) * ax + Q[6]) * ax + Q[7];
+    r = 0.5 + (0.5 - exp(-x * x) * top / bot);
+    return (x < 0.0) ? -r : r;
+  } else if (ax <= 5.8) {
+    x2 = x * x;
+    t = 1.0 / x2;
+    top = (((R[0] * t + R[1]) * t + R[2]) * t + R[3]) * t + R[4];
+    bot = (((S[0] * t + S[1]) * t + S[2]) * t + S[3]) * t + 1.0;
+    r = (C - top / (x2 * bot)) / ax;
+    r = 0.5 + (0.5 - exp(-x2) * r);
+    return (x < 0.0) ? -r : r;
+  }
+  return (x < 0.0) ? -1.0 : 1.0;
+}
+
+/* algorithms.f90:94-169 : heap sort into DESCENDING order?  No: the routine as written
+ * builds a max-heap and pops to the back, i.e. ASCENDING; the caller negates before and
+ * after (dos_utils.f90:1374-1376) to get descending.  Restated 1-based like the source. */
+void odo_heap_sort(int num_items, double *weight0) {
+  double *weight = weight0 - 1; /* 1-based view */
+  int i, ir, j, l;
+  double wta;
+  if (num_items < 2) return;
+  l = num_items / 2 + 1;
+  ir = num_items;
+  for (;;) {
+    if (l > 1) {
+      l = l - 1;
+      wta = weight[l];
+    } else {
+      wta = weight[ir];
+      weight[ir] = weight[1];
+      ir = ir - 1;
+      if (ir == 1) {
+        weight[1] = wta;
+        return;
+      }
+    }
+    i = l;
+    j = l + l;
+    while (j <= ir) {
+      if (j < ir) {
+        if (weight[j] < weight[j + 1]) j = j + 1;
+      }
+      if (wta < weight[j]) {
+        weight[i] = weight[j];
+        i = j;
+        j = j + j;
+      } else {
+        j = ir + 1;
+      }
+    }
+    weight[i] = wta;
+  }
+}
+
+/* algorithms.f90:309-340 */
+int odo_dist_array(int num_elements, int num_nodes, int *elements_per_node) {
+  int loop;
+  for (loop = 0; loop < num_nodes; ++loop) elements_per_node[loop] = num_elements / num_nodes;
+  if (num_elements < num_nodes) return 1;
+  if (elements_per_node[0] * num_nodes != num_elements) {
+    for (loop = 0; loop <= num_elements - elements_per_node[0] * num_nodes - 1; ++loop)
+      elements_per_node[loop] += 1;
+  }
+  return 0;
+}
+
+/* dos_utils.f90:1320-1388 */
+void odo_doslin_sub_cell_corners(const double grad[3], const double step[3], double energy,
+                                 const double recip[9], double EV[5]) {
+  int m, n, o, nn = 0, i;
+  double stepp[3], t[3], DE[8];
+  for (m = -1; m <= 1; m += 2)
+    for (n = -1; n <= 1; n += 2)
+      for (o = -1; o <= 1; o += 2) {
+        stepp[0] = step[0] * m;
+        stepp[1] = step[1] * n;
+        stepp[2] = step[2] * o;
+        /* stepp = matmul(recip_lattice, stepp)  :1364 */
+        for (i = 0; i < 3; ++i)
+          t[i] = RL(recip, i, 0) * stepp[0] + RL(recip, i, 1) * stepp[1] + RL(recip, i, 2) * stepp[2];
+        /* DE = dot_product(grad, stepp)  :1367 */
+        DE[nn] = grad[0] * t[0] + grad[1] * t[1] + grad[2] * t[2];
+        nn++;
+      }
+  for (i = 0; i < 8; ++i) DE[i] = -DE[i]; /* :1374 */
+  odo_heap_sort(8, DE);
+  for (i = 0; i < 8; ++i) DE[i] = -DE[i]; /* :1376 */
+  EV[0] = energy;
+  for (i = 1; i <= 4; ++i) EV[i] = EV[0] + DE[4 + i - 1]; /* DE(4+i), 1-based  :1386 */
+}
+
+/* dos_utils.f90:1391-1528 */
+double odo_doslin(double e0, double e1, double e2, double e3, double e4, double e, double *cuml,
+                  int *err) {
+  double doslin, in, alpha, e_use;
+  int shift;
+  if (!((e4 <= e3) && (e3 <= e2) && (e2 <= e1) && (e1 <= e0))) { /* :1430 stop */
+    if (err) *err = 1;
+    *cuml = 0.0;
+    return 0.0;
+  }
+  if (e <= e4) { /* :1438 */
+    *cuml = 0.0;
+    return 0.0;
+  }
+  if (e >= (2.0 * e0 - e4)) { /* :1448 */
+    *cuml = 1.0;
+    return 0.0;
+  }
+  if ((e1 == e2) && (e1 == e3) && (e3 == e4)) { /* :1458 */
+    alpha = 1.0;
+  } else {
+    alpha = 1.0 / ((e1 - e3) * (e1 - e4) + (e3 - e4) * (e3 - e4) / 3.0 - (e1 - e2) * (e1 - e2) / 3.0 +
+                   (e1 + e2 - e3 - e4) * (e0 - e1));
+  }
+  if (e > e0) { /* :1469 */
+    e_use = 2.0 * e0 - e;
+    shift = 1;
+  } else {
+    e_use = e;
+    shift = 0;
+  }
+  if (e_use <= e4) { /* :1479 */
+    doslin = 0.0;
+    in = 0.0;
+  } else if (e_use < e3) {
+    doslin = (e_use - e4) * (e_use - e4) / (e3 - e4) / 2.0;
+    in = (e_use - e4) * (e_use - e4) * (e_use - e4) / (e3 - e4) / 6.0;
+  } else if (e_use < e2) {
+    doslin = (e_use - (e3 + e4) / 2.0);
+    in = ((e3 - e4) * (e3 - e4) / 3.0 + (e_use - e3) * (e_use - e4)) / 2.0;
+  } else if (e_use < e1) {
+    doslin = (e1 + e2 - e3 - e4) / 2.0;
+    if (e1 != e2) doslin = doslin - (e1 - e_use) * (e1 - e_use) / (e1 - e2) / 2.0;
+    in = ((e2 - e4) * (e_use - e3) + (e1 - e3) * (e_use - e2) + (e3 - e4) * (e3 - e4) / 3.0 +
+          ((e1 - e_use) * (e1 - e_use) * (e1 - e_use) - (e1 - e2) * (e1 - e2) * (e1 - e2)) / (e1 - e2) / 3.0) /
+         2.0;
+  } else if (e_use <= e0) {
+    if ((e1 + e2 - e3 - e4) > 0.0) {
+      doslin = (e1 + e2 - e3 - e4) / 2.0;
+      in = ((e1 - e3) * (e1 - e4) + (e3 - e4) * (e3 - e4) / 3.0 - (e1 - e2) * (e1 - e2) / 3.0 +
+            (e1 + e2 - e3 - e4) * (e_use - e1)) /
+           2.0;
+    } else {
+      doslin = 1.0 / (e0 - e4) / 2.0;
+      in = (e_use - e4) / (e0 - e4) / 2.0;
+    }
+  } else { /* :1511 stop */
+    if (err) *err = 2;
+    *cuml = 0.0;
+    return 0.0;
+  }
+  doslin = doslin * alpha;
+  if (shift)
+    in = 1.0 - in * alpha;
+  else
+    in = in * alpha;
+  *cuml = in;
+  return doslin;
+}
+
+void odo_minmax(const double *a, long n, double *mn, double *mx) {
+  double lo = DBL_MAX, hi = -DBL_MAX;
+  long i;
+  for (i = 0; i < n; ++i) {
+    if (a[i] < lo) lo = a[i];
+    if (a[i] > hi) hi = a[i];
+  }
+  *mn = lo;
+  *mx = hi;
+}
+
+/* dos_utils.f90:927-1010.  min/max_band_energy_in are minval/maxval(band_energy) (after the
+ * MIN/MAX reduce of :968/:976 the +-5 eV pad commutes with the reduction). */
+void odo_dos_energy_scale(double minval_be, double maxval_be, double dos_min_energy,
+                          double dos_max_energy, int have_min, int have_max, double dos_spacing,
+                          int *dos_nbins, double *emin_out, double *delta_bins_out) {
+  double min_band_energy, max_band_energy;
+  min_band_energy = have_min ? dos_min_energy : minval_be - 5.0; /* :963-967 */
+  max_band_energy = have_max ? dos_max_energy : maxval_be + 5.0; /* :971-975 */
+  if (*dos_nbins < 0) {                                         /* :980 */
+    *dos_nbins = abs((int)ceil((max_band_energy - min_band_energy) / dos_spacing));
+    max_band_energy = min_band_energy + (*dos_nbins) * dos_spacing; /* :988 */
+  }
+  *delta_bins_out = (max_band_energy - min_band_energy) / (double)(*dos_nbins - 1); /* :994 */
+  *emin_out = min_band_energy;
+}
+
+static void adaptive_prefactor(const odo_system *sys, const odo_broadening *br, double step[3],
+                               double *adaptive_smearing_temp) {
+  int i;
+  double sub_cell_length[3];
+  /* :1210 */
+  for (i = 0; i < 3; ++i) step[i] = 1.0 / (double)sys->kpoint_grid_dim[i] / 2.0;
+  /* :1212-1215 */
+  for (i = 0; i < 3; ++i) {
+    const double *r = sys->recip_lattice;
+    sub_cell_length[i] = sqrt(RL(r, i, 0) * RL(r, i, 0) + RL(r, i, 1) * RL(r, i, 1) + RL(r, i, 2) * RL(r, i, 2)) * step[i];
+  }
+  *adaptive_smearing_temp =
+      br->adaptive_smearing * (sub_cell_length[0] + sub_cell_length[1] + sub_cell_length[2]) / 3.0;
+}
+
+/* dos_utils.f90:1228-1280 restricted to k-points [ik0, ik1).  Accumulates (no zeroing). */
+static int calculate_dos_range(char dos_type, const odo_system *sys, const odo_broadening *br,
+                               const double *E, int nbins, double delta_bins, const double *mw,
+                               int mw_norb, int mw_nb, int mw_nk, int ik0, int ik1, double *dos,
+                               double *intdos, double *wdos) {
+  int linear = (dos_type == 'l'), adaptive = (dos_type == 'a'), fixed = (dos_type == 'f');
+  int ik, is, ib, idos, iorb, err = 0;
+  double step[3] = {0, 0, 0}, adaptive_smearing_temp = 0.0, width = 0.0, grad[3] = {0, 0, 0}, EV[5];
+  double dos_temp, cuml, intdos_accum;
+  const int nb = sys->nb, ns = sys->ns;
+  if (!(linear || adaptive || fixed)) return 3;
+  if (linear || adaptive) adaptive_prefactor(sys, br, step, &adaptive_smearing_temp);
+  if (fixed) width = br->fixed_smearing;
+
+  for (ik = ik0; ik < ik1; ++ik) {
+    const double kw = sys->kpoint_weight[ik];
+    for (is = 0; is < ns; ++is) {
+      for (ib = 0; ib < nb; ++ib) {
+        const double eb = BE(sys, ib, is, ik);
+        if (linear || adaptive) {
+          grad[0] = BG(sys, ib, 0, ik, is);
+          grad[1] = BG(sys, ib, 1, ik, is);
+          grad[2] = BG(sys, ib, 2, ik, is);
+        }
+        /* force_adaptive is never set here (:1238, quirk Q8) */
+        if (linear) odo_doslin_sub_cell_corners(grad, step, eb, sys->recip_lattice, EV);
+        if (adaptive) width = sqrt(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]) * adaptive_smearing_temp;
+        if (br->finite_bin_correction && (width < delta_bins)) width = delta_bins; /* :1244 */
+        intdos_accum = 0.0;
+        for (idos = 0; idos < nbins; ++idos) {
+          if (linear) {
+            dos_temp = odo_doslin(EV[0], EV[1], EV[2], EV[3], EV[4], E[idos], &cuml, &err) *
+                       sys->electrons_per_state * kw;
+            intdos[idos + (size_t)nbins * is] += sys->electrons_per_state * kw * cuml;
+          } else {
+            dos_temp = odo_gaussian(eb, width, E[idos]) * sys->electrons_per_state * kw;
+            if (br->numerical_intdos) {
+              intdos_accum += dos_temp;
+              intdos[idos + (size_t)nbins * is] += intdos_accum;
+            } else {
+              intdos[idos + (size_t)nbins * is] +=
+                  0.5 * (1.0 + odo_erf((E[idos] - eb) / (ODO_SQRT_TWO * width))) *
+                  sys->electrons_per_state * kw;
+            }
+          }
+          dos[idos + (size_t)nbins * is] += dos_temp;
+          if (mw) { /* :1267-1276 */
+            if (ik < mw_nk && ib < mw_nb) {
+              for (iorb = 0; iorb < mw_norb; ++iorb)
+                wdos[idos + (size_t)nbins * (is + (size_t)ns * iorb)] +=
+                    dos_temp * mw[iorb + (size_t)mw_norb * (ib + (size_t)mw_nb * (ik + (size_t)mw_nk * is))];
+            }
+          }
+        }
+      }
+    }
+  }
+  return err;
+}
+
+/* dos_utils.f90:1282-1315 : post-smear of the linear DOS and numerical-intdos scaling */
+static void calculate_dos_epilogue(char dos_type, const odo_system *sys, const odo_broadening *br,
+                                   const double *E, int nbins, double delta_bins, double *dos,
+                                   double *intdos) {
+  int linear = (dos_type == 'l');
+  int is, idos, i;
+  if (linear && br->linear_smearing > 0.0) {
+    double *dos_smear = (double *)calloc((size_t)nbins * sys->ns, sizeof(double));
+    for (is = 0; is < sys->ns; ++is)
+      for (idos = 0; idos < nbins; ++idos)
+        for (i = 0; i < nbins; ++i)
+          dos_smear[idos + (size_t)nbins * is] +=
+              dos[i + (size_t)nbins * is] * odo_gaussian(E[idos], br->linear_smearing, E[i]) * delta_bins;
+    memcpy(dos, dos_smear, sizeof(double) * (size_t)nbins * sys->ns);
+    free(dos_smear);
+  }
+  if (!linear && br->numerical_intdos) {
+    size_t n = (size_t)nbins * sys->ns, j;
+    for (j = 0; j < n; ++j) intdos[j] *= delta_bins;
+  }
+}
+
+int odo_calculate_dos(char dos_type, const odo_system *sys, const odo_broadening *br, const double *E,
+                      int nbins, double delta_bins, const double *mw, int mw_norb, int mw_nb, int mw_nk,
+                      double *dos, double *intdos, double *wdos) {
+  int err;
+  memset(dos, 0, sizeof(double) * (size_t)nbins * sys->ns);
+  memset(intdos, 0, sizeof(double) * (size_t)nbins * sys->ns);
+  if (mw) memset(wdos, 0, sizeof(double) * (size_t)nbins * sys->ns * mw_norb);
+  err = calculate_dos_range(dos_type, sys, br, E, nbins, delta_bins, mw, mw_norb, mw_nb, mw_nk, 0, sys->nk,
+                            dos, intdos, wdos);
+  calculate_dos_epilogue(dos_type, sys, br, E, nbins, delta_bins, dos, intdos);
+  return err;
+}
+
+typedef struct {
+  char type;
+  const odo_system *sys;
+  const odo_broadening *br;
+  const double *E;
+  int nbins;
+  double delta_bins;
+  const double *mw;
+  int mw_norb, mw_nb, mw_nk;
+  int ik0, ik1;
+  double *dos, *intdos, *wdos;
+  int err;
+  /* jdos extras */
+  double efermi, scissor_op;
+  const int *exclude_bands;
+  int num_exclude_bands;
+  int n_geom;
+} mt_job;
+
+static void *dos_worker(void *p) {
+  mt_job *j = (mt_job *)p;
+  j->err = calculate_dos_range(j->type, j->sys, j->br, j->E, j->nbins, j->delta_bins, j->mw, j->mw_norb,
+                               j->mw_nb, j->mw_nk, j->ik0, j->ik1, j->dos, j->intdos, j->wdos);
+  /* the reference post-smears / scales the RANK-LOCAL arrays before the merge (Q16) */
+  calculate_dos_epilogue(j->type, j->sys, j->br, j->E, j->nbins, j->delta_bins, j->dos, j->intdos);
+  return NULL;
+}
+
+int odo_calculate_dos_mt(int nthreads, char dos_type, const odo_system *sys, const odo_broadening *br,
+                         const double *E, int nbins, double delta_bins, const double *mw, int mw_norb,
+                         int mw_nb, int mw_nk, double *dos, double *intdos, double *wdos) {
+  int t, err = 0, ik = 0;
+  size_t n1 = (size_t)nbins * sys->ns, nw = mw ? n1 * mw_norb : 0, j;
+  int *per;
+  mt_job *jobs;
+  pthread_t *th;
+  if (nthreads > sys->nk) nthreads = sys->nk;
+  if (nthreads < 1) nthreads = 1;
+  per = (int *)malloc(sizeof(int) * nthreads);
+  jobs = (mt_job *)calloc(nthreads, sizeof(mt_job));
+  th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+  odo_dist_array(sys->nk, nthreads, per);
+  for (t = 0; t < nthreads; ++t) {
+    mt_job *jb = &jobs[t];
+    jb->type = dos_type; jb->sys = sys; jb->br = br; jb->E = E; jb->nbins = nbins;
+    jb->delta_bins = delta_bins; jb->mw = mw; jb->mw_norb = mw_norb; jb->mw_nb = mw_nb; jb->mw_nk = mw_nk;
+    jb->ik0 = ik; jb->ik1 = ik + per[t]; ik += per[t];
+    jb->dos = (double *)calloc(n1, sizeof(double));
+    jb->intdos = (double *)calloc(n1, sizeof(double));
+    jb->wdos = mw ? (double *)calloc(nw, sizeof(double)) : NULL;
+    pthread_create(&th[t], NULL, dos_worker, jb);
+  }
+  memset(dos, 0, sizeof(double) * n1);
+  memset(intdos, 0, sizeof(double) * n1);
+  if (mw) memset(wdos, 0, sizeof(double) * nw);
+  for (t = 0; t < nthreads; ++t) {
+    pthread_join(th[t], NULL);
+    if (jobs[t].err) err = jobs[t].err;
+    for (j = 0; j < n1; ++j) { dos[j] += jobs[t].dos[j]; intdos[j] += jobs[t].intdos[j]; }
+    for (j = 0; j < nw; ++j) wdos[j] += jobs[t].wdos[j];
+    free(jobs[t].dos); free(jobs[t].intdos); free(jobs[t].wdos);
+  }
+  free(per); free(jobs); free(th);
+  return err;
+}
+
+/* dos_utils.f90:1651-1800 */
+int odo_calculate_dos_at_e(char dos_type, const odo_system *sys, const odo_broadening *br,
+                           double delta_bins, double energy, const double *mw, int mw_norb, int mw_nb,
+                           int mw_nk, double *dos_at_e, double *wdos_at_e) {
+  int linear = (dos_type == 'l'), adaptive = (dos_type == 'a'), fixed = (dos_type == 'f');
+  int ik, is, ib, iorb, err = 0, force_adaptive;
+  double step[3] = {0, 0, 0}, adaptive_smearing_temp = 0.0, width = 0.0, grad[3] = {0, 0, 0}, EV[5];
+  double dos_temp, cuml, gnorm;
+  if (!(linear || adaptive || fixed)) return 3;
+  for (is = 0; is < sys->ns; ++is) dos_at_e[is] = 0.0;
+  if (linear || adaptive || br->hybrid_linear) adaptive_prefactor(sys, br, step, &adaptive_smearing_temp);
+  if (fixed) width = br->fixed_smearing;
+  if (wdos_at_e)
+    for (is = 0; is < sys->ns * mw_norb; ++is) wdos_at_e[is] = 0.0;
+  for (ik = 0; ik < sys->nk; ++ik)
+    for (is = 0; is < sys->ns; ++is)
+      for (ib = 0; ib < sys->nb; ++ib) {
+        const double eb = BE(sys, ib, is, ik);
+        if (linear || adaptive) {
+          grad[0] = BG(sys, ib, 0, ik, is);
+          grad[1] = BG(sys, ib, 1, ik, is);
+          grad[2] = BG(sys, ib, 2, ik, is);
+        }
+        gnorm = sqrt(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);
+        force_adaptive = 0;
+        if (br->hybrid_linear && (br->hybrid_linear_grad_tol > gnorm)) force_adaptive = 1; /* :1758 */
+        if (linear && !force_adaptive) odo_doslin_sub_cell_corners(grad, step, eb, sys->recip_lattice, EV);
+        if (adaptive || force_adaptive) width = gnorm * adaptive_smearing_temp;
+        if (br->finite_bin_correction) {
+          if (width < delta_bins) width = delta_bins;
+        }
+        if (linear && !force_adaptive)
+          dos_temp = odo_doslin(EV[0], EV[1], EV[2], EV[3], EV[4], energy, &cuml, &err) *
+                     sys->electrons_per_state * sys->kpoint_weight[ik];
+        else
+          dos_temp = odo_gaussian(eb, width, energy) * sys->electrons_per_state * sys->kpoint_weight[ik];
+        dos_at_e[is] += dos_temp;
+        if (wdos_at_e && mw && ik < mw_nk && ib < mw_nb)
+          for (iorb = 0; iorb < mw_norb; ++iorb)
+            wdos_at_e[is + (size_t)sys->ns * iorb] +=
+                dos_temp * mw[iorb + (size_t)mw_norb * (ib + (size_t)mw_nb * (ik + (size_t)mw_nk * is))];
+      }
+  return err;
+}
+
+/* dos_utils.f90:798-850 */
+double odo_calc_efermi_from_intdos(const double *intdos, const double *E, int nbins, int ns,
+                                   const double *num_electrons) {
+  const double tolerance = 0.0001;
+  double nel = 0.0, efermi, s, sref;
+  int idos, i, is;
+  for (is = 0; is < ns; ++is) nel += num_electrons[is];
+  /* 1-based idos; Fortran leaves idos = nbins+1 if the loop never exits */
+  for (idos = 1; idos <= nbins; ++idos) {
+    s = 0.0;
+    for (is = 0; is < ns; ++is) s += intdos[(idos - 1) + (size_t)nbins * is];
+    if (s > (nel + (tolerance / 2.0))) break;
+  }
+  if (idos > nbins) idos = nbins; /* out-of-bounds read in the reference; clamp */
+  efermi = E[idos - 1];
+  sref = 0.0;
+  if (idos - 1 >= 1)
+    for (is = 0; is < ns; ++is) sref += intdos[(idos - 2) + (size_t)nbins * is];
+  for (i = idos; i >= 1; --i) {
+    s = 0.0;
+    for (is = 0; is < ns; ++is) s += intdos[(i - 1) + (size_t)nbins * is];
+    if (s < (sref - (tolerance / 2.0))) break;
+  }
+  if (i < 1) i = 1; /* E(0) would be out of bounds in the reference; clamp */
+  return (efermi + E[i - 1]) / 2.0;
+}
+
+/* dos_utils.f90:326-365 */
+double odo_efermi_insulator(const odo_system *sys, const double *num_electrons) {
+  double vbm = -DBL_MAX, cbm = DBL_MAX;
+  int ik, is, top_occ_band;
+  for (ik = 0; ik < sys->nk; ++ik)
+    for (is = 0; is < sys->ns; ++is) {
+      top_occ_band = (int)ceil(num_electrons[is] / sys->electrons_per_state); /* 1-based */
+      if (BE(sys, top_occ_band - 1, is, ik) > vbm) vbm = BE(sys, top_occ_band - 1, is, ik);
+      if (num_electrons[is] + 1 <= sys->nb) {
+        if (BE(sys, top_occ_band, is, ik) < cbm) cbm = BE(sys, top_occ_band, is, ik);
+      }
+    }
+  if (cbm == DBL_MAX) return vbm + 0.5;
+  return vbm + 0.5 * (cbm - vbm);
+}
+
+/* jdos_utils.f90:193-218 */
+void odo_jdos_energy_scale(double max_band_energy, double efermi, double jdos_spacing,
+                           double *jdos_max_energy, int *jdos_nbins, double *delta_bins) {
+  if (*jdos_max_energy < 0.0) *jdos_max_energy = efermi - max_band_energy; /* :197 (sic) */
+  *jdos_nbins = abs((int)ceil(*jdos_max_energy / jdos_spacing));
+  *jdos_max_energy = (*jdos_nbins) * jdos_spacing;
+  *delta_bins = *jdos_max_energy / (double)(*jdos_nbins - 1);
+}
+
+/* jdos_utils.f90:348-398 restricted to [ik0,ik1).  Accumulates. */
+static int calculate_jdos_range(char jdos_type, const odo_system *sys, const odo_broadening *br,
+                                const double *E, int nbins, double delta_bins, double efermi,
+                                double scissor_op, const int *exclude_bands, int num_exclude_bands,
+                                const double *mw, int n_geom, int ik0, int ik1, double *jdos,
+                                double *wjdos) {
+  int linear = (jdos_type == 'l'), adaptive = (jdos_type == 'a'), fixed = (jdos_type == 'f');
+  int ik, is, ib, jb, idos, N2, x, skip, err = 0, force_adaptive;
+  const int nb = sys->nb, ns = sys->ns, nk = sys->nk;
+  double step[3] = {0, 0, 0}, adaptive_smearing_temp = 0.0, width = 0.0, grad[3] = {0, 0, 0}, EV[5];
+  double dos_temp, cuml, gnorm, centre;
+  if (!(linear || adaptive || fixed)) return 3;
+  if (linear || adaptive || br->hybrid_linear) adaptive_prefactor(sys, br, step, &adaptive_smearing_temp);
+  if (fixed) width = br->fixed_smearing;
+  for (ik = ik0; ik < ik1; ++ik) {
+    const double w = sys->electrons_per_state * sys->kpoint_weight[ik];
+    for (is = 0; is < ns; ++is) {
+      for (ib = 0; ib < nb; ++ib) {
+        if (num_exclude_bands > 0) {
+          skip = 0;
+          for (x = 0; x < num_exclude_bands; ++x)
+            if (exclude_bands[x] == ib + 1) skip = 1;
+          if (skip) continue;
+        }
+        if (BE(sys, ib, is, ik) >= efermi) continue; /* :358 */
+        for (jb = 0; jb < nb; ++jb) {
+          if (BE(sys, jb, is, ik) < efermi) continue; /* :360 */
+          if (linear || adaptive) {
+            grad[0] = BG(sys, jb, 0, ik, is) - BG(sys, ib, 0, ik, is);
+            grad[1] = BG(sys, jb, 1, ik, is) - BG(sys, ib, 1, ik, is);
+            grad[2] = BG(sys, jb, 2, ik, is) - BG(sys, ib, 2, ik, is);
+          }
+          gnorm = sqrt(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);
+          force_adaptive = 0;
+          if (br->hybrid_linear && (br->hybrid_linear_grad_tol > gnorm)) force_adaptive = 1; /* :365 */
+          centre = BE(sys, jb, is, ik) - BE(sys, ib, is, ik) + scissor_op;
+          if (linear && !force_adaptive) odo_doslin_sub_cell_corners(grad, step, centre, sys->recip_lattice, EV);
+          if (adaptive || force_adaptive) width = gnorm * adaptive_smearing_temp;
+          if (br->finite_bin_correction && (width < delta_bins)) width = delta_bins; /* :372 */
+          for (idos = 0; idos < nbins; ++idos) {
+            if (linear && !force_adaptive)
+              dos_temp = odo_doslin(EV[0], EV[1], EV[2], EV[3], EV[4], E[idos], &cuml, &err);
+            else
+              dos_temp = odo_gaussian(centre, width, E[idos]);
+            jdos[idos + (size_t)nbins * is] += dos_temp * w; /* :383 */
+            if (mw) {
+              for (N2 = 0; N2 < n_geom; ++N2)
+                wjdos[idos + (size_t)nbins * (is + (size_t)ns * N2)] +=
+                    dos_temp *
+                    mw[ib + (size_t)nb * (jb + (size_t)nb * (ik + (size_t)nk * (is + (size_t)ns * N2)))] *
+                    sys->electrons_per_state * sys->kpoint_weight[ik]; /* :389-390 */
+            }
+          }
+        }
+      }
+    }
+  }
+  return err;
+}
+
+int odo_calculate_jdos(char jdos_type, const odo_system *sys, const odo_broadening *br, const double *E,
+                       int nbins, double delta_bins, double efermi, double scissor_op,
+                       const int *exclude_bands, int num_exclude_bands, const double *mw, int n_geom,
+                       double *jdos, double *wjdos) {
+  memset(jdos, 0, sizeof(double) * (size_t)nbins * sys->ns);
+  if (mw) memset(wjdos, 0, sizeof(double) * (size_t)nbins * sys->ns * n_geom);
+  return calculate_jdos_range(jdos_type, sys, br, E, nbins, delta_bins, efermi, scissor_op, exclude_bands,
+                              num_exclude_bands, mw, n_geom, 0, sys->nk, jdos, wjdos);
+}
+
+static void *jdos_worker(void *p) {
+  mt_job *j = (mt_job *)p;
+  j->err = calculate_jdos_range(j->type, j->sys, j->br, j->E, j->nbins, j->delta_bins, j->efermi,
+                                j->scissor_op, j->exclude_bands, j->num_exclude_bands, j->mw, j->n_geom,
+                                j->ik0, j->ik1, j->dos, j->wdos);
+  return NULL;
+}
+
+int odo_calculate_jdos_mt(int nthreads, char jdos_type, const odo_system *sys, const odo_broadening *br,
+                          const double *E, int nbins, double delta_bins, double efermi,
+                          double scissor_op, const int *exclude_bands, int num_exclude_bands,
+                          const double *mw, int n_geom, double *jdos, double *wjdos) {
+  int t, err = 0, ik = 0;
+  size_t n1 = (size_t)nbins * sys->ns, nw = mw ? n1 * n_geom : 0, j;
+  int *per;
+  mt_job *jobs;
+  pthread_t *th;
+  if (nthreads > sys->nk) nthreads = sys->nk;
+  if (nthreads < 1) nthreads = 1;
+  per = (int *)malloc(sizeof(int) * nthreads);
+  jobs = (mt_job *)calloc(nthreads, sizeof(mt_job));
+  th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+  odo_dist_array(sys->nk, nthreads, per);
+  for (t = 0; t < nthreads; ++t) {
+    mt_job *jb = &jobs[t];
+    jb->type = jdos_type; jb->sys = sys; jb->br = br; jb->E = E; jb->nbins = nbins;
+    jb->delta_bins = delta_bins; jb->mw = mw; jb->n_geom = n_geom; jb->efermi = efermi;
+    jb->scissor_op = scissor_op; jb->exclude_bands = exclude_bands; jb->num_exclude_bands = num_exclude_bands;
+    jb->ik0 = ik; jb->ik1 = ik + per[t]; ik += per[t];
+    jb->dos = (double *)calloc(n1, sizeof(double));
+    jb->wdos = mw ? (double *)calloc(nw, sizeof(double)) : NULL;
+    pthread_create(&th[t], NULL, jdos_worker, jb);
+  }
+  memset(jdos, 0, sizeof(double) * n1);
+  if (mw) memset(wjdos, 0, sizeof(double) * nw);
+  for (t = 0; t < nthreads; ++t) {
+    pthread_join(th[t], NULL);
+    if (jobs[t].err) err = jobs[t].err;
+    for (j = 0; j < n1; ++j) jdos[j] += jobs[t].dos[j];
+    for (j = 0; j < nw; ++j) wjdos[j] += jobs[t].wdos[j];
+    free(jobs[t].dos); free(jobs[t].wdos);
+  }
+  free(per); free(jobs); free(th);
+  return err;
+}
+
+/* ---- complex helpers: optical_mat(ib,jb,i,ik,is), (re,im) interleaved ---- */
+typedef struct { double re, im; } cplx;
+static inline cplx cget(const double *a, size_t idx) { cplx c = {a[2 * idx], a[2 * idx + 1]}; return c; }
+static inline cplx cadd(cplx a, cplx b) { cplx c = {a.re + b.re, a.im + b.im}; return c; }
+static inline cplx cscale(double s, cplx a) { cplx c = {s * a.re, s * a.im}; return c; }
+static inline cplx cdivr(cplx a, double s) { cplx c = {a.re / s, a.im / s}; return c; }
+/* real(a*conjg(b)) */
+static inline double re_a_conjb(cplx a, cplx b) { return a.re * b.re + a.im * b.im; }
+#define SYM(s, a, b, n) ((s)[(a) + 3 * ((b) + 3 * (size_t)(n))])
+
+/* optics.f90:157-435 */
+int odo_make_weights(const odo_system *sys, const double *optical_mat, int geom, const double optics_qdir[3],
+                     const double *symops, int num_symm, double efermi, double scissor_op, double *mwout) {
+  const int nb = sys->nb, ns = sys->ns, nk = sys->nk;
+  const int n_geom = (geom == ODO_GEOM_TENSOR) ? 6 : 1;
+  const int N_in = 1;
+  double qdir[3] = {0, 0, 0}, qdir1[3] = {0, 0, 0}, qdir2[3] = {0, 0, 0};
+  double q_weight = 0, q_weight1 = 0, q_weight2 = 0, factor, sgn;
+  int N, N_spin, n1, n2, N2, N3, i, j;
+  cplx g[3], om[3];
+  size_t total = (size_t)nb * nb * nk * ns * n_geom, t;
+  for (t = 0; t < total; ++t) mwout[t] = 0.0; /* :220 */
+
+  if (geom == ODO_GEOM_POLAR) { /* :222-227 ; note 'unpolar' contains 'polar' -> handled first below */
+    for (i = 0; i < 3; ++i) qdir[i] = optics_qdir[i];
+    q_weight = sqrt(qdir[0] * qdir[0] + qdir[1] * qdir[1] + qdir[2] * qdir[2]);
+    if (q_weight < 0.001) return 1;
+  }
+  if (geom == ODO_GEOM_UNPOLAR) { /* :222-244 (index(...,'polar')>0 is also true for 'unpolar') */
+    for (i = 0; i < 3; ++i) qdir[i] = optics_qdir[i];
+    q_weight = sqrt(qdir[0] * qdir[0] + qdir[1] * qdir[1] + qdir[2] * qdir[2]);
+    if (q_weight < 0.001) return 1;
+    if (optics_qdir[2] == 0) {
+      qdir1[0] = 0.0; qdir1[1] = 0.0; qdir1[2] = 1.0;
+    } else {
+      qdir1[0] = 1.0; qdir1[1] = 1.0;
+      qdir1[2] = -(optics_qdir[0] + optics_qdir[1]) / optics_qdir[2];
+    }
+    qdir2[0] = (optics_qdir[1] * qdir1[2]) - (optics_qdir[2] * qdir1[1]);
+    qdir2[1] = (optics_qdir[2] * qdir1[0]) - (optics_qdir[0] * qdir1[2]);
+    qdir2[2] = (optics_qdir[0] * qdir1[1]) - (optics_qdir[1] * qdir1[0]);
+    q_weight1 = sqrt(qdir1[0] * qdir1[0] + qdir1[1] * qdir1[1] + qdir1[2] * qdir1[2]);
+    q_weight2 = sqrt(qdir2[0] * qdir2[0] + qdir2[1] * qdir2[1] + qdir2[2] * qdir2[2]);
+  }
+
+#define MW(a, b, k, s, gI) mwout[(a) + (size_t)nb * ((b) + (size_t)nb * ((k) + (size_t)nk * ((s) + (size_t)ns * (gI))))]
+#define OM(a, b, c, k, s) cget(optical_mat, (a) + (size_t)nb * ((b) + (size_t)nb * ((c) + 3 * ((k) + (size_t)nk * (s)))))
+
+  for (N = 0; N < nk; ++N)
+    for (N_spin = 0; N_spin < ns; ++N_spin)
+      for (n1 = 0; n1 < nb; ++n1)
+        for (n2 = n1; n2 < nb; ++n2) {
+          const double e1 = BE(sys, n1, N_spin, N), e2 = BE(sys, n2, N_spin, N);
+          if (e1 > efermi && n1 != n2) continue; /* :261 */
+          if (e2 < efermi && n1 != n2) continue; /* :262 */
+          factor = 0.0;
+          if (n2 == n1)
+            factor = 1.0;
+          else if (e2 > efermi)
+            factor = 1.0 / ((e2 - e1 + scissor_op) * (e2 - e1 + scissor_op));
+          for (i = 0; i < 3; ++i) om[i] = OM(n1, n2, i, N, N_spin);
+          if (geom == ODO_GEOM_UNPOLAR) {
+            if (num_symm == 0) {
+              g[0] = cdivr(cadd(cadd(cscale(qdir1[0], om[0]), cscale(qdir1[1], om[1])), cscale(qdir1[2], om[2])), q_weight1);
+              g[1] = cdivr(cadd(cadd(cscale(qdir2[0], om[0]), cscale(qdir2[1], om[1])), cscale(qdir2[2], om[2])), q_weight2);
+              MW(n1, n2, N, N_spin, 0) = 0.5 * factor * (re_a_conjb(g[0], g[0]) + re_a_conjb(g[1], g[1]));
+            } else {
+              for (N2 = 0; N2 < num_symm; ++N2)
+                for (N3 = 1; N3 <= 1 + N_in; ++N3) {
+                  sgn = (N3 == 1) ? 1.0 : -1.0; /* (-1)**(N3+1) */
+                  for (i = 0; i < 3; ++i) {
+                    qdir[i] = 0.0;
+                    for (j = 0; j < 3; ++j) qdir[i] = qdir[i] + sgn * (SYM(symops, j, i, N2) * qdir1[j]);
+                  }
+                  g[0] = cdivr(cadd(cadd(cscale(qdir[0], om[0]), cscale(qdir[1], om[1])), cscale(qdir[2], om[2])), q_weight1);
+                  MW(n1, n2, N, N_spin, 0) = MW(n1, n2, N, N_spin, 0) +
+                                             (0.5 / (double)(num_symm * (N_in + 1))) * re_a_conjb(g[0], g[0]) * factor;
+                  for (i = 0; i < 3; ++i) {
+                    qdir[i] = 0.0;
+                    for (j = 0; j < 3; ++j) qdir[i] = qdir[i] + sgn * (SYM(symops, j, i, N2) * qdir2[j]);
+                  }
+                  g[0] = cdivr(cadd(cadd(cscale(qdir[0], om[0]), cscale(qdir[1], om[1])), cscale(qdir[2], om[2])), q_weight2);
+                  MW(n1, n2, N, N_spin, 0) = MW(n1, n2, N, N_spin, 0) +
+                                             (0.5 / (double)(num_symm * (N_in + 1))) * re_a_conjb(g[0], g[0]) * factor;
+                }
+            }
+          } else if (geom == ODO_GEOM_POLAR) {
+            if (num_symm == 0) {
+              for (i = 0; i < 3; ++i) qdir[i] = optics_qdir[i];
+              g[0] = cdivr(cadd(cadd(cscale(qdir[0], om[0]), cscale(qdir[1], om[1])), cscale(qdir[2], om[2])), q_weight);
+              MW(n1, n2, N, N_spin, 0) = factor * re_a_conjb(g[0], g[0]);
+            } else {
+              for (N2 = 0; N2 < num_symm; ++N2)
+                for (N3 = 1; N3 <= 1 + N_in; ++N3) {
+                  sgn = (N3 == 1) ? 1.0 : -1.0;
+                  for (i = 0; i < 3; ++i) {
+                    qdir[i] = 0.0;
+                    for (j = 0; j < 3; ++j) qdir[i] = qdir[i] + sgn * (SYM(symops, j, i, N2) * optics_qdir[j]);
+                  }
+                  g[0] = cdivr(cadd(cadd(cscale(qdir[0], om[0]), cscale(qdir[1], om[1])), cscale(qdir[2], om[2])), q_weight);
+                  MW(n1, n2, N, N_spin, 0) = MW(n1, n2, N, N_spin, 0) +
+                                             (1.0 / (double)(num_symm * (N_in + 1))) * factor * re_a_conjb(g[0], g[0]);
+                }
+            }
+          } else if (geom == ODO_GEOM_POLY) {
+            if (num_symm == 0) {
+              MW(n1, n2, N, N_spin, 0) =
+                  (factor / 3.0) * (re_a_conjb(om[0], om[0]) + re_a_conjb(om[1], om[1]) + re_a_conjb(om[2], om[2]));
+            } else {
+              for (N2 = 0; N2 < num_symm; ++N2)
+                for (N3 = 1; N3 <= 1 + N_in; ++N3) {
+                  sgn = (N3 == 1) ? 1.0 : -1.0;
+                  for (i = 0; i < 3; ++i) {
+                    qdir[i] = sgn * SYM(symops, 0, i, N2);
+                    qdir1[i] = sgn * SYM(symops, 1, i, N2);
+                    qdir2[i] = sgn * SYM(symops, 2, i, N2);
+                  }
+                  g[0] = cadd(cadd(cscale(qdir[0], om[0]), cscale(qdir[1], om[1])), cscale(qdir[2], om[2]));
+                  g[1] = cadd(cadd(cscale(qdir1[0], om[0]), cscale(qdir1[1], om[1])), cscale(qdir1[2], om[2]));
+                  g[2] = cadd(cadd(cscale(qdir2[0], om[0]), cscale(qdir2[1], om[1])), cscale(qdir2[2], om[2]));
+                  MW(n1, n2, N, N_spin, 0) =
+                      MW(n1, n2, N, N_spin, 0) +
+                      (1.0 / (double)(num_symm * (N_in + 1))) * factor *
+                          ((re_a_conjb(g[0], g[0]) + re_a_conjb(g[1], g[1]) + re_a_conjb(g[2], g[2])) / 3.0);
+                }
+            }
+          } else if (geom == ODO_GEOM_TENSOR) {
+            if (num_symm == 0) {
+              MW(n1, n2, N, N_spin, 0) = factor * re_a_conjb(om[0], om[0]);
+              MW(n1, n2, N, N_spin, 1) = factor * re_a_conjb(om[1], om[1]);
+              MW(n1, n2, N, N_spin, 2) = factor * re_a_conjb(om[2], om[2]);
+              MW(n1, n2, N, N_spin, 3) = factor * re_a_conjb(om[0], om[1]);
+              MW(n1, n2, N, N_spin, 4) = factor * re_a_conjb(om[0], om[2]);
+              MW(n1, n2, N, N_spin, 5) = factor * re_a_conjb(om[1], om[2]);
+            } else {
+              const double den = (double)(num_symm * (N_in + 1));
+              for (N2 = 0; N2 < num_symm; ++N2)
+                for (N3 = 1; N3 <= 1 + N_in; ++N3) {
+                  sgn = (N3 == 1) ? 1.0 : -1.0;
+                  for (i = 0; i < 3; ++i) {
+                    g[i].re = 0.0; g[i].im = 0.0;
+                    for (j = 0; j < 3; ++j) g[i] = cadd(g[i], cscale(sgn * SYM(symops, i, j, N2), om[j]));
+                  }
+                  MW(n1, n2, N, N_spin, 0) += factor * re_a_conjb(g[0], g[0]) / den;
+                  MW(n1, n2, N, N_spin, 1) += factor * re_a_conjb(g[1], g[1]) / den;
+                  MW(n1, n2, N, N_spin, 2) += factor * re_a_conjb(g[2], g[2]) / den;
+                  MW(n1, n2, N, N_spin, 3) += factor * re_a_conjb(g[0], g[1]) / den;
+                  MW(n1, n2, N, N_spin, 4) += factor * re_a_conjb(g[0], g[2]) / den;
+                  MW(n1, n2, N, N_spin, 5) += factor * re_a_conjb(g[1], g[2]) / den;
+                }
+            }
+          }
+        }
+#undef MW
+#undef OM
+  return 0;
+}
+
+/* optics.f90:495-551 (interband).  Physical constants optics.f90:68-72; the 1E-20 / 1E-30
+ * literals are SINGLE precision in the reference (quirk Q11). */
+void odo_calc_epsilon_2(const double *wjdos, int nbins, int ns, int n_geom, double cell_volume,
+                        double *epsilon2) {
+  const double epsilon_0 = 8.8541878176E-12, e_charge = 1.602176487E-19;
+  const double c20 = (double)1E-20f, c30 = (double)1E-30f;
+  const double epsilon2_const = (e_charge * ODO_PI * c20) / (cell_volume * c30 * epsilon_0);
+  int N2, is, ie;
+  for (N2 = 0; N2 < n_geom; ++N2) {
+    for (ie = 0; ie < nbins; ++ie) epsilon2[ie + (size_t)nbins * N2] = 0.0;
+    for (is = 0; is < ns; ++is)
+      for (ie = 1; ie < nbins; ++ie) /* N_energy = 2, jdos_nbins (Q12) */
+        epsilon2[ie + (size_t)nbins * N2] += epsilon2_const * wjdos[ie + (size_t)nbins * (is + (size_t)ns * N2)];
+  }
+}
+
+/* optics.f90:569-621 (no intraband) */
+void odo_calc_epsilon_1(const double *epsilon2, const double *E, int nbins, int n_geom, double *epsilon1) {
+  int N2, i, j;
+  const double dE = E[1] - E[0];
+  for (N2 = 0; N2 < n_geom; ++N2)
+    for (i = 0; i < nbins; ++i) {
+      double q = 0.0;
+      for (j = 0; j < nbins; ++j)
+        if (j != i) {
+          const double energy1 = E[i], energy2 = E[j];
+          q = q + (((energy2 * epsilon2[j + (size_t)nbins * N2]) / ((energy2 * energy2) - (energy1 * energy1))) * dE);
+        }
+      if (N2 < 3)
+        epsilon1[i + (size_t)nbins * N2] = ((2.0 / ODO_PI) * q) + 1.0;
+      else
+        epsilon1[i + (size_t)nbins * N2] = ((2.0 / ODO_PI) * q);
+    }
+}
+
+/* core.f90:84-168 */
+int odo_core_prepare_matrix_elements(const odo_system *sys, const double *elnes_mat, int norb, int polar,
+                                     const double core_qdir[3], const double *symops, int num_sym,
+                                     int core_type, double efermi, double *mwout) {
+  const int nb = sys->nb, ns = sys->ns, nk = sys->nk, N_in = 1;
+  double qdir[3] = {0, 0, 0}, q_weight = 0.0, sgn;
+  int N, N_spin, n_eigen, orb, N2, N3, i, j;
+  size_t total = (size_t)norb * nb * nk * ns, t;
+  cplx g, m[3];
+  if (num_sym > 1) return 1; /* :106 */
+  for (t = 0; t < total; ++t) mwout[t] = 0.0;
+  if (polar) {
+    for (i = 0; i < 3; ++i) qdir[i] = core_qdir[i];
+    q_weight = sqrt(pow(qdir[0], 2.0) + pow(qdir[1], 2.0) + pow(qdir[2], 2.0));
+    if (q_weight < 0.001) return 2;
+  }
+#define EM(o, b, c, k, s) cget(elnes_mat, (o) + (size_t)norb * ((b) + (size_t)nb * ((c) + 3 * ((k) + (size_t)nk * (s)))))
+#define MWC(o, b, k, s) mwout[(o) + (size_t)norb * ((b) + (size_t)nb * ((k) + (size_t)nk * (s)))]
+  for (N = 0; N < nk; ++N)
+    for (N_spin = 0; N_spin < ns; ++N_spin)
+      for (n_eigen = 0; n_eigen < nb; ++n_eigen) {
+        const double e = BE(sys, n_eigen, N_spin, N);
+        if (e < efermi && core_type == 0) continue; /* absorption :125 */
+        if (e > efermi && core_type == 1) continue; /* emission   :126 */
+        for (orb = 0; orb < norb; ++orb) {
+          for (i = 0; i < 3; ++i) m[i] = EM(orb, n_eigen, i, N, N_spin);
+          if (polar) {
+            if (num_sym == 0) {
+              g = cdivr(cadd(cadd(cscale(qdir[0], m[0]), cscale(qdir[1], m[1])), cscale(qdir[2], m[2])), q_weight);
+              MWC(orb, n_eigen, N, N_spin) = re_a_conjb(g, g);
+            } else {
+              for (N2 = 0; N2 < num_sym; ++N2)
+                for (N3 = 1; N3 <= 1 + N_in; ++N3) {
+                  sgn = (N3 == 1) ? 1.0 : -1.0;
+                  for (i = 0; i < 3; ++i) {
+                    qdir[i] = 0.0;
+                    for (j = 0; j < 3; ++j) qdir[i] = qdir[i] + sgn * (SYM(symops, j, i, N2) * core_qdir[j]);
+                  }
+                  g = cdivr(cadd(cadd(cscale(qdir[0], m[0]), cscale(qdir[1], m[1])), cscale(qdir[2], m[2])), q_weight);
+                  MWC(orb, n_eigen, N, N_spin) =
+                      MWC(orb, n_eigen, N, N_spin) + (1.0 / (double)(num_sym * (N_in + 1))) * re_a_conjb(g, g);
+                }
+            }
+          } else {
+            MWC(orb, n_eigen, N, N_spin) =
+                (re_a_conjb(m[0], m[0]) + re_a_conjb(m[1], m[1]) + re_a_conjb(m[2], m[2])) / 3.0;
+          }
+        }
+      }
+#undef EM
+#undef MWC
+  return 0;
+}
+
+/* projection_utils.f90:64-99 */
+void odo_projection_merge(const double *pdos_weights, const int *mask, int norb_in, int nproj, int nb,
+                          int nk, int ns, double *mwout) {
+  size_t state, nstates = (size_t)nb * nk * ns;
+  int p, orb;
+  for (state = 0; state < nstates; ++state)
+    for (p = 0; p < nproj; ++p) {
+      double acc = 0.0;
+      for (orb = 0; orb < norb_in; ++orb)
+        if (mask[orb + (size_t)norb_in * p] == 1) acc = acc + pdos_weights[orb + (size_t)norb_in * state];
+      mwout[p + (size_t)nproj * state] = acc;
+    }
+}
+
+/* electronic.f90:280-291 */
+void odo_gradient_from_ome(const double *optical_mat, int nb, int nk, int ns, double *band_gradient) {
+  int ib, i, ik, is;
+  for (is = 0; is < ns; ++is)
+    for (ik = 0; ik < nk; ++ik)
+      for (i = 0; i < 3; ++i)
+        for (ib = 0; ib < nb; ++ib)
+          band_gradient[ib + (size_t)nb * (i + 3 * (ik + (size_t)nk * is))] =
+              optical_mat[2 * (ib + (size_t)nb * (ib + (size_t)nb * (i + 3 * (ik + (size_t)nk * is))))];
+}
