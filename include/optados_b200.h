@@ -1,0 +1,246 @@
+/*
+ * optados_b200.h -- C ABI of liboptados_b200.so
+ *
+ * B200-native (sm_100a, FP64 CUDA) replacement for the Brillouin-zone spectral-integration hot
+ * path of OptaDOS.  The reference (optados-developers/optados, Fortran) has no plugin / FFI API:
+ * its tasks call module procedures that read module-global arrays.  This header is the boundary
+ * a maintainer binds with ISO_C_BINDING (see INTEGRATION.md and optados_b200/fortran/): every
+ * entry point below names the reference routine whose body it replaces (paths relative to
+ * optados/src/ in the reference tree).
+ *
+ * Conventions
+ *   - all functions return int: 0 = OK, non-zero = error; od_last_error(ctx) gives the message the
+ *     Fortran shim forwards to io_error (io.f90:91).  No exceptions cross the ABI.
+ *   - arrays are the reference's: IEEE double, Fortran column-major, first index fastest; complex
+ *     arrays are (re,im) pairs.  Layouts are repeated at each entry point.
+ *   - the caller owns every array it passes; `mem` says where an input lives (OD_MEM_HOST: the
+ *     library copies it to HBM; OD_MEM_DEVICE: a device pointer the library uses in place and
+ *     that must stay valid until the next od_set_* of the same array or od_ctx_destroy).
+ *     Output arrays are always host memory unless the name says _device.
+ *   - calls are blocking and not re-entrant per ctx.  There is no CPU fallback: without a CUDA
+ *     device od_ctx_create fails.
+ *   - one ctx = one GPU = one k-point shard (the reference's "node", algorithms.f90:309).  With
+ *     od_ctx_create_rank the ctx also owns an NCCL communicator and the *_merge / od_allreduce_*
+ *     calls combine the shards (replacing comms_reduce, comms.F90:556); results are then valid on
+ *     every rank (allreduce, a superset of the reference's reduce-to-root).
+ */
+#ifndef OPTADOS_B200_H
+#define OPTADOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct od_ctx od_ctx;
+
+enum { OD_MEM_HOST = 0, OD_MEM_DEVICE = 1 };
+enum { OD_OK = 0, OD_ERR_ARG = 1, OD_ERR_CUDA = 2, OD_ERR_STATE = 3, OD_ERR_NCCL = 4, OD_ERR_DOSLIN = 5, OD_ERR_REF = 6 };
+
+/* optics_geom (parameters.f90:346; optics.f90:213-244) and core_type (parameters.f90:373-378) */
+enum { OD_GEOM_POLYCRYS = 0, OD_GEOM_POLAR = 1, OD_GEOM_UNPOLAR = 2, OD_GEOM_TENSOR = 3 };
+enum { OD_CORE_ABSORPTION = 0, OD_CORE_EMISSION = 1, OD_CORE_ALL = 2 };
+/* efermi_choice (parameters.f90:257; dos_utils.f90:317-380) */
+enum { OD_EFERMI_OPTADOS = 0, OD_EFERMI_FILE = 1, OD_EFERMI_USER = 2, OD_EFERMI_INSULATOR = 3 };
+
+/* ---------------------------------------------------------------- context ------------------ */
+const char *od_version(void);
+/* single GPU, no communicator (the reference's serial build: comms.F90 stubs) */
+int od_ctx_create(int device, od_ctx **ctx);
+/* one rank per GPU (the reference's MPI build: comms_setup, comms.F90:85).  id128 is the 128-byte
+ * NCCL unique id produced by od_comm_get_unique_id on rank 0 and broadcast by the host program. */
+int od_comm_get_unique_id(void *id128);
+int od_ctx_create_rank(int device, int rank, int nranks, const void *id128, od_ctx **ctx);
+int od_ctx_destroy(od_ctx *ctx);
+const char *od_last_error(const od_ctx *ctx);
+int od_ctx_rank(const od_ctx *ctx);
+int od_ctx_nranks(const od_ctx *ctx);
+int od_synchronize(od_ctx *ctx);
+/* number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches) */
+long long od_kernel_launches(const od_ctx *ctx);
+/* device-side milliseconds (CUDA events on the ctx stream) spent in the main accumulation kernels
+ * since the last reset, and the number of in-window (unit, bin) contributions they evaluated */
+int od_profile_reset(od_ctx *ctx);
+int od_profile_get(od_ctx *ctx, double *accumulate_ms, double *prepare_ms, double *contributions, long long *accumulate_launches);
+
+/* device memory helpers (so weight arrays can stay resident between calls) */
+int od_device_malloc(od_ctx *ctx, size_t nbytes, void **dptr);
+int od_device_free(od_ctx *ctx, void *dptr);
+int od_memcpy_h2d(od_ctx *ctx, void *dst_device, const void *src_host, size_t nbytes);
+int od_memcpy_d2h(od_ctx *ctx, void *dst_host, const void *src_device, size_t nbytes);
+
+/* algor_dist_array (algorithms.f90:309): k-points per rank, remainder to the lowest ranks */
+int od_dist_array(int num_elements, int num_nodes, int *elements_per_node);
+
+/* comms_reduce_real (comms.F90:556) on a HOST buffer, result valid on every rank. op: 's','m'(in),'M'(ax) */
+int od_allreduce(od_ctx *ctx, double *host_buf, size_t n, char op);
+
+/* ---------------------------------------------------------------- module data --------------- */
+/* od_cell / od_electronic data the hot loops read (cell.f90:43-56, electronic.f90:38-41,605-611):
+ *   recip_lattice(3,3) [i+3*j], kpoint_grid_dim(3), kpoint_weight(nk_local), electrons_per_state */
+int od_set_system(od_ctx *ctx, int nk_local, int ns, int nb, const double recip_lattice[9],
+                  const int kpoint_grid_dim[3], const double *kpoint_weight, double electrons_per_state);
+/* band_energy(nb,ns,nk_local) in eV (electronic.f90:38, filled :554-601) */
+int od_set_bands(od_ctx *ctx, const double *band_energy, int mem);
+/* band_gradient(nb,3,nk_local,ns) in eV Ang (electronic.f90:39; elec_read_band_gradient :170-299) */
+int od_set_gradients(od_ctx *ctx, const double *band_gradient, int mem);
+/* the "diag of OME" branch of elec_read_band_gradient (electronic.f90:276-291):
+ * band_gradient(ib,:,ik,is) = Re(optical_mat(ib,ib,:,ik,is)); optical_mat(nb,nb,3,nk,ns) complex */
+int od_set_gradients_from_ome(od_ctx *ctx, const double *optical_mat, int mem);
+/* copy the resident gradients back (tests) */
+int od_get_gradients(od_ctx *ctx, double *band_gradient_host);
+/* minval / maxval(band_energy) over this rank, then MIN/MAX-allreduced if the ctx has a communicator
+ * (dos_utils.f90:964-977, jdos_utils.f90:194-196) */
+int od_band_minmax(od_ctx *ctx, double *min_band_energy, double *max_band_energy);
+
+/* broadening flags read by the hot loops (parameters.f90:246-289) */
+typedef struct od_broadening {
+  double adaptive_smearing;      /* default 0.4 */
+  double fixed_smearing;         /* default 0.3 */
+  double linear_smearing;        /* default 0.0 */
+  int finite_bin_correction;     /* default 1 */
+  int numerical_intdos;          /* default 0 */
+  int hybrid_linear;             /* default 0 */
+  double hybrid_linear_grad_tol; /* default 0.01 */
+} od_broadening;
+void od_broadening_defaults(od_broadening *b);
+
+/* ---------------------------------------------------------------- hot loops ------------------ */
+/* calculate_dos (dos_utils.f90:1140-1317): rank-local partial spectra on the grid
+ * E(i) = emin + (i-1)*delta_bins, i = 1..nbins (dos_utils.f90:994-997).
+ *   dos_type 'f' | 'a' | 'l'
+ *   matrix_weights(mw_norb, mw_nb, mw_nk, ns) or NULL (dos_utils.f90:1267-1276)
+ *   out: dos(nbins,ns), intdos(nbins,ns), weighted_dos(nbins,ns,mw_norb) (NULL if no weights)
+ * With merge != 0 the partial spectra are sum-allreduced over the communicator on the device before
+ * they are copied out (= calculate_dos followed by dos_utils_merge, dos_utils.f90:1013-1053). */
+int od_calculate_dos(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins,
+                     const od_broadening *br, const double *matrix_weights, int mw_norb, int mw_nb,
+                     int mw_nk, int mw_mem, int merge, double *dos, double *intdos, double *weighted_dos);
+
+/* calculate_dos_at_e (dos_utils.f90:1651-1800) [+ dos_utils_merge_at_e :1803 when merge != 0]
+ *   out: dos_at_e(ns), weighted_dos_at_e(ns, mw_norb) or NULL */
+int od_calculate_dos_at_e(od_ctx *ctx, char dos_type, double energy, double delta_bins,
+                          const od_broadening *br, const double *matrix_weights, int mw_norb, int mw_nb,
+                          int mw_nk, int mw_mem, int merge, double *dos_at_e, double *weighted_dos_at_e);
+
+/* calculate_jdos (jdos_utils.f90:280-404) on E(i) = (i-1)*delta_bins [+ jdos_utils_merge :407].
+ *   matrix_weights(nb,nb,nk,ns,n_geom) or NULL;  exclude_bands are 1-based band indices
+ *   out: jdos(nbins,ns), weighted_jdos(nbins,ns,n_geom) or NULL
+ * NB merge reduces the whole weighted_jdos, not only its first N_geom slice (jdos_utils.f90:437 is
+ * an MPI bug for optics_geom = tensor; the serial reference is unaffected). */
+int od_calculate_jdos(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br,
+                      double efermi, double scissor_op, const int *exclude_bands, int num_exclude_bands,
+                      const double *matrix_weights, int n_geom, int mw_mem, int merge, double *jdos,
+                      double *weighted_jdos);
+
+/* calculate_jdos with make_weights (optics.f90:157-435) fused in: the optical weights are formed on
+ * chip from optical_mat(nb,nb,3,nk,ns) (complex, eV Ang) and matrix_weights(nb,nb,nk,ns,N_geom) is
+ * never materialised.  symops(3,3,num_symm) = crystal_symmetry_operations (cell.f90:675-682). */
+int od_calculate_jdos_optics(od_ctx *ctx, char jdos_type, double delta_bins, int nbins,
+                             const od_broadening *br, double efermi, double scissor_op,
+                             const int *exclude_bands, int num_exclude_bands, const double *optical_mat,
+                             int ome_mem, int geom, const double qdir[3], const double *symops, int num_symm,
+                             int merge, double *jdos, double *weighted_jdos);
+
+/* ---------------------------------------------------------------- weight builders ------------ */
+/* make_weights (optics.f90:157-435): out matrix_weights(nb,nb,nk,ns,N_geom), N_geom = 6 for tensor
+ * else 1.  out_mem selects a host or (caller-allocated) device output. */
+int od_make_weights(od_ctx *ctx, const double *optical_mat, int ome_mem, int geom, const double qdir[3],
+                    const double *symops, int num_symm, double efermi, double scissor_op,
+                    double *matrix_weights, int out_mem);
+/* core_prepare_matrix_elements (core.f90:84-168): elnes_mat(norb,nb,3,nk,ns) complex ->
+ * matrix_weights(norb,nb,nk,ns).  Returns OD_ERR_REF if num_sym > 1 (core.f90:106). */
+int od_core_prepare_matrix_elements(od_ctx *ctx, const double *elnes_mat, int elnes_mem, int norb, int polar,
+                                    const double qdir[3], const double *symops, int num_sym, int core_type,
+                                    double efermi, double *matrix_weights, int out_mem);
+/* projection_merge (projection_utils.f90:64-99) with projection_array flattened by the caller to
+ * mask(norb_in, nproj) in {0,1}: pdos_weights(norb_in,nb,nk,ns) -> matrix_weights(nproj,nb,nk,ns) */
+int od_projection_merge(od_ctx *ctx, const double *pdos_weights, int pw_mem, const int *mask, int norb_in,
+                        int nproj, double *matrix_weights, int out_mem);
+/* calc_epsilon_2 interband part (optics.f90:495-551): epsilon2(nbins, n_geom) */
+int od_calc_epsilon_2(od_ctx *ctx, const double *weighted_jdos, int nbins, int ns, int n_geom,
+                      double cell_volume, double *epsilon2);
+
+/* ---------------------------------------------------------------- task drivers --------------- */
+/* Host-side mirror of the reference's L3 drivers: same control flow, flags and side effects, with
+ * the module-global results kept inside the ctx and read back with the od_*_get calls. */
+typedef struct od_dos_params {
+  int fixed, adaptive, linear;   /* broadening switches (parameters.f90:232-234, compare_dos) */
+  od_broadening br;
+  double dos_spacing;            /* parameters.f90:459-461: default is the SINGLE literal 0.005 */
+  int dos_nbins;                 /* in/out: < 0 = derive; sticky afterwards (quirk Q4, dos_utils.f90:980) */
+  int have_dos_min_energy, have_dos_max_energy;
+  double dos_min_energy, dos_max_energy;
+  int efermi_choice;             /* OD_EFERMI_* */
+  double efermi_user, efermi_castep;
+  int nspins_electrons;          /* entries of num_electrons used */
+  double num_electrons[2];       /* electronic.f90: num_electrons(nspins) */
+  int dos_per_volume;            /* parameters.f90: dos_per_volume */
+  double cell_volume;
+} od_dos_params;
+void od_dos_params_defaults(od_dos_params *p);
+
+typedef struct od_dos_result {
+  int nbins;
+  double emin, delta_bins;                             /* E(i) = emin + (i-1)*delta_bins */
+  double efermi_fixed, efermi_adaptive, efermi_linear; /* calc_efermi_from_intdos (dos_utils.f90:798) */
+  int have_fixed, have_adaptive, have_linear, have_weighted;
+  int weighted_norb;
+} od_dos_result;
+
+/* dos_utils_calculate (dos_utils.f90:92-293): energy scale, one calculate_dos + merge per enabled
+ * broadening (weighted spectrum only with the "most complex" one, :179-208), Fermi analysis. */
+int od_dos_utils_calculate(od_ctx *ctx, od_dos_params *p, const double *matrix_weights, int mw_norb,
+                           int mw_nb, int mw_nk, int mw_mem, od_dos_result *res);
+/* read back dos_<type>, intdos_<type> (nbins,ns) / weighted_dos (nbins,ns,norb) of the last call */
+int od_dos_get(od_ctx *ctx, char dos_type, double *dos, double *intdos);
+int od_dos_get_weighted(od_ctx *ctx, double *weighted_dos);
+/* calc_efermi_from_intdos (dos_utils.f90:798-850) on host arrays */
+double od_calc_efermi_from_intdos(const double *intdos, double emin, double delta_bins, int nbins, int ns,
+                                  const double *num_electrons);
+/* dos_utils_set_efermi (dos_utils.f90:296-388).  For OD_EFERMI_OPTADOS runs od_dos_utils_calculate. */
+int od_dos_utils_set_efermi(od_ctx *ctx, od_dos_params *p, double *efermi);
+
+typedef struct od_jdos_params {
+  int fixed, adaptive, linear;
+  od_broadening br;
+  double jdos_spacing;    /* parameters.f90:321 default 0.01 */
+  double jdos_max_energy; /* in/out: < 0 = derive (jdos_utils.f90:193-197) */
+  double scissor_op;      /* parameters.f90:351 */
+  int num_exclude_bands;
+  const int *exclude_bands;
+  double efermi;
+  int dos_per_volume;
+  double cell_volume;
+} od_jdos_params;
+void od_jdos_params_defaults(od_jdos_params *p);
+typedef struct od_jdos_result {
+  int nbins;
+  double delta_bins; /* E(i) = (i-1)*delta_bins */
+  int have_fixed, have_adaptive, have_linear, have_weighted, n_geom;
+} od_jdos_result;
+/* jdos_utils_calculate (jdos_utils.f90:61-174).  Exactly one of matrix_weights / optical_mat may be
+ * non-NULL; with optical_mat the optical weights are fused (see od_calculate_jdos_optics). */
+int od_jdos_utils_calculate(od_ctx *ctx, od_jdos_params *p, const double *matrix_weights, int n_geom, int mw_mem,
+                            const double *optical_mat, int ome_mem, int geom, const double qdir[3],
+                            const double *symops, int num_symm, od_jdos_result *res);
+int od_jdos_get(od_ctx *ctx, char jdos_type, double *jdos);
+int od_jdos_get_weighted(od_ctx *ctx, double *weighted_jdos);
+
+/* ---------------------------------------------------------------- synthetic inputs ----------- */
+/* cosine-band synthetic band structure generated directly in HBM
+ * (E_n(k) = c_n + t_n (cos 2pi k1 + cos 2pi k2 + cos 2pi k3), analytic gradients, per-(k,s) sorted).
+ * Fills band_energy / band_gradient / kpoint_weight of the ctx for the k-points [k_first,
+ * k_first + nk_local) of a grid[0] x grid[1] x grid[2] MP mesh (k3 fastest) and calls od_set_system. */
+int od_synth_bands(od_ctx *ctx, const int grid[3], long long k_first, int nk_local, int ns, int nb,
+                   double lattice_a, uint64_t seed);
+/* copy the resident arrays of the ctx back to the host (for parity tests against the oracle) */
+int od_get_bands(od_ctx *ctx, double *band_energy_host);
+int od_get_kweights(od_ctx *ctx, double *kpoint_weight_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTADOS_B200_H */

@@ -1,0 +1,425 @@
+"""optados_b200 -- thin ctypes binding of liboptados_b200.so (the C ABI in include/optados_b200.h).
+
+The product is the CUDA library; this module only loads it and marshals numpy arrays, so that the
+parity tests and bench.py can call the same entry points a Fortran host binds with ISO_C_BINDING
+(optados_b200/fortran/od_b200.f90).  There is no CPU fallback: if the library is missing or no
+CUDA device is present the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liboptados_b200.so")
+
+OD_MEM_HOST, OD_MEM_DEVICE = 0, 1
+GEOM = {"polycrys": 0, "polar": 1, "unpolar": 2, "tensor": 3}
+CORE_TYPE = {"absorption": 0, "emission": 1, "all": 2}
+EFERMI = {"optados": 0, "file": 1, "user": 2, "insulator": 3}
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+class Broadening(C.Structure):
+    _fields_ = [("adaptive_smearing", C.c_double), ("fixed_smearing", C.c_double), ("linear_smearing", C.c_double),
+                ("finite_bin_correction", C.c_int), ("numerical_intdos", C.c_int), ("hybrid_linear", C.c_int),
+                ("hybrid_linear_grad_tol", C.c_double)]
+
+
+class DosParams(C.Structure):
+    _fields_ = [("fixed", C.c_int), ("adaptive", C.c_int), ("linear", C.c_int), ("br", Broadening),
+                ("dos_spacing", C.c_double), ("dos_nbins", C.c_int),
+                ("have_dos_min_energy", C.c_int), ("have_dos_max_energy", C.c_int),
+                ("dos_min_energy", C.c_double), ("dos_max_energy", C.c_double),
+                ("efermi_choice", C.c_int), ("efermi_user", C.c_double), ("efermi_castep", C.c_double),
+                ("nspins_electrons", C.c_int), ("num_electrons", C.c_double * 2),
+                ("dos_per_volume", C.c_int), ("cell_volume", C.c_double)]
+
+
+class DosResult(C.Structure):
+    _fields_ = [("nbins", C.c_int), ("emin", C.c_double), ("delta_bins", C.c_double),
+                ("efermi_fixed", C.c_double), ("efermi_adaptive", C.c_double), ("efermi_linear", C.c_double),
+                ("have_fixed", C.c_int), ("have_adaptive", C.c_int), ("have_linear", C.c_int),
+                ("have_weighted", C.c_int), ("weighted_norb", C.c_int)]
+
+
+class JdosParams(C.Structure):
+    _fields_ = [("fixed", C.c_int), ("adaptive", C.c_int), ("linear", C.c_int), ("br", Broadening),
+                ("jdos_spacing", C.c_double), ("jdos_max_energy", C.c_double), ("scissor_op", C.c_double),
+                ("num_exclude_bands", C.c_int), ("exclude_bands", c_ip), ("efermi", C.c_double),
+                ("dos_per_volume", C.c_int), ("cell_volume", C.c_double)]
+
+
+class JdosResult(C.Structure):
+    _fields_ = [("nbins", C.c_int), ("delta_bins", C.c_double), ("have_fixed", C.c_int), ("have_adaptive", C.c_int),
+                ("have_linear", C.c_int), ("have_weighted", C.c_int), ("n_geom", C.c_int)]
+
+
+class OptadosB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"optados_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load liboptados_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()); "
+                          "optados_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L.od_version.restype = C.c_char_p
+    L.od_last_error.restype = C.c_char_p
+    L.od_last_error.argtypes = [C.c_void_p]
+    L.od_kernel_launches.restype = C.c_longlong
+    L.od_kernel_launches.argtypes = [C.c_void_p]
+    L.od_calc_efermi_from_intdos.restype = C.c_double
+    L.od_calc_efermi_from_intdos.argtypes = [c_dp, C.c_double, C.c_double, C.c_int, C.c_int, c_dp]
+    _lib = L
+    return L
+
+
+EXPORTS = [
+    "od_version", "od_ctx_create", "od_comm_get_unique_id", "od_ctx_create_rank", "od_ctx_destroy", "od_last_error",
+    "od_ctx_rank", "od_ctx_nranks", "od_synchronize", "od_kernel_launches", "od_profile_reset", "od_profile_get",
+    "od_device_malloc", "od_device_free", "od_memcpy_h2d", "od_memcpy_d2h", "od_dist_array", "od_allreduce",
+    "od_set_system", "od_set_bands", "od_set_gradients", "od_set_gradients_from_ome", "od_get_gradients",
+    "od_band_minmax", "od_broadening_defaults", "od_calculate_dos", "od_calculate_dos_at_e", "od_calculate_jdos",
+    "od_calculate_jdos_optics", "od_make_weights", "od_core_prepare_matrix_elements", "od_projection_merge",
+    "od_calc_epsilon_2", "od_dos_params_defaults", "od_dos_utils_calculate", "od_dos_get", "od_dos_get_weighted",
+    "od_calc_efermi_from_intdos", "od_dos_utils_set_efermi", "od_jdos_params_defaults", "od_jdos_utils_calculate",
+    "od_jdos_get", "od_jdos_get_weighted", "od_synth_bands", "od_get_bands", "od_get_kweights",
+]
+
+
+def f64(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def broadening(adaptive_smearing=0.4, fixed_smearing=0.3, linear_smearing=0.0, finite_bin_correction=True,
+               numerical_intdos=False, hybrid_linear=False, hybrid_linear_grad_tol=0.01):
+    return Broadening(adaptive_smearing, fixed_smearing, linear_smearing, int(finite_bin_correction),
+                      int(numerical_intdos), int(hybrid_linear), hybrid_linear_grad_tol)
+
+
+def dist_array(num_elements, num_nodes):
+    per = (C.c_int * num_nodes)()
+    rc = load().od_dist_array(C.c_int(num_elements), C.c_int(num_nodes), per)
+    if rc:
+        raise OptadosB200Error(rc, "Fewer kpoints than nodes. Reduce the number of nodes used!")
+    return list(per)
+
+
+def get_unique_id():
+    buf = C.create_string_buffer(128)
+    rc = load().od_comm_get_unique_id(buf)
+    if rc:
+        raise OptadosB200Error(rc, "od_comm_get_unique_id failed")
+    return buf.raw
+
+
+class Context:
+    """One GPU / one k-point shard.  Methods map 1:1 onto the C ABI."""
+
+    def __init__(self, device=0, rank=0, nranks=1, unique_id=None):
+        self.L = load()
+        self.h = C.c_void_p()
+        if nranks > 1:
+            rc = self.L.od_ctx_create_rank(C.c_int(device), C.c_int(rank), C.c_int(nranks), unique_id, C.byref(self.h))
+        else:
+            rc = self.L.od_ctx_create(C.c_int(device), C.byref(self.h))
+        if rc:
+            raise OptadosB200Error(rc, "od_ctx_create failed (no CUDA device? optados_b200 has no CPU fallback)")
+        self.nk = self.ns = self.nb = 0
+        self._keep = {}
+
+    def close(self):
+        if self.h:
+            self.L.od_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise OptadosB200Error(rc, self.L.od_last_error(self.h).decode())
+
+    # ---- module data
+    def set_system(self, nk, ns, nb, recip_lattice, kpoint_grid_dim, kpoint_weight, electrons_per_state):
+        r = f64(recip_lattice).ravel(order="F")
+        g = np.asarray(kpoint_grid_dim, dtype=np.int32)
+        kw = None if kpoint_weight is None else f64(kpoint_weight)
+        self._ck(self.L.od_set_system(self.h, C.c_int(nk), C.c_int(ns), C.c_int(nb), _p(r), g.ctypes.data_as(c_ip), _p(kw),
+                                      C.c_double(electrons_per_state)))
+        self.nk, self.ns, self.nb = nk, ns, nb
+
+    def set_bands(self, band_energy):
+        a = f64(band_energy)
+        self._ck(self.L.od_set_bands(self.h, _p(a), OD_MEM_HOST))
+        self._ck(self.L.od_synchronize(self.h))
+
+    def set_gradients(self, band_gradient):
+        a = f64(band_gradient)
+        self._ck(self.L.od_set_gradients(self.h, _p(a), OD_MEM_HOST))
+        self._ck(self.L.od_synchronize(self.h))
+
+    def set_gradients_from_ome(self, optical_mat):
+        a = np.asfortranarray(optical_mat, dtype=np.complex128)
+        self._ck(self.L.od_set_gradients_from_ome(self.h, a.ctypes.data_as(c_dp), OD_MEM_HOST))
+
+    def synth_bands(self, grid, k_first, nk_local, ns, nb, lattice_a=5.43, seed=2):
+        g = np.asarray(grid, dtype=np.int32)
+        self._ck(self.L.od_synth_bands(self.h, g.ctypes.data_as(c_ip), C.c_longlong(k_first), C.c_int(nk_local), C.c_int(ns),
+                                       C.c_int(nb), C.c_double(lattice_a), C.c_uint64(seed)))
+        self.nk, self.ns, self.nb = nk_local, ns, nb
+
+    def get_bands(self):
+        a = np.zeros((self.nb, self.ns, self.nk), order="F")
+        self._ck(self.L.od_get_bands(self.h, _p(a)))
+        return a
+
+    def get_gradients(self):
+        a = np.zeros((self.nb, 3, self.nk, self.ns), order="F")
+        self._ck(self.L.od_get_gradients(self.h, _p(a)))
+        return a
+
+    def get_kweights(self):
+        a = np.zeros(self.nk)
+        self._ck(self.L.od_get_kweights(self.h, _p(a)))
+        return a
+
+    def band_minmax(self):
+        mn, mx = C.c_double(), C.c_double()
+        self._ck(self.L.od_band_minmax(self.h, C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+    def allreduce(self, a, op="s"):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self._ck(self.L.od_allreduce(self.h, _p(a), C.c_size_t(a.size), C.c_char(op.encode())))
+        return a
+
+    # ---- hot loops
+    def calculate_dos(self, dos_type, emin, delta_bins, nbins, br=None, mw=None, merge=False):
+        br = br or broadening()
+        dos = np.zeros((nbins, self.ns), order="F")
+        intdos = np.zeros((nbins, self.ns), order="F")
+        wdos = None
+        norb = mwnb = mwnk = 0
+        if mw is not None:
+            mw = f64(mw)
+            norb, mwnb, mwnk = mw.shape[0], mw.shape[1], mw.shape[2]
+            wdos = np.zeros((nbins, self.ns, norb), order="F")
+        self._ck(self.L.od_calculate_dos(self.h, C.c_char(dos_type.encode()), C.c_double(emin), C.c_double(delta_bins),
+                                         C.c_int(nbins), C.byref(br), _p(mw), C.c_int(norb), C.c_int(mwnb), C.c_int(mwnk),
+                                         C.c_int(OD_MEM_HOST), C.c_int(int(merge)), _p(dos), _p(intdos), _p(wdos)))
+        return dos, intdos, wdos
+
+    def calculate_dos_at_e(self, dos_type, energy, delta_bins, br=None, mw=None, merge=False):
+        br = br or broadening()
+        d = np.zeros(self.ns)
+        w = None
+        norb = mwnb = mwnk = 0
+        if mw is not None:
+            mw = f64(mw)
+            norb, mwnb, mwnk = mw.shape[0], mw.shape[1], mw.shape[2]
+            w = np.zeros((self.ns, norb), order="F")
+        self._ck(self.L.od_calculate_dos_at_e(self.h, C.c_char(dos_type.encode()), C.c_double(energy), C.c_double(delta_bins),
+                                              C.byref(br), _p(mw), C.c_int(norb), C.c_int(mwnb), C.c_int(mwnk),
+                                              C.c_int(OD_MEM_HOST), C.c_int(int(merge)), _p(d), _p(w)))
+        return d, w
+
+    def calculate_jdos(self, jdos_type, delta_bins, nbins, efermi, br=None, scissor_op=0.0, exclude_bands=(), mw=None,
+                       merge=False):
+        br = br or broadening()
+        jdos = np.zeros((nbins, self.ns), order="F")
+        wj = None
+        ng = 0
+        if mw is not None:
+            mw = f64(mw)
+            ng = mw.shape[4]
+            wj = np.zeros((nbins, self.ns, ng), order="F")
+        ex = np.asarray(exclude_bands, dtype=np.int32)
+        self._ck(self.L.od_calculate_jdos(self.h, C.c_char(jdos_type.encode()), C.c_double(delta_bins), C.c_int(nbins),
+                                          C.byref(br), C.c_double(efermi), C.c_double(scissor_op), ex.ctypes.data_as(c_ip),
+                                          C.c_int(ex.size), _p(mw), C.c_int(ng), C.c_int(OD_MEM_HOST), C.c_int(int(merge)),
+                                          _p(jdos), _p(wj)))
+        return jdos, wj
+
+    def calculate_jdos_optics(self, jdos_type, delta_bins, nbins, efermi, optical_mat, geom, qdir=(0, 0, 1), symops=None,
+                              br=None, scissor_op=0.0, exclude_bands=(), merge=False):
+        br = br or broadening()
+        ng = 6 if geom == "tensor" else 1
+        jdos = np.zeros((nbins, self.ns), order="F")
+        wj = np.zeros((nbins, self.ns, ng), order="F")
+        om = np.asfortranarray(optical_mat, dtype=np.complex128)
+        q = f64(np.asarray(qdir, dtype=np.float64))
+        nsym = 0 if symops is None else symops.shape[2]
+        so = None if symops is None else f64(symops)
+        ex = np.asarray(exclude_bands, dtype=np.int32)
+        self._ck(self.L.od_calculate_jdos_optics(self.h, C.c_char(jdos_type.encode()), C.c_double(delta_bins), C.c_int(nbins),
+                                                 C.byref(br), C.c_double(efermi), C.c_double(scissor_op),
+                                                 ex.ctypes.data_as(c_ip), C.c_int(ex.size), om.ctypes.data_as(c_dp),
+                                                 C.c_int(OD_MEM_HOST), C.c_int(GEOM[geom]), _p(q), _p(so), C.c_int(nsym),
+                                                 C.c_int(int(merge)), _p(jdos), _p(wj)))
+        return jdos, wj
+
+    # ---- weight builders
+    def make_weights(self, optical_mat, geom, efermi, qdir=(0, 0, 1), symops=None, scissor_op=0.0):
+        om = np.asfortranarray(optical_mat, dtype=np.complex128)
+        ng = 6 if geom == "tensor" else 1
+        mw = np.zeros((self.nb, self.nb, self.nk, self.ns, ng), order="F")
+        q = f64(np.asarray(qdir, dtype=np.float64))
+        nsym = 0 if symops is None else symops.shape[2]
+        so = None if symops is None else f64(symops)
+        self._ck(self.L.od_make_weights(self.h, om.ctypes.data_as(c_dp), C.c_int(OD_MEM_HOST), C.c_int(GEOM[geom]), _p(q), _p(so),
+                                        C.c_int(nsym), C.c_double(efermi), C.c_double(scissor_op), _p(mw), C.c_int(OD_MEM_HOST)))
+        return mw
+
+    def core_prepare_matrix_elements(self, elnes_mat, core_type, efermi, polar=False, qdir=(0, 0, 1), symops=None):
+        em = np.asfortranarray(elnes_mat, dtype=np.complex128)
+        norb = em.shape[0]
+        mw = np.zeros((norb, self.nb, self.nk, self.ns), order="F")
+        q = f64(np.asarray(qdir, dtype=np.float64))
+        nsym = 0 if symops is None else symops.shape[2]
+        so = None if symops is None else f64(symops)
+        self._ck(self.L.od_core_prepare_matrix_elements(self.h, em.ctypes.data_as(c_dp), C.c_int(OD_MEM_HOST), C.c_int(norb),
+                                                        C.c_int(int(polar)), _p(q), _p(so), C.c_int(nsym),
+                                                        C.c_int(CORE_TYPE[core_type]), C.c_double(efermi), _p(mw),
+                                                        C.c_int(OD_MEM_HOST)))
+        return mw
+
+    def projection_merge(self, pdos_weights, mask):
+        pw = f64(pdos_weights)
+        m = np.asfortranarray(mask, dtype=np.int32)
+        norb, nproj = m.shape
+        mw = np.zeros((nproj, self.nb, self.nk, self.ns), order="F")
+        self._ck(self.L.od_projection_merge(self.h, _p(pw), C.c_int(OD_MEM_HOST), m.ctypes.data_as(c_ip), C.c_int(norb),
+                                            C.c_int(nproj), _p(mw), C.c_int(OD_MEM_HOST)))
+        return mw
+
+    def calc_epsilon_2(self, wjdos, cell_volume):
+        wj = f64(wjdos)
+        B, ns, ng = wj.shape
+        e2 = np.zeros((B, ng), order="F")
+        self._ck(self.L.od_calc_epsilon_2(self.h, _p(wj), C.c_int(B), C.c_int(ns), C.c_int(ng), C.c_double(cell_volume), _p(e2)))
+        return e2
+
+    # ---- task drivers
+    def dos_params(self, broadening_type="adaptive", dos_spacing=None, dos_nbins=-1, num_electrons=(0.0,), efermi="optados",
+                   br=None, **kw):
+        p = DosParams()
+        self.L.od_dos_params_defaults(C.byref(p))
+        p.fixed = p.adaptive = p.linear = 0
+        for t in ([broadening_type] if isinstance(broadening_type, str) else broadening_type):
+            setattr(p, t, 1)
+        if dos_spacing is not None:
+            p.dos_spacing = dos_spacing
+        p.dos_nbins = dos_nbins
+        p.efermi_choice = EFERMI[efermi]
+        ne = list(num_electrons)
+        p.nspins_electrons = len(ne)
+        for i, v in enumerate(ne[:2]):
+            p.num_electrons[i] = v
+        if br is not None:
+            p.br = br
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def dos_utils_calculate(self, p, mw=None):
+        res = DosResult()
+        norb = mwnb = mwnk = 0
+        if mw is not None:
+            mw = f64(mw)
+            norb, mwnb, mwnk = mw.shape[0], mw.shape[1], mw.shape[2]
+        self._ck(self.L.od_dos_utils_calculate(self.h, C.byref(p), _p(mw), C.c_int(norb), C.c_int(mwnb), C.c_int(mwnk),
+                                               C.c_int(OD_MEM_HOST), C.byref(res)))
+        out = dict(nbins=res.nbins, emin=res.emin, delta=res.delta_bins,
+                   E=res.emin + np.arange(res.nbins, dtype=np.float64) * res.delta_bins,
+                   efermi_fixed=res.efermi_fixed, efermi_adaptive=res.efermi_adaptive, efermi_linear=res.efermi_linear)
+        for t, have in (("fixed", res.have_fixed), ("adaptive", res.have_adaptive), ("linear", res.have_linear)):
+            if have:
+                d = np.zeros((res.nbins, self.ns), order="F")
+                i = np.zeros((res.nbins, self.ns), order="F")
+                self._ck(self.L.od_dos_get(self.h, C.c_char(t[0].encode()), _p(d), _p(i)))
+                out["dos_" + t], out["intdos_" + t] = d, i
+        if res.have_weighted:
+            w = np.zeros((res.nbins, self.ns, res.weighted_norb), order="F")
+            self._ck(self.L.od_dos_get_weighted(self.h, _p(w)))
+            out["weighted_dos"] = w
+        return out
+
+    def dos_utils_set_efermi(self, p):
+        ef = C.c_double()
+        self._ck(self.L.od_dos_utils_set_efermi(self.h, C.byref(p), C.byref(ef)))
+        return ef.value
+
+    def jdos_utils_calculate(self, efermi, broadening_type="adaptive", jdos_spacing=0.01, jdos_max_energy=-1.0, br=None,
+                             scissor_op=0.0, exclude_bands=(), mw=None, optical_mat=None, geom="polycrys", qdir=(0, 0, 1),
+                             symops=None):
+        p = JdosParams()
+        self.L.od_jdos_params_defaults(C.byref(p))
+        p.fixed = p.adaptive = p.linear = 0
+        for t in ([broadening_type] if isinstance(broadening_type, str) else broadening_type):
+            setattr(p, t, 1)
+        p.jdos_spacing, p.jdos_max_energy, p.scissor_op, p.efermi = jdos_spacing, jdos_max_energy, scissor_op, efermi
+        if br is not None:
+            p.br = br
+        ex = np.asarray(exclude_bands, dtype=np.int32)
+        p.num_exclude_bands = ex.size
+        p.exclude_bands = ex.ctypes.data_as(c_ip)
+        ng = 0
+        if mw is not None:
+            mw = f64(mw)
+            ng = mw.shape[4]
+        om = None if optical_mat is None else np.asfortranarray(optical_mat, dtype=np.complex128)
+        q = f64(np.asarray(qdir, dtype=np.float64))
+        nsym = 0 if symops is None else symops.shape[2]
+        so = None if symops is None else f64(symops)
+        res = JdosResult()
+        self._ck(self.L.od_jdos_utils_calculate(self.h, C.byref(p), _p(mw), C.c_int(ng), C.c_int(OD_MEM_HOST),
+                                                None if om is None else om.ctypes.data_as(c_dp), C.c_int(OD_MEM_HOST),
+                                                C.c_int(GEOM[geom]), _p(q), _p(so), C.c_int(nsym), C.byref(res)))
+        out = dict(nbins=res.nbins, delta=res.delta_bins, E=np.arange(res.nbins, dtype=np.float64) * res.delta_bins,
+                   jdos_max_energy=p.jdos_max_energy)
+        for t, have in (("fixed", res.have_fixed), ("adaptive", res.have_adaptive), ("linear", res.have_linear)):
+            if have:
+                d = np.zeros((res.nbins, self.ns), order="F")
+                self._ck(self.L.od_jdos_get(self.h, C.c_char(t[0].encode()), _p(d)))
+                out["jdos_" + t] = d
+        if res.have_weighted:
+            w = np.zeros((res.nbins, self.ns, res.n_geom), order="F")
+            self._ck(self.L.od_jdos_get_weighted(self.h, _p(w)))
+            out["weighted_jdos"] = w
+        return out
+
+    # ---- bookkeeping
+    def kernel_launches(self):
+        return int(self.L.od_kernel_launches(self.h))
+
+    def profile_reset(self):
+        self._ck(self.L.od_profile_reset(self.h))
+
+    def profile_get(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        n = C.c_longlong()
+        self._ck(self.L.od_profile_get(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return dict(accumulate_ms=a.value, prepare_ms=b.value, contributions=c.value, accumulate_launches=n.value)
+
+    def synchronize(self):
+        self._ck(self.L.od_synchronize(self.h))

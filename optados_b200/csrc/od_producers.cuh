@@ -1,0 +1,159 @@
+// od_producers.cuh -- unit -> record producers shared by the dense and the narrow engines.
+#pragma once
+#include "od_accum.cuh"
+
+// Broadening set-up common to calculate_dos / calculate_dos_at_e / calculate_jdos
+// (dos_utils.f90:1208-1218, jdos_utils.f90:324-334)
+struct BroadSpec {
+  int type;  // 0 fixed, 1 adaptive, 2 linear
+  double fixed_w, adapt_temp, delta_bins;
+  int fbc;
+  int honor_hybrid;  // calculate_dos ignores hybrid_linear (Q8); at_e and jdos honour it
+  int hybrid;
+  double hybrid_tol;
+  double step[3];
+  double rs[9];  // recip_lattice, column-major
+};
+
+// width / corners of one unit from its centre energy and gradient
+__device__ __forceinline__ void od_make_record(const BroadSpec &b, double centre, const double grad[3], double omega, RecOut &r) {
+  r.e0 = centre;
+  r.omega = omega;
+  double width = 0.0;
+  bool force_adaptive = false;
+  double gnorm = 0.0;
+  if (b.type != 0) gnorm = sqrt(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);  // sqrt(dot_product(grad,grad))
+  // hybrid_linear only changes anything for the linear scheme (for 'f' the reference tests an
+  // unset gradient); dos_utils.f90:1758, jdos_utils.f90:365
+  if (b.type == 2 && b.honor_hybrid && b.hybrid && (b.hybrid_tol > gnorm)) force_adaptive = true;
+  if (b.type == 2 && !force_adaptive) {
+    double EV[5];
+    od_sub_cell_corners(grad, b.step, b.rs, centre, EV);                             // dos_utils.f90:1240
+    r.mode = 1;
+    r.p1 = EV[1]; r.p2 = EV[2]; r.p3 = EV[3]; r.p4 = EV[4];
+    return;
+  }
+  if (b.type == 0) width = b.fixed_w;
+  // NB for type 'l' with force_adaptive the reference starts from width = 0 (jdos_utils.f90:324,368)
+  if (b.type == 1 || force_adaptive) width = gnorm * b.adapt_temp;                   // dos_utils.f90:1241
+  if (b.fbc && (width < b.delta_bins)) width = b.delta_bins;                          // dos_utils.f90:1244
+  r.mode = 0;
+  r.p1 = width; r.p2 = r.p3 = r.p4 = 0.0;
+}
+
+// ------------------------------------------------------------------ DOS / PDOS / core
+struct DosProducer {
+  long long units_per_z;  // nb * nk
+  int nb, ns, nk;
+  const double *bands, *grads, *kw;
+  double eps;
+  BroadSpec b;
+  const double *mw;  // matrix_weights(norb, mw_nb, mw_nk, ns) or null
+  int norb, mw_nb, mw_nk;
+  int og;  // orbitals per z-slice group (== NW of the kernel)
+
+  __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
+    const int is = z % ns, grp = z / ns;
+    const int ib = (int)(u % nb);
+    const long long ik = u / nb;
+    const double e = bands[ib + (size_t)nb * (is + (size_t)ns * ik)];
+    double g[3] = {0.0, 0.0, 0.0};
+    if (b.type != 0) {
+      const size_t gi = ib + (size_t)nb * (3 * (ik + (size_t)nk * is));
+      g[0] = grads[gi];
+      g[1] = grads[gi + nb];
+      g[2] = grads[gi + 2 * (size_t)nb];
+    }
+    od_make_record(b, e, g, eps * kw[ik], r);
+    if (mw) {
+      const bool in = (ik < mw_nk) && (ib < mw_nb);  // dos_utils.f90:1268-1269
+      const size_t row = (size_t)norb * (ib + (size_t)mw_nb * (ik + (size_t)mw_nk * is));
+#pragma unroll
+      for (int a = 0; a < OD_MAXW; ++a) {
+        const int o = grp * og + a;
+        r.wt[a] = (in && a < og && o < norb) ? mw[row + o] : 0.0;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ JDOS / optics
+// optics weights in contracted form: weight_g = factor * sum_{i<=j} C[g][ij] * Re(M_i conj(M_j)),
+// C built on the host from optics_geom, q and the symmetry operations (see od_weights.cu).
+struct OpticsCoef {
+  int n_geom;
+  double c[6][6];  // [geom component][xx, yy, zz, xy, xz, yz]  (off-diagonals already doubled)
+};
+
+__device__ __forceinline__ void od_ome_products(const double *om, size_t idx, size_t comp_stride, double P[6]) {
+  // om: complex (re,im) pairs; element (n1,n2,i) at idx + i*comp_stride
+  const double2 a = reinterpret_cast<const double2 *>(om)[idx];
+  const double2 b = reinterpret_cast<const double2 *>(om)[idx + comp_stride];
+  const double2 c = reinterpret_cast<const double2 *>(om)[idx + 2 * comp_stride];
+  P[0] = a.x * a.x + a.y * a.y;
+  P[1] = b.x * b.x + b.y * b.y;
+  P[2] = c.x * c.x + c.y * c.y;
+  P[3] = a.x * b.x + a.y * b.y;
+  P[4] = a.x * c.x + a.y * c.y;
+  P[5] = b.x * c.x + b.y * c.y;
+}
+
+struct JdosProducer {
+  long long units_per_z;  // nb * nb * nk
+  int nb, ns, nk;
+  const double *bands, *grads, *kw;
+  double eps, efermi, scissor;
+  BroadSpec b;
+  const int *exclude;  // device, 1-based band indices
+  int n_exclude;
+  const double *mw;    // matrix_weights(nb,nb,nk,ns,n_geom) or null
+  const double *ome;   // optical_mat(nb,nb,3,nk,ns) complex or null (fused make_weights)
+  int n_geom;
+  OpticsCoef coef;
+
+  __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
+    const int is = z;
+    const int ib = (int)(u % nb);
+    const long long t = u / nb;
+    const int jb = (int)(t % nb);
+    const long long ik = t / nb;
+    r.mode = -1;
+    for (int x = 0; x < n_exclude; ++x)
+      if (exclude[x] == ib + 1) return;                         // jdos_utils.f90:355-357
+    const size_t eb = (size_t)nb * (is + (size_t)ns * ik);
+    const double ei = bands[eb + ib], ej = bands[eb + jb];
+    if (ei >= efermi) return;                                   // :358
+    if (ej < efermi) return;                                    // :360
+    double g[3] = {0.0, 0.0, 0.0};
+    if (b.type != 0) {
+      const size_t gi = (size_t)nb * (3 * (ik + (size_t)nk * is));
+      g[0] = grads[gi + jb] - grads[gi + ib];
+      g[1] = grads[gi + nb + jb] - grads[gi + nb + ib];
+      g[2] = grads[gi + 2 * (size_t)nb + jb] - grads[gi + 2 * (size_t)nb + ib];
+    }
+    od_make_record(b, ej - ei + scissor, g, eps * kw[ik], r);   // :366-372, :383
+    if (mw) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+        if (a < n_geom) r.wt[a] = mw[ib + (size_t)nb * (jb + (size_t)nb * (ik + (size_t)nk * (is + (size_t)ns * a)))];
+    } else if (ome) {
+      // make_weights fused (optics.f90:259-269): only n2 >= n1 is ever filled; strict >/< tests
+      double wt[6] = {0, 0, 0, 0, 0, 0};
+      if (jb >= ib && !(ei > efermi && ib != jb) && !(ej < efermi && ib != jb)) {
+        double factor = 0.0;
+        if (jb == ib) factor = 1.0;
+        else if (ej > efermi) factor = 1.0 / ((ej - ei + scissor) * (ej - ei + scissor));
+        double P[6];
+        const size_t nb2 = (size_t)nb * nb;
+        od_ome_products(ome, ib + (size_t)nb * jb + nb2 * 3 * (ik + (size_t)nk * is), nb2, P);
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+          if (a < n_geom)
+            wt[a] = factor * (coef.c[a][0] * P[0] + coef.c[a][1] * P[1] + coef.c[a][2] * P[2] + coef.c[a][3] * P[3] +
+                              coef.c[a][4] * P[4] + coef.c[a][5] * P[5]);
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) r.wt[a] = wt[a];
+    }
+  }
+};

@@ -1,0 +1,423 @@
+// od_spectral.cu -- C-ABI entry points of the hot loops: calculate_dos (dos_utils.f90:1140),
+// calculate_dos_at_e (:1651), calculate_jdos (jdos_utils.f90:280) and their merges.
+#include <algorithm>
+#include <cmath>
+
+#include "od_internal.h"
+#include "od_producers.cuh"
+#include "od_spectral.h"
+
+// ------------------------------------------------------------------ helpers
+static int type_index(char t) { return t == 'f' ? 0 : t == 'a' ? 1 : t == 'l' ? 2 : -1; }
+
+int od_make_broadspec(od_ctx *ctx, char type, const od_broadening *br, double delta_bins, bool honor_hybrid, BroadSpec *out) {
+  const int ti = type_index(type);
+  if (ti < 0) return od_fail(ctx, OD_ERR_ARG, "unknown dos_type '%c' (dos_utils.f90:1205)", type);
+  if (!br) return od_fail(ctx, OD_ERR_ARG, "null od_broadening");
+  BroadSpec b;
+  const GridGeom g = od_grid_geom(ctx, br->adaptive_smearing);
+  b.type = ti;
+  b.fixed_w = br->fixed_smearing;
+  b.adapt_temp = g.adaptive_smearing_temp;
+  b.delta_bins = delta_bins;
+  b.fbc = br->finite_bin_correction ? 1 : 0;
+  b.honor_hybrid = honor_hybrid ? 1 : 0;
+  b.hybrid = br->hybrid_linear ? 1 : 0;
+  b.hybrid_tol = br->hybrid_linear_grad_tol;
+  for (int i = 0; i < 3; ++i) b.step[i] = g.step[i];
+  for (int i = 0; i < 9; ++i) b.rs[i] = g.recip[i];
+  *out = b;
+  return OD_OK;
+}
+
+static int check_ready(od_ctx *ctx, bool need_grad) {
+  if (!ctx) return OD_ERR_ARG;
+  if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system has not been called");
+  if (!ctx->bands.p) return od_fail(ctx, OD_ERR_STATE, "band_energy not set (od_set_bands)");
+  if (!ctx->kweight.p) return od_fail(ctx, OD_ERR_STATE, "kpoint_weight not set");
+  if (need_grad && !ctx->grads.p) return od_fail(ctx, OD_ERR_STATE, "band_gradient not set (od_set_gradients)");
+  return OD_OK;
+}
+
+namespace {
+// numerical_intdos (dos_utils.f90:1256-1258, :1315): intdos(j) = delta * sum_{i<=j} dos(i)
+__global__ void numerical_intdos_kernel(const double *__restrict__ dos, double *__restrict__ intdos, int nbins, int ns, double delta) {
+  const int is = blockIdx.x * blockDim.x + threadIdx.x;
+  if (is >= ns) return;
+  double run = 0.0;
+  for (int j = 0; j < nbins; ++j) {
+    run += dos[(size_t)is * nbins + j];
+    intdos[(size_t)is * nbins + j] = run * delta;
+  }
+}
+
+// linear_smearing post-smear (dos_utils.f90:1282-1309)
+__global__ void linear_smear_kernel(const double *__restrict__ dos, double *__restrict__ out, int nbins, int ns, double emin,
+                                    double delta, double smear) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int is = blockIdx.y;
+  if (j >= nbins) return;
+  const double Ej = emin + (double)j * delta;
+  double s = 0.0;
+  for (int i = 0; i < nbins; ++i) {
+    const double Ei = emin + (double)i * delta;
+    s += dos[(size_t)is * nbins + i] * od_gaussian(Ej, smear, Ei) * delta;
+  }
+  out[(size_t)is * nbins + j] = s;
+}
+}  // namespace
+
+// Launch the dense engine for a producer and reduce the chunk partials into `accum` (device).
+// dest: nz*nacc offsets into accum (or -1).
+template <int NW, bool INT, class Producer>
+static int run_dense(od_ctx *ctx, const Producer &prod, const GridSpec &grid, int nz, const std::vector<long long> &dest,
+                     double *accum) {
+  constexpr int NACC = 1 + (INT ? 1 : 0) + NW;
+  const int ntiles = (grid.nbins + OD_TILE - 1) / OD_TILE;
+  const long long units = prod.units_per_z;
+  long long max_chunks = (units + OD_TILE - 1) / OD_TILE;
+  long long want = ((long long)ctx->sm_count * 16 + (long long)ntiles * nz - 1) / ((long long)ntiles * nz);
+  long long nchunks = std::max<long long>(1, std::min<long long>({want, max_chunks, 65535}));
+  long long chunk_units = (units + nchunks - 1) / nchunks;
+  chunk_units = (chunk_units + OD_TILE - 1) / OD_TILE * OD_TILE;
+  nchunks = (units + chunk_units - 1) / chunk_units;
+  if (nchunks < 1) nchunks = 1;
+  const size_t pbytes = sizeof(double) * (size_t)nchunks * nz * NACC * grid.nbins;
+  OD_CHECK(od_buf_ensure(ctx, ctx->partial, pbytes));
+  OD_CHECK(od_buf_ensure(ctx, ctx->keys, sizeof(long long) * dest.size() + sizeof(int) * 4));
+  int *bad = reinterpret_cast<int *>(ctx->keys.as<char>() + sizeof(long long) * dest.size());
+  OD_CUDA(ctx, cudaMemcpyAsync(ctx->keys.p, dest.data(), sizeof(long long) * dest.size(), cudaMemcpyHostToDevice, ctx->stream));
+  OD_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+  dim3 g(ntiles, (unsigned)nchunks, nz);
+  OD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  od_dense_kernel<NW, INT, Producer><<<g, OD_TILE, 0, ctx->stream>>>(prod, grid, chunk_units, ctx->partial.as<double>(), bad);
+  OD_LAUNCH_CHECK(ctx);
+  dim3 rg((grid.nbins + 255) / 256, nz * NACC);
+  od_reduce_partials<<<rg, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), (int)nchunks, nz, NACC, grid.nbins,
+                                                  ctx->keys.as<long long>(), accum);
+  OD_LAUNCH_CHECK(ctx);
+  OD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  int hbad = 0;
+  OD_CUDA(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->prof.accumulate_ms += ms;
+  ctx->prof.accumulate_launches += 1;
+  if (hbad) return od_fail(ctx, OD_ERR_DOSLIN, "doslin: input arguments incorrect (dos_utils.f90:1431/1514)");
+  return OD_OK;
+}
+
+// ------------------------------------------------------------------ calculate_dos
+int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins, const od_broadening *br,
+                            const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_out) {
+  OD_CHECK(check_ready(ctx, dos_type != 'f'));
+  if (nbins < 2) return od_fail(ctx, OD_ERR_ARG, "nbins = %d", nbins);
+  if (!(delta_bins > 0.0)) return od_fail(ctx, OD_ERR_ARG, "delta_bins must be positive");
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int ns = ctx->ns;
+  if (mw_dev && (norb < 1 || mw_nb < 1 || mw_nk < 1)) return od_fail(ctx, OD_ERR_ARG, "bad matrix_weights bounds");
+  if (mw_dev && mw_nk != ctx->nk) return od_fail(ctx, OD_ERR_REF, "ERROR : DOS : mw%%nkpoints not equal to nkpoints. (dos_utils.f90:159)");
+  if (!mw_dev) norb = 0;
+
+  DosProducer p;
+  p.units_per_z = (long long)ctx->nb * ctx->nk;
+  p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk;
+  p.bands = ctx->bands.as<double>(); p.grads = ctx->grads.as<double>(); p.kw = ctx->kweight.as<double>();
+  p.eps = ctx->eps;
+  OD_CHECK(od_make_broadspec(ctx, dos_type, br, delta_bins, /*honor_hybrid=*/false, &p.b));
+  p.mw = mw_dev; p.norb = norb; p.mw_nb = mw_nb; p.mw_nk = mw_nk; p.og = OD_MAXW;
+
+  GridSpec grid{emin, delta_bins, nbins};
+  const size_t n1 = (size_t)nbins * ns;
+  const size_t ntot = 2 * n1 + n1 * norb;
+  OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * (ntot + n1)));
+  double *accum = ctx->accum.as<double>();
+  OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * ntot, ctx->stream));
+
+  if (!mw_dev) {
+    std::vector<long long> dest(ns * 2);
+    for (int is = 0; is < ns; ++is) {
+      dest[is * 2 + 0] = (long long)is * nbins;
+      dest[is * 2 + 1] = (long long)(n1 + (size_t)is * nbins);
+    }
+    OD_CHECK((run_dense<0, true, DosProducer>(ctx, p, grid, ns, dest, accum)));
+  } else {
+    const int ngroups = (norb + OD_MAXW - 1) / OD_MAXW;
+    const int nz = ns * ngroups;
+    constexpr int NACC = 2 + OD_MAXW;
+    std::vector<long long> dest((size_t)nz * NACC, -1);
+    for (int g = 0; g < ngroups; ++g)
+      for (int is = 0; is < ns; ++is) {
+        const int z = is + ns * g;
+        if (g == 0) {
+          dest[(size_t)z * NACC + 0] = (long long)is * nbins;
+          dest[(size_t)z * NACC + 1] = (long long)(n1 + (size_t)is * nbins);
+        }
+        for (int a = 0; a < OD_MAXW; ++a) {
+          const int o = g * OD_MAXW + a;
+          if (o < norb) dest[(size_t)z * NACC + 2 + a] = (long long)(2 * n1 + (size_t)nbins * (is + (size_t)ns * o));
+        }
+      }
+    OD_CHECK((run_dense<OD_MAXW, true, DosProducer>(ctx, p, grid, nz, dest, accum)));
+  }
+
+  // rank-local epilogue, before the merge like the reference (quirk Q16)
+  if (dos_type == 'l' && br->linear_smearing > 0.0) {
+    double *tmp = accum + ntot;
+    dim3 g((nbins + 127) / 128, ns);
+    linear_smear_kernel<<<g, 128, 0, ctx->stream>>>(accum, tmp, nbins, ns, emin, delta_bins, br->linear_smearing);
+    OD_LAUNCH_CHECK(ctx);
+    OD_CUDA(ctx, cudaMemcpyAsync(accum, tmp, sizeof(double) * n1, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (dos_type != 'l' && br->numerical_intdos) {
+    numerical_intdos_kernel<<<1, 32, 0, ctx->stream>>>(accum, accum + n1, nbins, ns, delta_bins);
+    OD_LAUNCH_CHECK(ctx);
+  }
+  if (merge) OD_CHECK(od_allreduce_device(ctx, accum, ntot, 's'));  // dos_utils_merge (dos_utils.f90:1041-1043)
+  *accum_out = accum;
+  return OD_OK;
+}
+
+extern "C" int od_calculate_dos(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins, const od_broadening *br,
+                                const double *matrix_weights, int mw_norb, int mw_nb, int mw_nk, int mw_mem, int merge,
+                                double *dos, double *intdos, double *weighted_dos) {
+  if (!ctx) return OD_ERR_ARG;
+  if (!dos || !intdos) return od_fail(ctx, OD_ERR_ARG, "null output array");
+  if (matrix_weights && !weighted_dos) return od_fail(ctx, OD_ERR_ARG, "matrix_weights given without weighted_dos");
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const double *mw_dev = nullptr;
+  if (matrix_weights) {
+    if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system has not been called");
+    const size_t bytes = sizeof(double) * (size_t)mw_norb * mw_nb * mw_nk * ctx->ns;
+    const void *d = nullptr;
+    OD_CHECK(od_stage_in(ctx, matrix_weights, bytes, mw_mem, ctx->mw_tmp, &d));
+    mw_dev = static_cast<const double *>(d);
+  }
+  double *accum = nullptr;
+  OD_CHECK(od_calculate_dos_device(ctx, dos_type, emin, delta_bins, nbins, br, mw_dev, mw_norb, mw_nb, mw_nk, merge, &accum));
+  const size_t n1 = (size_t)nbins * ctx->ns;
+  OD_CUDA(ctx, cudaMemcpyAsync(dos, accum, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaMemcpyAsync(intdos, accum + n1, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
+  if (matrix_weights)
+    OD_CUDA(ctx, cudaMemcpyAsync(weighted_dos, accum + 2 * n1, sizeof(double) * n1 * mw_norb, cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OD_OK;
+}
+
+// ------------------------------------------------------------------ calculate_dos_at_e
+namespace {
+// One warp walks a contiguous slice of units; lane 0..31 own orbitals o = lane, lane+32, ... (<= 8 each)
+// and every lane carries the same dos_at_e partial.  Per-warp partials are summed on the host in order.
+__global__ void __launch_bounds__(128)
+dos_at_e_kernel(DosProducer prod, double energy, long long units_per_warp, double *__restrict__ part /* [nwarps][ns][1+norb] */,
+                int *__restrict__ bad_flag) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int is = blockIdx.y;
+  const long long u0 = warp * units_per_warp;
+  long long u1 = u0 + units_per_warp;
+  if (u1 > prod.units_per_z) u1 = prod.units_per_z;
+  double acc = 0.0, accw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int bad = 0;
+  const int norb = prod.mw ? prod.norb : 0;
+  for (long long base = u0; base < u1; base += 32) {
+    // each lane builds one record, then the warp evaluates the 32 of them in turn
+    RecOut r;
+    r.mode = -1;
+    DosProducer p2 = prod;
+    p2.mw = nullptr;
+    if (base + lane < u1) p2(base + lane, is, r);
+    double d = 0.0, cum;
+    if (r.mode == 0) d = od_gaussian(r.e0, r.p1, energy) * r.omega;                       // dos_utils.f90:1777
+    else if (r.mode == 1) d = od_doslin(r.e0, r.p1, r.p2, r.p3, r.p4, energy, &cum, &bad) * r.omega;  // :1774
+    // lane-ordered sum (fixed order -> reproducible)
+    for (int l = 0; l < 32; ++l) {
+      const double dl = __shfl_sync(0xffffffffu, d, l);
+      acc += dl;
+      if (norb > 0 && dl != 0.0) {
+        const long long u = base + l;
+        if (u < u1) {
+          const int ib = (int)(u % prod.nb);
+          const long long ik = u / prod.nb;
+          if (ik < prod.mw_nk && ib < prod.mw_nb) {
+            const size_t row = (size_t)norb * (ib + (size_t)prod.mw_nb * (ik + (size_t)prod.mw_nk * is));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int o = lane + 32 * k;
+              if (o < norb) accw[k] += dl * prod.mw[row + o];                              // :1787
+            }
+          }
+        }
+      }
+    }
+  }
+  if (bad) atomicOr(bad_flag, bad);
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  (void)nwarps;
+  double *out = part + ((size_t)warp * gridDim.y + is) * (1 + norb);
+  if (lane == 0) out[0] = acc;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int o = lane + 32 * k;
+    if (o < norb) out[1 + o] = accw[k];
+  }
+}
+}  // namespace
+
+extern "C" int od_calculate_dos_at_e(od_ctx *ctx, char dos_type, double energy, double delta_bins, const od_broadening *br,
+                                     const double *matrix_weights, int mw_norb, int mw_nb, int mw_nk, int mw_mem, int merge,
+                                     double *dos_at_e, double *weighted_dos_at_e) {
+  OD_CHECK(check_ready(ctx, dos_type != 'f'));
+  if (!dos_at_e) return od_fail(ctx, OD_ERR_ARG, "null output array");
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int ns = ctx->ns;
+  int norb = 0;
+  const double *mw_dev = nullptr;
+  if (matrix_weights && weighted_dos_at_e) {
+    if (mw_norb < 1 || mw_norb > 256) return od_fail(ctx, OD_ERR_ARG, "calculate_dos_at_e supports 1..256 weight columns, got %d", mw_norb);
+    if (mw_nk != ctx->nk) return od_fail(ctx, OD_ERR_REF, "ERROR : DOS : mw%%nkpoints not equal to nkpoints. (dos_utils.f90:1587)");
+    const void *d = nullptr;
+    OD_CHECK(od_stage_in(ctx, matrix_weights, sizeof(double) * (size_t)mw_norb * mw_nb * mw_nk * ns, mw_mem, ctx->mw_tmp, &d));
+    mw_dev = static_cast<const double *>(d);
+    norb = mw_norb;
+  }
+  DosProducer p;
+  p.units_per_z = (long long)ctx->nb * ctx->nk;
+  p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk;
+  p.bands = ctx->bands.as<double>(); p.grads = ctx->grads.as<double>(); p.kw = ctx->kweight.as<double>();
+  p.eps = ctx->eps;
+  OD_CHECK(od_make_broadspec(ctx, dos_type, br, delta_bins, /*honor_hybrid=*/true, &p.b));
+  p.mw = mw_dev; p.norb = norb; p.mw_nb = mw_nb; p.mw_nk = mw_nk; p.og = 0;
+
+  const long long units = p.units_per_z;
+  long long nwarps = std::min<long long>((units + 31) / 32, (long long)ctx->sm_count * 16);
+  if (nwarps < 1) nwarps = 1;
+  long long upw = (units + nwarps - 1) / nwarps;
+  upw = (upw + 31) / 32 * 32;
+  nwarps = (units + upw - 1) / upw;
+  const int blocks = (int)((nwarps + 3) / 4);
+  const long long nwarps_launched = (long long)blocks * 4;
+  const size_t per = (size_t)(1 + norb);
+  const size_t nvals = (size_t)nwarps_launched * ns * per;
+  OD_CHECK(od_buf_ensure(ctx, ctx->partial, sizeof(double) * nvals + 16));
+  OD_CUDA(ctx, cudaMemsetAsync(ctx->partial.p, 0, sizeof(double) * nvals + 16, ctx->stream));
+  int *bad = reinterpret_cast<int *>(ctx->partial.as<char>() + sizeof(double) * nvals);
+  dim3 g(blocks, ns);
+  dos_at_e_kernel<<<g, 128, 0, ctx->stream>>>(p, energy, upw, ctx->partial.as<double>(), bad);
+  OD_LAUNCH_CHECK(ctx);
+  std::vector<double> h(nvals);
+  int hbad = 0;
+  OD_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->partial.p, sizeof(double) * nvals, cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (hbad) return od_fail(ctx, OD_ERR_DOSLIN, "doslin: input arguments incorrect (dos_utils.f90:1431/1514)");
+  std::vector<double> res((size_t)ns * per, 0.0);
+  for (long long w = 0; w < nwarps_launched; ++w)
+    for (int is = 0; is < ns; ++is)
+      for (size_t k = 0; k < per; ++k) res[(size_t)is * per + k] += h[((size_t)w * ns + is) * per + k];
+  if (merge) OD_CHECK(od_allreduce(ctx, res.data(), res.size(), 's'));  // dos_utils_merge_at_e (dos_utils.f90:1830-1832)
+  for (int is = 0; is < ns; ++is) {
+    dos_at_e[is] = res[(size_t)is * per];
+    for (int o = 0; o < norb; ++o) weighted_dos_at_e[is + (size_t)ns * o] = res[(size_t)is * per + 1 + o];
+  }
+  return OD_OK;
+}
+
+// ------------------------------------------------------------------ calculate_jdos
+int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br, double efermi,
+                             double scissor_op, const int *exclude_bands, int num_exclude_bands, const double *mw_dev,
+                             const double *ome_dev, const OpticsCoef *coef, int n_geom, int merge, double **accum_out) {
+  OD_CHECK(check_ready(ctx, jdos_type != 'f'));
+  if (nbins < 2) return od_fail(ctx, OD_ERR_ARG, "nbins = %d", nbins);
+  if (!(delta_bins > 0.0)) return od_fail(ctx, OD_ERR_ARG, "delta_bins must be positive");
+  if ((mw_dev || ome_dev) && n_geom != 1 && n_geom != 6) return od_fail(ctx, OD_ERR_ARG, "N_geom must be 1 or 6, got %d", n_geom);
+  if (!mw_dev && !ome_dev) n_geom = 0;
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int ns = ctx->ns;
+
+  JdosProducer p;
+  p.units_per_z = (long long)ctx->nb * ctx->nb * ctx->nk;
+  p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk;
+  p.bands = ctx->bands.as<double>(); p.grads = ctx->grads.as<double>(); p.kw = ctx->kweight.as<double>();
+  p.eps = ctx->eps; p.efermi = efermi; p.scissor = scissor_op;
+  OD_CHECK(od_make_broadspec(ctx, jdos_type, br, delta_bins, /*honor_hybrid=*/true, &p.b));
+  p.exclude = nullptr; p.n_exclude = 0;
+  if (num_exclude_bands > 0) {
+    if (!exclude_bands) return od_fail(ctx, OD_ERR_ARG, "null exclude_bands");
+    OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(int) * (size_t)num_exclude_bands));
+    OD_CUDA(ctx, cudaMemcpyAsync(ctx->small.p, exclude_bands, sizeof(int) * (size_t)num_exclude_bands, cudaMemcpyHostToDevice, ctx->stream));
+    p.exclude = ctx->small.as<int>();
+    p.n_exclude = num_exclude_bands;
+  }
+  p.mw = mw_dev; p.ome = ome_dev; p.n_geom = n_geom;
+  if (coef) p.coef = *coef; else memset(&p.coef, 0, sizeof(p.coef));
+
+  GridSpec grid{0.0, delta_bins, nbins};  // E(i) = (i-1)*delta_bins (jdos_utils.f90:217)
+  const size_t n1 = (size_t)nbins * ns;
+  const size_t ntot = n1 + n1 * n_geom;
+  OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * ntot));
+  double *accum = ctx->accum.as<double>();
+  OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * ntot, ctx->stream));
+  const int nacc = 1 + n_geom;
+  std::vector<long long> dest((size_t)ns * nacc);
+  for (int is = 0; is < ns; ++is) {
+    dest[(size_t)is * nacc] = (long long)is * nbins;
+    for (int a = 0; a < n_geom; ++a) dest[(size_t)is * nacc + 1 + a] = (long long)(n1 + (size_t)nbins * (is + (size_t)ns * a));
+  }
+  if (n_geom == 0) OD_CHECK((run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+  else if (n_geom == 1) OD_CHECK((run_dense<1, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+  else OD_CHECK((run_dense<6, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+  if (merge) OD_CHECK(od_allreduce_device(ctx, accum, ntot, 's'));  // jdos_utils_merge (jdos_utils.f90:435-437)
+  *accum_out = accum;
+  return OD_OK;
+}
+
+static int jdos_copy_out(od_ctx *ctx, const double *accum, int nbins, int n_geom, double *jdos, double *wjdos) {
+  const size_t n1 = (size_t)nbins * ctx->ns;
+  OD_CUDA(ctx, cudaMemcpyAsync(jdos, accum, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
+  if (wjdos && n_geom > 0)
+    OD_CUDA(ctx, cudaMemcpyAsync(wjdos, accum + n1, sizeof(double) * n1 * n_geom, cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return OD_OK;
+}
+
+extern "C" int od_calculate_jdos(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br, double efermi,
+                                 double scissor_op, const int *exclude_bands, int num_exclude_bands, const double *matrix_weights,
+                                 int n_geom, int mw_mem, int merge, double *jdos, double *weighted_jdos) {
+  if (!ctx) return OD_ERR_ARG;
+  if (!jdos) return od_fail(ctx, OD_ERR_ARG, "null output array");
+  if (matrix_weights && !weighted_jdos) return od_fail(ctx, OD_ERR_ARG, "matrix_weights given without weighted_jdos");
+  if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system has not been called");
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const double *mw_dev = nullptr;
+  if (matrix_weights) {
+    const size_t bytes = sizeof(double) * (size_t)ctx->nb * ctx->nb * ctx->nk * ctx->ns * n_geom;
+    const void *d = nullptr;
+    OD_CHECK(od_stage_in(ctx, matrix_weights, bytes, mw_mem, ctx->mw_tmp, &d));
+    mw_dev = static_cast<const double *>(d);
+  }
+  double *accum = nullptr;
+  OD_CHECK(od_calculate_jdos_device(ctx, jdos_type, delta_bins, nbins, br, efermi, scissor_op, exclude_bands, num_exclude_bands,
+                                    mw_dev, nullptr, nullptr, n_geom, merge, &accum));
+  return jdos_copy_out(ctx, accum, nbins, matrix_weights ? n_geom : 0, jdos, weighted_jdos);
+}
+
+extern "C" int od_calculate_jdos_optics(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br,
+                                        double efermi, double scissor_op, const int *exclude_bands, int num_exclude_bands,
+                                        const double *optical_mat, int ome_mem, int geom, const double qdir[3],
+                                        const double *symops, int num_symm, int merge, double *jdos, double *weighted_jdos) {
+  if (!ctx) return OD_ERR_ARG;
+  if (!jdos || !weighted_jdos || !optical_mat) return od_fail(ctx, OD_ERR_ARG, "null array");
+  if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system has not been called");
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  OpticsCoef coef;
+  OD_CHECK(od_optics_coefficients(ctx, geom, qdir, symops, num_symm, &coef));
+  const size_t bytes = sizeof(double) * 2 * (size_t)ctx->nb * ctx->nb * 3 * ctx->nk * ctx->ns;
+  const void *d = nullptr;
+  OD_CHECK(od_stage_in(ctx, optical_mat, bytes, ome_mem, ctx->in_tmp, &d));
+  double *accum = nullptr;
+  OD_CHECK(od_calculate_jdos_device(ctx, jdos_type, delta_bins, nbins, br, efermi, scissor_op, exclude_bands, num_exclude_bands,
+                                    nullptr, static_cast<const double *>(d), &coef, coef.n_geom, merge, &accum));
+  return jdos_copy_out(ctx, accum, nbins, coef.n_geom, jdos, weighted_jdos);
+}

@@ -1,0 +1,285 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's golden
+outputs.  Needs a B200: run with `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): <= 1e-10 relative on integrated DOS / JDOS,
+<= 1e-9 max-abs relative to peak on broadened spectra.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_npz, rel_to_peak
+from fxutil import fixture, oracle_sys, pdos_mask
+
+pytestmark = pytest.mark.gpu
+
+TOL_SPEC = 1e-9    # max-abs relative to peak, broadened spectra
+TOL_INT = 1e-10    # relative, integrated spectra
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import optados_b200
+    return optados_b200
+
+
+def gpu_ctx(ob, fx, odo, gradient="auto"):
+    s = oracle_sys(odo, fx, gradient)
+    ctx = ob.Context(0)
+    ctx.set_system(s.nk, s.ns, s.nb, s.recip_lattice, s.kpoint_grid_dim, s.kpoint_weight, s.electrons_per_state)
+    ctx.set_bands(s.band_energy)
+    if "optical_mat" in fx and "band_gradient" not in fx:
+        ctx.set_gradients_from_ome(fx["optical_mat"])      # electronic.f90:276-291 on the device
+        assert np.array_equal(ctx.get_gradients(), s.band_gradient)
+    elif s.band_gradient is not None:
+        ctx.set_gradients(s.band_gradient)
+    return ctx, s
+
+
+def assert_int(a, b):
+    scale = np.abs(b).max()
+    assert np.abs(a - b).max() <= TOL_INT * scale, np.abs(a - b).max() / scale
+
+
+@pytest.mark.parametrize("fxname", ["si2_optics", "si2_optics_no_spin", "si2_dos", "si2_core"])
+@pytest.mark.parametrize("dos_type", ["f", "a", "l"])
+def test_calculate_dos_vs_oracle(ob, odo, fxname, dos_type):
+    fx = fixture(fxname)
+    ctx, s = gpu_ctx(ob, fx, odo)
+    E, delta, n = odo.dos_energy_scale(s, 0.05)
+    ref = odo.calculate_dos(dos_type, s, odo.make_broadening(), E, delta)
+    dos, intdos, _ = ctx.calculate_dos(dos_type, E[0], delta, n)
+    assert rel_to_peak(dos, ref[0]) < TOL_SPEC
+    assert_int(intdos, ref[1])
+    ctx.close()
+
+
+def test_dos_golden_adaptive_dat(ob, odo):
+    """BASELINE config 1 end to end through the driver, against the reference's golden file."""
+    fx = fixture("si2_optics")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params("adaptive", dos_spacing=0.1, num_electrons=fx["num_electrons"])
+    r = ctx.dos_utils_calculate(p)
+    g = load_npz("gold_testopt_dos_adaptive_dat")["block0"]
+    assert r["nbins"] == 482 and p.dos_nbins == 482
+    ef = r["efermi_adaptive"]
+    assert np.abs((r["E"] - ef) - g[:, 0]).max() < 1e-10
+    assert rel_to_peak(r["dos_adaptive"][:, 0], g[:, 1]) < 2e-12
+    assert rel_to_peak(-r["dos_adaptive"][:, 1], g[:, 2]) < 2e-12
+    assert rel_to_peak(r["intdos_adaptive"][:, 0], g[:, 3]) < 2e-12
+    assert rel_to_peak(-r["intdos_adaptive"][:, 1], g[:, 4]) < 2e-12
+    ctx.close()
+
+
+def test_dos_golden_linear_dome(ob, odo):
+    fx = fixture("si2_dos")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params("linear", dos_spacing=0.1, num_electrons=fx["num_electrons"])
+    r = ctx.dos_utils_calculate(p)
+    g = load_npz("gold_testopt_dos_linear_dome")["block0"]
+    assert np.abs((r["E"] - r["efermi_linear"]) - g[:, 0]).max() < 1e-10
+    assert rel_to_peak(r["dos_linear"][:, 0], g[:, 1]) < 2e-12
+    assert rel_to_peak(r["intdos_linear"][:, 0], g[:, 3]) < 2e-12
+    ctx.close()
+
+
+def test_compare_dos_and_options(ob, odo):
+    """several broadenings at once (Q14), numerical_intdos, linear_smearing, no FBC, sticky nbins (Q4)."""
+    fx = fixture("si2_dos")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    mw = odo.projection_merge(fx["pdos_weights"], pdos_mask(fx, [dict(am=0), dict(am=1)]))
+    p = ctx.dos_params(["fixed", "adaptive", "linear"], dos_spacing=0.07, num_electrons=fx["num_electrons"])
+    r = ctx.dos_utils_calculate(p, mw=mw)
+    E, delta, n = odo.dos_energy_scale(s, 0.07)
+    assert n == r["nbins"] and abs(delta - r["delta"]) < 1e-15
+    for t in ("fixed", "adaptive", "linear"):
+        ref = odo.calculate_dos(t[0], s, odo.make_broadening(), E, delta, mw if t == "linear" else None)
+        assert rel_to_peak(r["dos_" + t], ref[0]) < TOL_SPEC
+        assert_int(r["intdos_" + t], ref[1])
+        assert abs(r["efermi_" + t] - odo.calc_efermi_from_intdos(ref[1], E, s.num_electrons)) < 1e-9
+        if t == "linear":   # weighted spectrum only with the most complex scheme
+            assert rel_to_peak(r["weighted_dos"], ref[2]) < TOL_SPEC
+    # second call: dos_nbins is now sticky and the grid is NOT re-snapped
+    r2 = ctx.dos_utils_calculate(p)
+    E2, delta2, n2 = odo.dos_energy_scale(s, 0.07, dos_nbins=n)
+    assert r2["nbins"] == n and abs(r2["delta"] - delta2) < 1e-15 and abs(delta2 - delta) > 1e-12
+    for kw in (dict(numerical_intdos=True), dict(finite_bin_correction=False), dict(linear_smearing=0.2)):
+        bro, brg = odo.make_broadening(**kw), ob.broadening(**kw)
+        for t in ("a", "l"):
+            ref = odo.calculate_dos(t, s, bro, E, delta)
+            dos, intdos, _ = ctx.calculate_dos(t, E[0], delta, n, br=brg)
+            assert rel_to_peak(dos, ref[0]) < TOL_SPEC, (kw, t)
+            assert_int(intdos, ref[1])
+    ctx.close()
+
+
+@pytest.mark.parametrize("test,fxname,projectors", [
+    ("testopt_pdos_angular", "si2_optics", [dict(am=l) for l in range(4)]),
+    ("testopt_pdos_string2", "si2_dos", [dict(species=1, rank=1, am=1)]),
+    ("testopt_pdos_string3", "si2_optics_no_spin", [dict(species=1, rank=1), dict(species=1, rank=2, am=0)]),
+])
+def test_pdos(ob, odo, test, fxname, projectors):
+    fx = fixture(fxname)
+    ctx, s = gpu_ctx(ob, fx, odo)
+    mask = pdos_mask(fx, projectors)
+    mw = ctx.projection_merge(fx["pdos_weights"], mask)
+    assert np.array_equal(mw, odo.projection_merge(fx["pdos_weights"], mask))
+    p = ctx.dos_params("adaptive", dos_spacing=0.1, num_electrons=fx["num_electrons"])
+    r = ctx.dos_utils_calculate(p, mw=mw)
+    ref = odo.dos_utils_calculate(s, "adaptive", dos_spacing=0.1, mw=mw)
+    assert rel_to_peak(r["weighted_dos"], ref["wdos"]) < TOL_SPEC
+    g = load_npz("gold_" + test)["block0"]
+    for pi in range(len(projectors)):
+        assert rel_to_peak(r["weighted_dos"][:, 0, pi], g[:, 1 + pi]) < 2e-7   # golden printed es14.7
+    ctx.close()
+
+
+def test_pdos_many_projectors(ob, odo):
+    """more weight columns than one kernel slice carries (groups of 8) and mw bounds smaller than nb."""
+    fx = fixture("si2_dos")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    rng = np.random.default_rng(7)
+    norb, mwnb = 19, s.nb - 3
+    mw = np.asfortranarray(rng.random((norb, mwnb, s.nk, s.ns)))
+    E, delta, n = odo.dos_energy_scale(s, 0.05)
+    for t in ("a", "l"):
+        ref = odo.calculate_dos(t, s, odo.make_broadening(), E, delta, mw)
+        dos, intdos, wdos = ctx.calculate_dos(t, E[0], delta, n, mw=mw)
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC
+        assert rel_to_peak(wdos, ref[2]) < TOL_SPEC
+    ctx.close()
+
+
+@pytest.mark.parametrize("dos_type", ["f", "a", "l"])
+def test_dos_at_e(ob, odo, dos_type):
+    fx = fixture("si2_dos")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    rng = np.random.default_rng(3)
+    mw = np.asfortranarray(rng.random((40, s.nb, s.nk, s.ns)))
+    for hyb in (False, True):
+        bro = odo.make_broadening(hybrid_linear=hyb, hybrid_linear_grad_tol=2.0)
+        brg = ob.broadening(hybrid_linear=hyb, hybrid_linear_grad_tol=2.0)
+        for energy in (4.3, -2.0, 11.7):
+            d_ref, w_ref = odo.calculate_dos_at_e(dos_type, s, bro, 0.05, energy, mw)
+            d, w = ctx.calculate_dos_at_e(dos_type, energy, 0.05, br=brg, mw=mw)
+            assert np.abs(d - d_ref).max() <= 1e-12 * max(1.0, np.abs(d_ref).max())
+            assert np.abs(w - w_ref).max() <= 1e-12 * max(1.0, np.abs(w_ref).max())
+    ctx.close()
+
+
+@pytest.mark.parametrize("fxname,jtype", [("si2_dos", "a"), ("si2_dos", "f"), ("si2_optics_no_spin", "l"), ("si2_dos", "l")])
+def test_jdos_vs_oracle(ob, odo, fxname, jtype):
+    fx = fixture(fxname)
+    ctx, s = gpu_ctx(ob, fx, odo)
+    ef = odo.dos_utils_calculate(s, {"a": "adaptive", "f": "fixed", "l": "linear"}[jtype], dos_spacing=0.1)["efermi"]
+    E, delta, n = odo.jdos_energy_scale(s, ef)
+    for kw in (dict(), dict(scissor_op=0.7, exclude_bands=(2, 3)), dict(hybrid=True)):
+        hyb = kw.pop("hybrid", False)
+        bro = odo.make_broadening(hybrid_linear=hyb, hybrid_linear_grad_tol=3.0)
+        brg = ob.broadening(hybrid_linear=hyb, hybrid_linear_grad_tol=3.0)
+        ref, _ = odo.calculate_jdos(jtype, s, bro, E, delta, ef, **kw)
+        jd, _ = ctx.calculate_jdos(jtype, delta, n, ef, br=brg, **kw)
+        assert rel_to_peak(jd, ref) < TOL_SPEC, kw
+    ctx.close()
+
+
+def test_jdos_golden(ob, odo):
+    fx = fixture("si2_dos")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params("adaptive", dos_spacing=0.1, num_electrons=fx["num_electrons"])
+    ef = ctx.dos_utils_set_efermi(p)
+    r = ctx.jdos_utils_calculate(ef, "adaptive")
+    g = load_npz("gold_testopt_jdos_adaptive_dome")["block0"]
+    assert r["nbins"] == g.shape[0]
+    assert rel_to_peak(r["jdos_adaptive"][:, 0], g[:, 1]) < 2e-12
+    assert rel_to_peak(-r["jdos_adaptive"][:, 1], g[:, 2]) < 2e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("geom", ["polar", "tensor", "polycrys", "unpolar"])
+@pytest.mark.parametrize("with_sym", [True, False])
+def test_make_weights_and_optics(ob, odo, geom, with_sym):
+    fx = fixture("si2_optics")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    ef = odo.dos_utils_calculate(s, "adaptive", dos_spacing=0.1)["efermi"]
+    symops = fx["symops"] if with_sym else None
+    q = (0.5, 0.5, 0.25)
+    mw_ref = odo.make_weights(s, fx["optical_mat"], geom, ef, qdir=q, symops=symops)
+    mw = ctx.make_weights(fx["optical_mat"], geom, ef, qdir=q, symops=symops)
+    assert np.abs(mw - mw_ref).max() <= 1e-12 * np.abs(mw_ref).max()
+    ref = odo.jdos_utils_calculate(s, ef, "adaptive", jdos_spacing=0.01, jdos_max_energy=30.0, mw=mw_ref)
+    # materialised weights, as the reference does
+    r1 = ctx.jdos_utils_calculate(ef, "adaptive", jdos_max_energy=30.0, mw=mw)
+    # fused: weights formed on chip from the OME, matrix_weights never materialised
+    r2 = ctx.jdos_utils_calculate(ef, "adaptive", jdos_max_energy=30.0, optical_mat=fx["optical_mat"], geom=geom, qdir=q,
+                                  symops=symops)
+    for r in (r1, r2):
+        assert r["nbins"] == ref["nbins"] == 3000
+        assert rel_to_peak(r["jdos_adaptive"], ref["jdos"]) < TOL_SPEC
+        assert rel_to_peak(r["weighted_jdos"], ref["wjdos"]) < TOL_SPEC
+    e2 = ctx.calc_epsilon_2(r2["weighted_jdos"], s.cell_volume)
+    assert rel_to_peak(e2, odo.calc_epsilon_2(ref["wjdos"], s.cell_volume)) < TOL_SPEC
+    if with_sym and geom in ("polar", "tensor"):
+        G = load_npz("gold_testopt_optics_" + geom)
+        for c in range(e2.shape[1]):
+            assert rel_to_peak(e2[:, c], G[f"block{c}"][:, 2]) < TOL_SPEC
+    ctx.close()
+
+
+@pytest.mark.parametrize("btype,core_type,polar", [("adaptive", "emission", True), ("linear", "all", False),
+                                                   ("adaptive", "absorption", False)])
+def test_core(ob, odo, btype, core_type, polar):
+    fx = fixture("si2_core")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params(btype, dos_spacing=0.01, num_electrons=fx["num_electrons"])
+    ef = ctx.dos_utils_set_efermi(p)                      # first pass (dos_utils_set_efermi)
+    first = odo.dos_utils_calculate(s, btype, dos_spacing=0.01)
+    assert abs(ef - first["efermi"]) < 1e-9
+    q = (0.5, 0.5, 0.25)
+    mw_ref = odo.core_prepare_matrix_elements(s, fx["elnes_mat"], core_type, ef, polar=polar, qdir=q, symops=fx["symops"])
+    mw = ctx.core_prepare_matrix_elements(fx["elnes_mat"], core_type, ef, polar=polar, qdir=q, symops=fx["symops"])
+    assert np.abs(mw - mw_ref).max() <= 1e-12 * np.abs(mw_ref).max()
+    r = ctx.dos_utils_calculate(p, mw=mw)                 # second pass: sticky dos_nbins (Q4)
+    E, delta, n = odo.dos_energy_scale(s, 0.01, dos_nbins=first["nbins"])
+    assert r["nbins"] == n and abs(r["delta"] - delta) < 1e-15
+    ref = odo.calculate_dos(btype[0], s, odo.make_broadening(), E, delta, mw_ref)
+    assert rel_to_peak(r["weighted_dos"], ref[2]) < TOL_SPEC
+    ctx.close()
+
+
+def test_efermi_insulator_and_errors(ob, odo):
+    fx = fixture("si2_dos")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params("adaptive", dos_spacing=0.1, num_electrons=fx["num_electrons"], efermi="insulator")
+    assert abs(ctx.dos_utils_set_efermi(p) - odo.efermi_insulator(s)) < 1e-12
+    with pytest.raises(ob.OptadosB200Error):
+        ctx.calculate_dos("q", 0.0, 0.1, 100)             # unknown dos_type (dos_utils.f90:1205)
+    with pytest.raises(ob.OptadosB200Error):
+        bad = np.zeros((3, s.nb, s.nk + 1, s.ns), order="F")
+        ctx.calculate_dos("a", 0.0, 0.1, 100, mw=bad)     # mw%nkpoints /= nkpoints (dos_utils.f90:159)
+    with pytest.raises(ob.OptadosB200Error):
+        fxc = fixture("si2_optics")
+        c2, s2 = gpu_ctx(ob, fxc, odo)
+        c2.core_prepare_matrix_elements(np.zeros((2, s2.nb, 3, s2.nk, s2.ns), dtype=complex), "all", 0.0,
+                                        symops=fxc["symops"])   # num_sym > 1 (core.f90:106)
+    ctx.close()
+
+
+def test_synthetic_small_vs_oracle(ob, odo):
+    """synthetic cosine bands generated on the device, read back, and pushed through the oracle:
+    narrow windows on a fine grid (the regime of BASELINE configs 2-5, scaled down)."""
+    ctx = ob.Context(0)
+    grid, ns, nb = (6, 5, 4), 2, 12
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=2)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    assert np.all(np.diff(be, axis=0) >= 0)               # per-(k,s) ascending
+    a = 5.43
+    recip = np.eye(3) * (2 * np.pi / a)
+    s = odo.Sys(be, kw, recip, grid, bg, electrons_per_state=1.0, num_electrons=[6.0, 6.0])
+    E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=1500)
+    for t in ("a", "l", "f"):
+        ref = odo.calculate_dos(t, s, odo.make_broadening(fixed_smearing=0.05), E, delta)
+        dos, intdos, _ = ctx.calculate_dos(t, E[0], delta, n, br=ob.broadening(fixed_smearing=0.05))
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC, t
+        assert_int(intdos, ref[1])
+    ctx.close()
