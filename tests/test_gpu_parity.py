@@ -155,7 +155,9 @@ def test_dos_at_e(ob, odo, dos_type):
     ctx, s = gpu_ctx(ob, fx, odo)
     rng = np.random.default_rng(3)
     mw = np.asfortranarray(rng.random((40, s.nb, s.nk, s.ns)))
-    for hyb in (False, True):
+    # hybrid_linear with a FIXED scheme makes the reference test an unset gradient (undefined
+    # behaviour, dos_utils.f90:1754-1758); the library ignores the flag unless the scheme is linear
+    for hyb in ((False,) if dos_type == "f" else (False, True)):
         bro = odo.make_broadening(hybrid_linear=hyb, hybrid_linear_grad_tol=2.0)
         brg = ob.broadening(hybrid_linear=hyb, hybrid_linear_grad_tol=2.0)
         for energy in (4.3, -2.0, 11.7):
@@ -173,7 +175,7 @@ def test_jdos_vs_oracle(ob, odo, fxname, jtype):
     ef = odo.dos_utils_calculate(s, {"a": "adaptive", "f": "fixed", "l": "linear"}[jtype], dos_spacing=0.1)["efermi"]
     E, delta, n = odo.jdos_energy_scale(s, ef)
     for kw in (dict(), dict(scissor_op=0.7, exclude_bands=(2, 3)), dict(hybrid=True)):
-        hyb = kw.pop("hybrid", False)
+        hyb = kw.pop("hybrid", False) and jtype != "f"   # see test_dos_at_e
         bro = odo.make_broadening(hybrid_linear=hyb, hybrid_linear_grad_tol=3.0)
         brg = ob.broadening(hybrid_linear=hyb, hybrid_linear_grad_tol=3.0)
         ref, _ = odo.calculate_jdos(jtype, s, bro, E, delta, ef, **kw)
