@@ -35,6 +35,7 @@ extern "C" {
 #endif
 
 typedef struct od_ctx od_ctx;
+typedef struct od_broadening od_broadening; /* defined below */
 
 enum { OD_MEM_HOST = 0, OD_MEM_DEVICE = 1 };
 enum { OD_OK = 0, OD_ERR_ARG = 1, OD_ERR_CUDA = 2, OD_ERR_STATE = 3, OD_ERR_NCCL = 4, OD_ERR_DOSLIN = 5, OD_ERR_REF = 6 };
@@ -58,12 +59,32 @@ const char *od_last_error(const od_ctx *ctx);
 int od_ctx_rank(const od_ctx *ctx);
 int od_ctx_nranks(const od_ctx *ctx);
 int od_synchronize(od_ctx *ctx);
+/* engine selection for calculate_dos: OD_ENGINE_AUTO (narrow-window engine with the dense engine for
+ * wide windows) or OD_ENGINE_DENSE (dense bin-owner engine only: the reference's arithmetic, slow) */
+enum { OD_ENGINE_AUTO = 0, OD_ENGINE_DENSE = 1 };
+int od_set_engine(od_ctx *ctx, int engine);
 /* number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches) */
 long long od_kernel_launches(const od_ctx *ctx);
 /* device-side milliseconds (CUDA events on the ctx stream) spent in the main accumulation kernels
  * since the last reset, and the number of in-window (unit, bin) contributions they evaluated */
 int od_profile_reset(od_ctx *ctx);
 int od_profile_get(od_ctx *ctx, double *accumulate_ms, double *prepare_ms, double *contributions, long long *accumulate_launches);
+
+/* device-side stopwatch on the ctx stream (CUDA events): start, ... library calls ..., stop -> ms */
+int od_timer_start(od_ctx *ctx);
+int od_timer_stop(od_ctx *ctx, double *elapsed_ms);
+/* sustained FP64 FMA throughput of this GPU (all SMs, dependent-chain-free DFMA loop of about
+ * `seconds`), in TFLOP/s (2 flops per FMA) -- the denominator of the FP64 roofline, measured in place
+ * because MEASURED_PEAKS.json carries no FP64 entry */
+int od_measure_fp64_peak(od_ctx *ctx, double seconds, double *tflops);
+/* in-window (unit, bin) contributions of a calculate_dos pass on this rank, the unit of the
+ * throughput metric: gaussian W = floor(2 sqrt(60) w / dE) + 1,
+ * linear W = floor(2 (e0 - e4) / dE) + 1, each clipped to the grid */
+int od_count_contributions(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins,
+                           const od_broadening *br, double *contributions);
+/* pinned host memory for the end-to-end path (cudaHostAlloc) */
+int od_host_alloc_pinned(size_t nbytes, void **hptr);
+int od_host_free_pinned(void *hptr);
 
 /* device memory helpers (so weight arrays can stay resident between calls) */
 int od_device_malloc(od_ctx *ctx, size_t nbytes, void **dptr);

@@ -96,6 +96,8 @@ EXPORTS = [
     "od_calc_epsilon_2", "od_dos_params_defaults", "od_dos_utils_calculate", "od_dos_get", "od_dos_get_weighted",
     "od_calc_efermi_from_intdos", "od_dos_utils_set_efermi", "od_jdos_params_defaults", "od_jdos_utils_calculate",
     "od_jdos_get", "od_jdos_get_weighted", "od_synth_bands", "od_get_bands", "od_get_kweights",
+    "od_timer_start", "od_timer_stop", "od_measure_fp64_peak", "od_count_contributions", "od_host_alloc_pinned",
+    "od_host_free_pinned", "od_set_engine",
 ]
 
 
@@ -423,3 +425,52 @@ class Context:
 
     def synchronize(self):
         self._ck(self.L.od_synchronize(self.h))
+
+    def set_engine(self, engine):
+        """'auto' (narrow-window engine + dense for wide windows) or 'dense'"""
+        self._ck(self.L.od_set_engine(self.h, C.c_int({"auto": 0, "dense": 1}[engine])))
+
+    def timer_start(self):
+        self._ck(self.L.od_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.L.od_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def measure_fp64_peak(self, seconds=0.3):
+        t = C.c_double()
+        self._ck(self.L.od_measure_fp64_peak(self.h, C.c_double(seconds), C.byref(t)))
+        return t.value
+
+    def count_contributions(self, dos_type, emin, delta_bins, nbins, br=None):
+        br = br or broadening()
+        n = C.c_double()
+        self._ck(self.L.od_count_contributions(self.h, C.c_char(dos_type.encode()), C.c_double(emin), C.c_double(delta_bins),
+                                               C.c_int(nbins), C.byref(br), C.byref(n)))
+        return n.value
+
+    def set_bands_ptr(self, host_ptr):
+        """od_set_bands from a raw (e.g. pinned) host pointer; asynchronous on the ctx stream."""
+        self._ck(self.L.od_set_bands(self.h, C.c_void_p(host_ptr), OD_MEM_HOST))
+
+    def set_gradients_ptr(self, host_ptr):
+        self._ck(self.L.od_set_gradients(self.h, C.c_void_p(host_ptr), OD_MEM_HOST))
+
+    def get_bands_ptr(self, host_ptr):
+        self._ck(self.L.od_get_bands(self.h, C.c_void_p(host_ptr)))
+
+    def get_gradients_ptr(self, host_ptr):
+        self._ck(self.L.od_get_gradients(self.h, C.c_void_p(host_ptr)))
+
+
+def host_alloc_pinned(nbytes):
+    p = C.c_void_p()
+    rc = load().od_host_alloc_pinned(C.c_size_t(nbytes), C.byref(p))
+    if rc:
+        raise OptadosB200Error(rc, f"cudaHostAlloc({nbytes}) failed")
+    return p.value
+
+
+def host_free_pinned(ptr):
+    load().od_host_free_pinned(C.c_void_p(ptr))

@@ -159,6 +159,13 @@ extern "C" int od_ctx_rank(const od_ctx *ctx) { return ctx ? ctx->rank : 0; }
 extern "C" int od_ctx_nranks(const od_ctx *ctx) { return ctx ? ctx->nranks : 1; }
 extern "C" long long od_kernel_launches(const od_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int od_set_engine(od_ctx *ctx, int engine) {
+  if (!ctx) return OD_ERR_ARG;
+  if (engine != OD_ENGINE_AUTO && engine != OD_ENGINE_DENSE) return od_fail(ctx, OD_ERR_ARG, "unknown engine %d", engine);
+  ctx->engine = engine;
+  return OD_OK;
+}
+
 extern "C" int od_synchronize(od_ctx *ctx) {
   if (!ctx) return OD_ERR_ARG;
   OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

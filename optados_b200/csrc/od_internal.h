@@ -43,6 +43,7 @@ struct od_ctx {
   long long launches = 0;
   Profile prof;
   int sm_count = 148;
+  int engine = 0;  // OD_ENGINE_*
 
   // module data (od_cell / od_electronic)
   bool have_system = false;

@@ -2,6 +2,7 @@
 // calculate_dos_at_e (:1651), calculate_jdos (jdos_utils.f90:280) and their merges.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "od_internal.h"
 #include "od_producers.cuh"
@@ -67,47 +68,6 @@ __global__ void linear_smear_kernel(const double *__restrict__ dos, double *__re
 }
 }  // namespace
 
-// Launch the dense engine for a producer and reduce the chunk partials into `accum` (device).
-// dest: nz*nacc offsets into accum (or -1).
-template <int NW, bool INT, class Producer>
-static int run_dense(od_ctx *ctx, const Producer &prod, const GridSpec &grid, int nz, const std::vector<long long> &dest,
-                     double *accum) {
-  constexpr int NACC = 1 + (INT ? 1 : 0) + NW;
-  const int ntiles = (grid.nbins + OD_TILE - 1) / OD_TILE;
-  const long long units = prod.units_per_z;
-  long long max_chunks = (units + OD_TILE - 1) / OD_TILE;
-  long long want = ((long long)ctx->sm_count * 16 + (long long)ntiles * nz - 1) / ((long long)ntiles * nz);
-  long long nchunks = std::max<long long>(1, std::min<long long>({want, max_chunks, 65535}));
-  long long chunk_units = (units + nchunks - 1) / nchunks;
-  chunk_units = (chunk_units + OD_TILE - 1) / OD_TILE * OD_TILE;
-  nchunks = (units + chunk_units - 1) / chunk_units;
-  if (nchunks < 1) nchunks = 1;
-  const size_t pbytes = sizeof(double) * (size_t)nchunks * nz * NACC * grid.nbins;
-  OD_CHECK(od_buf_ensure(ctx, ctx->partial, pbytes));
-  OD_CHECK(od_buf_ensure(ctx, ctx->keys, sizeof(long long) * dest.size() + sizeof(int) * 4));
-  int *bad = reinterpret_cast<int *>(ctx->keys.as<char>() + sizeof(long long) * dest.size());
-  OD_CUDA(ctx, cudaMemcpyAsync(ctx->keys.p, dest.data(), sizeof(long long) * dest.size(), cudaMemcpyHostToDevice, ctx->stream));
-  OD_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-  dim3 g(ntiles, (unsigned)nchunks, nz);
-  OD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  od_dense_kernel<NW, INT, Producer><<<g, OD_TILE, 0, ctx->stream>>>(prod, grid, chunk_units, ctx->partial.as<double>(), bad);
-  OD_LAUNCH_CHECK(ctx);
-  dim3 rg((grid.nbins + 255) / 256, nz * NACC);
-  od_reduce_partials<<<rg, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), (int)nchunks, nz, NACC, grid.nbins,
-                                                  ctx->keys.as<long long>(), accum);
-  OD_LAUNCH_CHECK(ctx);
-  OD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  int hbad = 0;
-  OD_CUDA(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-  ctx->prof.accumulate_ms += ms;
-  ctx->prof.accumulate_launches += 1;
-  if (hbad) return od_fail(ctx, OD_ERR_DOSLIN, "doslin: input arguments incorrect (dos_utils.f90:1431/1514)");
-  return OD_OK;
-}
-
 // ------------------------------------------------------------------ calculate_dos
 int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins, const od_broadening *br,
                             const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_out) {
@@ -135,13 +95,16 @@ int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delt
   double *accum = ctx->accum.as<double>();
   OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * ntot, ctx->stream));
 
-  if (!mw_dev) {
+  const bool force_dense = ctx->engine == OD_ENGINE_DENSE;
+  if (!mw_dev && !force_dense) {
+    OD_CHECK(od_narrow_dos(ctx, p, grid, dos_type == 'l', accum));
+  } else if (!mw_dev) {
     std::vector<long long> dest(ns * 2);
     for (int is = 0; is < ns; ++is) {
       dest[is * 2 + 0] = (long long)is * nbins;
       dest[is * 2 + 1] = (long long)(n1 + (size_t)is * nbins);
     }
-    OD_CHECK((run_dense<0, true, DosProducer>(ctx, p, grid, ns, dest, accum)));
+    OD_CHECK((od_run_dense<0, true, DosProducer>(ctx, p, grid, ns, dest, accum)));
   } else {
     const int ngroups = (norb + OD_MAXW - 1) / OD_MAXW;
     const int nz = ns * ngroups;
@@ -159,7 +122,7 @@ int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delt
           if (o < norb) dest[(size_t)z * NACC + 2 + a] = (long long)(2 * n1 + (size_t)nbins * (is + (size_t)ns * o));
         }
       }
-    OD_CHECK((run_dense<OD_MAXW, true, DosProducer>(ctx, p, grid, nz, dest, accum)));
+    OD_CHECK((od_run_dense<OD_MAXW, true, DosProducer>(ctx, p, grid, nz, dest, accum)));
   }
 
   // rank-local epilogue, before the merge like the reference (quirk Q16)
@@ -365,9 +328,9 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
     dest[(size_t)is * nacc] = (long long)is * nbins;
     for (int a = 0; a < n_geom; ++a) dest[(size_t)is * nacc + 1 + a] = (long long)(n1 + (size_t)nbins * (is + (size_t)ns * a));
   }
-  if (n_geom == 0) OD_CHECK((run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
-  else if (n_geom == 1) OD_CHECK((run_dense<1, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
-  else OD_CHECK((run_dense<6, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+  if (n_geom == 0) OD_CHECK((od_run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+  else if (n_geom == 1) OD_CHECK((od_run_dense<1, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+  else OD_CHECK((od_run_dense<6, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   if (merge) OD_CHECK(od_allreduce_device(ctx, accum, ntot, 's'));  // jdos_utils_merge (jdos_utils.f90:435-437)
   *accum_out = accum;
   return OD_OK;

@@ -1,6 +1,9 @@
 // od_spectral.h -- internal (device-pointer) forms of the hot-loop entry points.
 #pragma once
 #include "od_internal.h"
+#include <algorithm>
+#include <vector>
+
 #include "od_producers.cuh"
 
 int od_make_broadspec(od_ctx *ctx, char type, const od_broadening *br, double delta_bins, bool honor_hybrid, BroadSpec *out);
@@ -15,3 +18,48 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
 
 // contracted optics coefficients (optics.f90:213-435), see od_weights.cu
 int od_optics_coefficients(od_ctx *ctx, int geom, const double qdir[3], const double *symops, int num_symm, OpticsCoef *coef);
+
+// narrow (sorted, recurrence) engine for calculate_dos without weights (od_narrow.cu)
+int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bool linear, double *accum);
+
+// Launch the dense engine for a producer and reduce the chunk partials into `accum` (device).
+// dest: nz*nacc offsets into accum (or -1).
+template <int NW, bool INT, class Producer>
+int od_run_dense(od_ctx *ctx, const Producer &prod, const GridSpec &grid, int nz, const std::vector<long long> &dest,
+                     double *accum) {
+  constexpr int NACC = 1 + (INT ? 1 : 0) + NW;
+  const int ntiles = (grid.nbins + OD_TILE - 1) / OD_TILE;
+  const long long units = prod.units_per_z;
+  long long max_chunks = (units + OD_TILE - 1) / OD_TILE;
+  long long want = ((long long)ctx->sm_count * 16 + (long long)ntiles * nz - 1) / ((long long)ntiles * nz);
+  long long nchunks = std::max<long long>(1, std::min<long long>({want, max_chunks, 65535}));
+  long long chunk_units = (units + nchunks - 1) / nchunks;
+  chunk_units = (chunk_units + OD_TILE - 1) / OD_TILE * OD_TILE;
+  nchunks = (units + chunk_units - 1) / chunk_units;
+  if (nchunks < 1) nchunks = 1;
+  const size_t pbytes = sizeof(double) * (size_t)nchunks * nz * NACC * grid.nbins;
+  OD_CHECK(od_buf_ensure(ctx, ctx->partial, pbytes));
+  OD_CHECK(od_buf_ensure(ctx, ctx->keys, sizeof(long long) * dest.size() + sizeof(int) * 4));
+  int *bad = reinterpret_cast<int *>(ctx->keys.as<char>() + sizeof(long long) * dest.size());
+  OD_CUDA(ctx, cudaMemcpyAsync(ctx->keys.p, dest.data(), sizeof(long long) * dest.size(), cudaMemcpyHostToDevice, ctx->stream));
+  OD_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+  dim3 g(ntiles, (unsigned)nchunks, nz);
+  OD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  od_dense_kernel<NW, INT, Producer><<<g, OD_TILE, 0, ctx->stream>>>(prod, grid, chunk_units, ctx->partial.as<double>(), bad);
+  OD_LAUNCH_CHECK(ctx);
+  dim3 rg((grid.nbins + 255) / 256, nz * NACC);
+  od_reduce_partials<<<rg, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), (int)nchunks, nz, NACC, grid.nbins,
+                                                  ctx->keys.as<long long>(), accum);
+  OD_LAUNCH_CHECK(ctx);
+  OD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  int hbad = 0;
+  OD_CUDA(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->prof.accumulate_ms += ms;
+  ctx->prof.accumulate_launches += 1;
+  if (hbad) return od_fail(ctx, OD_ERR_DOSLIN, "doslin: input arguments incorrect (dos_utils.f90:1431/1514)");
+  return OD_OK;
+}
+
