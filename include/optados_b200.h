@@ -65,10 +65,13 @@ enum { OD_ENGINE_AUTO = 0, OD_ENGINE_DENSE = 1 };
 int od_set_engine(od_ctx *ctx, int engine);
 /* number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches) */
 long long od_kernel_launches(const od_ctx *ctx);
-/* device-side milliseconds (CUDA events on the ctx stream) spent in the main accumulation kernels
- * since the last reset, and the number of in-window (unit, bin) contributions they evaluated */
+/* device-side milliseconds (CUDA events on the ctx stream) spent in the accumulation kernels and in the
+ * prepare (classify + sort) passes since the last reset; the in-window (record, bin) pairs the narrow
+ * engine evaluated (contributions) and the lane-steps it spent on them (lane_steps >= contributions:
+ * the ratio is the lane efficiency of the record groups) */
 int od_profile_reset(od_ctx *ctx);
-int od_profile_get(od_ctx *ctx, double *accumulate_ms, double *prepare_ms, double *contributions, long long *accumulate_launches);
+int od_profile_get(od_ctx *ctx, double *accumulate_ms, double *prepare_ms, double *contributions, double *lane_steps,
+                   long long *accumulate_launches);
 
 /* device-side stopwatch on the ctx stream (CUDA events): start, ... library calls ..., stop -> ms */
 int od_timer_start(od_ctx *ctx);

@@ -418,10 +418,11 @@ class Context:
         self._ck(self.L.od_profile_reset(self.h))
 
     def profile_get(self):
-        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        a, b, c, d = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         n = C.c_longlong()
-        self._ck(self.L.od_profile_get(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
-        return dict(accumulate_ms=a.value, prepare_ms=b.value, contributions=c.value, accumulate_launches=n.value)
+        self._ck(self.L.od_profile_get(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(n)))
+        return dict(accumulate_ms=a.value, prepare_ms=b.value, contributions=c.value, lane_steps=d.value,
+                    accumulate_launches=n.value)
 
     def synchronize(self):
         self._ck(self.L.od_synchronize(self.h))

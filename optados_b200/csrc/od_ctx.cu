@@ -145,7 +145,7 @@ extern "C" int od_ctx_destroy(od_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(ctx->comm));
   DevBuf *bufs[] = {&ctx->kweight, &ctx->bands, &ctx->grads, &ctx->partial, &ctx->accum, &ctx->small, &ctx->recs,
-                    &ctx->keys, &ctx->scratch_a, &ctx->scratch_b, &ctx->mw_tmp, &ctx->in_tmp};
+                    &ctx->keys, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->mw_tmp, &ctx->in_tmp};
   for (DevBuf *b : bufs) od_buf_release(*b);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -178,12 +178,13 @@ extern "C" int od_profile_reset(od_ctx *ctx) {
   return OD_OK;
 }
 
-extern "C" int od_profile_get(od_ctx *ctx, double *accumulate_ms, double *prepare_ms, double *contributions,
+extern "C" int od_profile_get(od_ctx *ctx, double *accumulate_ms, double *prepare_ms, double *contributions, double *lane_steps,
                               long long *accumulate_launches) {
   if (!ctx) return OD_ERR_ARG;
   if (accumulate_ms) *accumulate_ms = ctx->prof.accumulate_ms;
   if (prepare_ms) *prepare_ms = ctx->prof.prepare_ms;
   if (contributions) *contributions = ctx->prof.contributions;
+  if (lane_steps) *lane_steps = ctx->prof.lane_steps;
   if (accumulate_launches) *accumulate_launches = ctx->prof.accumulate_launches;
   return OD_OK;
 }

@@ -20,7 +20,7 @@ struct DevBuf {
 };
 
 struct Profile {
-  double accumulate_ms = 0.0, prepare_ms = 0.0, contributions = 0.0;
+  double accumulate_ms = 0.0, prepare_ms = 0.0, contributions = 0.0, lane_steps = 0.0;
   long long accumulate_launches = 0;
 };
 
@@ -54,7 +54,7 @@ struct od_ctx {
   DevBuf kweight, bands, grads;
 
   // scratch
-  DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, mw_tmp, in_tmp;
+  DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, mw_tmp, in_tmp;
 
   Spectra dos_res, jdos_res;
 };
