@@ -254,9 +254,9 @@ prep_scatter_kernel(DosProducer prod, PrepSpec ps, const unsigned *__restrict__ 
 // ---------------------------------------------------------------- accumulate
 // R(u) = P5(u)/Q6(u) ~ erfcx(u / sqrt 2), u in [0, 8.45]; all coefficients positive (tools/fit_erfcx.py).
 // Kept in constant memory so that they enter the FMAs as constant-bank operands (no register, no UMOV).
-__constant__ double c_P[6] = {913.67854424431436856, 802.96638201765452004, 355.14175547719036648,
+static const double h_P[6] = {913.67854424431436856, 802.96638201765452004, 355.14175547719036648,
                               89.133859365727141543, 12.593079456648224345, 0.7978004363933496607};
-__constant__ double c_Q[6] = {913.67854424432351188, 1531.976386005259472, 1120.6427893189240945,
+static const double h_Q[6] = {913.67854424432351188, 1531.976386005259472, 1120.6427893189240945,
                               460.29258012431025649, 112.76898276075761223, 15.779603335732765349};
 
 __device__ __forceinline__ double rcp_newton(double q) {
@@ -266,19 +266,24 @@ __device__ __forceinline__ double rcp_newton(double q) {
   return fma(y, e, y);  // ~2^-46 relative
 }
 
-__device__ __forceinline__ double erfcx_ratio(double u) {
-  double p = c_P[5];
-  p = fma(p, u, c_P[4]);
-  p = fma(p, u, c_P[3]);
-  p = fma(p, u, c_P[2]);
-  p = fma(p, u, c_P[1]);
-  p = fma(p, u, c_P[0]);
-  double q = u + c_Q[5];
-  q = fma(q, u, c_Q[4]);
-  q = fma(q, u, c_Q[3]);
-  q = fma(q, u, c_Q[2]);
-  q = fma(q, u, c_Q[1]);
-  q = fma(q, u, c_Q[0]);
+struct ErfcxCoef {
+  double P[6], Q[6];
+};
+
+// cf points into the kernel parameter block, so the coefficients enter the FMAs as c[0x0][..] operands
+__device__ __forceinline__ double erfcx_ratio(double u, const ErfcxCoef &cf) {
+  double p = cf.P[5];
+  p = fma(p, u, cf.P[4]);
+  p = fma(p, u, cf.P[3]);
+  p = fma(p, u, cf.P[2]);
+  p = fma(p, u, cf.P[1]);
+  p = fma(p, u, cf.P[0]);
+  double q = u + cf.Q[5];
+  q = fma(q, u, cf.Q[4]);
+  q = fma(q, u, cf.Q[3]);
+  q = fma(q, u, cf.Q[2]);
+  q = fma(q, u, cf.Q[1]);
+  q = fma(q, u, cf.Q[0]);
   return p * rcp_newton(q);
 }
 
@@ -295,6 +300,7 @@ struct NarrowArgs {
   int bpad, cell;
   unsigned long long *next_chunk;
   unsigned long long *stats;             // [0] lane-steps spent, [1] in-window (record, bin) pairs
+  ErfcxCoef cf;
   double *out_dos, *out_int, *out_step;  // [ns * bpad + NR_T]
 };
 
@@ -312,11 +318,12 @@ __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int bas
 }
 
 // direct (non-recurrence) evaluation of one Gaussian record at one bin: used by the rare irregular groups
-__device__ __forceinline__ void gauss_direct(double e, double w, double om, double Ej, int j, int cabs, double &d, double &s) {
+__device__ __forceinline__ void gauss_direct(double e, double w, double om, double Ej, int j, int cabs, const ErfcxCoef &cf, double &d,
+                                             double &s) {
   const double z = (Ej - e) / w;
   const double gp = exp(-0.5 * z * z);
   d = OD_INV_SQRT_TWO_PI * gp / w * om;
-  const double h = 0.5 * om * gp * erfcx_ratio(fabs(z));
+  const double h = 0.5 * om * gp * erfcx_ratio(fabs(z), cf);
   s = (j < cabs) ? h : -h;
 }
 
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
               d = od_doslin(a0, a1, a2, a3, a4, Ej, &cum, &bad) * ao;
               s = ((r < c_l) ? cum : cum - 1.0) * ao;
             } else {
-              gauss_direct(a0, a1, ao, Ej, r, c_l, d, s);
+              gauss_direct(a0, a1, ao, Ej, r, c_l, A.cf, d, s);
             }
             if (d != 0.0) atomicAdd(&A.out_dos[k_l + r], d);
             if (s != 0.0) atomicAdd(&A.out_int[k_l + r], s);
@@ -415,25 +422,61 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
       __syncwarp();
 
       const double E0 = emin + (double)(jb - a) * delta;  // energy of relative bin 0
+      // Two streams per lane when the window allows it (Wc >= 64): stream 1 walks bins lane .. lane+H-1
+      // and never wraps, stream 2 starts H = ceil(Wc/2) bins further on and wraps once.  At any step the
+      // two 32-bin footprints are >= 32 bins apart (cyclically), so all 64 accesses hit different bins;
+      // the two dependent chains per lane double the ILP and halve the per-bin loop / wrap overhead.
+      const bool dual = Wc >= 64;
+      const int H = dual ? (Wc + 1) >> 1 : Wc;
+      const int n2 = dual ? Wc - H : 0;
       if (!LINEAR) {
         const double invw = 1.0 / p1, del = delta * invw;
         const double amp = om * invw * OD_INV_SQRT_TWO_PI;
         const double cl = p1 * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
         const double q = exp(-del * del), hd2 = 0.5 * del * del;
-        const double zB = (E0 - e0) * invw, zA = zB + (double)lane * del;
+        const double zB = (E0 - e0) * invw;
         const double gB = amp * exp(-0.5 * zB * zB), rB = exp(-fma(zB, del, hd2));
-        double g = amp * exp(-0.5 * zA * zA), rr = exp(-fma(zA, del, hd2)), z = zA;
-        int r = lane;
+        double z1 = zB + (double)lane * del;
+        double g1 = amp * exp(-0.5 * z1 * z1), rr1 = exp(-fma(z1, del, hd2));
+        int r1 = lane;
+        if (dual) {
+          double z2 = zB + (double)(lane + H) * del;
+          double g2 = amp * exp(-0.5 * z2 * z2), rr2 = exp(-fma(z2, del, hd2));
+          int r2 = lane + H;
 #pragma unroll 1
-        for (int t = 0; t < Wc; ++t) {
-          double2 acc = tw[r];
-          const double h = (g * cl) * erfcx_ratio(fabs(z));
-          acc.x += g;
-          acc.y += flip_sign_if(h, r >= cabs);
-          tw[r] = acc;
-          g *= rr; rr *= q; z += del;
-          ++r;
-          if (r == Wc) { r = 0; g = gB; rr = rB; z = zB; }
+          for (int t = 0; t < n2; ++t) {
+            // capture this step's inputs, then advance the recurrences at once so that the next step's
+            // operands are ready long before the rational chains below have drained
+            const double u1 = fabs(z1), u2 = fabs(z2), c1 = g1, c2 = g2;
+            double2 *q1 = tw + r1, *q2 = tw + r2;
+            const bool f1 = r1 >= cabs, f2 = r2 >= cabs;
+            g1 *= rr1; rr1 *= q; z1 += del; ++r1;
+            g2 *= rr2; rr2 *= q; z2 += del; ++r2;
+            if (r2 == Wc) { r2 = 0; g2 = gB; rr2 = rB; z2 = zB; }
+            double2 acc1 = *q1;
+            double2 acc2 = *q2;
+            const double h1 = (c1 * cl) * erfcx_ratio(u1, A.cf);
+            const double h2 = (c2 * cl) * erfcx_ratio(u2, A.cf);
+            acc1.x += c1;
+            acc1.y += flip_sign_if(h1, f1);
+            acc2.x += c2;
+            acc2.y += flip_sign_if(h2, f2);
+            *q1 = acc1;
+            *q2 = acc2;
+            __syncwarp();
+          }
+        }
+        // single stream: the whole window when Wc < 64, else the odd leftover bin of stream 1
+#pragma unroll 1
+        for (int t = n2; t < H; ++t) {
+          double2 acc = tw[r1];
+          const double h = (g1 * cl) * erfcx_ratio(fabs(z1), A.cf);
+          acc.x += g1;
+          acc.y += flip_sign_if(h, r1 >= cabs);
+          tw[r1] = acc;
+          g1 *= rr1; rr1 *= q; z1 += del;
+          ++r1;
+          if (r1 == Wc) { r1 = 0; g1 = gB; rr1 = rB; z1 = zB; }
           __syncwarp();
         }
       } else {
@@ -449,10 +492,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
         const double two_d = 2.0 * dd;
         const double xB = E0 - p4;
         const long long ia = __double_as_longlong(aa), ib = __double_as_longlong(bb), ic = __double_as_longlong(cc);
-        double xl = xB + (double)lane * delta;
-        int r = lane;
-#pragma unroll 1
-        for (int t = 0; t < Wc; ++t) {
+        auto lin_step = [&](int r, double xl) {
           const bool above = r >= cabs;               // E_j > e0: mirror (dos_utils.f90:1469)
           double x = above ? two_d - xl : xl;         // e_use - e4
           x = __hiloint2double(max(__double2hiint(x), 0), __double2loint(x));  // bins outside (e4, 2 e0 - e4): x -> +0
@@ -470,9 +510,28 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
           acc.x = fma(D, sc, acc.x);
           acc.y = fma(I, flip_sign_if(sc, above), acc.y);
           tw[r] = acc;
-          xl += delta;
-          ++r;
-          if (r == Wc) { r = 0; xl = xB; }
+        };
+        double xl1 = xB + (double)lane * delta;
+        int r1 = lane;
+        if (dual) {
+          double xl2 = xB + (double)(lane + H) * delta;
+          int r2 = lane + H;
+#pragma unroll 1
+          for (int t = 0; t < n2; ++t) {
+            lin_step(r1, xl1);
+            lin_step(r2, xl2);
+            xl1 += delta; ++r1;
+            xl2 += delta; ++r2;
+            if (r2 == Wc) { r2 = 0; xl2 = xB; }
+            __syncwarp();
+          }
+        }
+#pragma unroll 1
+        for (int t = n2; t < H; ++t) {
+          lin_step(r1, xl1);
+          xl1 += delta;
+          ++r1;
+          if (r1 == Wc) { r1 = 0; xl1 = xB; }
           __syncwarp();
         }
       }
@@ -620,6 +679,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bo
     A.cell = ps.cell;
     A.next_chunk = wide + 4;
     A.stats = wide + 5;
+    for (int i = 0; i < 6; ++i) { A.cf.P[i] = h_P[i]; A.cf.Q[i] = h_Q[i]; }
     A.out_dos = ndos;
     A.out_int = nint;
     A.out_step = stephist;
