@@ -71,6 +71,10 @@ struct PrepSpec {
   int cell;      // bins per position cell (power of two)
   int ncells;    // ns * bpad / cell
   int nbuckets;  // NR_NCLS * ncells; bucket = class * ncells + cell
+  double gwin;      // half-width of a Gaussian window in units of w (erf window for DOS, cut-off for JDOS)
+  int with_int;     // integrated spectrum wanted (DOS): off-grid units still contribute their step
+  int linear_pass;  // a linear pass sends Gaussian records (hybrid_linear fall-back) to the dense engine
+  int ng;           // weight columns carried beside each record (JDOS / optics)
 };
 
 struct Cls {
@@ -84,18 +88,19 @@ __device__ __forceinline__ int width_class(int wlen) {
   return (wlen > 24) + (wlen > 32) + (wlen > 44) + (wlen > 60) + (wlen > 84) + (wlen > 116) + (wlen > 160);
 }
 
-__device__ __forceinline__ Cls classify(const RecOut &r, const GridSpec &g) {
+__device__ __forceinline__ Cls classify(const RecOut &r, const PrepSpec &ps) {
+  const GridSpec &g = ps.grid;
   Cls c;
   double lo, hi, centre;
   const double inv = 1.0 / g.delta;
   bool degenerate = false;
   if (r.mode == 0) {
-    lo = r.e0 - NR_ERFWIN * r.p1;
-    hi = r.e0 + NR_ERFWIN * r.p1;
+    lo = r.e0 - ps.gwin * r.p1;
+    hi = r.e0 + ps.gwin * r.p1;
     centre = ceil((r.e0 - g.emin) * inv);  // first bin with E_j >= e
     // Gaussians narrower than dE/8 (only possible with finite_bin_correction off) would overflow the
     // recurrence ratio: leave them to the exact dense engine
-    degenerate = !(r.p1 * 8.0 >= g.delta);
+    degenerate = !(r.p1 * 8.0 >= g.delta) || ps.linear_pass;
   } else {
     lo = r.p4;
     hi = 2.0 * r.e0 - r.p4;
@@ -126,20 +131,24 @@ __device__ __forceinline__ Cls classify(const RecOut &r, const GridSpec &g) {
 }
 
 // ---------------------------------------------------------------- pass A: keys + per-CTA histogram row
+template <class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
-prep_hist_kernel(DosProducer prod, PrepSpec ps, unsigned *__restrict__ keys, unsigned *__restrict__ table /* [gridDim.x][nbuckets] */,
+prep_hist_kernel(Producer prod, PrepSpec ps, unsigned *__restrict__ keys, unsigned *__restrict__ table /* [gridDim.x][nbuckets] */,
                  unsigned long long *__restrict__ wide_count /* [ns] */) {
   extern __shared__ unsigned sh_hist[];
   for (int i = threadIdx.x; i < ps.nbuckets; i += blockDim.x) sh_hist[i] = 0;
   __syncthreads();
-  const long long total = prod.units_per_z * prod.ns;
   unsigned long long wide0 = 0, wide1 = 0;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int is = (int)(t / prod.units_per_z);
-    const long long u = t - (long long)is * prod.units_per_z;
+  const unsigned upz = (unsigned)prod.units_per_z, stride = gridDim.x * blockDim.x;
+  for (int is = 0; is < prod.ns; ++is)
+  for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < upz; u += stride) {
+    const size_t t = (size_t)is * upz + u;
     RecOut r;
+    r.mode = -1;
     prod(u, is, r);
-    const Cls c = classify(r, ps.grid);
+    Cls c;
+    c.kind = 2;
+    if (r.mode >= 0) c = classify(r, ps);
     unsigned key;
     if (c.kind == 0) {
       key = (unsigned)(width_class(c.wlen) * ps.ncells + (is * ps.bpad + c.klo) / ps.cell);
@@ -205,28 +214,31 @@ __global__ void __launch_bounds__(1024) scan_kernel(const unsigned *__restrict__
 }
 
 // ---------------------------------------------------------------- pass B: scatter (shared-memory cursors)
-template <bool LINEAR>
+template <bool LINEAR, class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
-prep_scatter_kernel(DosProducer prod, PrepSpec ps, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,
-                    const unsigned *__restrict__ base, void *__restrict__ recs_v, double *__restrict__ stephist,
+prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,
+                    const unsigned *__restrict__ base, void *__restrict__ recs_v, double *__restrict__ wts, double *__restrict__ stephist,
                     unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor, long long wide_stride) {
   extern __shared__ unsigned sh_cur[];
   const unsigned *row = table + (size_t)blockIdx.x * ps.nbuckets;
   for (int i = threadIdx.x; i < ps.nbuckets; i += blockDim.x) sh_cur[i] = base[i] + row[i];
   __syncthreads();
-  const long long total = prod.units_per_z * prod.ns;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+  const unsigned upz = (unsigned)prod.units_per_z, stride = gridDim.x * blockDim.x;
+  for (int is = 0; is < prod.ns; ++is)
+  for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < upz; u += stride) {
+    const size_t t = (size_t)is * upz + u;
     const unsigned key = keys[t];
-    const int is = (int)(t / prod.units_per_z);
-    const long long u = t - (long long)is * prod.units_per_z;
     if (key == KEY_WIDE) {
       const unsigned long long pos = atomicAdd(&wide_cursor[is], 1ull);
       widelist[(size_t)is * wide_stride + pos] = (unsigned)u;
       continue;
     }
+    if (key == KEY_DROP && !ps.with_int) continue;  // null pair / off-grid unit without a step
     RecOut r;
+    r.mode = -1;
     prod(u, is, r);
-    const Cls c = classify(r, ps.grid);
+    if (r.mode < 0) continue;
+    const Cls c = classify(r, ps);
     if (key == KEY_DROP) {  // off the grid: only its step (rare)
       if (c.cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + c.cstep], r.omega);
       continue;
@@ -248,6 +260,7 @@ prep_scatter_kernel(DosProducer prod, PrepSpec ps, const unsigned *__restrict__ 
       o.klo = is * ps.bpad + klo; o.cpos = (unsigned short)cpos; o.wlen = (unsigned short)wlen;
       reinterpret_cast<GRec *>(recs_v)[pos] = o;
     }
+    for (int a = 0; a < ps.ng; ++a) wts[(size_t)pos * ps.ng + a] = r.wt[a];
   }
 }
 
@@ -301,7 +314,11 @@ struct NarrowArgs {
   unsigned long long *next_chunk;
   unsigned long long *stats;             // [0] lane-steps spent, [1] in-window (record, bin) pairs
   ErfcxCoef cf;
-  double *out_dos, *out_int, *out_step;  // [ns * bpad + NR_T]
+  double *out_dos, *out_int, *out_step;  // [ns * bpad + NR_T]; JD mode: out_dos / out_int are the two channels
+  // JD (JDOS / optics) mode: channel pass `chan` accumulates K*m0 and K*m1 with (m0, m1) =
+  // (1, wt[0]) for chan 0 and (wt[2 chan - 1], wt[2 chan]) after that; wts[rec * ng + a]
+  const double *wts;
+  int ng, chan;
 };
 
 __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, const NarrowArgs &A, int lane) {
@@ -327,7 +344,7 @@ __device__ __forceinline__ void gauss_direct(double e, double w, double om, doub
   s = (j < cabs) ? h : -h;
 }
 
-template <bool LINEAR>
+template <bool LINEAR, bool JD>
 __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) {
   extern __shared__ double2 sh_tiles[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -363,6 +380,12 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
           e0 = r.e; p1 = r.w; om = r.om; klo = r.klo; wlen = r.wlen; cpos = r.cpos;
         }
       }
+      double m0 = 1.0, m1 = 0.0;  // JD channel multipliers
+      if (JD && valid) {
+        const double *w = A.wts + (size_t)idx * A.ng;
+        if (A.chan == 0) { m1 = A.ng > 0 ? w[0] : 0.0; }
+        else { m0 = w[2 * A.chan - 1]; m1 = (2 * A.chan < A.ng) ? w[2 * A.chan] : 0.0; }
+      }
       // ---- the group's common window [gl, gl + Wc)
       const int gl = __reduce_min_sync(0xffffffffu, klo);
       const int gh = __reduce_max_sync(0xffffffffu, valid ? klo + wlen - 1 : -0x3fffffff);
@@ -387,8 +410,9 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
           const int jb_l = __shfl_sync(0xffffffffu, jb, l);
           const double a0 = __shfl_sync(0xffffffffu, e0, l), a1 = __shfl_sync(0xffffffffu, p1, l), a2 = __shfl_sync(0xffffffffu, p2, l);
           const double a3 = __shfl_sync(0xffffffffu, p3, l), a4 = __shfl_sync(0xffffffffu, p4, l), ao = __shfl_sync(0xffffffffu, om, l);
+          const double b0 = __shfl_sync(0xffffffffu, m0, l), b1 = __shfl_sync(0xffffffffu, m1, l);
           if (w_l == 0) continue;
-          if (lane == 0 && jb_l + c_l < A.grid.nbins) atomicAdd(&A.out_step[k_l + c_l], ao);
+          if (!JD && lane == 0 && jb_l + c_l < A.grid.nbins) atomicAdd(&A.out_step[k_l + c_l], ao);
           for (int r = lane; r < w_l; r += 32) {
             const double Ej = emin + (double)(jb_l + r) * delta;
             double d, s;
@@ -399,6 +423,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
             } else {
               gauss_direct(a0, a1, ao, Ej, r, c_l, A.cf, d, s);
             }
+            if (JD) { s = d * b1; d = d * b0; }
             if (d != 0.0) atomicAdd(&A.out_dos[k_l + r], d);
             if (s != 0.0) atomicAdd(&A.out_int[k_l + r], s);
           }
@@ -418,7 +443,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
 
       // ---- the steps H: one add per record into the warp-private step tile.  Several records of a
       //      group usually share their centre bin, so this one place uses shared-memory atomics.
-      if (valid) atomicAdd(stile + off + cabs, om);
+      if (!JD && valid) atomicAdd(stile + off + cabs, om);
       __syncwarp();
 
       const double E0 = emin + (double)(jb - a) * delta;  // energy of relative bin 0
@@ -455,12 +480,17 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
             if (r2 == Wc) { r2 = 0; g2 = gB; rr2 = rB; z2 = zB; }
             double2 acc1 = *q1;
             double2 acc2 = *q2;
-            const double h1 = (c1 * cl) * erfcx_ratio(u1, A.cf);
-            const double h2 = (c2 * cl) * erfcx_ratio(u2, A.cf);
-            acc1.x += c1;
-            acc1.y += flip_sign_if(h1, f1);
-            acc2.x += c2;
-            acc2.y += flip_sign_if(h2, f2);
+            if (JD) {
+              acc1.x = fma(c1, m0, acc1.x); acc1.y = fma(c1, m1, acc1.y);
+              acc2.x = fma(c2, m0, acc2.x); acc2.y = fma(c2, m1, acc2.y);
+            } else {
+              const double h1 = (c1 * cl) * erfcx_ratio(u1, A.cf);
+              const double h2 = (c2 * cl) * erfcx_ratio(u2, A.cf);
+              acc1.x += c1;
+              acc1.y += flip_sign_if(h1, f1);
+              acc2.x += c2;
+              acc2.y += flip_sign_if(h2, f2);
+            }
             *q1 = acc1;
             *q2 = acc2;
             __syncwarp();
@@ -470,9 +500,13 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
 #pragma unroll 1
         for (int t = n2; t < H; ++t) {
           double2 acc = tw[r1];
-          const double h = (g1 * cl) * erfcx_ratio(fabs(z1), A.cf);
-          acc.x += g1;
-          acc.y += flip_sign_if(h, r1 >= cabs);
+          if (JD) {
+            acc.x = fma(g1, m0, acc.x); acc.y = fma(g1, m1, acc.y);
+          } else {
+            const double h = (g1 * cl) * erfcx_ratio(fabs(z1), A.cf);
+            acc.x += g1;
+            acc.y += flip_sign_if(h, r1 >= cabs);
+          }
           tw[r1] = acc;
           g1 *= rr1; rr1 *= q; z1 += del;
           ++r1;
@@ -507,8 +541,13 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
           const double D = s1 ? D1 : (s2 ? D2 : (s3 ? D3 : hh));
           const double I = s1 ? I1 : (s2 ? I2 : (s3 ? I3 : I4));
           double2 acc = tw[r];
-          acc.x = fma(D, sc, acc.x);
-          acc.y = fma(I, flip_sign_if(sc, above), acc.y);
+          if (JD) {
+            acc.x = fma(D, sc * m0, acc.x);
+            acc.y = fma(D, sc * m1, acc.y);
+          } else {
+            acc.x = fma(D, sc, acc.x);
+            acc.y = fma(I, flip_sign_if(sc, above), acc.y);
+          }
           tw[r] = acc;
         };
         double xl1 = xB + (double)lane * delta;
@@ -545,9 +584,10 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
 }
 
 // dense-engine producer over the compacted list of wide units
+template <class Inner>
 struct WideListProducer {
   long long units_per_z;  // max over spins of the wide count
-  DosProducer inner;
+  Inner inner;
   const unsigned *list;
   long long stride;
   unsigned long long count[2];
@@ -588,118 +628,175 @@ __global__ void __launch_bounds__(1024) combine_kernel(const double *__restrict_
   }
 }
 
+// JD mode: out[dest(c) + is*nbins + j] += channel array c
+__global__ void combine_channels_kernel(const double *__restrict__ chan, size_t chan_stride, int nchan, int nbins, int bpad, int ns,
+                                        const long long *__restrict__ dest, double *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y / ns, is = blockIdx.y % ns;
+  if (j >= nbins || c >= nchan || dest[c] < 0) return;
+  out[dest[c] + (size_t)is * nbins + j] += chan[(size_t)c * chan_stride + (size_t)is * bpad + j];
+}
+
+struct Scratch {
+  PrepSpec ps;
+  size_t nout;
+  unsigned *keys, *table, *colsum, *base;
+  unsigned long long *wide;  // [0..1] wide counts, [2..3] wide cursors, [4] next_chunk, [5..6] stats
+  double *stephist, *chan;   // chan: 2 * npass arrays of nout doubles (DOS: dos, int)
+};
+
+template <class Producer>
+int narrow_prepare(od_ctx *ctx, const Producer &prod, Scratch &S, bool linear, unsigned *h_nrec, unsigned long long h_wide[2],
+                   long long *wide_stride) {
+  const PrepSpec &ps = S.ps;
+  const int prows = ctx->sm_count;  // one prepare CTA per SM; pass A and pass B MUST use the same grid
+  const size_t hist_smem = sizeof(unsigned) * ps.nbuckets;
+  OD_CUDA(ctx, cudaMemsetAsync(S.wide, 0, sizeof(unsigned long long) * 5, ctx->stream));
+  OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+  prep_hist_kernel<Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod, ps, S.keys, S.table, S.wide);
+  OD_LAUNCH_CHECK(ctx);
+  prep_colscan_kernel<<<(ps.nbuckets + 255) / 256, 256, 0, ctx->stream>>>(S.table, prows, ps.nbuckets, S.colsum);
+  OD_LAUNCH_CHECK(ctx);
+  scan_kernel<<<1, 1024, 0, ctx->stream>>>(S.colsum, ps.nbuckets, S.base);
+  OD_LAUNCH_CHECK(ctx);
+  OD_CUDA(ctx, cudaMemcpyAsync(h_wide, S.wide, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaMemcpyAsync(h_nrec, S.base + ps.nbuckets, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *wide_stride = (long long)std::max(h_wide[0], h_wide[1]);
+  const size_t rec_bytes = linear ? sizeof(LRec) : sizeof(GRec);
+  OD_CHECK(od_buf_ensure(ctx, ctx->recs, rec_bytes * (size_t)*h_nrec + 256));
+  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_b, sizeof(unsigned) * (size_t)*wide_stride * prod.ns + 256));
+  if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * (size_t)*h_nrec * ps.ng + 256));
+  double *wts = ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
+  if (linear) {
+    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<true, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+    prep_scatter_kernel<true, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(
+        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride);
+  } else {
+    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<false, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+    prep_scatter_kernel<false, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(
+        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride);
+  }
+  OD_LAUNCH_CHECK(ctx);
+  return OD_OK;
+}
+
+template <bool JD>
+int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int chan, double *out0, double *out1) {
+  NarrowArgs A;
+  A.recs = ctx->recs.p;
+  A.nrec = (long long)nrec;
+  A.grid = S.ps.grid;
+  A.bpad = S.ps.bpad;
+  A.cell = S.ps.cell;
+  A.next_chunk = S.wide + 4;
+  A.stats = S.wide + 5;
+  for (int i = 0; i < 6; ++i) { A.cf.P[i] = h_P[i]; A.cf.Q[i] = h_Q[i]; }
+  A.out_dos = out0;
+  A.out_int = out1;
+  A.out_step = S.stephist;
+  A.wts = S.ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
+  A.ng = S.ps.ng;
+  A.chan = chan;
+  OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
+  const size_t smem = (sizeof(double2) + sizeof(double)) * NR_T * NR_WARPS;
+  const long long nchunks = ((long long)nrec + NR_CHUNK - 1) / NR_CHUNK;
+  const int blocks = (int)std::min<long long>((long long)ctx->sm_count * 2, (nchunks + NR_WARPS - 1) / NR_WARPS);
+  if (linear) {
+    OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<true, JD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    narrow_kernel<true, JD><<<blocks, NR_WARPS * 32, smem, ctx->stream>>>(A);
+  } else {
+    OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<false, JD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    narrow_kernel<false, JD><<<blocks, NR_WARPS * 32, smem, ctx->stream>>>(A);
+  }
+  OD_LAUNCH_CHECK(ctx);
+  return OD_OK;
+}
+
+// carve the scratch buffers for a grid / unit count / number of channel arrays
+int narrow_scratch(od_ctx *ctx, const GridSpec &grid, int ns, long long total_units, int nchan_arrays, Scratch &S) {
+  PrepSpec &ps = S.ps;
+  ps.grid = grid;
+  ps.cell = 8;
+  for (;;) {
+    ps.bpad = ((grid.nbins + NR_T + ps.cell - 1) / ps.cell) * ps.cell;
+    ps.ncells = ns * ps.bpad / ps.cell;
+    ps.nbuckets = NR_NCLS * ps.ncells;
+    if (ps.nbuckets <= NR_MAXBUCKETS) break;
+    ps.cell *= 2;
+  }
+  if (ps.cell > 128) return od_fail(ctx, OD_ERR_ARG, "narrow engine: energy grid too large (%d bins)", grid.nbins);
+  S.nout = (size_t)ns * ps.bpad + NR_T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_csum = take(sizeof(unsigned) * ps.nbuckets);
+  const size_t o_base = take(sizeof(unsigned) * (ps.nbuckets + 1));
+  const size_t o_wide = take(sizeof(unsigned long long) * 8);
+  const size_t o_step = take(sizeof(double) * S.nout);
+  const size_t o_chan = take(sizeof(double) * S.nout * nchan_arrays);
+  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_a, off));
+  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_c, sizeof(unsigned) * (size_t)ctx->sm_count * ps.nbuckets));
+  OD_CHECK(od_buf_ensure(ctx, ctx->keys, sizeof(unsigned) * (size_t)total_units + 1024));
+  char *sa = ctx->scratch_a.as<char>();
+  OD_CUDA(ctx, cudaMemsetAsync(sa, 0, off, ctx->stream));
+  S.keys = ctx->keys.as<unsigned>();
+  S.table = ctx->scratch_c.as<unsigned>();
+  S.colsum = reinterpret_cast<unsigned *>(sa + o_csum);
+  S.base = reinterpret_cast<unsigned *>(sa + o_base);
+  S.wide = reinterpret_cast<unsigned long long *>(sa + o_wide);
+  S.stephist = reinterpret_cast<double *>(sa + o_step);
+  S.chan = reinterpret_cast<double *>(sa + o_chan);
+  return OD_OK;
+}
+
+struct EventTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  EventTimer() { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+  ~EventTimer() { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  void start(cudaStream_t s) { cudaEventRecord(e0, s); }
+  void stop(cudaStream_t s) { cudaEventRecord(e1, s); }
+  double ms() { float m = 0.f; cudaEventSynchronize(e1); cudaEventElapsedTime(&m, e0, e1); return m; }
+};
+
+int collect_stats(od_ctx *ctx, const Scratch &S) {
+  unsigned long long h_stats[2] = {0, 0};
+  OD_CUDA(ctx, cudaMemcpyAsync(h_stats, S.wide + 5, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof.lane_steps += (double)h_stats[0];
+  ctx->prof.contributions += (double)h_stats[1];
+  return OD_OK;
+}
+
 }  // namespace
 
 // Narrow pipeline for calculate_dos without weights.  accum = [dos(B,ns) | intdos(B,ns)], zeroed by the caller.
 int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bool linear, double *accum) {
   const int ns = prod.ns, nbins = grid.nbins;
   const long long total = prod.units_per_z * ns;
-  if (total >= (1ll << 32)) return od_fail(ctx, OD_ERR_ARG, "narrow engine: more than 2^32 units per call");
-  PrepSpec ps;
-  ps.grid = grid;
-  ps.cell = 8;
-  for (;;) {
-    ps.bpad = ((nbins + NR_T + ps.cell - 1) / ps.cell) * ps.cell;
-    ps.ncells = ns * ps.bpad / ps.cell;
-    ps.nbuckets = NR_NCLS * ps.ncells;
-    if (ps.nbuckets <= NR_MAXBUCKETS) break;
-    ps.cell *= 2;
-  }
-  if (ps.cell > 128) return od_fail(ctx, OD_ERR_ARG, "narrow engine: energy grid too large (%d bins)", nbins);
-  const int prows = ctx->sm_count;  // one prepare CTA per SM; pass A and pass B MUST use the same grid
+  if (total >= (1ll << 32) || prod.units_per_z >= (1ll << 31))
+    return od_fail(ctx, OD_ERR_ARG, "narrow engine: more than 2^31 units per spin channel in one call");
+  Scratch S;
+  OD_CHECK(narrow_scratch(ctx, grid, ns, total, 2, S));
+  S.ps.gwin = NR_ERFWIN;
+  S.ps.with_int = 1;
+  S.ps.linear_pass = 0;  // calculate_dos ignores hybrid_linear (quirk Q8): a linear pass has no Gaussian records
+  S.ps.ng = 0;
+  double *ndos = S.chan, *nint = S.chan + S.nout;
 
-  // scratch_a: colsum | base | wide counters | out_step | out_dos | out_int     (zeroed)
-  // scratch_c: table[prows][nbuckets]
-  const size_t nout = (size_t)ns * ps.bpad + NR_T;
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  const size_t o_csum = take(sizeof(unsigned) * ps.nbuckets);
-  const size_t o_base = take(sizeof(unsigned) * (ps.nbuckets + 1));
-  const size_t o_wide = take(sizeof(unsigned long long) * 8);
-  const size_t o_step = take(sizeof(double) * nout);
-  const size_t o_ndos = take(sizeof(double) * nout);
-  const size_t o_nint = take(sizeof(double) * nout);
-  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_a, off));
-  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_c, sizeof(unsigned) * (size_t)prows * ps.nbuckets));
-  OD_CHECK(od_buf_ensure(ctx, ctx->keys, sizeof(unsigned) * (size_t)total + 1024));
-  char *sa = ctx->scratch_a.as<char>();
-  OD_CUDA(ctx, cudaMemsetAsync(sa, 0, off, ctx->stream));
-  unsigned *keys = ctx->keys.as<unsigned>();
-  unsigned *table = ctx->scratch_c.as<unsigned>();
-  unsigned *colsum = reinterpret_cast<unsigned *>(sa + o_csum);
-  unsigned *base = reinterpret_cast<unsigned *>(sa + o_base);
-  unsigned long long *wide = reinterpret_cast<unsigned long long *>(sa + o_wide);  // [0..1] counts, [2..3] cursors, [4] next_chunk
-  double *stephist = reinterpret_cast<double *>(sa + o_step);
-  double *ndos = reinterpret_cast<double *>(sa + o_ndos);
-  double *nint = reinterpret_cast<double *>(sa + o_nint);
-
-  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
-  OD_CUDA(ctx, cudaEventCreate(&e0));
-  OD_CUDA(ctx, cudaEventCreate(&e1));
-  OD_CUDA(ctx, cudaEventCreate(&e2));
-  OD_CUDA(ctx, cudaEventCreate(&e3));
-  const size_t hist_smem = sizeof(unsigned) * ps.nbuckets;
-  OD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-  OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-  prep_hist_kernel<<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod, ps, keys, table, wide);
-  OD_LAUNCH_CHECK(ctx);
-  prep_colscan_kernel<<<(ps.nbuckets + 255) / 256, 256, 0, ctx->stream>>>(table, prows, ps.nbuckets, colsum);
-  OD_LAUNCH_CHECK(ctx);
-  scan_kernel<<<1, 1024, 0, ctx->stream>>>(colsum, ps.nbuckets, base);
-  OD_LAUNCH_CHECK(ctx);
-  unsigned long long h_wide[2] = {0, 0};
+  EventTimer tp, ta;
   unsigned h_nrec = 0;
-  OD_CUDA(ctx, cudaMemcpyAsync(h_wide, wide, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
-  OD_CUDA(ctx, cudaMemcpyAsync(&h_nrec, base + ps.nbuckets, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const long long wide_stride = (long long)std::max(h_wide[0], h_wide[1]);
-  const size_t rec_bytes = linear ? sizeof(LRec) : sizeof(GRec);
-  OD_CHECK(od_buf_ensure(ctx, ctx->recs, rec_bytes * (size_t)h_nrec + 256));
-  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_b, sizeof(unsigned) * (size_t)wide_stride * ns + 256));
-  if (linear) {
-    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-    prep_scatter_kernel<true><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod, ps, keys, table, base, ctx->recs.p, stephist,
-                                                                                ctx->scratch_b.as<unsigned>(), wide + 2, wide_stride);
-  } else {
-    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-    prep_scatter_kernel<false><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod, ps, keys, table, base, ctx->recs.p, stephist,
-                                                                                 ctx->scratch_b.as<unsigned>(), wide + 2, wide_stride);
-  }
-  OD_LAUNCH_CHECK(ctx);
-  OD_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
-
-  // ---- accumulate the narrow records
-  OD_CUDA(ctx, cudaEventRecord(e2, ctx->stream));
-  if (h_nrec > 0) {
-    NarrowArgs A;
-    A.recs = ctx->recs.p;
-    A.nrec = (long long)h_nrec;
-    A.grid = grid;
-    A.bpad = ps.bpad;
-    A.cell = ps.cell;
-    A.next_chunk = wide + 4;
-    A.stats = wide + 5;
-    for (int i = 0; i < 6; ++i) { A.cf.P[i] = h_P[i]; A.cf.Q[i] = h_Q[i]; }
-    A.out_dos = ndos;
-    A.out_int = nint;
-    A.out_step = stephist;
-    const size_t smem = (sizeof(double2) + sizeof(double)) * NR_T * NR_WARPS;
-    const long long nchunks = ((long long)h_nrec + NR_CHUNK - 1) / NR_CHUNK;
-    const int blocks = (int)std::min<long long>((long long)ctx->sm_count * 2, (nchunks + NR_WARPS - 1) / NR_WARPS);
-    if (linear) {
-      OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      narrow_kernel<true><<<blocks, NR_WARPS * 32, smem, ctx->stream>>>(A);
-    } else {
-      OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      narrow_kernel<false><<<blocks, NR_WARPS * 32, smem, ctx->stream>>>(A);
-    }
-    OD_LAUNCH_CHECK(ctx);
-  }
-  OD_CUDA(ctx, cudaEventRecord(e3, ctx->stream));
+  unsigned long long h_wide[2] = {0, 0};
+  long long wide_stride = 0;
+  tp.start(ctx->stream);
+  OD_CHECK(narrow_prepare(ctx, prod, S, linear, &h_nrec, h_wide, &wide_stride));
+  tp.stop(ctx->stream);
+  ta.start(ctx->stream);
+  if (h_nrec > 0) OD_CHECK(narrow_launch<false>(ctx, S, linear, h_nrec, 0, ndos, nint));
+  ta.stop(ctx->stream);
 
   // ---- the wide units through the dense engine (adds into accum)
   if (wide_stride > 0) {
-    WideListProducer wp;
+    WideListProducer<DosProducer> wp;
     wp.units_per_z = wide_stride;
     wp.inner = prod;
     wp.list = ctx->scratch_b.as<unsigned>();
@@ -712,24 +809,81 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bo
       dest[is * 2 + 0] = (long long)is * nbins;
       dest[is * 2 + 1] = (long long)(n1 + (size_t)is * nbins);
     }
-    OD_CHECK((od_run_dense<0, true, WideListProducer>(ctx, wp, grid, ns, dest, accum)));
+    OD_CHECK((od_run_dense<0, true, WideListProducer<DosProducer>>(ctx, wp, grid, ns, dest, accum)));
   }
-  combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, stephist, nbins, ps.bpad, accum, accum + (size_t)nbins * ns);
+  combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, nbins, S.ps.bpad, accum, accum + (size_t)nbins * ns);
+  OD_LAUNCH_CHECK(ctx);
+  OD_CHECK(collect_stats(ctx, S));
+  ctx->prof.prepare_ms += tp.ms();
+  ctx->prof.accumulate_ms += ta.ms();
+  ctx->prof.accumulate_launches += (h_nrec > 0) ? 1 : 0;
+  return OD_OK;
+}
+
+// Narrow pipeline for calculate_jdos (optionally with n_geom weight columns, materialised or formed on chip
+// from the optical matrix elements by the producer).  accum = [jdos(B,ns) | weighted_jdos(B,ns,n_geom)], zeroed
+// by the caller.  Pair slots are processed in k-point slabs of < 2^30 slots.
+int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &grid, bool linear, int n_geom, double *accum) {
+  const int ns = prod_in.ns, nbins = grid.nbins, nb = prod_in.nb;
+  const long long nk = prod_in.units_per_z / ((long long)nb * nb);
+  const long long slab_k = std::max<long long>(1, (1ll << 30) / ((long long)nb * nb));
+  const int npass = 1 + n_geom / 2;  // channel pairs: (jdos, w1) (w2, w3) (w4, w5) (w6, -)
+  Scratch S;
+  OD_CHECK(narrow_scratch(ctx, grid, ns, std::min(nk, slab_k) * nb * nb * ns, 2 * npass, S));
+  S.ps.gwin = OD_SQRT60;   // the Gaussian cut-off (algorithms.f90:83); no erf window in JDOS
+  S.ps.with_int = 0;
+  S.ps.linear_pass = linear ? 1 : 0;  // hybrid_linear fall-back records (jdos_utils.f90:365) -> dense engine
+  S.ps.ng = n_geom;
+  const size_t n1 = (size_t)nbins * ns;
+  for (long long k0 = 0; k0 < nk; k0 += slab_k) {
+    JdosProducer prod = prod_in;
+    prod.k_first = prod_in.k_first + k0;
+    prod.units_per_z = std::min(slab_k, nk - k0) * nb * nb;
+    EventTimer tp, ta;
+    unsigned h_nrec = 0;
+    unsigned long long h_wide[2] = {0, 0};
+    long long wide_stride = 0;
+    tp.start(ctx->stream);
+    OD_CHECK(narrow_prepare(ctx, prod, S, linear, &h_nrec, h_wide, &wide_stride));
+    tp.stop(ctx->stream);
+    ta.start(ctx->stream);
+    if (h_nrec > 0)
+      for (int c = 0; c < npass; ++c)
+        OD_CHECK(narrow_launch<true>(ctx, S, linear, h_nrec, c, S.chan + (size_t)(2 * c) * S.nout, S.chan + (size_t)(2 * c + 1) * S.nout));
+    ta.stop(ctx->stream);
+    if (wide_stride > 0) {
+      WideListProducer<JdosProducer> wp;
+      wp.units_per_z = wide_stride;
+      wp.inner = prod;
+      wp.list = ctx->scratch_b.as<unsigned>();
+      wp.stride = wide_stride;
+      wp.count[0] = h_wide[0];
+      wp.count[1] = h_wide[1];
+      const int nacc = 1 + n_geom;
+      std::vector<long long> dest((size_t)ns * nacc);
+      for (int is = 0; is < ns; ++is) {
+        dest[(size_t)is * nacc] = (long long)is * nbins;
+        for (int a = 0; a < n_geom; ++a) dest[(size_t)is * nacc + 1 + a] = (long long)(n1 + (size_t)nbins * (is + (size_t)ns * a));
+      }
+      if (n_geom == 0) OD_CHECK((od_run_dense<0, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum)));
+      else if (n_geom == 1) OD_CHECK((od_run_dense<1, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum)));
+      else OD_CHECK((od_run_dense<6, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum)));
+    }
+    OD_CHECK(collect_stats(ctx, S));
+    OD_CUDA(ctx, cudaMemsetAsync(S.wide + 5, 0, sizeof(unsigned long long) * 2, ctx->stream));
+    ctx->prof.prepare_ms += tp.ms();
+    ctx->prof.accumulate_ms += ta.ms();
+    ctx->prof.accumulate_launches += (h_nrec > 0) ? npass : 0;
+  }
+  // channel arrays -> [jdos | weighted_jdos]: array 0 = jdos, array a (a >= 1) = geometry component a
+  std::vector<long long> dest(2 * npass, -1);
+  dest[0] = 0;
+  for (int a = 1; a <= n_geom; ++a) dest[a] = (long long)(n1 + (size_t)nbins * ns * (a - 1));
+  OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(long long) * dest.size()));
+  OD_CUDA(ctx, cudaMemcpyAsync(ctx->small.p, dest.data(), sizeof(long long) * dest.size(), cudaMemcpyHostToDevice, ctx->stream));
+  dim3 g((nbins + 255) / 256, 2 * npass * ns);
+  combine_channels_kernel<<<g, 256, 0, ctx->stream>>>(S.chan, S.nout, 2 * npass, nbins, S.ps.bpad, ns, ctx->small.as<long long>(), accum);
   OD_LAUNCH_CHECK(ctx);
   OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  float ms_prep = 0.f, ms_acc = 0.f;
-  cudaEventElapsedTime(&ms_prep, e0, e1);
-  cudaEventElapsedTime(&ms_acc, e2, e3);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaEventDestroy(e2);
-  cudaEventDestroy(e3);
-  ctx->prof.prepare_ms += ms_prep;
-  ctx->prof.accumulate_ms += ms_acc;
-  ctx->prof.accumulate_launches += (h_nrec > 0) ? 1 : 0;
-  unsigned long long h_stats[2] = {0, 0};
-  OD_CUDA(ctx, cudaMemcpy(h_stats, wide + 5, sizeof(h_stats), cudaMemcpyDeviceToHost));
-  ctx->prof.lane_steps += (double)h_stats[0];
-  ctx->prof.contributions += (double)h_stats[1];
   return OD_OK;
 }

@@ -54,8 +54,10 @@ struct DosProducer {
 
   __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
     const int is = z % ns, grp = z / ns;
-    const int ib = (int)(u % nb);
-    const long long ik = u / nb;
+    // units_per_z = nb * nk < 2^32 whenever the engines accept the job: 32-bit division
+    const unsigned uu = (unsigned)u;
+    const long long ik = (units_per_z <= 0xffffffffll) ? (long long)(uu / (unsigned)nb) : u / nb;
+    const int ib = (int)(u - ik * nb);
     const double e = bands[ib + (size_t)nb * (is + (size_t)ns * ik)];
     double g[3] = {0.0, 0.0, 0.0};
     if (b.type != 0) {
@@ -99,7 +101,8 @@ __device__ __forceinline__ void od_ome_products(const double *om, size_t idx, si
 }
 
 struct JdosProducer {
-  long long units_per_z;  // nb * nb * nk
+  long long units_per_z;  // nb * nb * (k-points of this slab)
+  long long k_first;      // first k-point of the slab (the arrays are indexed with the rank's full nk)
   int nb, ns, nk;
   const double *bands, *grads, *kw;
   double eps, efermi, scissor;
@@ -116,7 +119,7 @@ struct JdosProducer {
     const int ib = (int)(u % nb);
     const long long t = u / nb;
     const int jb = (int)(t % nb);
-    const long long ik = t / nb;
+    const long long ik = k_first + t / nb;
     r.mode = -1;
     for (int x = 0; x < n_exclude; ++x)
       if (exclude[x] == ib + 1) return;                         // jdos_utils.f90:355-357

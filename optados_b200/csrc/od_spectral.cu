@@ -301,6 +301,7 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
 
   JdosProducer p;
   p.units_per_z = (long long)ctx->nb * ctx->nb * ctx->nk;
+  p.k_first = 0;
   p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk;
   p.bands = ctx->bands.as<double>(); p.grads = ctx->grads.as<double>(); p.kw = ctx->kweight.as<double>();
   p.eps = ctx->eps; p.efermi = efermi; p.scissor = scissor_op;
@@ -328,7 +329,15 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
     dest[(size_t)is * nacc] = (long long)is * nbins;
     for (int a = 0; a < n_geom; ++a) dest[(size_t)is * nacc + 1 + a] = (long long)(n1 + (size_t)nbins * (is + (size_t)ns * a));
   }
-  if (n_geom == 0) OD_CHECK((od_run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+  // the exclude list lives in ctx->small, which the narrow engine also uses: it gets its own copy
+  if (ctx->engine != OD_ENGINE_DENSE) {
+    if (num_exclude_bands > 0) {
+      OD_CHECK(od_buf_ensure(ctx, ctx->in_tmp2, sizeof(int) * (size_t)num_exclude_bands));
+      OD_CUDA(ctx, cudaMemcpyAsync(ctx->in_tmp2.p, exclude_bands, sizeof(int) * (size_t)num_exclude_bands, cudaMemcpyHostToDevice, ctx->stream));
+      p.exclude = ctx->in_tmp2.as<int>();
+    }
+    OD_CHECK(od_narrow_jdos(ctx, p, grid, jdos_type == 'l', n_geom, accum));
+  } else if (n_geom == 0) OD_CHECK((od_run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   else if (n_geom == 1) OD_CHECK((od_run_dense<1, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   else OD_CHECK((od_run_dense<6, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   if (merge) OD_CHECK(od_allreduce_device(ctx, accum, ntot, 's'));  // jdos_utils_merge (jdos_utils.f90:435-437)

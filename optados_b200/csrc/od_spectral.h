@@ -21,6 +21,8 @@ int od_optics_coefficients(od_ctx *ctx, int geom, const double qdir[3], const do
 
 // narrow (sorted, recurrence) engine for calculate_dos without weights (od_narrow.cu)
 int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bool linear, double *accum);
+// narrow engine for calculate_jdos: accum = [jdos(B,ns) | weighted_jdos(B,ns,n_geom)]
+int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod, const GridSpec &grid, bool linear, int n_geom, double *accum);
 
 // Launch the dense engine for a producer and reduce the chunk partials into `accum` (device).
 // dest: nz*nacc offsets into accum (or -1).

@@ -315,3 +315,43 @@ def test_narrow_engine_vs_oracle_and_dense(ob, odo, fbc):
         assert abs(intdos[-1].sum() - kw.sum() * nb * ns) < 1e-9 * nb * ns
         assert np.all(np.diff(intdos, axis=0) > -1e-12)
     ctx.close()
+
+
+@pytest.mark.parametrize("jtype", ["a", "l", "f"])
+def test_narrow_jdos_and_optics_vs_oracle(ob, odo, jtype):
+    """JDOS / weighted JDOS through the narrow engine (pairs become records, weights ride beside them in
+    channel passes) on synthetic bands with narrow windows: against the oracle and the dense engine;
+    materialised weights, fused polycrystalline and fused tensor optics."""
+    ctx = ob.Context(0)
+    grid, ns, nb = (10, 8, 6), 2, 20
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=21)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0, num_electrons=[10.0, 10.0])
+    ef = odo.efermi_insulator(s)
+    E, delta, n = odo.jdos_energy_scale(s, ef, jdos_spacing=0.004, jdos_max_energy=14.0)
+    assert n == 3500
+    bro, brg = odo.make_broadening(fixed_smearing=0.02), ob.broadening(fixed_smearing=0.02)
+    rng = np.random.default_rng(5)
+    om = np.asfortranarray(rng.normal(0, 0.1, (nb, nb, 3, nk, ns)) + 1j * rng.normal(0, 0.1, (nb, nb, 3, nk, ns)))
+    mw1 = np.asfortranarray(rng.random((nb, nb, nk, ns, 1)))
+    # plain JDOS and materialised weights
+    ref_j, ref_w = odo.calculate_jdos(jtype, s, bro, E, delta, ef, scissor_op=0.3, exclude_bands=(2,), mw=mw1, nthreads=8)
+    for eng in ("auto", "dense"):
+        ctx.set_engine(eng)
+        jd, wj = ctx.calculate_jdos(jtype, delta, n, ef, br=brg, scissor_op=0.3, exclude_bands=(2,), mw=mw1)
+        assert rel_to_peak(jd, ref_j) < TOL_SPEC, eng
+        assert rel_to_peak(wj, ref_w) < TOL_SPEC, eng
+        jd0, _ = ctx.calculate_jdos(jtype, delta, n, ef, br=brg, scissor_op=0.3, exclude_bands=(2,))
+        assert rel_to_peak(jd0, ref_j) < TOL_SPEC, eng
+    # fused optics weights (make_weights on chip), 1 and 6 geometry components
+    ctx.set_engine("auto")
+    for geom in ("polycrys", "tensor", "polar"):
+        mw = odo.make_weights(s, om, geom, ef, qdir=(0.3, 0.5, 0.25))
+        rj, rw = odo.calculate_jdos(jtype, s, bro, E, delta, ef, mw=mw, nthreads=8)
+        jd, wj = ctx.calculate_jdos_optics(jtype, delta, n, ef, om, geom, qdir=(0.3, 0.5, 0.25), br=brg)
+        assert rel_to_peak(jd, rj) < TOL_SPEC, geom
+        assert rel_to_peak(wj, rw) < TOL_SPEC, geom
+    p = ctx.profile_get()
+    assert p["contributions"] > 0 and p["lane_steps"] >= p["contributions"]
+    ctx.close()
