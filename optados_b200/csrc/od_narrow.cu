@@ -75,6 +75,7 @@ struct PrepSpec {
   int with_int;     // integrated spectrum wanted (DOS): off-grid units still contribute their step
   int linear_pass;  // a linear pass sends Gaussian records (hybrid_linear fall-back) to the dense engine
   int ng;           // weight columns carried beside each record (JDOS / optics)
+  int want_unit;    // also record each record's unit index (PDOS / core: weights are gathered from matrix_weights)
 };
 
 struct Cls {
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(const unsigned *__restrict__
 template <bool LINEAR, class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
 prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,
-                    const unsigned *__restrict__ base, void *__restrict__ recs_v, double *__restrict__ wts, double *__restrict__ stephist,
+                    const unsigned *__restrict__ base, void *__restrict__ recs_v, double *__restrict__ wts, unsigned *__restrict__ runit,
+                    double *__restrict__ stephist,
                     unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor, long long wide_stride) {
   extern __shared__ unsigned sh_cur[];
   const unsigned *row = table + (size_t)blockIdx.x * ps.nbuckets;
@@ -261,6 +263,7 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
       reinterpret_cast<GRec *>(recs_v)[pos] = o;
     }
     for (int a = 0; a < ps.ng; ++a) wts[(size_t)pos * ps.ng + a] = r.wt[a];
+    if (ps.want_unit) runit[pos] = u;
   }
 }
 
@@ -318,7 +321,12 @@ struct NarrowArgs {
   // JD (JDOS / optics) mode: channel pass `chan` accumulates K*m0 and K*m1 with (m0, m1) =
   // (1, wt[0]) for chan 0 and (wt[2 chan - 1], wt[2 chan]) after that; wts[rec * ng + a]
   const double *wts;
-  int ng, chan;
+  int ng;
+  int col0, col1;  // weight column feeding m0 / m1; -1 = the constant 1, -2 = zero
+  // PDOS / core: weights gathered from matrix_weights(norb, mw_nb, mw_nk, ns) by unit index
+  const unsigned *runit;
+  const double *mw;
+  int norb, mw_nb, mw_nk, nb, mw_ns;
 };
 
 __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, const NarrowArgs &A, int lane) {
@@ -382,9 +390,18 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
       }
       double m0 = 1.0, m1 = 0.0;  // JD channel multipliers
       if (JD && valid) {
-        const double *w = A.wts + (size_t)idx * A.ng;
-        if (A.chan == 0) { m1 = A.ng > 0 ? w[0] : 0.0; }
-        else { m0 = w[2 * A.chan - 1]; m1 = (2 * A.chan < A.ng) ? w[2 * A.chan] : 0.0; }
+        const double *w = nullptr;
+        if (A.runit) {
+          const unsigned u = A.runit[idx];
+          const unsigned ik = u / (unsigned)A.nb, ib = u - ik * (unsigned)A.nb;
+          const int is = klo >= A.bpad ? 1 : 0;
+          if ((int)ik < A.mw_nk && (int)ib < A.mw_nb)  // dos_utils.f90:1268-1269
+            w = A.mw + (size_t)A.norb * (ib + (size_t)A.mw_nb * (ik + (size_t)A.mw_nk * is));
+        } else if (A.wts) {
+          w = A.wts + (size_t)idx * A.ng;
+        }
+        m0 = A.col0 == -1 ? 1.0 : ((A.col0 >= 0 && w) ? w[A.col0] : 0.0);
+        m1 = A.col1 == -1 ? 1.0 : ((A.col1 >= 0 && w) ? w[A.col1] : 0.0);
       }
       // ---- the group's common window [gl, gl + Wc)
       const int gl = __reduce_min_sync(0xffffffffu, klo);
@@ -593,8 +610,9 @@ struct WideListProducer {
   unsigned long long count[2];
   __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
     r.mode = -1;
-    if ((unsigned long long)u >= count[z]) return;
-    inner((long long)list[(size_t)z * stride + u], z, r);
+    const int is = z % inner.ns;  // z may also carry an orbital group (dense weighted DOS)
+    if ((unsigned long long)u >= count[is]) return;
+    inner((long long)list[(size_t)is * stride + u], z, r);
   }
 };
 
@@ -667,22 +685,30 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod, Scratch &S, bool linear, u
   OD_CHECK(od_buf_ensure(ctx, ctx->recs, rec_bytes * (size_t)*h_nrec + 256));
   OD_CHECK(od_buf_ensure(ctx, ctx->scratch_b, sizeof(unsigned) * (size_t)*wide_stride * prod.ns + 256));
   if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * (size_t)*h_nrec * ps.ng + 256));
+  if (ps.want_unit) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_e, sizeof(unsigned) * (size_t)*h_nrec + 256));
   double *wts = ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
+  unsigned *runit = ps.want_unit ? ctx->scratch_e.as<unsigned>() : nullptr;
   if (linear) {
     OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<true, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
     prep_scatter_kernel<true, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(
-        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride);
+        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride);
   } else {
     OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<false, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
     prep_scatter_kernel<false, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(
-        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride);
+        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride);
   }
   OD_LAUNCH_CHECK(ctx);
   return OD_OK;
 }
 
+struct MwGather {
+  const double *mw = nullptr;
+  int norb = 0, mw_nb = 0, mw_nk = 0, nb = 0;
+};
+
 template <bool JD>
-int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int chan, double *out0, double *out1) {
+int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int col0, int col1, double *out0, double *out1,
+                  const MwGather *gather = nullptr) {
   NarrowArgs A;
   A.recs = ctx->recs.p;
   A.nrec = (long long)nrec;
@@ -697,7 +723,13 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
   A.out_step = S.stephist;
   A.wts = S.ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
   A.ng = S.ps.ng;
-  A.chan = chan;
+  A.col0 = col0;
+  A.col1 = col1;
+  A.runit = nullptr; A.mw = nullptr; A.norb = A.mw_nb = A.mw_nk = A.nb = A.mw_ns = 0;
+  if (gather) {
+    A.runit = ctx->scratch_e.as<unsigned>();
+    A.mw = gather->mw; A.norb = gather->norb; A.mw_nb = gather->mw_nb; A.mw_nk = gather->mw_nk; A.nb = gather->nb;
+  }
   OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
   const size_t smem = (sizeof(double2) + sizeof(double)) * NR_T * NR_WARPS;
   const long long nchunks = ((long long)nrec + NR_CHUNK - 1) / NR_CHUNK;
@@ -769,8 +801,13 @@ int collect_stats(od_ctx *ctx, const Scratch &S) {
 
 }  // namespace
 
-// Narrow pipeline for calculate_dos without weights.  accum = [dos(B,ns) | intdos(B,ns)], zeroed by the caller.
-int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bool linear, double *accum) {
+// Narrow pipeline for calculate_dos.  accum = [dos(B,ns) | intdos(B,ns) | weighted_dos(B,ns,norb)], zeroed by the
+// caller.  With matrix_weights (prod_in.mw != null) the sorted records are walked once more per pair of weight
+// columns (the Gaussian recurrence / doslin evaluation is cheap; the weights are gathered by unit index).
+int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid, bool linear, double *accum) {
+  DosProducer prod = prod_in;
+  prod.mw = nullptr;  // the prepare passes and the DOS pass do not need the weights
+  const int norb = prod_in.mw ? prod_in.norb : 0;
   const int ns = prod.ns, nbins = grid.nbins;
   const long long total = prod.units_per_z * ns;
   if (total >= (1ll << 32) || prod.units_per_z >= (1ll << 31))
@@ -781,6 +818,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bo
   S.ps.with_int = 1;
   S.ps.linear_pass = 0;  // calculate_dos ignores hybrid_linear (quirk Q8): a linear pass has no Gaussian records
   S.ps.ng = 0;
+  S.ps.want_unit = norb > 0;
   double *ndos = S.chan, *nint = S.chan + S.nout;
 
   EventTimer tp, ta;
@@ -791,32 +829,68 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bo
   OD_CHECK(narrow_prepare(ctx, prod, S, linear, &h_nrec, h_wide, &wide_stride));
   tp.stop(ctx->stream);
   ta.start(ctx->stream);
-  if (h_nrec > 0) OD_CHECK(narrow_launch<false>(ctx, S, linear, h_nrec, 0, ndos, nint));
+  if (h_nrec > 0) OD_CHECK(narrow_launch<false>(ctx, S, linear, h_nrec, -2, -2, ndos, nint));
+  const size_t n1 = (size_t)nbins * ns;
+  combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, nbins, S.ps.bpad, accum, accum + n1);
+  OD_LAUNCH_CHECK(ctx);
+  int wpasses = 0;
+  if (h_nrec > 0 && norb > 0) {
+    // weighted spectrum: columns (2c, 2c+1) per pass, K * matrix_weights(o, ib, ik, is) (dos_utils.f90:1271)
+    MwGather gth;
+    gth.mw = prod_in.mw; gth.norb = norb; gth.mw_nb = prod_in.mw_nb; gth.mw_nk = prod_in.mw_nk; gth.nb = prod_in.nb;
+    OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(long long) * 2));
+    for (int c = 0; 2 * c < norb; ++c, ++wpasses) {
+      OD_CUDA(ctx, cudaMemsetAsync(S.chan, 0, sizeof(double) * 2 * S.nout, ctx->stream));
+      OD_CHECK(narrow_launch<true>(ctx, S, linear, h_nrec, 2 * c, 2 * c + 1 < norb ? 2 * c + 1 : -2, ndos, nint, &gth));
+      const long long dest[2] = {(long long)(2 * n1 + n1 * (size_t)(2 * c)), 2 * c + 1 < norb ? (long long)(2 * n1 + n1 * (size_t)(2 * c + 1)) : -1};
+      OD_CUDA(ctx, cudaMemcpyAsync(ctx->small.p, dest, sizeof(dest), cudaMemcpyHostToDevice, ctx->stream));
+      dim3 g((nbins + 255) / 256, 2 * ns);
+      combine_channels_kernel<<<g, 256, 0, ctx->stream>>>(S.chan, S.nout, 2, nbins, S.ps.bpad, ns, ctx->small.as<long long>(), accum);
+      OD_LAUNCH_CHECK(ctx);
+      OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // dest is a stack array
+    }
+  }
   ta.stop(ctx->stream);
 
   // ---- the wide units through the dense engine (adds into accum)
   if (wide_stride > 0) {
     WideListProducer<DosProducer> wp;
     wp.units_per_z = wide_stride;
-    wp.inner = prod;
+    wp.inner = prod_in;
     wp.list = ctx->scratch_b.as<unsigned>();
     wp.stride = wide_stride;
     wp.count[0] = h_wide[0];
     wp.count[1] = h_wide[1];
-    const size_t n1 = (size_t)nbins * ns;
-    std::vector<long long> dest(ns * 2);
-    for (int is = 0; is < ns; ++is) {
-      dest[is * 2 + 0] = (long long)is * nbins;
-      dest[is * 2 + 1] = (long long)(n1 + (size_t)is * nbins);
+    if (norb == 0) {
+      std::vector<long long> dest(ns * 2);
+      for (int is = 0; is < ns; ++is) {
+        dest[is * 2 + 0] = (long long)is * nbins;
+        dest[is * 2 + 1] = (long long)(n1 + (size_t)is * nbins);
+      }
+      OD_CHECK((od_run_dense<0, true, WideListProducer<DosProducer>>(ctx, wp, grid, ns, dest, accum)));
+    } else {
+      const int ngroups = (norb + OD_MAXW - 1) / OD_MAXW, nz = ns * ngroups;
+      constexpr int NACC = 2 + OD_MAXW;
+      std::vector<long long> dest((size_t)nz * NACC, -1);
+      for (int g = 0; g < ngroups; ++g)
+        for (int is = 0; is < ns; ++is) {
+          const int z = is + ns * g;
+          if (g == 0) {
+            dest[(size_t)z * NACC + 0] = (long long)is * nbins;
+            dest[(size_t)z * NACC + 1] = (long long)(n1 + (size_t)is * nbins);
+          }
+          for (int a = 0; a < OD_MAXW; ++a) {
+            const int o = g * OD_MAXW + a;
+            if (o < norb) dest[(size_t)z * NACC + 2 + a] = (long long)(2 * n1 + (size_t)nbins * (is + (size_t)ns * o));
+          }
+        }
+      OD_CHECK((od_run_dense<OD_MAXW, true, WideListProducer<DosProducer>>(ctx, wp, grid, nz, dest, accum)));
     }
-    OD_CHECK((od_run_dense<0, true, WideListProducer<DosProducer>>(ctx, wp, grid, ns, dest, accum)));
   }
-  combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, nbins, S.ps.bpad, accum, accum + (size_t)nbins * ns);
-  OD_LAUNCH_CHECK(ctx);
   OD_CHECK(collect_stats(ctx, S));
   ctx->prof.prepare_ms += tp.ms();
   ctx->prof.accumulate_ms += ta.ms();
-  ctx->prof.accumulate_launches += (h_nrec > 0) ? 1 : 0;
+  ctx->prof.accumulate_launches += (h_nrec > 0) ? 1 + wpasses : 0;
   return OD_OK;
 }
 
@@ -834,6 +908,7 @@ int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &gri
   S.ps.with_int = 0;
   S.ps.linear_pass = linear ? 1 : 0;  // hybrid_linear fall-back records (jdos_utils.f90:365) -> dense engine
   S.ps.ng = n_geom;
+  S.ps.want_unit = 0;
   const size_t n1 = (size_t)nbins * ns;
   for (long long k0 = 0; k0 < nk; k0 += slab_k) {
     JdosProducer prod = prod_in;
@@ -848,8 +923,11 @@ int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &gri
     tp.stop(ctx->stream);
     ta.start(ctx->stream);
     if (h_nrec > 0)
-      for (int c = 0; c < npass; ++c)
-        OD_CHECK(narrow_launch<true>(ctx, S, linear, h_nrec, c, S.chan + (size_t)(2 * c) * S.nout, S.chan + (size_t)(2 * c + 1) * S.nout));
+      for (int c = 0; c < npass; ++c) {  // (jdos, w1) (w2, w3) (w4, w5) (w6, -)
+        const int col0 = c == 0 ? -1 : 2 * c - 1, col1 = 2 * c < n_geom ? 2 * c : -2;
+        OD_CHECK(narrow_launch<true>(ctx, S, linear, h_nrec, col0, col1, S.chan + (size_t)(2 * c) * S.nout,
+                                     S.chan + (size_t)(2 * c + 1) * S.nout));
+      }
     ta.stop(ctx->stream);
     if (wide_stride > 0) {
       WideListProducer<JdosProducer> wp;

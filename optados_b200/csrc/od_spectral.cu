@@ -96,7 +96,7 @@ int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delt
   OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * ntot, ctx->stream));
 
   const bool force_dense = ctx->engine == OD_ENGINE_DENSE;
-  if (!mw_dev && !force_dense) {
+  if (!force_dense) {
     OD_CHECK(od_narrow_dos(ctx, p, grid, dos_type == 'l', accum));
   } else if (!mw_dev) {
     std::vector<long long> dest(ns * 2);

@@ -355,3 +355,27 @@ def test_narrow_jdos_and_optics_vs_oracle(ob, odo, jtype):
     p = ctx.profile_get()
     assert p["contributions"] > 0 and p["lane_steps"] >= p["contributions"]
     ctx.close()
+
+
+@pytest.mark.parametrize("dos_type", ["a", "l"])
+def test_narrow_weighted_dos_vs_oracle(ob, odo, dos_type):
+    """PDOS / core-style weighted DOS through the narrow engine: the sorted records are walked once per pair
+    of weight columns, weights gathered from matrix_weights by unit index (odd column count, fewer weighted
+    bands than bands)."""
+    ctx = ob.Context(0)
+    grid, ns, nb = (12, 10, 8), 2, 16
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=31)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
+    E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=5000)
+    rng = np.random.default_rng(9)
+    mw = np.asfortranarray(rng.random((5, nb - 2, nk, ns)))
+    ref = odo.calculate_dos(dos_type, s, odo.make_broadening(), E, delta, mw, nthreads=8)
+    for eng in ("auto", "dense"):
+        ctx.set_engine(eng)
+        dos, intdos, wdos = ctx.calculate_dos(dos_type, E[0], delta, n, mw=mw)
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC, eng
+        assert_int(intdos, ref[1])
+        assert rel_to_peak(wdos, ref[2]) < TOL_SPEC, eng
+    ctx.close()
