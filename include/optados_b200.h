@@ -37,7 +37,10 @@ extern "C" {
 typedef struct od_ctx od_ctx;
 typedef struct od_broadening od_broadening; /* defined below */
 
-enum { OD_MEM_HOST = 0, OD_MEM_DEVICE = 1 };
+/* OD_MEM_HOST_DEFERRED (od_set_gradients only): the library keeps the HOST pointer (pinned memory advised; it must
+ * stay valid until the next od_set_gradients) and uploads the array slab by slab INSIDE calculate_dos /
+ * dos_utils_calculate, overlapped with the kernels working on the previous slab */
+enum { OD_MEM_HOST = 0, OD_MEM_DEVICE = 1, OD_MEM_HOST_DEFERRED = 2 };
 enum { OD_OK = 0, OD_ERR_ARG = 1, OD_ERR_CUDA = 2, OD_ERR_STATE = 3, OD_ERR_NCCL = 4, OD_ERR_DOSLIN = 5, OD_ERR_REF = 6 };
 
 /* optics_geom (parameters.f90:346; optics.f90:213-244) and core_type (parameters.f90:373-378) */

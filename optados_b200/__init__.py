@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "liboptados_b200.so")
 
-OD_MEM_HOST, OD_MEM_DEVICE = 0, 1
+OD_MEM_HOST, OD_MEM_DEVICE, OD_MEM_HOST_DEFERRED = 0, 1, 2
 GEOM = {"polycrys": 0, "polar": 1, "unpolar": 2, "tensor": 3}
 CORE_TYPE = {"absorption": 0, "emission": 1, "all": 2}
 EFERMI = {"optados": 0, "file": 1, "user": 2, "insulator": 3}
@@ -175,8 +175,14 @@ class Context:
         self._ck(self.L.od_set_bands(self.h, _p(a), OD_MEM_HOST))
         self._ck(self.L.od_synchronize(self.h))
 
-    def set_gradients(self, band_gradient):
+    def set_gradients(self, band_gradient, deferred=False):
+        """deferred=True: the library keeps the host pointer and uploads the array slab by slab inside
+        calculate_dos / dos_utils_calculate, overlapped with the kernels (the array is kept alive here)."""
         a = f64(band_gradient)
+        if deferred:
+            self._keep["grads"] = a
+            self._ck(self.L.od_set_gradients(self.h, _p(a), OD_MEM_HOST_DEFERRED))
+            return
         self._ck(self.L.od_set_gradients(self.h, _p(a), OD_MEM_HOST))
         self._ck(self.L.od_synchronize(self.h))
 
@@ -455,8 +461,8 @@ class Context:
         """od_set_bands from a raw (e.g. pinned) host pointer; asynchronous on the ctx stream."""
         self._ck(self.L.od_set_bands(self.h, C.c_void_p(host_ptr), OD_MEM_HOST))
 
-    def set_gradients_ptr(self, host_ptr):
-        self._ck(self.L.od_set_gradients(self.h, C.c_void_p(host_ptr), OD_MEM_HOST))
+    def set_gradients_ptr(self, host_ptr, deferred=False):
+        self._ck(self.L.od_set_gradients(self.h, C.c_void_p(host_ptr), OD_MEM_HOST_DEFERRED if deferred else OD_MEM_HOST))
 
     def get_bands_ptr(self, host_ptr):
         self._ck(self.L.od_get_bands(self.h, C.c_void_p(host_ptr)))

@@ -149,6 +149,12 @@ extern "C" int od_ctx_destroy(od_ctx *ctx) {
   for (DevBuf *b : bufs) od_buf_release(*b);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 2; ++i) {
+    od_buf_release(ctx->gslab[i]);
+    if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return OD_OK;
@@ -301,7 +307,21 @@ extern "C" int od_set_bands(od_ctx *ctx, const double *band_energy, int mem) {
 extern "C" int od_set_gradients(od_ctx *ctx, const double *band_gradient, int mem) {
   if (!ctx) return OD_ERR_ARG;
   if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system must be called first");
+  ctx->grads_host = nullptr;
+  if (mem == OD_MEM_HOST_DEFERRED) {
+    if (!band_gradient) return od_fail(ctx, OD_ERR_ARG, "null array");
+    od_buf_release(ctx->grads);
+    ctx->grads_host = band_gradient;
+    return OD_OK;
+  }
   return set_array(ctx, ctx->grads, band_gradient, (size_t)ctx->nb * 3 * ctx->nk * ctx->ns, mem);
+}
+
+int od_grads_resident(od_ctx *ctx) {
+  if (!ctx->grads_host) return OD_OK;
+  const double *h = ctx->grads_host;
+  ctx->grads_host = nullptr;
+  return set_array(ctx, ctx->grads, h, (size_t)ctx->nb * 3 * ctx->nk * ctx->ns, OD_MEM_HOST);
 }
 
 static int get_array(od_ctx *ctx, const DevBuf &src, double *dst, size_t n, const char *what) {
@@ -312,7 +332,7 @@ static int get_array(od_ctx *ctx, const DevBuf &src, double *dst, size_t n, cons
   return OD_OK;
 }
 extern "C" int od_get_bands(od_ctx *ctx, double *h) { return get_array(ctx, ctx->bands, h, (size_t)ctx->nb * ctx->ns * ctx->nk, "band_energy"); }
-extern "C" int od_get_gradients(od_ctx *ctx, double *h) { return get_array(ctx, ctx->grads, h, (size_t)ctx->nb * 3 * ctx->nk * ctx->ns, "band_gradient"); }
+extern "C" int od_get_gradients(od_ctx *ctx, double *h) { if (ctx) { int rc = od_grads_resident(ctx); if (rc) return rc; } return get_array(ctx, ctx->grads, h, (size_t)ctx->nb * 3 * ctx->nk * ctx->ns, "band_gradient"); }
 extern "C" int od_get_kweights(od_ctx *ctx, double *h) { return get_array(ctx, ctx->kweight, h, (size_t)ctx->nk, "kpoint_weight"); }
 
 // dos_utils.f90:1210-1216

@@ -111,16 +111,23 @@ extern "C" int od_dos_utils_calculate(od_ctx *ctx, od_dos_params *p, const doubl
   const int enabled[3] = {p->fixed, p->adaptive, p->linear};
   // weighted spectrum only with the most complex enabled scheme (dos_utils.f90:179-208)
   const bool wt[3] = {calc_weighted && !p->adaptive && !p->linear, calc_weighted && !p->linear, calc_weighted};
-  for (int t = 0; t < 3; ++t) {
-    if (!enabled[t]) continue;
-    double *accum = nullptr;
-    OD_CHECK(od_calculate_dos_device(ctx, types[t], emin, delta, nbins, &p->br, wt[t] ? mw_dev : nullptr, mw_norb, mw_nb, mw_nk,
-                                     /*merge=*/1, &accum));
-    OD_CHECK(pull(ctx, S.dos[t], accum, n1));
-    OD_CHECK(pull(ctx, S.intdos[t], accum + n1, n1));
+  // all enabled schemes in one sweep over the k-points (one upload of the gradients when they are streamed)
+  char tl[3];
+  bool wl[3];
+  int idx[3], nt = 0;
+  for (int t = 0; t < 3; ++t)
+    if (enabled[t]) { tl[nt] = types[t]; wl[nt] = wt[t]; idx[nt] = t; ++nt; }
+  double *accum = nullptr;
+  size_t stride = 0;
+  OD_CHECK(od_dos_accumulate(ctx, nt, tl, wl, emin, delta, nbins, &p->br, mw_dev, mw_norb, mw_nb, mw_nk, /*merge=*/1, &accum, &stride));
+  for (int i = 0; i < nt; ++i) {
+    const int t = idx[i];
+    double *acc = accum + stride * i;
+    OD_CHECK(pull(ctx, S.dos[t], acc, n1));
+    OD_CHECK(pull(ctx, S.intdos[t], acc + n1, n1));
     S.have[t] = true;
     if (wt[t]) {
-      OD_CHECK(pull(ctx, S.weighted, accum + 2 * n1, n1 * mw_norb));
+      OD_CHECK(pull(ctx, S.weighted, acc + 2 * n1, n1 * mw_norb));
       S.have_weighted = true;
       S.norb = mw_norb;
     }

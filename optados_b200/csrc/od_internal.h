@@ -52,6 +52,10 @@ struct od_ctx {
   int kgrid[3] = {1, 1, 1};
   double eps = 2.0;  // electrons_per_state
   DevBuf kweight, bands, grads;
+  const double *grads_host = nullptr;  // OD_MEM_HOST_DEFERRED: uploaded slab-wise by the DOS drivers
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  DevBuf gslab[2];
 
   // scratch
   DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, scratch_e, mw_tmp, in_tmp, in_tmp2;
@@ -99,3 +103,5 @@ GridGeom od_grid_geom(const od_ctx *ctx, double adaptive_smearing);
 
 // allreduce on a DEVICE buffer (no-op when nranks == 1)
 int od_allreduce_device(od_ctx *ctx, double *dbuf, size_t n, char op);
+// make deferred gradients resident (paths that do not stream)
+int od_grads_resident(od_ctx *ctx);

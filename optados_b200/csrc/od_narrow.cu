@@ -327,6 +327,7 @@ struct NarrowArgs {
   const unsigned *runit;
   const double *mw;
   int norb, mw_nb, mw_nk, nb, mw_ns;
+  long long k_first;
 };
 
 __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, const NarrowArgs &A, int lane) {
@@ -393,9 +394,10 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
         const double *w = nullptr;
         if (A.runit) {
           const unsigned u = A.runit[idx];
-          const unsigned ik = u / (unsigned)A.nb, ib = u - ik * (unsigned)A.nb;
+          const unsigned ikl = u / (unsigned)A.nb, ib = u - ikl * (unsigned)A.nb;
+          const long long ik = A.k_first + ikl;
           const int is = klo >= A.bpad ? 1 : 0;
-          if ((int)ik < A.mw_nk && (int)ib < A.mw_nb)  // dos_utils.f90:1268-1269
+          if (ik < A.mw_nk && (int)ib < A.mw_nb)  // dos_utils.f90:1268-1269
             w = A.mw + (size_t)A.norb * (ib + (size_t)A.mw_nb * (ik + (size_t)A.mw_nk * is));
         } else if (A.wts) {
           w = A.wts + (size_t)idx * A.ng;
@@ -704,6 +706,7 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod, Scratch &S, bool linear, u
 struct MwGather {
   const double *mw = nullptr;
   int norb = 0, mw_nb = 0, mw_nk = 0, nb = 0;
+  long long k_first = 0;
 };
 
 template <bool JD>
@@ -725,10 +728,11 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
   A.ng = S.ps.ng;
   A.col0 = col0;
   A.col1 = col1;
-  A.runit = nullptr; A.mw = nullptr; A.norb = A.mw_nb = A.mw_nk = A.nb = A.mw_ns = 0;
+  A.runit = nullptr; A.mw = nullptr; A.norb = A.mw_nb = A.mw_nk = A.nb = A.mw_ns = 0; A.k_first = 0;
   if (gather) {
     A.runit = ctx->scratch_e.as<unsigned>();
     A.mw = gather->mw; A.norb = gather->norb; A.mw_nb = gather->mw_nb; A.mw_nk = gather->mw_nk; A.nb = gather->nb;
+    A.k_first = gather->k_first;
   }
   OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
   const size_t smem = (sizeof(double2) + sizeof(double)) * NR_T * NR_WARPS;
@@ -838,6 +842,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
     // weighted spectrum: columns (2c, 2c+1) per pass, K * matrix_weights(o, ib, ik, is) (dos_utils.f90:1271)
     MwGather gth;
     gth.mw = prod_in.mw; gth.norb = norb; gth.mw_nb = prod_in.mw_nb; gth.mw_nk = prod_in.mw_nk; gth.nb = prod_in.nb;
+    gth.k_first = prod_in.k_first;
     OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(long long) * 2));
     for (int c = 0; 2 * c < norb; ++c, ++wpasses) {
       OD_CUDA(ctx, cudaMemsetAsync(S.chan, 0, sizeof(double) * 2 * S.nout, ctx->stream));

@@ -43,8 +43,10 @@ __device__ __forceinline__ void od_make_record(const BroadSpec &b, double centre
 
 // ------------------------------------------------------------------ DOS / PDOS / core
 struct DosProducer {
-  long long units_per_z;  // nb * nk
+  long long units_per_z;  // nb * (k-points of this slab)
+  long long k_first;      // first k-point of the slab: band_energy / kpoint_weight / matrix_weights use k_first + ik
   int nb, ns, nk;
+  int nk_g;               // k-extent of the array `grads` points to (the whole shard, or one streamed slab)
   const double *bands, *grads, *kw;
   double eps;
   BroadSpec b;
@@ -56,12 +58,13 @@ struct DosProducer {
     const int is = z % ns, grp = z / ns;
     // units_per_z = nb * nk < 2^32 whenever the engines accept the job: 32-bit division
     const unsigned uu = (unsigned)u;
-    const long long ik = (units_per_z <= 0xffffffffll) ? (long long)(uu / (unsigned)nb) : u / nb;
-    const int ib = (int)(u - ik * nb);
+    const long long ikl = (units_per_z <= 0xffffffffll) ? (long long)(uu / (unsigned)nb) : u / nb;  // within the slab
+    const int ib = (int)(u - ikl * nb);
+    const long long ik = k_first + ikl;
     const double e = bands[ib + (size_t)nb * (is + (size_t)ns * ik)];
     double g[3] = {0.0, 0.0, 0.0};
     if (b.type != 0) {
-      const size_t gi = ib + (size_t)nb * (3 * (ik + (size_t)nk * is));
+      const size_t gi = ib + (size_t)nb * (3 * (ikl + (size_t)nk_g * is));
       g[0] = grads[gi];
       g[1] = grads[gi + nb];
       g[2] = grads[gi + 2 * (size_t)nb];

@@ -36,7 +36,7 @@ static int check_ready(od_ctx *ctx, bool need_grad) {
   if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system has not been called");
   if (!ctx->bands.p) return od_fail(ctx, OD_ERR_STATE, "band_energy not set (od_set_bands)");
   if (!ctx->kweight.p) return od_fail(ctx, OD_ERR_STATE, "kpoint_weight not set");
-  if (need_grad && !ctx->grads.p) return od_fail(ctx, OD_ERR_STATE, "band_gradient not set (od_set_gradients)");
+  if (need_grad && !ctx->grads.p && !ctx->grads_host) return od_fail(ctx, OD_ERR_STATE, "band_gradient not set (od_set_gradients)");
   return OD_OK;
 }
 
@@ -69,77 +69,146 @@ __global__ void linear_smear_kernel(const double *__restrict__ dos, double *__re
 }  // namespace
 
 // ------------------------------------------------------------------ calculate_dos
-int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins, const od_broadening *br,
-                            const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_out) {
-  OD_CHECK(check_ready(ctx, dos_type != 'f'));
-  if (nbins < 2) return od_fail(ctx, OD_ERR_ARG, "nbins = %d", nbins);
-  if (!(delta_bins > 0.0)) return od_fail(ctx, OD_ERR_ARG, "delta_bins must be positive");
-  OD_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int ns = ctx->ns;
-  if (mw_dev && (norb < 1 || mw_nb < 1 || mw_nk < 1)) return od_fail(ctx, OD_ERR_ARG, "bad matrix_weights bounds");
-  if (mw_dev && mw_nk != ctx->nk) return od_fail(ctx, OD_ERR_REF, "ERROR : DOS : mw%%nkpoints not equal to nkpoints. (dos_utils.f90:159)");
-  if (!mw_dev) norb = 0;
-
+// one k-point slab of one broadening scheme, ADDED into accum = [dos | intdos | weighted_dos]
+static int dos_slab(od_ctx *ctx, char dos_type, const od_broadening *br, const GridSpec &grid, const double *mw_dev, int norb,
+                    int mw_nb, int mw_nk, long long k_first, int nk_slab, const double *grads_dev, int nk_g, double *accum) {
+  const int ns = ctx->ns, nbins = grid.nbins;
   DosProducer p;
-  p.units_per_z = (long long)ctx->nb * ctx->nk;
-  p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk;
-  p.bands = ctx->bands.as<double>(); p.grads = ctx->grads.as<double>(); p.kw = ctx->kweight.as<double>();
+  p.units_per_z = (long long)ctx->nb * nk_slab;
+  p.k_first = k_first;
+  p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk; p.nk_g = nk_g;
+  p.bands = ctx->bands.as<double>(); p.grads = grads_dev; p.kw = ctx->kweight.as<double>();
   p.eps = ctx->eps;
-  OD_CHECK(od_make_broadspec(ctx, dos_type, br, delta_bins, /*honor_hybrid=*/false, &p.b));
+  OD_CHECK(od_make_broadspec(ctx, dos_type, br, grid.delta, /*honor_hybrid=*/false, &p.b));
   p.mw = mw_dev; p.norb = norb; p.mw_nb = mw_nb; p.mw_nk = mw_nk; p.og = OD_MAXW;
-
-  GridSpec grid{emin, delta_bins, nbins};
   const size_t n1 = (size_t)nbins * ns;
-  const size_t ntot = 2 * n1 + n1 * norb;
-  OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * (ntot + n1)));
-  double *accum = ctx->accum.as<double>();
-  OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * ntot, ctx->stream));
-
-  const bool force_dense = ctx->engine == OD_ENGINE_DENSE;
-  if (!force_dense) {
-    OD_CHECK(od_narrow_dos(ctx, p, grid, dos_type == 'l', accum));
-  } else if (!mw_dev) {
+  if (ctx->engine != OD_ENGINE_DENSE) return od_narrow_dos(ctx, p, grid, dos_type == 'l', accum);
+  if (!mw_dev) {
     std::vector<long long> dest(ns * 2);
     for (int is = 0; is < ns; ++is) {
       dest[is * 2 + 0] = (long long)is * nbins;
       dest[is * 2 + 1] = (long long)(n1 + (size_t)is * nbins);
     }
-    OD_CHECK((od_run_dense<0, true, DosProducer>(ctx, p, grid, ns, dest, accum)));
-  } else {
-    const int ngroups = (norb + OD_MAXW - 1) / OD_MAXW;
-    const int nz = ns * ngroups;
-    constexpr int NACC = 2 + OD_MAXW;
-    std::vector<long long> dest((size_t)nz * NACC, -1);
-    for (int g = 0; g < ngroups; ++g)
-      for (int is = 0; is < ns; ++is) {
-        const int z = is + ns * g;
-        if (g == 0) {
-          dest[(size_t)z * NACC + 0] = (long long)is * nbins;
-          dest[(size_t)z * NACC + 1] = (long long)(n1 + (size_t)is * nbins);
-        }
-        for (int a = 0; a < OD_MAXW; ++a) {
-          const int o = g * OD_MAXW + a;
-          if (o < norb) dest[(size_t)z * NACC + 2 + a] = (long long)(2 * n1 + (size_t)nbins * (is + (size_t)ns * o));
-        }
+    return od_run_dense<0, true, DosProducer>(ctx, p, grid, ns, dest, accum);
+  }
+  const int ngroups = (norb + OD_MAXW - 1) / OD_MAXW;
+  const int nz = ns * ngroups;
+  constexpr int NACC = 2 + OD_MAXW;
+  std::vector<long long> dest((size_t)nz * NACC, -1);
+  for (int g = 0; g < ngroups; ++g)
+    for (int is = 0; is < ns; ++is) {
+      const int z = is + ns * g;
+      if (g == 0) {
+        dest[(size_t)z * NACC + 0] = (long long)is * nbins;
+        dest[(size_t)z * NACC + 1] = (long long)(n1 + (size_t)is * nbins);
       }
-    OD_CHECK((od_run_dense<OD_MAXW, true, DosProducer>(ctx, p, grid, nz, dest, accum)));
+      for (int a = 0; a < OD_MAXW; ++a) {
+        const int o = g * OD_MAXW + a;
+        if (o < norb) dest[(size_t)z * NACC + 2 + a] = (long long)(2 * n1 + (size_t)nbins * (is + (size_t)ns * o));
+      }
+    }
+  return od_run_dense<OD_MAXW, true, DosProducer>(ctx, p, grid, nz, dest, accum);
+}
+
+// Several broadening schemes over the rank's k-points in ONE sweep of k-point slabs.  With deferred (host)
+// gradients the slabs are uploaded on a second stream into two buffers while the kernels work on the
+// previous slab; otherwise there is a single slab.  accum_t = accum_base + t * stride:
+// [dos(B,ns) | intdos(B,ns) | weighted_dos(B,ns,norb) if weighted[t] | scratch(B,ns)]
+int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *weighted, double emin, double delta_bins, int nbins,
+                      const od_broadening *br, const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_base,
+                      size_t *accum_stride) {
+  bool need_grad = false;
+  for (int t = 0; t < ntypes; ++t) need_grad = need_grad || types[t] != 'f';
+  OD_CHECK(check_ready(ctx, need_grad));
+  if (nbins < 2) return od_fail(ctx, OD_ERR_ARG, "nbins = %d", nbins);
+  if (!(delta_bins > 0.0)) return od_fail(ctx, OD_ERR_ARG, "delta_bins must be positive");
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int ns = ctx->ns, nb = ctx->nb, nk = ctx->nk;
+  if (mw_dev && (norb < 1 || mw_nb < 1 || mw_nk < 1)) return od_fail(ctx, OD_ERR_ARG, "bad matrix_weights bounds");
+  if (mw_dev && mw_nk != nk) return od_fail(ctx, OD_ERR_REF, "ERROR : DOS : mw%%nkpoints not equal to nkpoints. (dos_utils.f90:159)");
+  if (!mw_dev) norb = 0;
+  for (int t = 0; t < ntypes; ++t) {
+    BroadSpec tmp;
+    OD_CHECK(od_make_broadspec(ctx, types[t], br, delta_bins, false, &tmp));  // validates dos_type
+  }
+  GridSpec grid{emin, delta_bins, nbins};
+  const size_t n1 = (size_t)nbins * ns;
+  const size_t stride = 2 * n1 + n1 * norb + n1;
+  OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * stride * ntypes));
+  double *accum = ctx->accum.as<double>();
+  OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * stride * ntypes, ctx->stream));
+
+  const bool streamed = ctx->grads_host != nullptr && need_grad;
+  if (!streamed) {
+    for (int t = 0; t < ntypes; ++t)
+      OD_CHECK(dos_slab(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, 0, nk, ctx->grads.as<double>(), nk,
+                        accum + stride * t));
+  } else {
+    if (!ctx->copy_stream) {
+      OD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        OD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+        OD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+      }
+    }
+    const int nslabs = std::max(1, std::min(8, nk / 1024));
+    const int slab_nk = (nk + nslabs - 1) / nslabs;
+    const size_t slab_elems = (size_t)nb * 3 * slab_nk * ns;
+    for (int i = 0; i < 2; ++i) OD_CHECK(od_buf_ensure(ctx, ctx->gslab[i], sizeof(double) * slab_elems));
+    auto issue_copy = [&](int s) -> int {
+      const int b = s & 1;
+      const long long k0 = (long long)s * slab_nk;
+      const int nks = (int)std::min<long long>(slab_nk, nk - k0);
+      if (s >= 2) OD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));  // buffer free again?
+      for (int is = 0; is < ns; ++is)  // band_gradient(nb,3,nk,ns) -> slab buffer (nb,3,nks,ns)
+        OD_CUDA(ctx, cudaMemcpyAsync(ctx->gslab[b].as<double>() + (size_t)nb * 3 * nks * is,
+                                     ctx->grads_host + (size_t)nb * 3 * (k0 + (size_t)nk * is), sizeof(double) * (size_t)nb * 3 * nks,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+      OD_CUDA(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+      return OD_OK;
+    };
+    OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // band_energy upload / memset ordered before the copy stream starts
+    OD_CHECK(issue_copy(0));
+    for (int s = 0; (long long)s * slab_nk < nk; ++s) {
+      const int b = s & 1;
+      const long long k0 = (long long)s * slab_nk;
+      const int nks = (int)std::min<long long>(slab_nk, nk - k0);
+      if ((long long)(s + 1) * slab_nk < nk) OD_CHECK(issue_copy(s + 1));
+      OD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+      for (int t = 0; t < ntypes; ++t)
+        OD_CHECK(dos_slab(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0, nks, ctx->gslab[b].as<double>(),
+                          nks, accum + stride * t));
+      OD_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
+    }
   }
 
-  // rank-local epilogue, before the merge like the reference (quirk Q16)
-  if (dos_type == 'l' && br->linear_smearing > 0.0) {
-    double *tmp = accum + ntot;
-    dim3 g((nbins + 127) / 128, ns);
-    linear_smear_kernel<<<g, 128, 0, ctx->stream>>>(accum, tmp, nbins, ns, emin, delta_bins, br->linear_smearing);
-    OD_LAUNCH_CHECK(ctx);
-    OD_CUDA(ctx, cudaMemcpyAsync(accum, tmp, sizeof(double) * n1, cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int t = 0; t < ntypes; ++t) {
+    double *acc = accum + stride * t;
+    const size_t ntot = 2 * n1 + (weighted[t] ? n1 * norb : 0);
+    // rank-local epilogue, before the merge like the reference (quirk Q16)
+    if (types[t] == 'l' && br->linear_smearing > 0.0) {
+      double *tmp = acc + stride - n1;
+      dim3 g((nbins + 127) / 128, ns);
+      linear_smear_kernel<<<g, 128, 0, ctx->stream>>>(acc, tmp, nbins, ns, emin, delta_bins, br->linear_smearing);
+      OD_LAUNCH_CHECK(ctx);
+      OD_CUDA(ctx, cudaMemcpyAsync(acc, tmp, sizeof(double) * n1, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (types[t] != 'l' && br->numerical_intdos) {
+      numerical_intdos_kernel<<<1, 32, 0, ctx->stream>>>(acc, acc + n1, nbins, ns, delta_bins);
+      OD_LAUNCH_CHECK(ctx);
+    }
+    if (merge) OD_CHECK(od_allreduce_device(ctx, acc, ntot, 's'));  // dos_utils_merge (dos_utils.f90:1041-1043)
   }
-  if (dos_type != 'l' && br->numerical_intdos) {
-    numerical_intdos_kernel<<<1, 32, 0, ctx->stream>>>(accum, accum + n1, nbins, ns, delta_bins);
-    OD_LAUNCH_CHECK(ctx);
-  }
-  if (merge) OD_CHECK(od_allreduce_device(ctx, accum, ntot, 's'));  // dos_utils_merge (dos_utils.f90:1041-1043)
-  *accum_out = accum;
+  *accum_base = accum;
+  *accum_stride = stride;
   return OD_OK;
+}
+
+int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins, const od_broadening *br,
+                            const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_out) {
+  const bool weighted = mw_dev != nullptr;
+  size_t stride = 0;
+  return od_dos_accumulate(ctx, 1, &dos_type, &weighted, emin, delta_bins, nbins, br, mw_dev, norb, mw_nb, mw_nk, merge, accum_out, &stride);
 }
 
 extern "C" int od_calculate_dos(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins, const od_broadening *br,
@@ -231,6 +300,7 @@ dos_at_e_kernel(DosProducer prod, double energy, long long units_per_warp, doubl
 extern "C" int od_calculate_dos_at_e(od_ctx *ctx, char dos_type, double energy, double delta_bins, const od_broadening *br,
                                      const double *matrix_weights, int mw_norb, int mw_nb, int mw_nk, int mw_mem, int merge,
                                      double *dos_at_e, double *weighted_dos_at_e) {
+  if (ctx) OD_CHECK(od_grads_resident(ctx));
   OD_CHECK(check_ready(ctx, dos_type != 'f'));
   if (!dos_at_e) return od_fail(ctx, OD_ERR_ARG, "null output array");
   OD_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -247,7 +317,8 @@ extern "C" int od_calculate_dos_at_e(od_ctx *ctx, char dos_type, double energy, 
   }
   DosProducer p;
   p.units_per_z = (long long)ctx->nb * ctx->nk;
-  p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk;
+  p.k_first = 0;
+  p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk; p.nk_g = ctx->nk;
   p.bands = ctx->bands.as<double>(); p.grads = ctx->grads.as<double>(); p.kw = ctx->kweight.as<double>();
   p.eps = ctx->eps;
   OD_CHECK(od_make_broadspec(ctx, dos_type, br, delta_bins, /*honor_hybrid=*/true, &p.b));
@@ -291,6 +362,7 @@ extern "C" int od_calculate_dos_at_e(od_ctx *ctx, char dos_type, double energy, 
 int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br, double efermi,
                              double scissor_op, const int *exclude_bands, int num_exclude_bands, const double *mw_dev,
                              const double *ome_dev, const OpticsCoef *coef, int n_geom, int merge, double **accum_out) {
+  if (ctx) OD_CHECK(od_grads_resident(ctx));
   OD_CHECK(check_ready(ctx, jdos_type != 'f'));
   if (nbins < 2) return od_fail(ctx, OD_ERR_ARG, "nbins = %d", nbins);
   if (!(delta_bins > 0.0)) return od_fail(ctx, OD_ERR_ARG, "delta_bins must be positive");

@@ -11,6 +11,10 @@ int od_make_broadspec(od_ctx *ctx, char type, const od_broadening *br, double de
 // results stay on the device: *accum_out -> [dos(B,ns) | intdos(B,ns) | weighted_dos(B,ns,norb)]
 int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins, const od_broadening *br,
                             const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_out);
+// several broadening schemes in one sweep over k-point slabs (streams deferred gradients); see od_spectral.cu
+int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *weighted, double emin, double delta_bins, int nbins,
+                      const od_broadening *br, const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_base,
+                      size_t *accum_stride);
 // *accum_out -> [jdos(B,ns) | weighted_jdos(B,ns,n_geom)]
 int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br, double efermi,
                              double scissor_op, const int *exclude_bands, int num_exclude_bands, const double *mw_dev,

@@ -97,10 +97,12 @@ extern "C" int od_count_contributions(od_ctx *ctx, char dos_type, double emin, d
                                       const od_broadening *br, double *contributions) {
   if (!ctx || !contributions) return OD_ERR_ARG;
   if (!ctx->have_system || !ctx->bands.p || !ctx->kweight.p) return od_fail(ctx, OD_ERR_STATE, "system / band_energy not set");
+  OD_CHECK(od_grads_resident(ctx));
   if (dos_type != 'f' && !ctx->grads.p) return od_fail(ctx, OD_ERR_STATE, "band_gradient not set");
   OD_CUDA(ctx, cudaSetDevice(ctx->device));
   DosProducer p;
   p.units_per_z = (long long)ctx->nb * ctx->nk;
+  p.k_first = 0; p.nk_g = ctx->nk;
   p.nb = ctx->nb; p.ns = ctx->ns; p.nk = ctx->nk;
   p.bands = ctx->bands.as<double>(); p.grads = ctx->grads.as<double>(); p.kw = ctx->kweight.as<double>();
   p.eps = ctx->eps;

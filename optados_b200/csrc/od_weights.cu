@@ -299,6 +299,7 @@ extern "C" int od_set_gradients_from_ome(od_ctx *ctx, const double *optical_mat,
   const size_t nks = (size_t)3 * ctx->nk * ctx->ns;
   const void *d = nullptr;
   OD_CHECK(od_stage_in(ctx, optical_mat, sizeof(double) * 2 * (size_t)ctx->nb * ctx->nb * nks, mem, ctx->in_tmp, &d));
+  ctx->grads_host = nullptr;
   if (!ctx->grads.owned) od_buf_release(ctx->grads);
   OD_CHECK(od_buf_ensure(ctx, ctx->grads, sizeof(double) * (size_t)ctx->nb * nks));
   gradient_from_ome_kernel<<<grid_for(ctx, (size_t)ctx->nb * nks, 256), 256, 0, ctx->stream>>>(static_cast<const double *>(d), ctx->nb, nks,
@@ -400,6 +401,7 @@ extern "C" int od_synth_bands(od_ctx *ctx, const int grid[3], long long k_first,
   }
   OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(double) * ct.size()));
   OD_CUDA(ctx, cudaMemcpyAsync(ctx->small.p, ct.data(), sizeof(double) * ct.size(), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->grads_host = nullptr;
   if (!ctx->bands.owned) od_buf_release(ctx->bands);
   if (!ctx->grads.owned) od_buf_release(ctx->grads);
   OD_CHECK(od_buf_ensure(ctx, ctx->bands, sizeof(double) * (size_t)nb * ns * nk_local));

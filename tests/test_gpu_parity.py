@@ -379,3 +379,24 @@ def test_narrow_weighted_dos_vs_oracle(ob, odo, dos_type):
         assert_int(intdos, ref[1])
         assert rel_to_peak(wdos, ref[2]) < TOL_SPEC, eng
     ctx.close()
+
+
+def test_streamed_gradients_match_resident(ob, odo):
+    """OD_MEM_HOST_DEFERRED: gradients uploaded slab by slab under the kernels (the end-to-end path of
+    bench.py) give the same spectra as the resident arrays, for several schemes in one sweep."""
+    ctx = ob.Context(0)
+    grid, ns, nb = (16, 16, 12), 2, 8
+    nk = grid[0] * grid[1] * grid[2]          # 3072 k-points -> 3 slabs
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=41)
+    be, bg = ctx.get_bands(), ctx.get_gradients()
+    p = ctx.dos_params(["fixed", "adaptive", "linear"], dos_nbins=3000, num_electrons=(4.0, 4.0))
+    ref = ctx.dos_utils_calculate(p)
+    ctx.set_gradients(bg, deferred=True)
+    p.dos_nbins = 3000
+    r = ctx.dos_utils_calculate(p)
+    for k in ("dos_fixed", "dos_adaptive", "dos_linear", "intdos_adaptive", "intdos_linear"):
+        assert np.abs(r[k] - ref[k]).max() <= 1e-13 * np.abs(ref[k]).max(), k
+    # a path that does not stream makes the array resident again
+    d, _ = ctx.calculate_dos_at_e("a", 3.0, r["delta"])
+    assert np.all(np.isfinite(d))
+    ctx.close()
