@@ -46,7 +46,7 @@ namespace {
 
 constexpr int NR_T = 512;        // bins per warp tile
 constexpr int NR_WMAX = 256;     // widest window (bins) the narrow engine takes
-constexpr int NR_CHUNK = 2048;   // records per work item
+constexpr int NR_CHUNK = 512;   // records per work item
 constexpr int NR_WARPS = 8;      // warps per CTA
 constexpr int NR_NCLS = 8;       // width classes
 constexpr int NR_MAXBUCKETS = 51200;  // x 4 B = 200 KB of shared memory in the prepare passes
