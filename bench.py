@@ -259,8 +259,16 @@ def main():
     achieved_tf = flops_step / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
     states = float(nk_gpu) * NB * NS
     hbm_gbs = 2.0 * states * BYTES_PER_STATE / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
+    traffic = None
+    try:   # DRAM bytes of the accumulation kernels from the committed ncu capture, scaled to this step's units
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        per_unit = sum(tr[k]["dram_bytes_read"] + tr[k]["dram_bytes_write"] for k in ("narrow_kernel<0,0>", "narrow_kernel<1,0>"))
+        traffic = per_unit / tr["units_per_profiled_launch"] * states
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                "traffic_note": "DRAM bytes per step of all accumulation launches (ncu dram__bytes_read+write, profiles/r01_traffic.json)",
                 "peak_source": "measured in this run: od_measure_fp64_peak (DFMA loop, all SMs); MEASURED_PEAKS.json has no FP64 entry",
                 "kernel": "accumulation kernels (adaptive + linear), CUDA events on the library stream",
                 "kernel_ms_per_step": acc_ms, "kernel_share_of_step": acc_ms / ms_step if ms_step > 0 else None,
