@@ -286,6 +286,38 @@ class Context:
                                                  C.c_int(int(merge)), _p(jdos), _p(wj)))
         return jdos, wj
 
+    # ---- raw-pointer variants (inputs already resident in HBM: OD_MEM_DEVICE)
+    def calculate_dos_ptr(self, dos_type, emin, delta_bins, nbins, mw_ptr, norb, mw_nb, mw_nk, mw_mem=OD_MEM_DEVICE, br=None,
+                          merge=False):
+        br = br or broadening()
+        dos = np.zeros((nbins, self.ns), order="F")
+        intdos = np.zeros((nbins, self.ns), order="F")
+        wdos = np.zeros((nbins, self.ns, norb), order="F")
+        self._ck(self.L.od_calculate_dos(self.h, C.c_char(dos_type.encode()), C.c_double(emin), C.c_double(delta_bins),
+                                         C.c_int(nbins), C.byref(br), C.c_void_p(mw_ptr), C.c_int(norb), C.c_int(mw_nb),
+                                         C.c_int(mw_nk), C.c_int(mw_mem), C.c_int(int(merge)), _p(dos), _p(intdos), _p(wdos)))
+        return dos, intdos, wdos
+
+    def calculate_jdos_optics_ptr(self, jdos_type, delta_bins, nbins, efermi, ome_ptr, geom, qdir=(0, 0, 1), br=None,
+                                  scissor_op=0.0, ome_mem=OD_MEM_DEVICE, merge=False):
+        br = br or broadening()
+        ng = 6 if geom == "tensor" else 1
+        jdos = np.zeros((nbins, self.ns), order="F")
+        wj = np.zeros((nbins, self.ns, ng), order="F")
+        q = f64(np.asarray(qdir, dtype=np.float64))
+        ex = np.zeros(1, dtype=np.int32)
+        self._ck(self.L.od_calculate_jdos_optics(self.h, C.c_char(jdos_type.encode()), C.c_double(delta_bins), C.c_int(nbins),
+                                                 C.byref(br), C.c_double(efermi), C.c_double(scissor_op),
+                                                 ex.ctypes.data_as(c_ip), C.c_int(0), C.c_void_p(ome_ptr), C.c_int(ome_mem),
+                                                 C.c_int(GEOM[geom]), _p(q), None, C.c_int(0), C.c_int(int(merge)), _p(jdos), _p(wj)))
+        return jdos, wj
+
+    def core_prepare_matrix_elements_ptr(self, elnes_ptr, norb, core_type, efermi, out_ptr, polar=False, qdir=(0, 0, 1)):
+        q = f64(np.asarray(qdir, dtype=np.float64))
+        self._ck(self.L.od_core_prepare_matrix_elements(self.h, C.c_void_p(elnes_ptr), C.c_int(OD_MEM_DEVICE), C.c_int(norb),
+                                                        C.c_int(int(polar)), _p(q), None, C.c_int(0), C.c_int(CORE_TYPE[core_type]),
+                                                        C.c_double(efermi), C.c_void_p(out_ptr), C.c_int(OD_MEM_DEVICE)))
+
     # ---- weight builders
     def make_weights(self, optical_mat, geom, efermi, qdir=(0, 0, 1), symops=None, scissor_op=0.0):
         om = np.asfortranarray(optical_mat, dtype=np.complex128)
