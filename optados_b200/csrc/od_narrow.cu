@@ -25,7 +25,7 @@
 //      become a prefix sum at the very end.  The linear scheme evaluates the four doslin pieces
 //      branch-free and selects.  Tiles are flushed to HBM with FP64 reductions only when a warp's
 //      window slides off its 512-bin tile or its chunk ends.
-//   3. Units whose window is wider than 256 bins (and degenerate ones) go to the dense bin-owner
+//   3. Units whose window is wider than 448 bins (and degenerate ones) go to the dense bin-owner
 //      engine (od_accum.cuh) through a compacted list; the partial spectra are then combined.
 //
 // Numerics vs the reference (tolerances: 1e-9 of peak on spectra, 1e-10 relative on intDOS):
@@ -45,11 +45,11 @@
 namespace {
 
 constexpr int NR_T = 512;        // bins per warp tile
-constexpr int NR_WMAX = 256;     // widest window (bins) the narrow engine takes
+constexpr int NR_WMAX = 448;     // widest window (bins) the narrow engine takes (Wc + 1 <= NR_T - cell)
 constexpr int NR_CHUNK = 512;   // records per work item
 constexpr int NR_WARPS = 8;      // warps per CTA
-constexpr int NR_NCLS = 8;       // width classes
-constexpr int NR_MAXBUCKETS = 51200;  // x 4 B = 200 KB of shared memory in the prepare passes
+constexpr int NR_NCLS = 10;      // width classes
+constexpr int NR_MAXBUCKETS = 52224;  // x 4 B = 204 KB of shared memory in the prepare passes
 constexpr int NR_PREP_THREADS = 1024;
 constexpr unsigned KEY_WIDE = 0xFFFFFFFEu, KEY_DROP = 0xFFFFFFFFu;
 
@@ -86,7 +86,7 @@ struct Cls {
 #define NR_ERFWIN (OD_ERF_CUT * OD_SQRT_TWO)  // 8.2024...: |z| beyond which the NSWC erf saturates
 
 __device__ __forceinline__ int width_class(int wlen) {
-  return (wlen > 24) + (wlen > 32) + (wlen > 44) + (wlen > 60) + (wlen > 84) + (wlen > 116) + (wlen > 160);
+  return (wlen > 24) + (wlen > 32) + (wlen > 44) + (wlen > 60) + (wlen > 84) + (wlen > 116) + (wlen > 160) + (wlen > 224) + (wlen > 320);
 }
 
 __device__ __forceinline__ Cls classify(const RecOut &r, const PrepSpec &ps) {
@@ -602,6 +602,177 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
   }
 }
 
+// ---------------------------------------------------------------- many-projector contraction (PDOS / core)
+// weighted_dos(bin, is, o) += sum_records K(bin; record) * matrix_weights(o, record)  is a banded GEMM: for a
+// tile of 64 bins only the records whose window reaches the tile contribute, and in the sorted record array
+// those are 8 contiguous ranges (one per width class).  One CTA = one work item (bin tile, orbital tile, record
+// segment): K-chunks of 32 records are expanded into a dense G[32][64] tile in shared memory (Gaussian by the
+// same two-multiply recurrence along bins, linear by the branch-free doslin pieces), their weight rows are
+// gathered (coalesced, 8 * BN bytes per record) into W[32][BN], and every thread keeps a register tile of
+// (64 * BN / 256) accumulators: 4 shared-memory loads feed 16 DFMAs.  FP64 DMMA tensor cores are not used: on
+// B200 their peak equals the DFMA peak this loop already runs on.
+constexpr int PG_BM = 64, PG_KC = 32, PG_SEG = 2048;
+
+
+struct PgItem {
+  int is, b0, otile;
+  unsigned rec0, rec1;
+};
+
+struct PgArgs {
+  const void *recs;
+  const unsigned *runit;
+  const PgItem *items;
+  int nitems;
+  unsigned long long *next_item;
+  GridSpec grid;
+  int bpad, ns;
+  const double *mw;
+  int norb, mw_nb, mw_nk, nb;
+  long long k_first;
+  double *wdos;  // weighted_dos(nbins, ns, norb)
+};
+
+template <int BN, bool LINEAR>
+__global__ void __launch_bounds__(256, 2) pdos_gemm_kernel(PgArgs A) {
+  constexpr int TX = BN / 4, TY = 256 / TX, BPT = PG_BM / TY;
+  __shared__ __align__(16) double sG[PG_BM][PG_KC];  // bin-major: the fill below and the FMA loop are both conflict-free
+  __shared__ __align__(16) double sW[PG_KC][BN];
+  __shared__ double sP[PG_KC][12];
+  __shared__ int sI[PG_KC][2];
+  __shared__ long long sRow[PG_KC];
+  __shared__ int s_item;
+  const int t = threadIdx.x, tx = t % TX, ty = t / TX;
+  const double delta = A.grid.delta, emin = A.grid.emin;
+  for (;;) {
+    if (t == 0) s_item = (int)atomicAdd(A.next_item, 1ull);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= A.nitems) break;
+    const PgItem item = A.items[it];
+    double acc[BPT][4];
+#pragma unroll
+    for (int i = 0; i < BPT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const int b0 = item.b0, is = item.is, obase = item.otile * BN;
+    for (unsigned r0 = item.rec0; r0 < item.rec1; r0 += PG_KC) {
+      __syncthreads();  // previous chunk consumed
+      if (t < PG_KC) {
+        const unsigned idx = r0 + t;
+        int klo = 0, wlen = 0;
+        long long row = -1;
+        double P[12] = {0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (idx < item.rec1) {
+          double e0, p1, p2 = 0, p3 = 0, p4 = 0, om;
+          if (LINEAR) {
+            const LRec r = reinterpret_cast<const LRec *>(A.recs)[idx];
+            e0 = r.e0; p1 = r.e1; p2 = r.e2; p3 = r.e3; p4 = r.e4; om = r.om; klo = r.klo - is * A.bpad; wlen = r.wlen;
+            const double aa = p3 - p4, bb = p2 - p4, cc = p1 - p4, dd = e0 - p4;
+            const double full = (cc - aa) * cc + aa * aa / 3.0 - (cc - bb) * (cc - bb) / 3.0;
+            P[0] = p4;                                   // e4
+            P[1] = 2.0 * dd;                             // mirror: x = two_d - xl above e0
+            P[2] = aa; P[3] = bb; P[4] = cc;
+            P[5] = 0.5 * (cc + bb - aa);                 // hh
+            P[6] = aa > 0.0 ? 0.5 / aa : 0.0;            // inv2a
+            P[7] = cc > bb ? 0.5 / (cc - bb) : 0.0;      // inv2cb
+            P[8] = om / (full + (cc + bb - aa) * (dd - cc));  // alpha * omega
+            P[9] = (double)(klo + r.cpos);               // first bin above e0
+          } else {
+            const GRec r = reinterpret_cast<const GRec *>(A.recs)[idx];
+            e0 = r.e; p1 = r.w; om = r.om; klo = r.klo - is * A.bpad; wlen = r.wlen;
+            const double invw = 1.0 / p1;
+            P[0] = e0; P[1] = invw; P[2] = om * invw * OD_INV_SQRT_TWO_PI; P[3] = delta * invw;
+          }
+          const unsigned u = A.runit[idx];
+          const unsigned ikl = u / (unsigned)A.nb, ib = u - ikl * (unsigned)A.nb;
+          const long long ik = A.k_first + ikl;
+          if (ik < A.mw_nk && (int)ib < A.mw_nb) row = (long long)A.norb * (ib + (long long)A.mw_nb * (ik + (long long)A.mw_nk * is));
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sP[t][i] = P[i];
+        sI[t][0] = klo; sI[t][1] = wlen;
+        sRow[t] = row;
+      }
+      __syncthreads();
+      {  // ---- G[k][bin]: thread -> record k, run of 8 bins
+        const int k = t & (PG_KC - 1), run = t >> 5;
+        const int klo = sI[k][0], wlen = sI[k][1];
+        const int j0 = b0 + run * 8;  // first grid bin of my run
+        const int lo = max(j0, klo), hi = min(j0 + 7, klo + wlen - 1);
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.0;
+        if (lo <= hi) {
+          if (!LINEAR) {
+            const double e0 = sP[k][0], invw = sP[k][1], amp = sP[k][2], del = sP[k][3];
+            const double z = (emin + (double)lo * delta - e0) * invw;
+            double g = amp * exp(-0.5 * z * z), rr = exp(-fma(z, del, 0.5 * del * del));
+            const double q = exp(-del * del);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = j0 + i;
+              if (j >= lo && j <= hi) { v[i] = g; g *= rr; rr *= q; }
+            }
+          } else {
+            const double e4 = sP[k][0], two_d = sP[k][1], aa = sP[k][2], bb = sP[k][3], cc = sP[k][4], hh = sP[k][5];
+            const double inv2a = sP[k][6], inv2cb = sP[k][7], sc = sP[k][8];
+            const int jc = (int)sP[k][9];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = j0 + i;
+              if (j >= lo && j <= hi) {
+                const double xl = emin + (double)j * delta - e4;
+                double x = (j >= jc) ? two_d - xl : xl;
+                x = fmax(x, 0.0);
+                const double y = cc - x;
+                const double D = x < aa ? x * x * inv2a : (x < bb ? x - 0.5 * aa : (x < cc ? hh - y * y * inv2cb : hh));
+                v[i] = D * sc;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sG[run * 8 + i][k] = v[i];
+      }
+      {  // ---- W[k][o]: coalesced gather of the weight rows
+        constexpr int EPT = PG_KC * BN / 256;  // elements per thread; consecutive threads -> consecutive orbitals
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          const int e = i * 256 + t, k = e / BN, oo = e % BN;
+          const long long row = sRow[k];
+          const int o = obase + oo;
+          sW[k][oo] = (row >= 0 && o < A.norb) ? A.mw[row + o] : 0.0;
+        }
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < PG_KC; ++k) {
+        double g[BPT], w[4];
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) g[i] = sG[ty * BPT + i][k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = sW[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < BPT; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(g[i], w[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+      const int bin = b0 + ty * BPT + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = obase + tx * 4 + j;
+        if (bin < A.grid.nbins && o < A.norb && acc[i][j] != 0.0)
+          atomicAdd(&A.wdos[(size_t)bin + (size_t)A.grid.nbins * (is + (size_t)A.ns * o)], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // dense-engine producer over the compacted list of wide units
 template <class Inner>
 struct WideListProducer {
@@ -838,7 +1009,47 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, nbins, S.ps.bpad, accum, accum + n1);
   OD_LAUNCH_CHECK(ctx);
   int wpasses = 0;
-  if (h_nrec > 0 && norb > 0) {
+  if (h_nrec > 0 && norb >= 8) {
+    // many projectors: banded GEMM over (bin tile, orbital tile, record segment) work items
+    const PrepSpec &ps = S.ps;
+    std::vector<unsigned> hbase((size_t)ps.nbuckets + 1);
+    OD_CUDA(ctx, cudaMemcpyAsync(hbase.data(), S.base, sizeof(unsigned) * hbase.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    static const int wmax[NR_NCLS] = {24, 32, 44, 60, 84, 116, 160, 224, 320, 448};
+    const int BN = norb > 32 ? 64 : (norb > 16 ? 32 : 16);
+    const int otiles = (norb + BN - 1) / BN;
+    std::vector<PgItem> items;
+    for (int is = 0; is < ns; ++is)
+      for (int b0 = 0; b0 < nbins; b0 += PG_BM)
+        for (int c = 0; c < NR_NCLS; ++c) {
+          const int g0 = is * ps.bpad + b0;
+          const int glo = std::max(is * ps.bpad, g0 - wmax[c] + 1), ghi = std::min(is * ps.bpad + nbins - 1, g0 + PG_BM - 1);
+          const unsigned r0 = hbase[(size_t)c * ps.ncells + glo / ps.cell], r1 = hbase[(size_t)c * ps.ncells + ghi / ps.cell + 1];
+          for (unsigned r = r0; r < r1; r += PG_SEG)
+            for (int ot = 0; ot < otiles; ++ot) items.push_back(PgItem{is, b0, ot, r, std::min(r1, r + (unsigned)PG_SEG)});
+        }
+    if (!items.empty()) {
+      OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(PgItem) * items.size() + 64));
+      OD_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_d.p, items.data(), sizeof(PgItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+      OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
+      PgArgs A;
+      A.recs = ctx->recs.p; A.runit = ctx->scratch_e.as<unsigned>(); A.items = ctx->scratch_d.as<PgItem>(); A.nitems = (int)items.size();
+      A.next_item = S.wide + 4; A.grid = grid; A.bpad = ps.bpad; A.ns = ns;
+      A.mw = prod_in.mw; A.norb = norb; A.mw_nb = prod_in.mw_nb; A.mw_nk = prod_in.mw_nk; A.nb = prod_in.nb; A.k_first = prod_in.k_first;
+      A.wdos = accum + 2 * n1;
+      const int blocks = (int)std::min<size_t>(items.size(), (size_t)ctx->sm_count * 2);
+#define PG_LAUNCH(BNV)                                                                         \
+  do {                                                                                         \
+    if (linear) pdos_gemm_kernel<BNV, true><<<blocks, 256, 0, ctx->stream>>>(A);                \
+    else pdos_gemm_kernel<BNV, false><<<blocks, 256, 0, ctx->stream>>>(A);                      \
+  } while (0)
+      if (BN == 64) PG_LAUNCH(64); else if (BN == 32) PG_LAUNCH(32); else PG_LAUNCH(16);
+#undef PG_LAUNCH
+      OD_LAUNCH_CHECK(ctx);
+      OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // items is a host vector
+      wpasses = 1;
+    }
+  } else if (h_nrec > 0 && norb > 0) {
     // weighted spectrum: columns (2c, 2c+1) per pass, K * matrix_weights(o, ib, ik, is) (dos_utils.f90:1271)
     MwGather gth;
     gth.mw = prod_in.mw; gth.norb = norb; gth.mw_nb = prod_in.mw_nb; gth.mw_nk = prod_in.mw_nk; gth.nb = prod_in.nb;

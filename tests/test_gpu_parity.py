@@ -357,8 +357,9 @@ def test_narrow_jdos_and_optics_vs_oracle(ob, odo, jtype):
     ctx.close()
 
 
+@pytest.mark.parametrize("norb", [5, 9, 19, 40])
 @pytest.mark.parametrize("dos_type", ["a", "l"])
-def test_narrow_weighted_dos_vs_oracle(ob, odo, dos_type):
+def test_narrow_weighted_dos_vs_oracle(ob, odo, dos_type, norb):
     """PDOS / core-style weighted DOS through the narrow engine: the sorted records are walked once per pair
     of weight columns, weights gathered from matrix_weights by unit index (odd column count, fewer weighted
     bands than bands)."""
@@ -370,7 +371,8 @@ def test_narrow_weighted_dos_vs_oracle(ob, odo, dos_type):
     s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
     E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=5000)
     rng = np.random.default_rng(9)
-    mw = np.asfortranarray(rng.random((5, nb - 2, nk, ns)))
+    # norb < 8: channel passes of the narrow kernel; >= 8: the banded-GEMM kernel (orbital tiles of 16 / 32 / 64)
+    mw = np.asfortranarray(rng.random((norb, nb - 2, nk, ns)))
     ref = odo.calculate_dos(dos_type, s, odo.make_broadening(), E, delta, mw, nthreads=8)
     for eng in ("auto", "dense"):
         ctx.set_engine(eng)
