@@ -533,63 +533,80 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
           __syncwarp();
         }
       } else {
-        // doslin (dos_utils.f90:1391-1528) in x = e_use - e4, with aa = e3-e4 <= bb = e2-e4 <= cc = e1-e4 <= dd = e0-e4
+        // doslin (dos_utils.f90:1391-1528) in x = e_use - e4 = dd - |E_j - e0| (the mirror of :1469), with
+        // aa = e3-e4 <= bb = e2-e4 <= cc = e1-e4 <= dd = e0-e4.  The five branches collapse into two smooth
+        // forms with clamped arguments (p = max(aa - x, 0), y = max(cc - x, 0)):
+        //   x <  bb:  D = x - aa/2 + p^2/(2 aa),          I = x^2/2 - aa x/2 + aa^2/6 - p^3/(6 aa)
+        //   x >= bb:  D = hh - y^2/(2 (cc-bb)),           I = hh x + k30 + y^3/(6 (cc-bb))
+        // (pieces 1|2 and 3|4 of the reference; identical polynomials, continuity at aa / cc used once).
         const double aa = p3 - p4, bb = p2 - p4, cc = p1 - p4, dd = e0 - p4;
-        const double hh = 0.5 * (cc + bb - aa);
+        const double hh = 0.5 * (cc + bb - aa), haa = 0.5 * aa;
         const double full = (cc - aa) * cc + aa * aa / 3.0 - (cc - bb) * (cc - bb) / 3.0;
         const double sc = valid ? om / (full + (cc + bb - aa) * (dd - cc)) : 0.0;  // alpha * omega
         const double inv2a = aa > 0.0 ? 0.5 / aa : 0.0, inv2cb = cc > bb ? 0.5 / (cc - bb) : 0.0;
+        const double i6a = inv2a * (1.0 / 3.0), i6cb = inv2cb * (1.0 / 3.0);
         const double a2_6 = aa * aa / 6.0;
         const double k30 = 0.5 * (aa * aa / 3.0 - cc * bb) - (cc - bb) * (cc - bb) / 6.0;
-        const double k40 = 0.5 * full - hh * cc;
-        const double two_d = 2.0 * dd;
-        const double xB = E0 - p4;
-        const long long ia = __double_as_longlong(aa), ib = __double_as_longlong(bb), ic = __double_as_longlong(cc);
-        auto lin_step = [&](int r, double xl) {
-          const bool above = r >= cabs;               // E_j > e0: mirror (dos_utils.f90:1469)
-          double x = above ? two_d - xl : xl;         // e_use - e4
-          x = __hiloint2double(max(__double2hiint(x), 0), __double2loint(x));  // bins outside (e4, 2 e0 - e4): x -> +0
-          const long long ix = __double_as_longlong(x);
-          const double x2 = x * x;
-          const double D1 = x2 * inv2a, I1 = D1 * x * (1.0 / 3.0);
-          const double D2 = x - 0.5 * aa, I2 = fma(0.5 * x, x - aa, a2_6);
-          const double y = cc - x, Y = y * y * inv2cb;
-          const double D3 = hh - Y, I3 = fma(Y * y, 1.0 / 3.0, fma(hh, x, k30));
-          const double I4 = fma(hh, x, k40);
-          const bool s1 = ix < ia, s2 = ix < ib, s3 = ix < ic;
-          const double D = s1 ? D1 : (s2 ? D2 : (s3 ? D3 : hh));
-          const double I = s1 ? I1 : (s2 ? I2 : (s3 ? I3 : I4));
-          double2 acc = tw[r];
-          if (JD) {
-            acc.x = fma(D, sc * m0, acc.x);
-            acc.y = fma(D, sc * m1, acc.y);
-          } else {
-            acc.x = fma(D, sc, acc.x);
-            acc.y = fma(I, flip_sign_if(sc, above), acc.y);
-          }
-          tw[r] = acc;
+        const double tB = E0 - e0;  // E_j - e0 at relative bin 0
+        const double scm0 = sc * m0, scm1 = sc * m1;
+        auto clamp0 = [](double v) {  // max(v, +0) on the sign / exponent word: negative -> < 2^-1022
+          return __hiloint2double(max(__double2hiint(v), 0), __double2loint(v));
         };
-        double xl1 = xB + (double)lane * delta;
+        auto lin_eval = [&](double t, double &D, double &I) {
+          const double x = clamp0(dd - fabs(t));  // bins outside (e4, 2 e0 - e4): x -> +0, D = I = 0
+          const double p = clamp0(aa - x), y = clamp0(cc - x);
+          const double pp = p * p, yy = y * y;
+          const double Dlo = fma(pp, inv2a, x - haa), Dhi = fma(-yy, inv2cb, hh);
+          const bool lo = x < bb;
+          D = lo ? Dlo : Dhi;
+          if (!JD) {
+            const double Ilo = fma(-(pp * p), i6a, fma(x, fma(x, 0.5, -haa), a2_6));
+            const double Ihi = fma(yy * y, i6cb, fma(hh, x, k30));
+            I = lo ? Ilo : Ihi;
+          }
+        };
+        double t1 = tB + (double)lane * delta;
         int r1 = lane;
         if (dual) {
-          double xl2 = xB + (double)(lane + H) * delta;
+          double t2 = tB + (double)(lane + H) * delta;
           int r2 = lane + H;
 #pragma unroll 1
           for (int t = 0; t < n2; ++t) {
-            lin_step(r1, xl1);
-            lin_step(r2, xl2);
-            xl1 += delta; ++r1;
-            xl2 += delta; ++r2;
-            if (r2 == Wc) { r2 = 0; xl2 = xB; }
+            double2 *q1 = tw + r1, *q2 = tw + r2;
+            double2 acc1 = *q1;
+            double2 acc2 = *q2;
+            double D1, I1 = 0, D2, I2 = 0;
+            lin_eval(t1, D1, I1);
+            lin_eval(t2, D2, I2);
+            if (JD) {
+              acc1.x = fma(D1, scm0, acc1.x); acc1.y = fma(D1, scm1, acc1.y);
+              acc2.x = fma(D2, scm0, acc2.x); acc2.y = fma(D2, scm1, acc2.y);
+            } else {
+              acc1.x = fma(D1, sc, acc1.x); acc1.y = fma(I1, flip_sign_if(sc, r1 >= cabs), acc1.y);
+              acc2.x = fma(D2, sc, acc2.x); acc2.y = fma(I2, flip_sign_if(sc, r2 >= cabs), acc2.y);
+            }
+            *q1 = acc1;
+            *q2 = acc2;
+            t1 += delta; ++r1;
+            t2 += delta; ++r2;
+            if (r2 == Wc) { r2 = 0; t2 = tB; }
             __syncwarp();
           }
         }
 #pragma unroll 1
         for (int t = n2; t < H; ++t) {
-          lin_step(r1, xl1);
-          xl1 += delta;
+          double2 acc = tw[r1];
+          double D, I = 0;
+          lin_eval(t1, D, I);
+          if (JD) {
+            acc.x = fma(D, scm0, acc.x); acc.y = fma(D, scm1, acc.y);
+          } else {
+            acc.x = fma(D, sc, acc.x); acc.y = fma(I, flip_sign_if(sc, r1 >= cabs), acc.y);
+          }
+          tw[r1] = acc;
+          t1 += delta;
           ++r1;
-          if (r1 == Wc) { r1 = 0; xl1 = xB; }
+          if (r1 == Wc) { r1 = 0; t1 = tB; }
           __syncwarp();
         }
       }
