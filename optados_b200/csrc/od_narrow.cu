@@ -44,8 +44,21 @@
 
 namespace {
 
-constexpr int NR_T = 512;        // bins per warp tile
-constexpr int NR_WMAX = 448;     // widest window (bins) the narrow engine takes (Wc + 1 <= NR_T - cell)
+#ifndef OD_X_UNROLL
+#define OD_X_UNROLL 1
+#endif
+#ifndef OD_X_ESTRIN
+#define OD_X_ESTRIN 0
+#endif
+#define OD_PRAGMA(x) _Pragma(#x)
+#define OD_UNROLL(n) OD_PRAGMA(unroll n)
+#ifndef OD_X_T
+#define OD_X_T 512
+#define OD_X_WMAX 448
+#define OD_X_MINB 2
+#endif
+constexpr int NR_T = OD_X_T;        // bins per warp tile
+constexpr int NR_WMAX = OD_X_WMAX;     // widest window (bins) the narrow engine takes (Wc + 1 <= NR_T - cell)
 constexpr int NR_CHUNK = 512;   // records per work item
 constexpr int NR_WARPS = 8;      // warps per CTA
 constexpr int NR_NCLS = 10;      // width classes
@@ -282,12 +295,31 @@ __device__ __forceinline__ double rcp_newton(double q) {
   return fma(y, e, y);  // ~2^-46 relative
 }
 
+// 1/x to ~1 ulp for normal x well inside the exponent range (per-record set-up: windows, widths, doslin
+// normalisation); an IEEE division costs ~25 instructions and a slow-path branch
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
 struct ErfcxCoef {
   double P[6], Q[6];
 };
 
 // cf points into the kernel parameter block, so the coefficients enter the FMAs as c[0x0][..] operands
 __device__ __forceinline__ double erfcx_ratio(double u, const ErfcxCoef &cf) {
+#if OD_X_ESTRIN
+  const double u2 = u * u, u4 = u2 * u2;
+  const double p01 = fma(cf.P[1], u, cf.P[0]), p23 = fma(cf.P[3], u, cf.P[2]), p45 = fma(cf.P[5], u, cf.P[4]);
+  const double q01 = fma(cf.Q[1], u, cf.Q[0]), q23 = fma(cf.Q[3], u, cf.Q[2]), q45 = fma(cf.Q[5], u, cf.Q[4]) + u2;
+  const double pe = fma(u4, p45, fma(u2, p23, p01));
+  const double qe = fma(u4, q45, fma(u2, q23, q01));
+  return pe * rcp_newton(qe);
+#endif
   double p = cf.P[5];
   p = fma(p, u, cf.P[4]);
   p = fma(p, u, cf.P[3]);
@@ -354,7 +386,7 @@ __device__ __forceinline__ void gauss_direct(double e, double w, double om, doub
 }
 
 template <bool LINEAR, bool JD>
-__global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) {
+__global__ void __launch_bounds__(NR_WARPS * 32, OD_X_MINB) narrow_kernel(NarrowArgs A) {
   extern __shared__ double2 sh_tiles[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2 *tile = sh_tiles + (size_t)warp * NR_T;
@@ -377,7 +409,17 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
     for (long long g0 = c0; g0 < c1; g0 += 32) {
       const long long idx = g0 + lane;
       const bool valid = idx < c1;
-      // ---- my record
+      // ---- my record (and a prefetch of the one this lane takes in the next group)
+#ifndef OD_X_GDIV
+#define OD_X_GDIV 1
+#endif
+#ifndef OD_X_NOPF
+#define OD_X_NOPF 0
+#endif
+      if (!OD_X_NOPF && idx + 32 < c1) {
+        const char *nx = reinterpret_cast<const char *>(A.recs) + (size_t)(idx + 32) * (LINEAR ? sizeof(LRec) : sizeof(GRec));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+      }
       double e0 = 0, p1 = 1, p2 = 0, p3 = 0, p4 = 0, om = 0;
       int klo = 0x3fffffff, wlen = 0, cpos = 0;
       if (valid) {
@@ -474,7 +516,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
       const int H = dual ? (Wc + 1) >> 1 : Wc;
       const int n2 = dual ? Wc - H : 0;
       if (!LINEAR) {
-        const double invw = 1.0 / p1, del = delta * invw;
+        const double invw = OD_X_GDIV ? 1.0 / p1 : fast_rcp(p1), del = delta * invw;
         const double amp = om * invw * OD_INV_SQRT_TWO_PI;
         const double cl = p1 * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
         const double q = exp(-del * del), hd2 = 0.5 * del * del;
@@ -487,7 +529,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
           double z2 = zB + (double)(lane + H) * del;
           double g2 = amp * exp(-0.5 * z2 * z2), rr2 = exp(-fma(z2, del, hd2));
           int r2 = lane + H;
-#pragma unroll 1
+OD_UNROLL(OD_X_UNROLL)
           for (int t = 0; t < n2; ++t) {
             // capture this step's inputs, then advance the recurrences at once so that the next step's
             // operands are ready long before the rational chains below have drained
@@ -541,12 +583,14 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
         // (pieces 1|2 and 3|4 of the reference; identical polynomials, continuity at aa / cc used once).
         const double aa = p3 - p4, bb = p2 - p4, cc = p1 - p4, dd = e0 - p4;
         const double hh = 0.5 * (cc + bb - aa), haa = 0.5 * aa;
-        const double full = (cc - aa) * cc + aa * aa / 3.0 - (cc - bb) * (cc - bb) / 3.0;
-        const double sc = valid ? om / (full + (cc + bb - aa) * (dd - cc)) : 0.0;  // alpha * omega
-        const double inv2a = aa > 0.0 ? 0.5 / aa : 0.0, inv2cb = cc > bb ? 0.5 / (cc - bb) : 0.0;
-        const double i6a = inv2a * (1.0 / 3.0), i6cb = inv2cb * (1.0 / 3.0);
-        const double a2_6 = aa * aa / 6.0;
-        const double k30 = 0.5 * (aa * aa / 3.0 - cc * bb) - (cc - bb) * (cc - bb) / 6.0;
+        constexpr double third = 1.0 / 3.0, sixth = 1.0 / 6.0, tiny = 1e-280;
+        const double cb = cc - bb;
+        const double full = (cc - aa) * cc + (aa * aa - cb * cb) * third;
+        const double sc = valid ? om * fast_rcp(full + (cc + bb - aa) * (dd - cc)) : 0.0;  // alpha * omega
+        const double inv2a = aa > tiny ? 0.5 * fast_rcp(aa) : 0.0, inv2cb = cb > tiny ? 0.5 * fast_rcp(cb) : 0.0;
+        const double i6a = inv2a * third, i6cb = inv2cb * third;
+        const double a2_6 = aa * aa * sixth;
+        const double k30 = 0.5 * (aa * aa * third - cc * bb) - cb * cb * sixth;
         const double tB = E0 - e0;  // E_j - e0 at relative bin 0
         const double scm0 = sc * m0, scm1 = sc * m1;
         auto clamp0 = [](double v) {  // max(v, +0) on the sign / exponent word: negative -> < 2^-1022
@@ -570,7 +614,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, 2) narrow_kernel(NarrowArgs A) 
         if (dual) {
           double t2 = tB + (double)(lane + H) * delta;
           int r2 = lane + H;
-#pragma unroll 1
+OD_UNROLL(OD_X_UNROLL)
           for (int t = 0; t < n2; ++t) {
             double2 *q1 = tw + r1, *q2 = tw + r2;
             double2 acc1 = *q1;
@@ -925,7 +969,7 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
   OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
   const size_t smem = (sizeof(double2) + sizeof(double)) * NR_T * NR_WARPS;
   const long long nchunks = ((long long)nrec + NR_CHUNK - 1) / NR_CHUNK;
-  const int blocks = (int)std::min<long long>((long long)ctx->sm_count * 2, (nchunks + NR_WARPS - 1) / NR_WARPS);
+  const int blocks = (int)std::min<long long>((long long)ctx->sm_count * OD_X_MINB, (nchunks + NR_WARPS - 1) / NR_WARPS);
   if (linear) {
     OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<true, JD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     narrow_kernel<true, JD><<<blocks, NR_WARPS * 32, smem, ctx->stream>>>(A);
