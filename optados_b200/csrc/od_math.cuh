@@ -126,6 +126,28 @@ __device__ __forceinline__ void od_cswap_desc(double &a, double &b) {
 // The eight DE values are formed exactly as the reference does (matmul then dot_product), sorted
 // descending (any correct sort yields the same multiset -> the same four lowest values), and
 // EV(1..4) = E + DE(5..8).
+// The same four lowest corners in closed form (narrow engine only; the dense engine keeps the corner-by-corner
+// restatement above).  A corner offset is sum_i sigma_i a_i with a_i = step_i * (grad . recip_lattice(:, i)), so with
+// the magnitudes sorted A >= B >= C the eight values are +-A +-B +-C and the four lowest are -A-B-C, -A-B+C, -A+B-C
+// and min(-A+B+C, A-B-C): 3 dot products and 3 compare-exchanges instead of 8 mat-vecs and a 19-comparator
+// network.  Differs from the reference arithmetic by rounding only (~1e-16 of |a|).
+__device__ __forceinline__ void od_sub_cell_corners_fast(const double grad[3], const double step[3], const double *rs,
+                                                         double energy, double EV[5]) {
+  double A = fabs(step[0] * (grad[0] * rs[0] + grad[1] * rs[1] + grad[2] * rs[2]));
+  double B = fabs(step[1] * (grad[0] * rs[3] + grad[1] * rs[4] + grad[2] * rs[5]));
+  double C = fabs(step[2] * (grad[0] * rs[6] + grad[1] * rs[7] + grad[2] * rs[8]));
+  double t;
+  if (A < B) { t = A; A = B; B = t; }
+  if (B < C) { t = B; B = C; C = t; }
+  if (A < B) { t = A; A = B; B = t; }
+  const double ab = A + B, amb = A - B;
+  EV[0] = energy;
+  EV[1] = energy + fmin(C - amb, amb - C);
+  EV[2] = energy - (amb + C);
+  EV[3] = energy - (ab - C);
+  EV[4] = energy - (ab + C);
+}
+
 __device__ __forceinline__ void od_sub_cell_corners(const double grad[3], const double step[3], const double *rs,
                                                     double energy, double EV[5]) {
   double DE[8];

@@ -189,42 +189,59 @@ prep_hist_kernel(Producer prod, PrepSpec ps, unsigned *__restrict__ keys, unsign
 }
 
 // column scan: table[c][b] <- sum_{c' < c} table[c'][b];  colsum[b] <- sum_c table[c][b]
+// (16 independent loads in flight per thread: the column is short, the round trips are what costs)
 __global__ void __launch_bounds__(256) prep_colscan_kernel(unsigned *__restrict__ table, int nrows, int nbuckets,
                                                           unsigned *__restrict__ colsum) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
   unsigned run = 0;
-  for (int c = 0; c < nrows; ++c) {
-    const unsigned v = table[(size_t)c * nbuckets + b];
-    table[(size_t)c * nbuckets + b] = run;
-    run += v;
+  for (int c0 = 0; c0 < nrows; c0 += 16) {
+    unsigned v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (c0 + i < nrows) ? table[(size_t)(c0 + i) * nbuckets + b] : 0u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (c0 + i < nrows) {
+        table[(size_t)(c0 + i) * nbuckets + b] = run;
+        run += v[i];
+      }
   }
   colsum[b] = run;
 }
 
-// exclusive scan of the bucket totals (single CTA); base[nbuckets] = number of narrow records
+// exclusive scan of the bucket totals (single CTA, one contiguous segment per thread); base[n] = number of
+// narrow records
 __global__ void __launch_bounds__(1024) scan_kernel(const unsigned *__restrict__ hist, int n, unsigned *__restrict__ base) {
-  __shared__ unsigned long long sh[1024];
-  __shared__ unsigned long long carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int b0 = 0; b0 < n; b0 += 1024) {
-    const int i = b0 + threadIdx.x;
-    const unsigned long long v = (i < n) ? hist[i] : 0ull;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      unsigned long long t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0ull;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (i < n) base[i] = (unsigned)(carry + sh[threadIdx.x] - v);
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
-    __syncthreads();
+  __shared__ unsigned warp_tot[32];
+  const int seg = (n + 1023) / 1024;
+  const int i0 = min(threadIdx.x * seg, n), i1 = min(i0 + seg, n);
+  unsigned sum = 0;
+  for (int i = i0; i < i1; ++i) sum += hist[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
-  if (threadIdx.x == 0) base[n] = (unsigned)carry;
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned w = warp_tot[lane];
+    unsigned wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;  // exclusive
+    if (lane == 31) base[n] = wi;
+  }
+  __syncthreads();
+  unsigned run = warp_tot[warp] + incl - sum;
+  for (int i = i0; i < i1; ++i) {
+    const unsigned v = hist[i];
+    base[i] = run;
+    run += v;
+  }
 }
 
 // ---------------------------------------------------------------- pass B: scatter (shared-memory cursors)
@@ -898,8 +915,10 @@ struct Scratch {
 };
 
 template <class Producer>
-int narrow_prepare(od_ctx *ctx, const Producer &prod, Scratch &S, bool linear, unsigned *h_nrec, unsigned long long h_wide[2],
+int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear, unsigned *h_nrec, unsigned long long h_wide[2],
                    long long *wide_stride) {
+  Producer prod = prod_in;
+  prod.b.fast_corners = 1;  // both passes; wide units are re-made by the dense engine with the reference's arithmetic
   const PrepSpec &ps = S.ps;
   const int prows = ctx->sm_count;  // one prepare CTA per SM; pass A and pass B MUST use the same grid
   const size_t hist_smem = sizeof(unsigned) * ps.nbuckets;

@@ -13,6 +13,7 @@ struct BroadSpec {
   double hybrid_tol;
   double step[3];
   double rs[9];  // recip_lattice, column-major
+  int fast_corners;  // narrow engine: closed-form sub-cell corners (od_sub_cell_corners_fast)
 };
 
 // width / corners of one unit from its centre energy and gradient
@@ -28,7 +29,8 @@ __device__ __forceinline__ void od_make_record(const BroadSpec &b, double centre
   if (b.type == 2 && b.honor_hybrid && b.hybrid && (b.hybrid_tol > gnorm)) force_adaptive = true;
   if (b.type == 2 && !force_adaptive) {
     double EV[5];
-    od_sub_cell_corners(grad, b.step, b.rs, centre, EV);                             // dos_utils.f90:1240
+    if (b.fast_corners) od_sub_cell_corners_fast(grad, b.step, b.rs, centre, EV);
+    else od_sub_cell_corners(grad, b.step, b.rs, centre, EV);                        // dos_utils.f90:1240
     r.mode = 1;
     r.p1 = EV[1]; r.p2 = EV[2]; r.p3 = EV[3]; r.p4 = EV[4];
     return;

@@ -25,6 +25,7 @@ int od_make_broadspec(od_ctx *ctx, char type, const od_broadening *br, double de
   b.honor_hybrid = honor_hybrid ? 1 : 0;
   b.hybrid = br->hybrid_linear ? 1 : 0;
   b.hybrid_tol = br->hybrid_linear_grad_tol;
+  b.fast_corners = 0;
   for (int i = 0; i < 3; ++i) b.step[i] = g.step[i];
   for (int i = 0; i < 9; ++i) b.rs[i] = g.recip[i];
   *out = b;
