@@ -711,143 +711,208 @@ struct PgArgs {
   double *wdos;  // weighted_dos(nbins, ns, norb)
 };
 
+// Shared-memory plan of one CTA (dynamic, two stages): G[2][BM][KS] (bin-major, KS = KC + 4), W[2][KC][BN + 4],
+// P[2][KC][12], row[2][KC], win[2][KC][2].  The +4 paddings make every fragment load below conflict-free.
+constexpr int PG_KS = PG_KC + 4;
+template <int BN>
+constexpr size_t pg_smem_bytes() {
+  return sizeof(double) * (2 * PG_BM * PG_KS + 2 * PG_KC * (BN + 4) + 2 * PG_KC * 12) + sizeof(long long) * 2 * PG_KC +
+         sizeof(int) * 4 * PG_KC;
+}
+
+// D(16x8) += A(16x8) B(8x8) in FP64 on the tensor cores.  Fragments (g = lane / 4, t = lane % 4):
+//   a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];  b0 = B[t][g], b1 = B[t+4][g];
+//   c0 = C[g][2t], c1 = C[g][2t+1], c2 = C[g+8][2t], c3 = C[g+8][2t+1]
+__device__ __forceinline__ void dmma_16x8x8(double (&c)[4], double a0, double a1, double a2, double a3, double b0, double b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+               : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+}
+
+// The contraction runs on the FP64 tensor cores (DMMA m16n8k8): with a 4x4 register tile per thread the CUDA-core
+// version of this loop was bound by shared-memory wavefronts (ncu: 90 % of the LSU wavefront peak at 35 % FP64-pipe
+// utilisation, profiles/), a DMMA needs 12 operand loads for 128 FMAs per thread instead of 64.  Measured DMMA peak
+// on B200: 37.1 TFLOP/s (the same pipe as DFMA).
+// The chunk loop is software-pipelined over three chunks with one barrier per chunk:
+//   chunk c+2: its 32 records (+ unit indices) are loaded by warp 0 before the MMA loop and turned into
+//              parameters after it;
+//   chunk c+1: weight rows are loaded (coalesced) into registers before the MMA loop and parked in shared memory
+//              after it; its G tile is expanded before the MMA loop;
+//   chunk c  : 4 k-steps of NB DMMAs per warp (warp tile 16 bins x 8 NB orbitals).
 template <int BN, bool LINEAR>
 __global__ void __launch_bounds__(256, 2) pdos_gemm_kernel(PgArgs A) {
-  constexpr int TX = BN / 4, TY = 256 / TX, BPT = PG_BM / TY;
-  __shared__ __align__(16) double sG[PG_BM][PG_KC];  // bin-major: the fill below and the FMA loop are both conflict-free
-  __shared__ __align__(16) double sW[PG_KC][BN];
-  __shared__ double sP[PG_KC][12];
-  __shared__ int sI[PG_KC][2];
-  __shared__ long long sRow[PG_KC];
+  constexpr int WS = BN + 4;             // row stride of the W tile
+  constexpr int NB = BN / 16;            // 8-orbital blocks per warp (8 warps = 4 bin blocks x 2 orbital halves)
+  constexpr int EPT = PG_KC * BN / 256;  // weight elements per thread and chunk
+  extern __shared__ __align__(16) unsigned char pg_smem[];
+  double *sG = reinterpret_cast<double *>(pg_smem);            // [2][BM][KS]
+  double *sW = sG + 2 * PG_BM * PG_KS;                         // [2][KC][WS]
+  double *sP = sW + 2 * PG_KC * WS;                            // [2][KC][12]
+  long long *sRow = reinterpret_cast<long long *>(sP + 2 * PG_KC * 12);  // [2][KC]
+  int *sI = reinterpret_cast<int *>(sRow + 2 * PG_KC);         // [2][KC][2]
   __shared__ int s_item;
-  const int t = threadIdx.x, tx = t % TX, ty = t / TX;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int fg = lane >> 2, ft = lane & 3;      // fragment coordinates
+  const int wm = warp >> 1, wn = warp & 1;      // warp tile: bins wm*16 .. +15, orbitals wn*8*NB .. +8*NB-1
   const double delta = A.grid.delta, emin = A.grid.emin;
+
+  struct RecRegs {
+    double e0, p1, p2, p3, p4, om;
+    int klo, wlen;
+    unsigned unit;
+    bool ok;
+  };
+
   for (;;) {
+    __syncthreads();
     if (t == 0) s_item = (int)atomicAdd(A.next_item, 1ull);
     __syncthreads();
     const int it = s_item;
     if (it >= A.nitems) break;
     const PgItem item = A.items[it];
-    double acc[BPT][4];
+    const int b0 = item.b0, is = item.is, obase = item.otile * BN;
+    const int nch = (int)((item.rec1 - item.rec0 + PG_KC - 1) / PG_KC);
+
+    auto load_rec = [&](int c, RecRegs &R) {  // warp 0: record `lane` of chunk c
+      const unsigned idx = item.rec0 + (unsigned)c * PG_KC + lane;
+      R.ok = c < nch && idx < item.rec1;
+      if (!R.ok) return;
+      if (LINEAR) {
+        const LRec r = reinterpret_cast<const LRec *>(A.recs)[idx];
+        R.e0 = r.e0; R.p1 = r.e1; R.p2 = r.e2; R.p3 = r.e3; R.p4 = r.e4; R.om = r.om; R.klo = r.klo; R.wlen = r.wlen;
+      } else {
+        const GRec r = reinterpret_cast<const GRec *>(A.recs)[idx];
+        R.e0 = r.e; R.p1 = r.w; R.om = r.om; R.klo = r.klo; R.wlen = r.wlen;
+      }
+      R.unit = A.runit[idx];
+    };
+    auto store_params = [&](int buf, const RecRegs &R) {  // warp 0
+      double *P = sP + ((size_t)buf * PG_KC + lane) * 12;
+      int klo = 0, wlen = 0;
+      long long row = -1;
+      if (R.ok) {
+        klo = R.klo - is * A.bpad; wlen = R.wlen;
+        if (LINEAR) {
+          const double aa = R.p3 - R.p4, bb = R.p2 - R.p4, cc = R.p1 - R.p4, dd = R.e0 - R.p4, cb = cc - bb;
+          const double full = (cc - aa) * cc + (aa * aa - cb * cb) * (1.0 / 3.0);
+          P[0] = R.e0; P[1] = dd; P[2] = aa; P[3] = bb; P[4] = cc;
+          P[5] = 0.5 * (cc + bb - aa);                                  // hh
+          P[6] = aa > 1e-280 ? 0.5 * fast_rcp(aa) : 0.0;                // inv2a
+          P[7] = cb > 1e-280 ? 0.5 * fast_rcp(cb) : 0.0;                // inv2cb
+          P[8] = R.om * fast_rcp(full + (cc + bb - aa) * (dd - cc));    // alpha * omega
+        } else {
+          const double invw = fast_rcp(R.p1), del = delta * invw;
+          P[0] = R.e0; P[1] = invw; P[2] = R.om * invw * OD_INV_SQRT_TWO_PI; P[3] = del; P[4] = exp(-del * del);
+        }
+        const unsigned ikl = R.unit / (unsigned)A.nb, ib = R.unit - ikl * (unsigned)A.nb;
+        const long long ik = A.k_first + ikl;
+        if (ik < A.mw_nk && (int)ib < A.mw_nb) row = (long long)A.norb * (ib + (long long)A.mw_nb * (ik + (long long)A.mw_nk * is));
+      }
+      sI[(buf * PG_KC + lane) * 2] = klo; sI[(buf * PG_KC + lane) * 2 + 1] = wlen;
+      sRow[buf * PG_KC + lane] = row;
+    };
+    auto load_w = [&](int buf, double (&wr)[EPT]) {  // rows of the chunk whose parameters sit in `buf`
 #pragma unroll
-    for (int i = 0; i < BPT; ++i)
+      for (int i = 0; i < EPT; ++i) {
+        const int e = i * 256 + t, k = e / BN, oo = e % BN;
+        const long long row = sRow[buf * PG_KC + k];
+        const int o = obase + oo;
+        wr[i] = (row >= 0 && o < A.norb) ? A.mw[row + o] : 0.0;
+      }
+    };
+    auto store_w = [&](int buf, const double (&wr)[EPT]) {
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        const int e = i * 256 + t, k = e / BN, oo = e % BN;
+        sW[((size_t)buf * PG_KC + k) * WS + oo] = wr[i];
+      }
+    };
+    auto fill_g = [&](int buf) {  // thread -> record k = lane, run of 8 bins = warp
+      const int k = lane, run = warp;
+      const int klo = sI[(buf * PG_KC + k) * 2], wlen = sI[(buf * PG_KC + k) * 2 + 1];
+      const double *P = sP + ((size_t)buf * PG_KC + k) * 12;
+      const int j0 = b0 + run * 8;
+      const int lo = max(j0, klo), hi = min(j0 + 7, klo + wlen - 1);
+      double v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.0;
+      if (lo <= hi) {
+        if (!LINEAR) {
+          const double e0 = P[0], invw = P[1], amp = P[2], del = P[3], q = P[4];
+          const double z = (emin + (double)lo * delta - e0) * invw;
+          double g = amp * exp(-0.5 * z * z), rr = exp(-fma(z, del, 0.5 * del * del));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = j0 + i;
+            if (j >= lo && j <= hi) { v[i] = g; g *= rr; rr *= q; }
+          }
+        } else {
+          const double e0 = P[0], dd = P[1], aa = P[2], bb = P[3], cc = P[4], hh = P[5], inv2a = P[6], inv2cb = P[7], sc = P[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = j0 + i;
+            if (j >= lo && j <= hi) {
+              const double x = fmax(dd - fabs(emin + (double)j * delta - e0), 0.0);
+              const double pq = fmax(aa - x, 0.0), y = fmax(cc - x, 0.0);
+              const double D = x < bb ? fma(pq * pq, inv2a, x - 0.5 * aa) : fma(-y * y, inv2cb, hh);
+              v[i] = D * sc;
+            }
+          }
+        }
+      }
+      double *dst = sG + ((size_t)buf * PG_BM + run * 8) * PG_KS + k;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[i * PG_KS] = v[i];
+    };
+
+    double acc[NB][4];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    const int b0 = item.b0, is = item.is, obase = item.otile * BN;
-    for (unsigned r0 = item.rec0; r0 < item.rec1; r0 += PG_KC) {
-      __syncthreads();  // previous chunk consumed
-      if (t < PG_KC) {
-        const unsigned idx = r0 + t;
-        int klo = 0, wlen = 0;
-        long long row = -1;
-        double P[12] = {0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (idx < item.rec1) {
-          double e0, p1, p2 = 0, p3 = 0, p4 = 0, om;
-          if (LINEAR) {
-            const LRec r = reinterpret_cast<const LRec *>(A.recs)[idx];
-            e0 = r.e0; p1 = r.e1; p2 = r.e2; p3 = r.e3; p4 = r.e4; om = r.om; klo = r.klo - is * A.bpad; wlen = r.wlen;
-            const double aa = p3 - p4, bb = p2 - p4, cc = p1 - p4, dd = e0 - p4;
-            const double full = (cc - aa) * cc + aa * aa / 3.0 - (cc - bb) * (cc - bb) / 3.0;
-            P[0] = p4;                                   // e4
-            P[1] = 2.0 * dd;                             // mirror: x = two_d - xl above e0
-            P[2] = aa; P[3] = bb; P[4] = cc;
-            P[5] = 0.5 * (cc + bb - aa);                 // hh
-            P[6] = aa > 0.0 ? 0.5 / aa : 0.0;            // inv2a
-            P[7] = cc > bb ? 0.5 / (cc - bb) : 0.0;      // inv2cb
-            P[8] = om / (full + (cc + bb - aa) * (dd - cc));  // alpha * omega
-            P[9] = (double)(klo + r.cpos);               // first bin above e0
-          } else {
-            const GRec r = reinterpret_cast<const GRec *>(A.recs)[idx];
-            e0 = r.e; p1 = r.w; om = r.om; klo = r.klo - is * A.bpad; wlen = r.wlen;
-            const double invw = 1.0 / p1;
-            P[0] = e0; P[1] = invw; P[2] = om * invw * OD_INV_SQRT_TWO_PI; P[3] = delta * invw;
-          }
-          const unsigned u = A.runit[idx];
-          const unsigned ikl = u / (unsigned)A.nb, ib = u - ikl * (unsigned)A.nb;
-          const long long ik = A.k_first + ikl;
-          if (ik < A.mw_nk && (int)ib < A.mw_nb) row = (long long)A.norb * (ib + (long long)A.mw_nb * (ik + (long long)A.mw_nk * is));
-        }
+
+    // ---- prologue: parameters of chunks 0 and 1, G and W of chunk 0
+    RecRegs R;
+    R.ok = false;
+    double wr[EPT];
+    if (warp == 0) { load_rec(0, R); store_params(0, R); load_rec(1, R); }
+    __syncthreads();
+    load_w(0, wr);
+    fill_g(0);
+    store_w(0, wr);
+    if (warp == 0) store_params(1, R);
+    __syncthreads();
+
+    for (int c = 0; c < nch; ++c) {
+      const int cur = c & 1, nxt = cur ^ 1;
+      const bool more = c + 1 < nch;
+      if (more) load_w(nxt, wr);
+      if (warp == 0) load_rec(c + 2, R);
+      if (more) fill_g(nxt);
+      const double *gp = sG + ((size_t)cur * PG_BM + wm * 16 + fg) * PG_KS + ft;
+      const double *wp = sW + ((size_t)cur * PG_KC + ft) * WS + wn * 8 * NB + fg;
 #pragma unroll
-        for (int i = 0; i < 12; ++i) sP[t][i] = P[i];
-        sI[t][0] = klo; sI[t][1] = wlen;
-        sRow[t] = row;
+      for (int kk = 0; kk < PG_KC; kk += 8) {
+        const double a0 = gp[kk], a1 = gp[8 * PG_KS + kk], a2 = gp[kk + 4], a3 = gp[8 * PG_KS + kk + 4];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const double b0v = wp[(size_t)kk * WS + nb * 8], b1v = wp[(size_t)(kk + 4) * WS + nb * 8];
+          dmma_16x8x8(acc[nb], a0, a1, a2, a3, b0v, b1v);
+        }
       }
+      if (more) store_w(nxt, wr);
+      if (warp == 0 && c + 2 < nch) store_params(cur, R);  // cur's parameters were last read before the previous barrier
       __syncthreads();
-      {  // ---- G[k][bin]: thread -> record k, run of 8 bins
-        const int k = t & (PG_KC - 1), run = t >> 5;
-        const int klo = sI[k][0], wlen = sI[k][1];
-        const int j0 = b0 + run * 8;  // first grid bin of my run
-        const int lo = max(j0, klo), hi = min(j0 + 7, klo + wlen - 1);
-        double v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.0;
-        if (lo <= hi) {
-          if (!LINEAR) {
-            const double e0 = sP[k][0], invw = sP[k][1], amp = sP[k][2], del = sP[k][3];
-            const double z = (emin + (double)lo * delta - e0) * invw;
-            double g = amp * exp(-0.5 * z * z), rr = exp(-fma(z, del, 0.5 * del * del));
-            const double q = exp(-del * del);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = j0 + i;
-              if (j >= lo && j <= hi) { v[i] = g; g *= rr; rr *= q; }
-            }
-          } else {
-            const double e4 = sP[k][0], two_d = sP[k][1], aa = sP[k][2], bb = sP[k][3], cc = sP[k][4], hh = sP[k][5];
-            const double inv2a = sP[k][6], inv2cb = sP[k][7], sc = sP[k][8];
-            const int jc = (int)sP[k][9];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = j0 + i;
-              if (j >= lo && j <= hi) {
-                const double xl = emin + (double)j * delta - e4;
-                double x = (j >= jc) ? two_d - xl : xl;
-                x = fmax(x, 0.0);
-                const double y = cc - x;
-                const double D = x < aa ? x * x * inv2a : (x < bb ? x - 0.5 * aa : (x < cc ? hh - y * y * inv2cb : hh));
-                v[i] = D * sc;
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sG[run * 8 + i][k] = v[i];
-      }
-      {  // ---- W[k][o]: coalesced gather of the weight rows
-        constexpr int EPT = PG_KC * BN / 256;  // elements per thread; consecutive threads -> consecutive orbitals
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-          const int e = i * 256 + t, k = e / BN, oo = e % BN;
-          const long long row = sRow[k];
-          const int o = obase + oo;
-          sW[k][oo] = (row >= 0 && o < A.norb) ? A.mw[row + o] : 0.0;
-        }
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int k = 0; k < PG_KC; ++k) {
-        double g[BPT], w[4];
-#pragma unroll
-        for (int i = 0; i < BPT; ++i) g[i] = sG[ty * BPT + i][k];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = sW[k][tx * 4 + j];
-#pragma unroll
-        for (int i = 0; i < BPT; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(g[i], w[j], acc[i][j]);
-      }
     }
 #pragma unroll
-    for (int i = 0; i < BPT; ++i) {
-      const int bin = b0 + ty * BPT + i;
+    for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int o = obase + tx * 4 + j;
-        if (bin < A.grid.nbins && o < A.norb && acc[i][j] != 0.0)
-          atomicAdd(&A.wdos[(size_t)bin + (size_t)A.grid.nbins * (is + (size_t)A.ns * o)], acc[i][j]);
+        const int bin = b0 + wm * 16 + fg + (j >> 1) * 8;
+        const int o = obase + wn * 8 * NB + nb * 8 + ft * 2 + (j & 1);
+        if (bin < A.grid.nbins && o < A.norb && acc[nb][j] != 0.0)
+          atomicAdd(&A.wdos[(size_t)bin + (size_t)A.grid.nbins * (is + (size_t)A.ns * o)], acc[nb][j]);
       }
-    }
-    __syncthreads();
   }
 }
 
@@ -1118,10 +1183,16 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
       A.mw = prod_in.mw; A.norb = norb; A.mw_nb = prod_in.mw_nb; A.mw_nk = prod_in.mw_nk; A.nb = prod_in.nb; A.k_first = prod_in.k_first;
       A.wdos = accum + 2 * n1;
       const int blocks = (int)std::min<size_t>(items.size(), (size_t)ctx->sm_count * 2);
-#define PG_LAUNCH(BNV)                                                                         \
-  do {                                                                                         \
-    if (linear) pdos_gemm_kernel<BNV, true><<<blocks, 256, 0, ctx->stream>>>(A);                \
-    else pdos_gemm_kernel<BNV, false><<<blocks, 256, 0, ctx->stream>>>(A);                      \
+#define PG_LAUNCH(BNV)                                                                                                   \
+  do {                                                                                                                   \
+    const int smem = (int)pg_smem_bytes<BNV>();                                                                          \
+    if (linear) {                                                                                                        \
+      OD_CUDA(ctx, cudaFuncSetAttribute(pdos_gemm_kernel<BNV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      pdos_gemm_kernel<BNV, true><<<blocks, 256, smem, ctx->stream>>>(A);                                                 \
+    } else {                                                                                                             \
+      OD_CUDA(ctx, cudaFuncSetAttribute(pdos_gemm_kernel<BNV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      pdos_gemm_kernel<BNV, false><<<blocks, 256, smem, ctx->stream>>>(A);                                                \
+    }                                                                                                                    \
   } while (0)
       if (BN == 64) PG_LAUNCH(64); else if (BN == 32) PG_LAUNCH(32); else PG_LAUNCH(16);
 #undef PG_LAUNCH
