@@ -38,6 +38,7 @@
 //     reproducible to rounding (~1e-16 relative), not bit for bit.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "od_internal.h"
 #include "od_spectral.h"
@@ -244,6 +245,18 @@ __global__ void __launch_bounds__(1024) scan_kernel(const unsigned *__restrict__
   }
 }
 
+// a record leaves as 16-byte stores (2 / 4 per record instead of one store per field: the LSU queue is what the
+// scatter pass runs out of)
+template <int N16>
+__device__ __forceinline__ void store_rec16(void *dst, const void *src) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  uint4 v[N16];
+#pragma unroll
+  for (int i = 0; i < N16; ++i) v[i] = s[i];
+#pragma unroll
+  for (int i = 0; i < N16; ++i) reinterpret_cast<uint4 *>(dst)[i] = v[i];
+}
+
 // ---------------------------------------------------------------- pass B: scatter (shared-memory cursors)
 template <bool LINEAR, class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
@@ -285,12 +298,12 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
       LRec o;
       o.e0 = r.e0; o.e1 = r.p1; o.e2 = r.p2; o.e3 = r.p3; o.e4 = r.p4; o.om = r.omega;
       o.klo = is * ps.bpad + klo; o.cpos = (unsigned short)cpos; o.wlen = (unsigned short)wlen; o.pad = 0.0;
-      reinterpret_cast<LRec *>(recs_v)[pos] = o;
+      reinterpret_cast<LRec *>(recs_v)[pos] = o;  // (16-byte stores measured slower here: register pressure)
     } else {
       GRec o;
       o.e = r.e0; o.w = r.p1; o.om = r.omega;
       o.klo = is * ps.bpad + klo; o.cpos = (unsigned short)cpos; o.wlen = (unsigned short)wlen;
-      reinterpret_cast<GRec *>(recs_v)[pos] = o;
+      store_rec16<sizeof(GRec) / 16>(reinterpret_cast<GRec *>(recs_v) + pos, &o);
     }
     for (int a = 0; a < ps.ng; ++a) wts[(size_t)pos * ps.ng + a] = r.wt[a];
     if (ps.want_unit) runit[pos] = u;
@@ -979,17 +992,25 @@ struct Scratch {
   double *stephist, *chan;   // chan: 2 * npass arrays of nout doubles (DOS: dos, int)
 };
 
+inline void strip_weights(DosProducer &p) { p.mw = nullptr; }
+inline void strip_weights(JdosProducer &p) { p.mw = nullptr; p.ome = nullptr; }
+inline void set_eager(DosProducer &) {}
+inline void set_eager(JdosProducer &p) { p.eager = 1; }
+
 template <class Producer>
 int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear, unsigned *h_nrec, unsigned long long h_wide[2],
                    long long *wide_stride) {
   Producer prod = prod_in;
   prod.b.fast_corners = 1;  // both passes; wide units are re-made by the dense engine with the reference's arithmetic
+  Producer prod_keys = prod;  // pass A only needs the windows: no weight columns, no optical matrix elements
+  strip_weights(prod_keys);
+  set_eager(prod);            // pass B only runs on slots pass A accepted: loads first, tests after
   const PrepSpec &ps = S.ps;
   const int prows = ctx->sm_count;  // one prepare CTA per SM; pass A and pass B MUST use the same grid
   const size_t hist_smem = sizeof(unsigned) * ps.nbuckets;
   OD_CUDA(ctx, cudaMemsetAsync(S.wide, 0, sizeof(unsigned long long) * 5, ctx->stream));
   OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-  prep_hist_kernel<Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod, ps, S.keys, S.table, S.wide);
+  prep_hist_kernel<Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod_keys, ps, S.keys, S.table, S.wide);
   OD_LAUNCH_CHECK(ctx);
   prep_colscan_kernel<<<(ps.nbuckets + 255) / 256, 256, 0, ctx->stream>>>(S.table, prows, ps.nbuckets, S.colsum);
   OD_LAUNCH_CHECK(ctx);
@@ -1266,11 +1287,15 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
 // by the caller.  Pair slots are processed in k-point slabs of < 2^30 slots.
 int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &grid, bool linear, int n_geom, double *accum) {
   const int ns = prod_in.ns, nbins = grid.nbins, nb = prod_in.nb;
-  const long long nk = prod_in.units_per_z / ((long long)nb * nb);
-  const long long slab_k = std::max<long long>(1, (1ll << 30) / ((long long)nb * nb));
+  const long long ppk = prod_in.pairs_per_k();  // pair slots per k-point
+  const long long nk = prod_in.units_per_z / ppk;
+  // pair slots per k-slab: small enough that the bucket-order scatter of one slab stays L2-friendly (see the DOS
+  // slabs in od_spectral.cu), and < 2^30 for the 32-bit unit arithmetic; OD_JDOS_SLAB_SLOTS overrides for experiments
+  const long long slab_slots = std::min<long long>(1ll << 30, getenv("OD_JDOS_SLAB_SLOTS") ? atoll(getenv("OD_JDOS_SLAB_SLOTS")) : (16ll << 20));
+  const long long slab_k = std::max<long long>(1, slab_slots / ppk);
   const int npass = 1 + n_geom / 2;  // channel pairs: (jdos, w1) (w2, w3) (w4, w5) (w6, -)
   Scratch S;
-  OD_CHECK(narrow_scratch(ctx, grid, ns, std::min(nk, slab_k) * nb * nb * ns, 2 * npass, S));
+  OD_CHECK(narrow_scratch(ctx, grid, ns, std::min(nk, slab_k) * ppk * ns, 2 * npass, S));
   S.ps.gwin = OD_SQRT60;   // the Gaussian cut-off (algorithms.f90:83); no erf window in JDOS
   S.ps.with_int = 0;
   S.ps.linear_pass = linear ? 1 : 0;  // hybrid_linear fall-back records (jdos_utils.f90:365) -> dense engine
@@ -1280,7 +1305,7 @@ int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &gri
   for (long long k0 = 0; k0 < nk; k0 += slab_k) {
     JdosProducer prod = prod_in;
     prod.k_first = prod_in.k_first + k0;
-    prod.units_per_z = std::min(slab_k, nk - k0) * nb * nb;
+    prod.units_per_z = std::min(slab_k, nk - k0) * ppk;
     EventTimer tp, ta;
     unsigned h_nrec = 0;
     unsigned long long h_wide[2] = {0, 0};

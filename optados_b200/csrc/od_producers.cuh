@@ -92,11 +92,8 @@ struct OpticsCoef {
   double c[6][6];  // [geom component][xx, yy, zz, xy, xz, yz]  (off-diagonals already doubled)
 };
 
-__device__ __forceinline__ void od_ome_products(const double *om, size_t idx, size_t comp_stride, double P[6]) {
-  // om: complex (re,im) pairs; element (n1,n2,i) at idx + i*comp_stride
-  const double2 a = reinterpret_cast<const double2 *>(om)[idx];
-  const double2 b = reinterpret_cast<const double2 *>(om)[idx + comp_stride];
-  const double2 c = reinterpret_cast<const double2 *>(om)[idx + 2 * comp_stride];
+__device__ __forceinline__ void od_ome_products(const double2 a, const double2 b, const double2 c, double P[6]) {
+  // a, b, c: the three cartesian components (re, im) of one optical matrix element
   P[0] = a.x * a.x + a.y * a.y;
   P[1] = b.x * b.x + b.y * b.y;
   P[2] = c.x * c.x + c.y * c.y;
@@ -105,10 +102,22 @@ __device__ __forceinline__ void od_ome_products(const double *om, size_t idx, si
   P[5] = b.x * c.x + b.y * c.y;
 }
 
+__device__ __forceinline__ void od_ome_products(const double *om, size_t idx, size_t comp_stride, double P[6]) {
+  // om: complex (re,im) pairs; element (n1,n2,i) at idx + i*comp_stride
+  const double2 *m = reinterpret_cast<const double2 *>(om);
+  od_ome_products(m[idx], m[idx + comp_stride], m[idx + 2 * comp_stride], P);
+}
+
 struct JdosProducer {
-  long long units_per_z;  // nb * nb * (k-points of this slab)
+  long long units_per_z;  // pairs_per_k() * (k-points of this slab)
   long long k_first;      // first k-point of the slab (the arrays are indexed with the rank's full nk)
   int nb, ns, nk;
+  // candidate bands (narrow engine): only bands that are occupied at some (k, spin) can be the lower band of a
+  // pair, only bands that are unoccupied somewhere the upper one; null = all nb x nb slots
+  const int *occ_list, *unocc_list;
+  int n_occ, n_unocc;
+  int eager;  // issue all loads of a slot before testing it (scatter pass of the narrow engine)
+  __host__ __device__ long long pairs_per_k() const { return occ_list ? (long long)n_occ * n_unocc : (long long)nb * nb; }
   const double *bands, *grads, *kw;
   double eps, efermi, scissor;
   BroadSpec b;
@@ -121,20 +130,48 @@ struct JdosProducer {
 
   __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
     const int is = z;
-    const int ib = (int)(u % nb);
-    const long long t = u / nb;
-    const int jb = (int)(t % nb);
-    const long long ik = k_first + t / nb;
+    int ib, jb;
+    long long ik;
+    if (occ_list) {
+      const unsigned uu = (unsigned)u;  // slabs hold < 2^30 pair slots
+      const unsigned t = uu / (unsigned)n_occ, tj = t / (unsigned)n_unocc;
+      ib = occ_list[uu - t * (unsigned)n_occ];
+      jb = unocc_list[t - tj * (unsigned)n_unocc];
+      ik = k_first + tj;
+    } else {
+      ib = (int)(u % nb);
+      const long long t = u / nb;
+      jb = (int)(t % nb);
+      ik = k_first + t / nb;
+    }
     r.mode = -1;
+    const size_t eb = (size_t)nb * (is + (size_t)ns * ik);
+    const size_t gi = (size_t)nb * (3 * (ik + (size_t)nk * is));
+    const size_t nb2 = (size_t)nb * nb;
+    const size_t oi = ib + (size_t)nb * jb + nb2 * 3 * (ik + (size_t)nk * is);
+    double g[3] = {0.0, 0.0, 0.0};
+    double2 m0 = make_double2(0.0, 0.0), m1 = m0, m2 = m0;
+    double ei, ej;
+    if (eager) {
+      // scatter pass: the key already says this slot is a pair, so issue every load before the first use
+      ei = bands[eb + ib]; ej = bands[eb + jb];
+      if (b.type != 0) {
+        const double a0 = grads[gi + jb], a1 = grads[gi + ib], b0 = grads[gi + nb + jb], b1 = grads[gi + nb + ib];
+        const double c0 = grads[gi + 2 * (size_t)nb + jb], c1 = grads[gi + 2 * (size_t)nb + ib];
+        g[0] = a0 - a1; g[1] = b0 - b1; g[2] = c0 - c1;
+      }
+      if (ome) {
+        m0 = reinterpret_cast<const double2 *>(ome)[oi];
+        m1 = reinterpret_cast<const double2 *>(ome)[oi + nb2];
+        m2 = reinterpret_cast<const double2 *>(ome)[oi + 2 * nb2];
+      }
+    }
     for (int x = 0; x < n_exclude; ++x)
       if (exclude[x] == ib + 1) return;                         // jdos_utils.f90:355-357
-    const size_t eb = (size_t)nb * (is + (size_t)ns * ik);
-    const double ei = bands[eb + ib], ej = bands[eb + jb];
+    if (!eager) { ei = bands[eb + ib]; ej = bands[eb + jb]; }
     if (ei >= efermi) return;                                   // :358
     if (ej < efermi) return;                                    // :360
-    double g[3] = {0.0, 0.0, 0.0};
-    if (b.type != 0) {
-      const size_t gi = (size_t)nb * (3 * (ik + (size_t)nk * is));
+    if (!eager && b.type != 0) {
       g[0] = grads[gi + jb] - grads[gi + ib];
       g[1] = grads[gi + nb + jb] - grads[gi + nb + ib];
       g[2] = grads[gi + 2 * (size_t)nb + jb] - grads[gi + 2 * (size_t)nb + ib];
@@ -152,8 +189,12 @@ struct JdosProducer {
         if (jb == ib) factor = 1.0;
         else if (ej > efermi) factor = 1.0 / ((ej - ei + scissor) * (ej - ei + scissor));
         double P[6];
-        const size_t nb2 = (size_t)nb * nb;
-        od_ome_products(ome, ib + (size_t)nb * jb + nb2 * 3 * (ik + (size_t)nk * is), nb2, P);
+        if (!eager) {
+          m0 = reinterpret_cast<const double2 *>(ome)[oi];
+          m1 = reinterpret_cast<const double2 *>(ome)[oi + nb2];
+          m2 = reinterpret_cast<const double2 *>(ome)[oi + 2 * nb2];
+        }
+        od_ome_products(m0, m1, m2, P);
 #pragma unroll
         for (int a = 0; a < 6; ++a)
           if (a < n_geom)

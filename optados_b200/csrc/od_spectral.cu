@@ -371,6 +371,17 @@ extern "C" int od_calculate_dos_at_e(od_ctx *ctx, char dos_type, double energy, 
 }
 
 // ------------------------------------------------------------------ calculate_jdos
+namespace {
+// flags[ib] = band ib lies below efermi at some (k, spin); flags[nb + ib] = at or above it somewhere
+__global__ void band_occupancy_kernel(const double *__restrict__ bands, int nb, size_t nstates, double efermi, int *__restrict__ flags) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nstates; i += (size_t)gridDim.x * blockDim.x) {
+    const int ib = (int)(i % (size_t)nb);
+    if (bands[i] < efermi) { if (!flags[ib]) flags[ib] = 1; }
+    else if (!flags[nb + ib]) flags[nb + ib] = 1;
+  }
+}
+}  // namespace
+
 int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br, double efermi,
                              double scissor_op, const int *exclude_bands, int num_exclude_bands, const double *mw_dev,
                              const double *ome_dev, const OpticsCoef *coef, int n_geom, int merge, double **accum_out) {
@@ -399,6 +410,7 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
     p.n_exclude = num_exclude_bands;
   }
   p.mw = mw_dev; p.ome = ome_dev; p.n_geom = n_geom;
+  p.occ_list = p.unocc_list = nullptr; p.n_occ = p.n_unocc = 0; p.eager = 0;
   if (coef) p.coef = *coef; else memset(&p.coef, 0, sizeof(p.coef));
 
   GridSpec grid{0.0, delta_bins, nbins};  // E(i) = (i-1)*delta_bins (jdos_utils.f90:217)
@@ -420,7 +432,39 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
       OD_CUDA(ctx, cudaMemcpyAsync(ctx->in_tmp2.p, exclude_bands, sizeof(int) * (size_t)num_exclude_bands, cudaMemcpyHostToDevice, ctx->stream));
       p.exclude = ctx->in_tmp2.as<int>();
     }
-    OD_CHECK(od_narrow_jdos(ctx, p, grid, jdos_type == 'l', n_geom, accum));
+    // candidate band lists: a pair (ib, jb) needs E_ib < efermi and E_jb >= efermi at the same (k, spin)
+    const int nb = ctx->nb;
+    const size_t excl_bytes = (sizeof(int) * (size_t)num_exclude_bands + 15) & ~(size_t)15;
+    OD_CHECK(od_buf_ensure(ctx, ctx->in_tmp2, excl_bytes + sizeof(int) * 4 * (size_t)nb));
+    if (num_exclude_bands > 0) p.exclude = ctx->in_tmp2.as<int>();  // (the buffer may have moved)
+    int *flags = reinterpret_cast<int *>(ctx->in_tmp2.as<char>() + excl_bytes);
+    OD_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)nb, ctx->stream));
+    const size_t nstates = (size_t)nb * ns * ctx->nk;
+    if (nstates > 0) {
+      band_occupancy_kernel<<<(unsigned)std::min<size_t>((nstates + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(p.bands, nb, nstates, efermi, flags);
+      OD_LAUNCH_CHECK(ctx);
+    }
+    std::vector<int> hflags(2 * (size_t)nb), lists;
+    OD_CUDA(ctx, cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * 2 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+    OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int ib = 0; ib < nb; ++ib) {
+      bool excluded = false;
+      for (int x = 0; x < num_exclude_bands; ++x) excluded = excluded || (exclude_bands[x] == ib + 1);  // jdos_utils.f90:355
+      if (hflags[ib] && !excluded) lists.push_back(ib);
+    }
+    p.n_occ = (int)lists.size();
+    for (int jb = 0; jb < nb; ++jb)
+      if (hflags[nb + jb]) lists.push_back(jb);
+    p.n_unocc = (int)lists.size() - p.n_occ;
+    if (p.n_occ > 0 && p.n_unocc > 0) {
+      int *dl = flags + 2 * (size_t)nb;
+      OD_CUDA(ctx, cudaMemcpyAsync(dl, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice, ctx->stream));
+      OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // lists is a host vector
+      p.occ_list = dl;
+      p.unocc_list = dl + p.n_occ;
+      p.units_per_z = p.pairs_per_k() * ctx->nk;
+      OD_CHECK(od_narrow_jdos(ctx, p, grid, jdos_type == 'l', n_geom, accum));
+    }  // else: no pair anywhere, the spectra stay zero
   } else if (n_geom == 0) OD_CHECK((od_run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   else if (n_geom == 1) OD_CHECK((od_run_dense<1, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   else OD_CHECK((od_run_dense<6, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
