@@ -5,13 +5,16 @@ NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused
 CSRC      := optados_b200/csrc
 SRCS      := $(CSRC)/od_ctx.cu $(CSRC)/od_spectral.cu $(CSRC)/od_weights.cu $(CSRC)/od_drivers.cu $(CSRC)/od_util.cu $(CSRC)/od_narrow.cu
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/optados_b200.h
-OBJS      := $(SRCS:.cu=.o)
+OBJS      := $(SRCS:.cu=.o) $(CSRC)/od_io.o
 LIB       := optados_b200/lib/liboptados_b200.so
 
 all: $(LIB) oracle
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
+
+$(CSRC)/od_io.o: $(CSRC)/od_io.cpp include/optados_b200.h
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -c $< -o $@
 
 $(LIB): $(OBJS)
 	@mkdir -p optados_b200/lib

@@ -41,7 +41,7 @@ typedef struct od_broadening od_broadening; /* defined below */
  * stay valid until the next od_set_gradients) and uploads the array slab by slab INSIDE calculate_dos /
  * dos_utils_calculate, overlapped with the kernels working on the previous slab */
 enum { OD_MEM_HOST = 0, OD_MEM_DEVICE = 1, OD_MEM_HOST_DEFERRED = 2 };
-enum { OD_OK = 0, OD_ERR_ARG = 1, OD_ERR_CUDA = 2, OD_ERR_STATE = 3, OD_ERR_NCCL = 4, OD_ERR_DOSLIN = 5, OD_ERR_REF = 6 };
+enum { OD_OK = 0, OD_ERR_ARG = 1, OD_ERR_CUDA = 2, OD_ERR_STATE = 3, OD_ERR_NCCL = 4, OD_ERR_DOSLIN = 5, OD_ERR_REF = 6, OD_ERR_IO = 7 };
 
 /* optics_geom (parameters.f90:346; optics.f90:213-244) and core_type (parameters.f90:373-378) */
 enum { OD_GEOM_POLYCRYS = 0, OD_GEOM_POLAR = 1, OD_GEOM_UNPOLAR = 2, OD_GEOM_TENSOR = 3 };
@@ -266,6 +266,54 @@ int od_synth_bands(od_ctx *ctx, const int grid[3], long long k_first, int nk_loc
 /* copy the resident arrays of the ctx back to the host (for parity tests against the oracle) */
 int od_get_bands(od_ctx *ctx, double *band_energy_host);
 int od_get_kweights(od_ctx *ctx, double *kpoint_weight_host);
+
+/* ---------------------------------------------------------------- input decoders (host) ------ */
+/* SURVEY.md section 8(f) rank 1.  What the reference's Fortran readers produce, from the same files, for host
+ * programs without the Fortran front end.  No ctx, no GPU: plain host functions, caller-allocated outputs in the
+ * reference's layouts (column-major) and units (eV, eV Ang); a failing call returns non-zero and leaves a message
+ * in od_io_last_error() (thread-local).  `fmt`: 'b' = the *_bin files (Fortran sequential unformatted; byte order
+ * detected, big-endian under the reference's build flags), 'l' = the legacy files (.cst_ome, .cst_vel,
+ * .pdos_weights, .eels_mat), 't' = the formatted *_fmt twins od2od writes (read as the test-suite reads them:
+ * fmt -> bin -> read, including the unit round trip of od2od.f90:152/229). */
+const char *od_io_last_error(void);
+
+/* <seed>.bands -- elec_read_band_energy, electronic.f90:445-618 */
+typedef struct od_bands_info {
+  int nkpoints, nspins, nbands;
+  double num_electrons[2];
+  double efermi_castep;       /* eV (read as f12.4 in Hartree, electronic.f90:511-512) */
+  double real_lattice[9];     /* Bohr, column-major: real_lattice(:, i) = lattice-vector line i */
+  double electrons_per_state; /* 2 without spin polarisation, else 1 (electronic.f90:604-610) */
+} od_bands_info;
+int od_read_bands_info(const char *path, od_bands_info *info);
+/* band_energy(nb, ns, nk) in eV, kpoint_r(3, nk) (may be NULL), kpoint_weight(nk) (may be NULL) */
+int od_read_bands(const char *path, const od_bands_info *info, double *band_energy, double *kpoint_r, double *kpoint_weight);
+
+/* cell_calc_lattice (cell.f90:924-980): Bohr lattice -> real_lattice (Ang, may be NULL), recip_lattice (1/Ang,
+ * incl. 2 pi), cell_volume (Ang^3, may be NULL); all 3x3 column-major */
+int od_cell_calc_lattice(const double *real_lattice_bohr, double *real_lattice, double *recip_lattice, double *cell_volume);
+/* cell_find_MP_grid (cell.f90:87-318): kpoints(3, nk) fractional -> kpoint_grid_dim(3) */
+int od_cell_find_mp_grid(const double *kpoints, int nk, int *grid);
+/* %block symmetry_ops of <seed>-out.cell (cell.f90:405-696) -> crystal_symmetry_operations(3, 3, n); with
+ * ops == NULL only counts */
+int od_read_symmetry_ops(const char *cell_path, int max_ops, double *ops, int *n_ops);
+
+/* optical_mat(nb, nb, 3, nk, ns) complex, eV Ang -- elec_read_optical_mat, electronic.f90:302-442 */
+int od_read_ome(const char *path, char fmt, int nb, int nk, int ns, double *optical_mat);
+/* band_gradient(nb, 3, nk, ns), eV Ang -- elec_read_band_gradient, electronic.f90:170-299 */
+int od_read_dome(const char *path, char fmt, int nb, int nk, int ns, double *band_gradient);
+
+/* pdos_weights(norb, nb, nk, ns) + orbital table + nbands_occ(nk, ns) -- elec_pdos_read, electronic.f90:1122-1276 */
+typedef struct od_pdos_info { int nkpoints, nspins, norbitals, nbands; } od_pdos_info;
+int od_read_pdos_info(const char *path, char fmt, od_pdos_info *info);
+int od_read_pdos(const char *path, char fmt, const od_pdos_info *info, int *species_no, int *rank_in_species, int *am_channel,
+                 int *nbands_occ, double *pdos_weights);
+
+/* elnes_mat(norb, nb, 3, nk, ns) complex + orbital table -- elec_read_elnes_mat, electronic.f90:811-992 */
+typedef struct od_elnes_info { int norbitals, nbands, nkpoints, nspins; } od_elnes_info;
+int od_read_elnes_info(const char *path, char fmt, od_elnes_info *info);
+int od_read_elnes(const char *path, char fmt, const od_elnes_info *info, int *species_no, int *rank_in_species, int *shell,
+                  int *am_channel, double *elnes_mat);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,9 @@ EXPORTS = [
     "od_jdos_get", "od_jdos_get_weighted", "od_synth_bands", "od_get_bands", "od_get_kweights",
     "od_timer_start", "od_timer_stop", "od_measure_fp64_peak", "od_count_contributions", "od_host_alloc_pinned",
     "od_host_free_pinned", "od_set_engine",
+    "od_io_last_error", "od_read_bands_info", "od_read_bands", "od_cell_calc_lattice", "od_cell_find_mp_grid",
+    "od_read_symmetry_ops", "od_read_ome", "od_read_dome", "od_read_pdos_info", "od_read_pdos", "od_read_elnes_info",
+    "od_read_elnes",
 ]
 
 
@@ -513,3 +516,106 @@ def host_alloc_pinned(nbytes):
 
 def host_free_pinned(ptr):
     load().od_host_free_pinned(C.c_void_p(ptr))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# input decoders (include/optados_b200.h, "input decoders"): host functions, no Context needed
+class BandsInfo(C.Structure):
+    _fields_ = [("nkpoints", C.c_int), ("nspins", C.c_int), ("nbands", C.c_int), ("num_electrons", C.c_double * 2),
+                ("efermi_castep", C.c_double), ("real_lattice", C.c_double * 9), ("electrons_per_state", C.c_double)]
+
+
+class PdosInfo(C.Structure):
+    _fields_ = [("nkpoints", C.c_int), ("nspins", C.c_int), ("norbitals", C.c_int), ("nbands", C.c_int)]
+
+
+class ElnesInfo(C.Structure):
+    _fields_ = [("norbitals", C.c_int), ("nbands", C.c_int), ("nkpoints", C.c_int), ("nspins", C.c_int)]
+
+
+def _io_ck(rc):
+    if rc:
+        L = load()
+        L.od_io_last_error.restype = C.c_char_p
+        raise OptadosB200Error(rc, L.od_io_last_error().decode())
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def read_bands(path):
+    """<seed>.bands -> dict in the reference's layouts (band_energy(nb, ns, nk) in eV, ...)"""
+    L = load()
+    info = BandsInfo()
+    _io_ck(L.od_read_bands_info(str(path).encode(), C.byref(info)))
+    nk, ns, nb = info.nkpoints, info.nspins, info.nbands
+    E = np.zeros((nb, ns, nk), order="F")
+    kr = np.zeros((3, nk), order="F")
+    kw = np.zeros(nk)
+    _io_ck(L.od_read_bands(str(path).encode(), C.byref(info), _p(E), _p(kr), _p(kw)))
+    return dict(nk=nk, ns=ns, nb=nb, num_electrons=np.array(info.num_electrons[:ns]), efermi_castep=info.efermi_castep,
+                real_lattice_bohr=np.array(info.real_lattice[:]).reshape((3, 3), order="F"), band_energy=E, kpoint_r=kr,
+                kpoint_weight=kw, electrons_per_state=info.electrons_per_state)
+
+
+def cell_calc_lattice(real_lattice_bohr):
+    rl = np.zeros((3, 3), order="F")
+    rc = np.zeros((3, 3), order="F")
+    vol = C.c_double()
+    _io_ck(load().od_cell_calc_lattice(_p(f64(real_lattice_bohr)), _p(rl), _p(rc), C.byref(vol)))
+    return rl, rc, vol.value
+
+
+def cell_find_mp_grid(kpoints):
+    k = f64(kpoints)
+    grid = np.zeros(3, dtype=np.int32)
+    _io_ck(load().od_cell_find_mp_grid(_p(k), C.c_int(k.shape[1]), _ip(grid)))
+    return grid
+
+
+def read_symmetry_ops(path):
+    L = load()
+    n = C.c_int()
+    _io_ck(L.od_read_symmetry_ops(str(path).encode(), C.c_int(0), None, C.byref(n)))
+    ops = np.zeros((3, 3, max(n.value, 1)), order="F")
+    _io_ck(L.od_read_symmetry_ops(str(path).encode(), C.c_int(n.value), _p(ops), C.byref(n)))
+    return ops[:, :, :n.value]
+
+
+def read_ome(path, fmt, nb, nk, ns):
+    """optical_mat(nb, nb, 3, nk, ns) complex, eV Ang; fmt 'b' (.ome_bin), 'l' (.cst_ome) or 't' (.ome_fmt)"""
+    om = np.zeros((nb, nb, 3, nk, ns), dtype=np.complex128, order="F")
+    _io_ck(load().od_read_ome(str(path).encode(), C.c_char(fmt.encode()), C.c_int(nb), C.c_int(nk), C.c_int(ns),
+                              om.ctypes.data_as(c_dp)))
+    return om
+
+
+def read_dome(path, fmt, nb, nk, ns):
+    g = np.zeros((nb, 3, nk, ns), order="F")
+    _io_ck(load().od_read_dome(str(path).encode(), C.c_char(fmt.encode()), C.c_int(nb), C.c_int(nk), C.c_int(ns), _p(g)))
+    return g
+
+
+def read_pdos(path, fmt):
+    L = load()
+    info = PdosInfo()
+    _io_ck(L.od_read_pdos_info(str(path).encode(), C.c_char(fmt.encode()), C.byref(info)))
+    nk, ns, norb, nb = info.nkpoints, info.nspins, info.norbitals, info.nbands
+    sp, rk, am = (np.zeros(norb, dtype=np.int32) for _ in range(3))
+    nocc = np.zeros((nk, ns), dtype=np.int32, order="F")
+    w = np.zeros((norb, nb, nk, ns), order="F")
+    _io_ck(L.od_read_pdos(str(path).encode(), C.c_char(fmt.encode()), C.byref(info), _ip(sp), _ip(rk), _ip(am), _ip(nocc), _p(w)))
+    return dict(pdos_weights=w, pdos_species=sp, pdos_rank=rk, pdos_am=am, nbands_occ=nocc)
+
+
+def read_elnes(path, fmt):
+    L = load()
+    info = ElnesInfo()
+    _io_ck(L.od_read_elnes_info(str(path).encode(), C.c_char(fmt.encode()), C.byref(info)))
+    norb, nb, nk, ns = info.norbitals, info.nbands, info.nkpoints, info.nspins
+    sp, rk, sh, am = (np.zeros(norb, dtype=np.int32) for _ in range(4))
+    m = np.zeros((norb, nb, 3, nk, ns), dtype=np.complex128, order="F")
+    _io_ck(L.od_read_elnes(str(path).encode(), C.c_char(fmt.encode()), C.byref(info), _ip(sp), _ip(rk), _ip(sh), _ip(am),
+                           m.ctypes.data_as(c_dp)))
+    return dict(elnes_mat=m, elnes_species=sp, elnes_rank=rk, elnes_shell=sh, elnes_am=am)
