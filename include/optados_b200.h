@@ -267,6 +267,23 @@ int od_synth_bands(od_ctx *ctx, const int grid[3], long long k_first, int nk_loc
 int od_get_bands(od_ctx *ctx, double *band_energy_host);
 int od_get_kweights(od_ctx *ctx, double *kpoint_weight_host);
 
+/* ---------------------------------------------------------------- O(B^2) post-processing ------ */
+/* the reference's root-only double loops over the energy grid, on the GPU.
+ * Host arrays in and out (a few B x N doubles); E(nbins) is the reference's grid array. */
+/* calc_epsilon_1 (optics.f90:569-621, interband): Kramers-Kronig transform; epsilon_2, epsilon_1 (nbins, N_geom);
+ * components 1-3 get the +1 of the diagonal, 4-6 do not */
+int od_calc_epsilon_1(od_ctx *ctx, const double *E, int nbins, int n_geom, const double *epsilon_2, double *epsilon_1);
+/* calc_loss_fn (optics.f90:622-720, interband, component 1): loss_fn = -Im(1/(eps1 + i eps2)); if
+ * loss_fn_broadened != NULL and optics_lossfn_broadening >= 1e-6 it receives the Gaussian-broadened (FWHM) copy */
+int od_calc_loss_fn(od_ctx *ctx, const double *E, int nbins, const double *epsilon_1, const double *epsilon_2,
+                    double lossfn_gaussian, double *loss_fn, double *loss_fn_broadened);
+/* core_lorentzian + core_gaussian (core.f90:70-76, 655-732): life-time and instrumental broadening of
+ * weighted_dos(nbins, ncols = ns * norb) -> weighted_dos_broadened; Lorentzian if width > 1e-14 or scale > 1e-5,
+ * Gaussian (applied to the Lorentzian result when both are on) if width > 1e-14 */
+int od_core_lai_broadening(od_ctx *ctx, const double *E, int nbins, int ncols, double efermi, double gaussian_width,
+                           double lorentzian_width, double lorentzian_scale, double lorentzian_offset,
+                           const double *weighted_dos, double *weighted_dos_broadened);
+
 /* ---------------------------------------------------------------- input decoders (host) ------ */
 /* SURVEY.md section 8(f) rank 1.  What the reference's Fortran readers produce, from the same files, for host
  * programs without the Fortran front end.  No ctx, no GPU: plain host functions, caller-allocated outputs in the

@@ -98,6 +98,7 @@ EXPORTS = [
     "od_jdos_get", "od_jdos_get_weighted", "od_synth_bands", "od_get_bands", "od_get_kweights",
     "od_timer_start", "od_timer_stop", "od_measure_fp64_peak", "od_count_contributions", "od_host_alloc_pinned",
     "od_host_free_pinned", "od_set_engine",
+    "od_calc_epsilon_1", "od_calc_loss_fn", "od_core_lai_broadening",
     "od_io_last_error", "od_read_bands_info", "od_read_bands", "od_cell_calc_lattice", "od_cell_find_mp_grid",
     "od_read_symmetry_ops", "od_read_ome", "od_read_dome", "od_read_pdos_info", "od_read_pdos", "od_read_elnes_info",
     "od_read_elnes",
@@ -464,6 +465,31 @@ class Context:
         self._ck(self.L.od_profile_get(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(n)))
         return dict(accumulate_ms=a.value, prepare_ms=b.value, contributions=c.value, lane_steps=d.value,
                     accumulate_launches=n.value)
+
+    def calc_epsilon_1(self, E, eps2):
+        """Kramers-Kronig (optics.f90:569-621): eps2 (nbins, N_geom) -> eps1"""
+        E = f64(E)
+        e2 = f64(np.asarray(eps2).reshape(E.size, -1))
+        e1 = np.zeros_like(e2, order="F")
+        self._ck(self.L.od_calc_epsilon_1(self.h, _p(E), C.c_int(E.size), C.c_int(e2.shape[1]), _p(e2), _p(e1)))
+        return e1
+
+    def calc_loss_fn(self, E, eps1, eps2, lossfn_gaussian=0.0):
+        E = f64(E)
+        a, b = f64(np.asarray(eps1).reshape(-1)[:E.size]), f64(np.asarray(eps2).reshape(-1)[:E.size])
+        lf, lb = np.zeros(E.size), np.zeros(E.size)
+        self._ck(self.L.od_calc_loss_fn(self.h, _p(E), C.c_int(E.size), _p(a), _p(b), C.c_double(lossfn_gaussian), _p(lf), _p(lb)))
+        return lf, (lb if abs(lossfn_gaussian) >= 1.0e-6 else None)
+
+    def core_lai_broadening(self, E, wdos, efermi, gaussian_width=0.0, lorentzian_width=0.0, lorentzian_scale=0.0,
+                            lorentzian_offset=0.0):
+        E = f64(E)
+        w = f64(wdos)
+        out = np.zeros_like(w, order="F")
+        self._ck(self.L.od_core_lai_broadening(self.h, _p(E), C.c_int(E.size), C.c_int(w.size // E.size), C.c_double(efermi),
+                                               C.c_double(gaussian_width), C.c_double(lorentzian_width),
+                                               C.c_double(lorentzian_scale), C.c_double(lorentzian_offset), _p(w), _p(out)))
+        return out
 
     def synchronize(self):
         self._ck(self.L.od_synchronize(self.h))

@@ -822,6 +822,62 @@ void odo_calc_epsilon_1(const double *epsilon2, const double *E, int nbins, int 
     }
 }
 
+/* optics.f90:622-720 (no intraband): loss_fn(:,1) = -Im(1/(eps1 + i eps2)) of component 1; with
+ * optics_lossfn_broadening, loss_fn(:,2) = the same convolved with a Gaussian of FWHM optics_lossfn_gaussian */
+void odo_calc_loss_fn(const double *epsilon1, const double *epsilon2, const double *E, int nbins, int broadening,
+                      double lossfn_gaussian, double *loss_fn, double *loss_fn_broadened) {
+  int i, j;
+  const double dE = E[1] - E[0];
+  for (i = 0; i < nbins; ++i) {
+    /* -aimag(1/g), g = eps1 + i eps2: complex division as gfortran does it is replaced by the closed form */
+    const double a = epsilon1[i], b = epsilon2[i];
+    loss_fn[i] = b / (a * a + b * b);
+  }
+  if (!broadening) return;
+  for (j = 0; j < nbins; ++j) loss_fn_broadened[j] = 0.0;
+  for (i = 0; i < nbins; ++i)
+    for (j = 0; j < nbins; ++j) {
+      const double g = pow((4.0 * log(2.0)) / ODO_PI, 0.5) * (1.0 / lossfn_gaussian) *
+                       exp(-4.0 * (log(2.0)) * pow((E[j] - E[i]) / lossfn_gaussian, 2.0));
+      loss_fn_broadened[j] = loss_fn_broadened[j] + (g * loss_fn[i] * dE);
+    }
+}
+
+/* core.f90:692-732 core_lorentzian: every bin of weighted_dos(:, col) becomes a Lorentzian whose half width
+ * grows linearly above efermi + offset (lifetime broadening); `out` is accumulated into (core.f90:72-75 zeroes it) */
+void odo_core_lorentzian(const double *wdos, const double *E, int nbins, int ncols, double efermi, double lorentzian_width,
+                         double lorentzian_scale, double lorentzian_offset, double *out) {
+  int c, i, j;
+  const double dE = E[1] - E[0];
+  for (c = 0; c < ncols; ++c)
+    for (i = 0; i < nbins; ++i) {
+      double L_width;
+      if (E[i] >= (lorentzian_offset + efermi))
+        L_width = 0.5 * (lorentzian_width + ((E[i] - efermi - lorentzian_offset) * lorentzian_scale));
+      else
+        L_width = 0.5 * lorentzian_width;
+      if ((L_width * ODO_PI) < dE) L_width = dE / ODO_PI;
+      for (j = 0; j < nbins; ++j) {
+        const double l = wdos[i + (size_t)nbins * c] * L_width / (ODO_PI * (pow(E[j] - E[i], 2.0) + pow(L_width, 2.0)));
+        out[j + (size_t)nbins * c] = out[j + (size_t)nbins * c] + (l * dE);
+      }
+    }
+}
+
+/* core.f90:655-690 core_gaussian: convolution with a Gaussian of FWHM gaussian_width; `in` is weighted_dos or,
+ * after core_lorentzian, the Lorentzian-broadened spectrum (the caller passes a copy and a zeroed `out`) */
+void odo_core_gaussian(const double *in, const double *E, int nbins, int ncols, double gaussian_width, double *out) {
+  int c, i, j;
+  const double dE = E[1] - E[0], G_width = gaussian_width;
+  for (c = 0; c < ncols; ++c)
+    for (i = 0; i < nbins; ++i)
+      for (j = 0; j < nbins; ++j) {
+        const double g = pow((4.0 * log(2.0)) / ODO_PI, 0.5) * (1 / G_width) *
+                         exp(-4.0 * (log(2.0)) * pow((E[j] - E[i]) / G_width, 2.0));
+        out[j + (size_t)nbins * c] = out[j + (size_t)nbins * c] + (g * in[i + (size_t)nbins * c] * dE);
+      }
+}
+
 /* core.f90:84-168 */
 int odo_core_prepare_matrix_elements(const odo_system *sys, const double *elnes_mat, int norb, int polar,
                                      const double core_qdir[3], const double *symops, int num_sym,

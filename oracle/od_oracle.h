@@ -135,6 +135,11 @@ void odo_calc_epsilon_2(const double *weighted_jdos, int nbins, int ns, int n_ge
 /* optics.f90:569 (no intraband): epsilon1(B, N_geom) */
 void odo_calc_epsilon_1(const double *epsilon2, const double *E, int nbins, int n_geom,
                         double *epsilon1);
+void odo_calc_loss_fn(const double *epsilon1, const double *epsilon2, const double *E, int nbins, int broadening,
+                      double lossfn_gaussian, double *loss_fn, double *loss_fn_broadened);
+void odo_core_lorentzian(const double *wdos, const double *E, int nbins, int ncols, double efermi, double lorentzian_width,
+                         double lorentzian_scale, double lorentzian_offset, double *out);
+void odo_core_gaussian(const double *in, const double *E, int nbins, int ncols, double gaussian_width, double *out);
 
 /* core.f90:84.  core_type: 0 absorption, 1 emission, 2 all.  polar: use qdir.  out (norb,nb,nk,ns).
  * returns 1 if num_sym > 1 (reference io_error) */

@@ -255,6 +255,36 @@ def calc_epsilon_1(eps2, E):
     return e1
 
 
+def calc_loss_fn(eps1, eps2, E, lossfn_gaussian=0.0):
+    """optics.f90:622-720, component 1, no intraband -> (loss_fn, broadened or None)"""
+    L = lib()
+    E = f64(E)
+    a, b = f64(np.asarray(eps1).reshape(-1)[:E.size]), f64(np.asarray(eps2).reshape(-1)[:E.size])
+    lf, lb = np.zeros(E.size), np.zeros(E.size)
+    br = abs(lossfn_gaussian) >= 1.0e-6          # parameters.f90:371
+    L.odo_calc_loss_fn(_p(a), _p(b), _p(E), C.c_int(E.size), C.c_int(int(br)), C.c_double(lossfn_gaussian), _p(lf), _p(lb))
+    return lf, (lb if br else None)
+
+
+def core_lai_broadening(wdos, E, efermi, gaussian_width=0.0, lorentzian_width=0.0, lorentzian_scale=0.0, lorentzian_offset=0.0):
+    """core.f90:70-76: weighted_dos(B, ns, norb) -> weighted_dos_broadened"""
+    L = lib()
+    E = f64(E)
+    w = f64(wdos)
+    ncols = w.size // E.size
+    out = np.zeros_like(w, order="F")
+    if lorentzian_width > 1e-14 or lorentzian_scale > 0.00001:          # parameters.f90:402, core.f90:74
+        L.odo_core_lorentzian(_p(w), _p(E), C.c_int(E.size), C.c_int(ncols), C.c_double(efermi), C.c_double(lorentzian_width),
+                              C.c_double(lorentzian_scale), C.c_double(lorentzian_offset), _p(out))
+        if gaussian_width > 1e-14:
+            tmp = out.copy(order="F")
+            out[...] = 0.0
+            L.odo_core_gaussian(_p(tmp), _p(E), C.c_int(E.size), C.c_int(ncols), C.c_double(gaussian_width), _p(out))
+    elif gaussian_width > 1e-14:
+        L.odo_core_gaussian(_p(w), _p(E), C.c_int(E.size), C.c_int(ncols), C.c_double(gaussian_width), _p(out))
+    return out
+
+
 CORE_TYPE = {"absorption": 0, "emission": 1, "all": 2}
 
 

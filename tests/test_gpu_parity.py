@@ -402,3 +402,99 @@ def test_streamed_gradients_match_resident(ob, odo):
     d, _ = ctx.calculate_dos_at_e("a", 3.0, r["delta"])
     assert np.all(np.isfinite(d))
     ctx.close()
+
+
+# ------------------------------------------------------------------ O(B^2) post-processing
+def _spectrum(nbins, ncols, seed):
+    rng = np.random.default_rng(seed)
+    E = -3.0 + 0.0125 * np.arange(nbins)
+    x = np.zeros((nbins, ncols), order="F")
+    for c in range(ncols):
+        for _ in range(6):
+            x[:, c] += rng.uniform(0.1, 2.0) * np.exp(-0.5 * ((E - rng.uniform(E[0], E[-1])) / rng.uniform(0.05, 1.5)) ** 2)
+    return E, x
+
+
+@pytest.mark.parametrize("nbins,n_geom", [(3000, 1), (2339, 6), (257, 3)])
+def test_epsilon_1_kramers_kronig(ob, odo, nbins, n_geom):
+    E, e2 = _spectrum(nbins, n_geom, 11)
+    E = E - E[0]                      # the JDOS grid starts at 0 (jdos_utils.f90:217)
+    e2[0, :] = 0.0                    # calc_epsilon_2 leaves bin 1 at zero (Q12)
+    ctx = ob.Context(0)
+    e1 = ctx.calc_epsilon_1(E, e2)
+    ref = odo.calc_epsilon_1(e2, E)
+    for c in range(n_geom):
+        assert rel_to_peak(e1[:, c], ref[:, c]) < 1e-12, c
+    ctx.close()
+
+
+def test_epsilon_1_and_loss_fn_golden(ob, odo):
+    """eps2 through the GPU JDOS path, then eps1 and the loss function on the GPU, against Si2_epsilon.dat (polar)
+    and Si2_loss_fn.dat (unpolar, linear, optics_lossfn_broadening 1.0) of the reference's test-suite."""
+    fx = fixture("si2_optics")
+    for geom, btype, test in (("polar", "adaptive", "testopt_optics_polar"), ("unpolar", "linear", "testopt_optics_unpolar")):
+        ctx, s = gpu_ctx(ob, fx, odo)
+        ef = odo.dos_utils_calculate(s, btype, dos_spacing=0.1)["efermi"]
+        mw = odo.make_weights(s, fx["optical_mat"], geom, ef, qdir=(0.5, 0.5, 0.25), symops=fx["symops"])
+        r = odo.jdos_utils_calculate(s, ef, btype, jdos_spacing=0.01, jdos_max_energy=30.0, mw=mw)
+        e2 = odo.calc_epsilon_2(r["wjdos"], s.cell_volume)
+        e1 = ctx.calc_epsilon_1(r["E"], e2)
+        g = load_npz("gold_" + test)["block0"]
+        if geom == "polar":
+            assert rel_to_peak(e1[:, 0], g[:, 1]) < 1e-12
+        else:
+            lf, lb = ctx.calc_loss_fn(r["E"], e1[:, 0], e2[:, 0], lossfn_gaussian=1.0)
+            assert rel_to_peak(lf, g[:, 1]) < 1e-11
+            assert rel_to_peak(lb, g[:, 2]) < 1e-11
+            lf0, none = ctx.calc_loss_fn(r["E"], e1[:, 0], e2[:, 0], lossfn_gaussian=0.0)
+            assert none is None and np.array_equal(lf0, lf)
+        ctx.close()
+
+
+@pytest.mark.parametrize("gw,lw,ls,off", [(0.0, 0.2, 0.1, 0.0), (0.5, 0.0, 0.0, 0.0), (0.8, 0.2, 0.1, 0.0), (1.0, 0.5, 0.1, 0.7),
+                                          (0.0, 0.0, 0.0, 0.0), (0.3, 0.0, 0.05, 0.0)])
+def test_core_lai_broadening_vs_oracle(ob, odo, gw, lw, ls, off):
+    E, w = _spectrum(2339, 5, 5)
+    w3 = np.asfortranarray(w.reshape((E.size, 1, 5), order="F"))
+    ctx = ob.Context(0)
+    got = ctx.core_lai_broadening(E, w3, 1.234, gaussian_width=gw, lorentzian_width=lw, lorentzian_scale=ls, lorentzian_offset=off)
+    ref = odo.core_lai_broadening(w3, E, 1.234, gaussian_width=gw, lorentzian_width=lw, lorentzian_scale=ls, lorentzian_offset=off)
+    if gw == 0.0 and lw == 0.0 and ls == 0.0:
+        assert not got.any() and not ref.any()
+    else:
+        for c in range(5):
+            assert rel_to_peak(got[:, 0, c], ref[:, 0, c]) < 1e-12, c
+    ctx.close()
+
+
+def test_core_lai_golden(ob, odo):
+    """testopt_core_all end to end on the GPU: linear weighted DOS of the ELNES weights, then Lorentzian + Gaussian
+    LAI broadening, against the third column of the reference's Si2_core_edge.dat."""
+    fx = fixture("si2_core")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    first = odo.dos_utils_calculate(s, "linear", dos_spacing=0.01)
+    ef = first["efermi"]
+    mw = ctx.core_prepare_matrix_elements(fx["elnes_mat"], "all", ef)
+    E, delta, n = odo.dos_energy_scale(s, 0.01, dos_nbins=first["nbins"])
+    _, _, wdos = ctx.calculate_dos("l", E[0], delta, n, mw=mw)
+    eps0, e_charge = 8.8541878176E-12, 1.602176487E-19
+    c = (e_charge * 3.141592653589793238462643383279502884197 * float(np.float32(1e-20))) / (s.cell_volume * float(np.float32(1e-30)) * eps0)
+    spec = wdos * 0.52917720859 ** 2 * c
+    lai = ctx.core_lai_broadening(E, spec, ef, gaussian_width=0.8, lorentzian_width=0.2, lorentzian_scale=0.1)
+    G = load_npz("gold_testopt_core_all")
+    ch2l = {1: 0, 2: 1, 3: 1, 4: 1, 5: 2, 6: 2, 7: 2, 8: 2, 9: 2}
+    keys = list(zip(fx["elnes_species"], fx["elnes_rank"], fx["elnes_shell"], [ch2l.get(int(a), 3) for a in fx["elnes_am"]]))
+    edges = []
+    for o, k in enumerate(keys):
+        if edges and edges[-1][0] == k:
+            edges[-1][1].append(o)
+        else:
+            edges.append((k, [o]))
+    assert len(edges) == len(G)
+    for i, (_, orbs) in enumerate(edges):
+        g = G[f"block{i}"]
+        col = sum(spec[:, 0, o] for o in orbs) / float(len(orbs))
+        colb = sum(lai[:, 0, o] for o in orbs) / float(len(orbs))
+        assert rel_to_peak(col, g[:, 1]) < TOL_SPEC, i
+        assert rel_to_peak(colb, g[:, 2]) < TOL_SPEC, i
+    ctx.close()

@@ -147,6 +147,16 @@ def test_optics_polar_epsilon(odo):
     assert rel_to_peak(e1[:, 0], g[:, 1]) < 1e-12
 
 
+def test_optics_unpolar_loss_fn(odo):
+    """Si2_loss_fn.dat of testopt_optics_unpolar: E, loss function, Gaussian-broadened loss function (FWHM 1 eV)"""
+    r, e1, e2 = _optics(odo, "unpolar", "linear")
+    g = gold("testopt_optics_unpolar")["block0"]
+    lf, lb = odo.calc_loss_fn(e1[:, 0], e2[:, 0], r["E"], lossfn_gaussian=1.0)
+    assert np.abs(r["E"] - g[:, 0]).max() < 1e-12
+    assert rel_to_peak(lf, g[:, 1]) < 1e-11
+    assert rel_to_peak(lb, g[:, 2]) < 1e-11
+
+
 def test_optics_tensor_epsilon(odo):
     r, e1, e2 = _optics(odo, "tensor", "adaptive")
     G = gold("testopt_optics_tensor")
@@ -194,6 +204,10 @@ def _edges(fx):
     return [e[1] for e in edges]
 
 
+# LAI broadening of each test's .odi: (LAI_gaussian_width, LAI_lorentzian_width, LAI_lorentzian_scale)
+LAI = {"testopt_core_polarised": (0.0, 0.2, 0.1), "testopt_core_emisson": (0.5, 0.0, 0.0), "testopt_core_all": (0.8, 0.2, 0.1)}
+
+
 @pytest.mark.parametrize("test,btype,core_type,polar", [
     ("testopt_core_polarised", "adaptive", "emission", True),
     ("testopt_core_emisson", "linear", "emission", True),
@@ -201,6 +215,9 @@ def _edges(fx):
 ])
 def test_core_si2(odo, test, btype, core_type, polar):
     fx, E, spec = _core(odo, "si2_core", btype, core_type, polar, 0.01)
+    ef = odo.dos_utils_calculate(oracle_sys(odo, fx), btype, dos_spacing=0.01)["efermi"]
+    gw, lw, ls = LAI[test]
+    lai = odo.core_lai_broadening(spec, E, ef, gaussian_width=gw, lorentzian_width=lw, lorentzian_scale=ls)   # core.f90:70-76
     G = gold(test)
     edges = _edges(fx)
     assert len(edges) == len(G) == 6
@@ -212,3 +229,7 @@ def test_core_si2(odo, test, btype, core_type, polar):
         for o in orbs:
             col = col + spec[:, 0, o] / float(len(orbs))
         assert rel_to_peak(col, g[:, 1]) < LIST17, (test, i)
+        colb = np.zeros(E.size)
+        for o in orbs:
+            colb = colb + lai[:, 0, o] / float(len(orbs))
+        assert rel_to_peak(colb, g[:, 2]) < 1e-12, (test, i, "LAI")
