@@ -95,12 +95,40 @@ def cfg5(scale):
             "weighted_contributions_per_s": contrib * norb / dt, "profile": prof}
 
 
+def post(scale):
+    """the reference's root-only O(B^2) passes on the grids of configs 4 and 5 (one GPU)"""
+    import numpy as np
+    ctx = ob.Context(0)
+    out = {"config": "post-processing"}
+    rng = np.random.default_rng(7)
+    for name, nbins, ncols in (("kk_eps1_cfg4_tensor", 3000, 6), ("kk_eps1_20k", 20000, 6), ("lai_cfg5", 20000, 16), ("loss_fn_20k", 20000, 1)):
+        E = 0.01 * np.arange(nbins)
+        x = np.asfortranarray(rng.random((nbins, ncols)))
+        if name.startswith("kk"):
+            fn = lambda: ctx.calc_epsilon_1(E, x)
+            pairs = nbins * nbins * ncols
+        elif name.startswith("lai"):
+            fn = lambda: ctx.core_lai_broadening(E, x, 50.0, gaussian_width=0.8, lorentzian_width=0.2, lorentzian_scale=0.1)
+            pairs = 2 * nbins * nbins * ncols
+        else:
+            fn = lambda: ctx.calc_loss_fn(E, 1.0 + x[:, 0], x[:, 0], lossfn_gaussian=1.0)
+            pairs = nbins * nbins
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        dt = (time.perf_counter() - t0) / 3
+        out[name] = {"bins": nbins, "columns": ncols, "ms": dt * 1e3, "pair_terms_per_s": pairs / dt}
+    ctx.close()
+    return out
+
+
 if __name__ == "__main__":
     scale = 1.0
-    which = [a for a in sys.argv[1:] if a.startswith("cfg")] or ["cfg3", "cfg4", "cfg5"]
+    which = [a for a in sys.argv[1:] if a.startswith("cfg") or a == "post"] or ["cfg3", "cfg4", "cfg5", "post"]
     if "--scale" in sys.argv:
         scale = float(sys.argv[sys.argv.index("--scale") + 1])
     for name in which:
-        r = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[name](scale)
+        r = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "post": post}[name](scale)
         print(json.dumps(r), flush=True)
         torch.cuda.empty_cache()
