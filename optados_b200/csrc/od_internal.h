@@ -58,7 +58,7 @@ struct od_ctx {
   DevBuf gslab[2];
 
   // scratch
-  DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, scratch_e, mw_tmp, in_tmp, in_tmp2;
+  DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, scratch_e, mw_tmp, in_tmp, in_tmp2, moments;
 
   Spectra dos_res, jdos_res;
 };

@@ -55,7 +55,7 @@ namespace {
 #define OD_UNROLL(n) OD_PRAGMA(unroll n)
 #ifndef OD_X_T
 #define OD_X_T 512
-#define OD_X_WMAX 448
+#define OD_X_WMAX OD_NARROW_WMAX
 #define OD_X_MINB 2
 #endif
 constexpr int NR_T = OD_X_T;        // bins per warp tile

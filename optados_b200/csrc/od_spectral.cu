@@ -129,17 +129,25 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
   if (mw_dev && (norb < 1 || mw_nb < 1 || mw_nk < 1)) return od_fail(ctx, OD_ERR_ARG, "bad matrix_weights bounds");
   if (mw_dev && mw_nk != nk) return od_fail(ctx, OD_ERR_REF, "ERROR : DOS : mw%%nkpoints not equal to nkpoints. (dos_utils.f90:159)");
   if (!mw_dev) norb = 0;
-  for (int t = 0; t < ntypes; ++t) {
-    BroadSpec tmp;
-    OD_CHECK(od_make_broadspec(ctx, types[t], br, delta_bins, false, &tmp));  // validates dos_type
-  }
   GridSpec grid{emin, delta_bins, nbins};
+  std::vector<BroadSpec> bspec((size_t)ntypes);
+  std::vector<char> fixedwide((size_t)ntypes, 0);  // fixed broadening with very wide windows: moment expansion
+  for (int t = 0; t < ntypes; ++t) {
+    OD_CHECK(od_make_broadspec(ctx, types[t], br, delta_bins, false, &bspec[t]));  // validates dos_type
+    fixedwide[t] = (!weighted[t] || !mw_dev) && od_fixedwide_applies(ctx, bspec[t], grid);
+  }
   const size_t n1 = (size_t)nbins * ns;
   const size_t stride = 2 * n1 + n1 * norb + n1;
   OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * stride * ntypes));
   double *accum = ctx->accum.as<double>();
   OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * stride * ntypes, ctx->stream));
 
+  for (int t = 0; t < ntypes; ++t)
+    if (fixedwide[t]) OD_CHECK(od_fixedwide_begin(ctx, bspec[t], grid));
+  auto one_slab = [&](int t, long long k0, int nks, const double *grads_dev, int nk_g) -> int {
+    if (fixedwide[t]) return od_fixedwide_accumulate(ctx, bspec[t], grid, k0, nks);
+    return dos_slab(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0, nks, grads_dev, nk_g, accum + stride * t);
+  };
   const bool streamed = ctx->grads_host != nullptr && need_grad;
   if (!streamed) {
     // resident inputs: k-point slabs of ~32M units.  The bucket-order scatter of one slab then has a write
@@ -150,8 +158,7 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
     for (long long k0 = 0; k0 < nk; k0 += slab_nk) {
       const int nks = (int)std::min<long long>(slab_nk, nk - k0);
       for (int t = 0; t < ntypes; ++t)
-        OD_CHECK(dos_slab(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0, nks,
-                          ctx->grads.p ? ctx->grads.as<double>() + (size_t)nb * 3 * k0 : nullptr, nk, accum + stride * t));
+        OD_CHECK(one_slab(t, k0, nks, ctx->grads.p ? ctx->grads.as<double>() + (size_t)nb * 3 * k0 : nullptr, nk));
     }
   } else {
     if (!ctx->copy_stream) {
@@ -187,9 +194,7 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
       const int nks = (int)std::min<long long>(slab_nk, nk - k0);
       if ((long long)(s + 1) * slab_nk < nk) OD_CHECK(issue_copy(s + 1));
       OD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
-      for (int t = 0; t < ntypes; ++t)
-        OD_CHECK(dos_slab(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0, nks, ctx->gslab[b].as<double>(),
-                          nks, accum + stride * t));
+      for (int t = 0; t < ntypes; ++t) OD_CHECK(one_slab(t, k0, nks, ctx->gslab[b].as<double>(), nks));
       OD_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
     }
   }
@@ -197,6 +202,7 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
   for (int t = 0; t < ntypes; ++t) {
     double *acc = accum + stride * t;
     const size_t ntot = 2 * n1 + (weighted[t] ? n1 * norb : 0);
+    if (fixedwide[t]) OD_CHECK(od_fixedwide_finish(ctx, bspec[t], grid, acc));
     // rank-local epilogue, before the merge like the reference (quirk Q16)
     if (types[t] == 'l' && br->linear_smearing > 0.0) {
       double *tmp = acc + stride - n1;

@@ -23,6 +23,14 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
 // contracted optics coefficients (optics.f90:213-435), see od_weights.cu
 int od_optics_coefficients(od_ctx *ctx, int geom, const double qdir[3], const double *symops, int num_symm, OpticsCoef *coef);
 
+// widest window (bins) the narrow engine takes; wider ones go to the dense engine or, for fixed broadening
+// without weights, to the moment expansion of od_fixedwide.cu
+#define OD_NARROW_WMAX 448
+bool od_fixedwide_applies(const od_ctx *ctx, const BroadSpec &b, const GridSpec &grid);
+int od_fixedwide_begin(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid);
+int od_fixedwide_accumulate(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, long long k_first, int nk_slab);
+int od_fixedwide_finish(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, double *accum);
+
 // narrow (sorted, recurrence) engine for calculate_dos without weights (od_narrow.cu)
 int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bool linear, double *accum);
 // narrow engine for calculate_jdos: accum = [jdos(B,ns) | weighted_jdos(B,ns,n_geom)]

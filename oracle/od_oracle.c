@@ -112,8 +112,9 @@ int odo_dist_array(int num_elements, int num_nodes, int *elements_per_node) {
   for (loop = 0; loop < num_nodes; ++loop) elements_per_node[loop] = num_elements / num_nodes;
   if (num_elements < num_nodes) return 1;
   if (elements_per_node[0] * num_nodes != num_elements) {
-    for (loop = 0; loop <= num_elements - elements_per_node[0] * num_nodes - 1; ++loop)
-      elements_per_node[loop] += 1;
+    /* a Fortran DO evaluates its bounds once, before elements_per_node(0) is incremented */
+    const int last = num_elements - elements_per_node[0] * num_nodes - 1;
+    for (loop = 0; loop <= last; ++loop) elements_per_node[loop] += 1;
   }
   return 0;
 }

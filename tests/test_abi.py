@@ -43,6 +43,7 @@ def test_dist_array_matches_reference():
     import optados_b200
     assert optados_b200.dist_array(10, 4) == [3, 3, 2, 2]
     assert optados_b200.dist_array(8, 8) == [1] * 8
+    assert optados_b200.dist_array(210, 8) == [27, 27] + [26] * 6      # remainder > 1: DO bounds are evaluated once
     assert optados_b200.dist_array(1000000, 8) == [125000] * 8
     with pytest.raises(optados_b200.OptadosB200Error):
         optados_b200.dist_array(3, 4)

@@ -498,3 +498,48 @@ def test_core_lai_golden(ob, odo):
         assert rel_to_peak(col, g[:, 1]) < TOL_SPEC, i
         assert rel_to_peak(colb, g[:, 2]) < TOL_SPEC, i
     ctx.close()
+
+
+# ------------------------------------------------------------------ fixed broadening with very wide windows
+@pytest.mark.parametrize("smear,nbins", [(0.3, 6000), (0.3, 20000), (0.08, 20000), (1.0, 3000)])
+def test_fixed_wide_windows_moment_expansion(ob, odo, smear, nbins):
+    """fixed_smearing >> dE: windows beyond what the narrow engine takes go through the moment expansion
+    (od_fixedwide.cu).  Against the oracle (the reference's per-state loop) and against the dense engine, on a
+    grid that cuts through the bands so that states below / above the grid are exercised too."""
+    ctx = ob.Context(0)
+    grid, ns, nb = (7, 6, 5), 2, 16
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=4)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
+    for lo, hi in ((be.min() - 5.0, be.max() + 5.0), (be.min() + 6.0, be.max() - 9.0)):
+        delta = (hi - lo) / (nbins - 1)
+        E = lo + delta * np.arange(nbins)
+        assert 2 * 8.2 * smear / delta > 448
+        ref = odo.calculate_dos("f", s, odo.make_broadening(fixed_smearing=smear), E, delta, nthreads=8)
+        ctx.set_engine("auto")
+        ctx.profile_reset()
+        dos, intdos, _ = ctx.calculate_dos("f", E[0], delta, nbins, br=ob.broadening(fixed_smearing=smear))
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC
+        assert_int(intdos, ref[1])
+        assert rel_to_peak(dos, ref[0]) < 1e-11            # the expansion is far inside the tolerance
+        if nbins <= 6000:
+            ctx.set_engine("dense")
+            dos_d, intdos_d, _ = ctx.calculate_dos("f", E[0], delta, nbins, br=ob.broadening(fixed_smearing=smear))
+            assert rel_to_peak(dos, dos_d) < 1e-11
+            assert_int(intdos, intdos_d)
+    ctx.close()
+
+
+def test_fixed_wide_on_reference_fixture(ob, odo):
+    """Si2 (reference fixture) with the default fixed_smearing 0.3 eV on a 5 meV grid, through the task driver"""
+    fx = fixture("si2_optics")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params("fixed", dos_spacing=0.005, num_electrons=fx["num_electrons"])
+    r = ctx.dos_utils_calculate(p)
+    ref = odo.dos_utils_calculate(s, "fixed", dos_spacing=0.005)
+    assert r["nbins"] == ref["nbins"]
+    assert rel_to_peak(r["dos_fixed"], ref["dos"]) < TOL_SPEC
+    assert_int(r["intdos_fixed"], ref["intdos"])
+    assert abs(r["efermi_fixed"] - ref["efermi"]) < 1e-9
+    ctx.close()

@@ -233,3 +233,15 @@ def test_core_si2(odo, test, btype, core_type, polar):
         for o in orbs:
             colb = colb + lai[:, 0, o] / float(len(orbs))
         assert rel_to_peak(colb, g[:, 2]) < 1e-12, (test, i, "LAI")
+
+
+def test_oracle_threads_match_serial(odo):
+    """the multi-threaded helper of the oracle (k-points split like algor_dist_array) against the serial loop,
+    with a k-point count that leaves a remainder > 1"""
+    fx = fixture("si2_core")          # 14 k-points
+    s = oracle_sys(odo, fx)
+    E, delta, n = odo.dos_energy_scale(s, 0.05)
+    for t in ("a", "l"):
+        a = odo.calculate_dos(t, s, odo.make_broadening(), E, delta)
+        b = odo.calculate_dos(t, s, odo.make_broadening(), E, delta, nthreads=4)     # 14 = 4 + 4 + 3 + 3
+        assert rel_to_peak(b[0], a[0]) < 1e-13 and rel_to_peak(b[1], a[1]) < 1e-13      # summation order only
