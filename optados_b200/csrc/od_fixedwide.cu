@@ -3,7 +3,7 @@
 // With one width w for every state, dos(E_j) = sum_s omega_s G(E_j - e_s) is a convolution of the state density
 // with one Gaussian; the only thing that keeps it from being a convolution ON THE GRID is the offset
 // delta_s = e_s - E_c of a state from its nearest grid point c.  That offset is small against w exactly when the
-// windows are wide (|delta|/w <= dE/2w < 0.02 once a window exceeds 448 bins), so the Taylor series in
+// windows are wide (|delta|/w <= dE/2w < 0.02 once a window exceeds 480 bins), so the Taylor series in
 // eta = delta/w converges in a handful of terms:
 //   G(x - delta)        = G(x) sum_p eta^p/p! He_p(z),                         z = x/w, He_p = Hermite (probabilists')
 //   Phi((x - delta)/w)  = Phi(z) - phi(z) sum_{p>=1} eta^p/p! He_{p-1}(z)

@@ -25,7 +25,7 @@
 //      become a prefix sum at the very end.  The linear scheme evaluates the four doslin pieces
 //      branch-free and selects.  Tiles are flushed to HBM with FP64 reductions only when a warp's
 //      window slides off its 512-bin tile or its chunk ends.
-//   3. Units whose window is wider than 448 bins (and degenerate ones) go to the dense bin-owner
+//   3. Units whose window is wider than 480 bins (and degenerate ones) go to the dense bin-owner
 //      engine (od_accum.cuh) through a compacted list; the partial spectra are then combined.
 //
 // Numerics vs the reference (tolerances: 1e-9 of peak on spectra, 1e-10 relative on intDOS):
@@ -1181,7 +1181,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
     std::vector<unsigned> hbase((size_t)ps.nbuckets + 1);
     OD_CUDA(ctx, cudaMemcpyAsync(hbase.data(), S.base, sizeof(unsigned) * hbase.size(), cudaMemcpyDeviceToHost, ctx->stream));
     OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    static const int wmax[NR_NCLS] = {24, 32, 44, 60, 84, 116, 160, 224, 320, 448};
+    static const int wmax[NR_NCLS] = {24, 32, 44, 60, 84, 116, 160, 224, 320, NR_WMAX};
     const int BN = norb > 32 ? 64 : (norb > 16 ? 32 : 16);
     const int otiles = (norb + BN - 1) / BN;
     std::vector<PgItem> items;

@@ -25,7 +25,7 @@ int od_optics_coefficients(od_ctx *ctx, int geom, const double qdir[3], const do
 
 // widest window (bins) the narrow engine takes; wider ones go to the dense engine or, for fixed broadening
 // without weights, to the moment expansion of od_fixedwide.cu
-#define OD_NARROW_WMAX 448
+#define OD_NARROW_WMAX 480
 bool od_fixedwide_applies(const od_ctx *ctx, const BroadSpec &b, const GridSpec &grid);
 int od_fixedwide_begin(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid);
 int od_fixedwide_accumulate(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, long long k_first, int nk_slab);

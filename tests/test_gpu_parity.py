@@ -515,7 +515,7 @@ def test_fixed_wide_windows_moment_expansion(ob, odo, smear, nbins):
     for lo, hi in ((be.min() - 5.0, be.max() + 5.0), (be.min() + 6.0, be.max() - 9.0)):
         delta = (hi - lo) / (nbins - 1)
         E = lo + delta * np.arange(nbins)
-        assert 2 * 8.2 * smear / delta > 448
+        assert 2 * 8.2 * smear / delta > 480
         ref = odo.calculate_dos("f", s, odo.make_broadening(fixed_smearing=smear), E, delta, nthreads=8)
         ctx.set_engine("auto")
         ctx.profile_reset()
