@@ -151,12 +151,40 @@ module od_b200
       integer(c_int), intent(in) :: mask(norb_in, nproj)
       real(c_double), intent(out) :: mw(*)
     end function
+    ! ---- root-only O(B^2) post-processing (optics.f90:569-621, :676-697; core.f90:655-732)
+    integer(c_int) function od_calc_epsilon_1(ctx, E, nbins, n_geom, epsilon_2, epsilon_1) bind(c, name='od_calc_epsilon_1')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nbins, n_geom
+      real(c_double), intent(in) :: E(nbins), epsilon_2(nbins, n_geom)
+      real(c_double), intent(out) :: epsilon_1(nbins, n_geom)
+    end function
+    integer(c_int) function od_calc_loss_fn(ctx, E, nbins, epsilon_1, epsilon_2, lossfn_gaussian, loss_fn, loss_fn_broadened) &
+      bind(c, name='od_calc_loss_fn')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nbins
+      real(c_double), value :: lossfn_gaussian
+      real(c_double), intent(in) :: E(nbins), epsilon_1(nbins), epsilon_2(nbins)
+      real(c_double), intent(out) :: loss_fn(nbins), loss_fn_broadened(nbins)
+    end function
+    integer(c_int) function od_core_lai_broadening(ctx, E, nbins, ncols, efermi, gaussian_width, lorentzian_width, &
+                                                   lorentzian_scale, lorentzian_offset, weighted_dos, weighted_dos_broadened) &
+      bind(c, name='od_core_lai_broadening')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nbins, ncols
+      real(c_double), value :: efermi, gaussian_width, lorentzian_width, lorentzian_scale, lorentzian_offset
+      real(c_double), intent(in) :: E(nbins), weighted_dos(nbins, ncols)
+      real(c_double), intent(out) :: weighted_dos_broadened(nbins, ncols)
+    end function
   end interface
 
   public :: b200_setup, b200_end, b200_upload_bands, b200_upload_gradients, b200_check
   public :: b200_calculate_dos, b200_calculate_dos_at_e, b200_calculate_jdos
   public :: b200_make_weights, b200_core_weights, b200_projection_merge, b200_broadening
   public :: od_allreduce, od_comm_get_unique_id
+  public :: od_calc_epsilon_1, od_calc_loss_fn, od_core_lai_broadening
 
 contains
 
