@@ -267,6 +267,53 @@ int od_synth_bands(od_ctx *ctx, const int grid[3], long long k_first, int nk_loc
 int od_get_bands(od_ctx *ctx, double *band_energy_host);
 int od_get_kweights(od_ctx *ctx, double *kpoint_weight_host);
 
+/* ---------------------------------------------------------------- task mirrors --------------- */
+/* two of the reference's tasks end to end, built from the entry points above.
+ * optics_calculate (optics.f90:78-155, interband): make_weights fused into the JDOS pass -> epsilon_2 ->
+ * Kramers-Kronig epsilon_1 -> (not for optics_geom = tensor) conductivity, refractive index, loss function,
+ * absorption, reflection of component 1 (optics.f90:722-825).  jdos.cell_volume is required. */
+typedef struct od_optics_params {
+  od_jdos_params jdos;    /* broadening switches, grid, efermi, scissor_op, excluded bands, cell_volume */
+  int geom;               /* OD_GEOM_* */
+  double qdir[3];         /* optics_qdir */
+  double lossfn_gaussian; /* optics_lossfn_broadening: FWHM in eV, < 1e-6 = off (parameters.f90:367-371) */
+} od_optics_params;
+void od_optics_params_defaults(od_optics_params *p);
+typedef struct od_optics_result {
+  int nbins, n_geom;
+  double delta_bins;      /* E(i) = (i-1)*delta_bins */
+  int have_derived;       /* 0 for optics_geom = tensor */
+  int have_loss_fn_broadened;
+} od_optics_result;
+int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const double *optical_mat, int ome_mem, const double *symops,
+                        int num_symm, od_optics_result *res);
+/* any pointer may be NULL: E(nbins), epsilon(nbins, 2, n_geom) with (:,1,:) = eps1 and (:,2,:) = eps2,
+ * conduct(nbins,2), refract(nbins,2), loss_fn(nbins, 1 or 2), absorp(nbins), reflect(nbins) */
+int od_optics_get(od_ctx *ctx, double *E, double *epsilon, double *conduct, double *refract, double *loss_fn,
+                  double *absorp, double *reflect);
+
+/* core_calculate (core.f90:38-83) + the unit factors of write_core (core.f90:317-323): dos_utils_set_efermi ->
+ * core_prepare_matrix_elements -> dos_utils_calculate(matrix_weights, weighted_dos) on the now-sticky grid (Q4) ->
+ * LAI broadening.  dos.cell_volume is required.  Edge bookkeeping (which orbitals form an edge) stays with the caller. */
+typedef struct od_core_params {
+  od_dos_params dos;
+  int core_type;          /* OD_CORE_* */
+  int polar;              /* core_geom = polarised */
+  double qdir[3];         /* core_qdir */
+  int lai_broadening;     /* core_LAI_broadening */
+  double lai_gaussian_width, lai_lorentzian_width, lai_lorentzian_scale, lai_lorentzian_offset;
+} od_core_params;
+void od_core_params_defaults(od_core_params *p);
+typedef struct od_core_result {
+  int nbins, norb;
+  double emin, delta_bins, efermi;
+  int have_broadened;
+} od_core_result;
+int od_core_calculate(od_ctx *ctx, od_core_params *p, const double *elnes_mat, int elnes_mem, int norb, const double *symops,
+                      int num_sym, od_core_result *res);
+/* E(nbins), weighted_dos(nbins, ns, norb) and its LAI-broadened copy, both in the units write_core prints */
+int od_core_get(od_ctx *ctx, double *E, double *weighted_dos, double *weighted_dos_broadened);
+
 /* ---------------------------------------------------------------- O(B^2) post-processing ------ */
 /* the reference's root-only double loops over the energy grid, on the GPU.
  * Host arrays in and out (a few B x N doubles); E(nbins) is the reference's grid array. */

@@ -57,6 +57,26 @@ class JdosResult(C.Structure):
                 ("have_linear", C.c_int), ("have_weighted", C.c_int), ("n_geom", C.c_int)]
 
 
+class OpticsParams(C.Structure):
+    _fields_ = [("jdos", JdosParams), ("geom", C.c_int), ("qdir", C.c_double * 3), ("lossfn_gaussian", C.c_double)]
+
+
+class OpticsResult(C.Structure):
+    _fields_ = [("nbins", C.c_int), ("n_geom", C.c_int), ("delta_bins", C.c_double), ("have_derived", C.c_int),
+                ("have_loss_fn_broadened", C.c_int)]
+
+
+class CoreParams(C.Structure):
+    _fields_ = [("dos", DosParams), ("core_type", C.c_int), ("polar", C.c_int), ("qdir", C.c_double * 3),
+                ("lai_broadening", C.c_int), ("lai_gaussian_width", C.c_double), ("lai_lorentzian_width", C.c_double),
+                ("lai_lorentzian_scale", C.c_double), ("lai_lorentzian_offset", C.c_double)]
+
+
+class CoreResult(C.Structure):
+    _fields_ = [("nbins", C.c_int), ("norb", C.c_int), ("emin", C.c_double), ("delta_bins", C.c_double), ("efermi", C.c_double),
+                ("have_broadened", C.c_int)]
+
+
 class OptadosB200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"optados_b200 error {code}: {msg}")
@@ -99,6 +119,8 @@ EXPORTS = [
     "od_timer_start", "od_timer_stop", "od_measure_fp64_peak", "od_count_contributions", "od_host_alloc_pinned",
     "od_host_free_pinned", "od_set_engine",
     "od_calc_epsilon_1", "od_calc_loss_fn", "od_core_lai_broadening",
+    "od_optics_params_defaults", "od_optics_calculate", "od_optics_get", "od_core_params_defaults", "od_core_calculate",
+    "od_core_get",
     "od_io_last_error", "od_read_bands_info", "od_read_bands", "od_cell_calc_lattice", "od_cell_find_mp_grid",
     "od_read_symmetry_ops", "od_read_ome", "od_read_dome", "od_read_pdos_info", "od_read_pdos", "od_read_elnes_info",
     "od_read_elnes",
@@ -450,6 +472,71 @@ class Context:
             w = np.zeros((res.nbins, self.ns, res.n_geom), order="F")
             self._ck(self.L.od_jdos_get_weighted(self.h, _p(w)))
             out["weighted_jdos"] = w
+        return out
+
+    # ---- task mirrors (optics_calculate, core_calculate)
+    def optics_calculate(self, optical_mat, efermi, cell_volume, broadening_type="adaptive", geom="polycrys", qdir=(1, 1, 1),
+                         symops=None, jdos_spacing=0.01, jdos_max_energy=-1.0, scissor_op=0.0, lossfn_gaussian=0.0, br=None):
+        p = OpticsParams()
+        self.L.od_optics_params_defaults(C.byref(p))
+        p.jdos.fixed = p.jdos.adaptive = p.jdos.linear = 0
+        for t in ([broadening_type] if isinstance(broadening_type, str) else broadening_type):
+            setattr(p.jdos, t, 1)
+        p.jdos.jdos_spacing, p.jdos.jdos_max_energy, p.jdos.scissor_op = jdos_spacing, jdos_max_energy, scissor_op
+        p.jdos.efermi, p.jdos.cell_volume = efermi, cell_volume
+        if br is not None:
+            p.jdos.br = br
+        p.geom, p.lossfn_gaussian = GEOM[geom], lossfn_gaussian
+        for i in range(3):
+            p.qdir[i] = float(qdir[i])
+        om = np.asfortranarray(optical_mat, dtype=np.complex128)
+        nsym = 0 if symops is None else symops.shape[2]
+        so = None if symops is None else f64(symops)
+        res = OpticsResult()
+        self._ck(self.L.od_optics_calculate(self.h, C.byref(p), om.ctypes.data_as(c_dp), C.c_int(OD_MEM_HOST), _p(so), C.c_int(nsym),
+                                            C.byref(res)))
+        n, ng = res.nbins, res.n_geom
+        out = dict(nbins=n, n_geom=ng, delta=res.delta_bins, E=np.zeros(n), epsilon=np.zeros((n, 2, ng), order="F"))
+        args = [_p(out["E"]), _p(out["epsilon"])]
+        if res.have_derived:
+            out.update(conduct=np.zeros((n, 2), order="F"), refract=np.zeros((n, 2), order="F"),
+                       loss_fn=np.zeros((n, 2 if res.have_loss_fn_broadened else 1), order="F"), absorp=np.zeros(n), reflect=np.zeros(n))
+            args += [_p(out[k]) for k in ("conduct", "refract", "loss_fn", "absorp", "reflect")]
+        else:
+            args += [None] * 5
+        self._ck(self.L.od_optics_get(self.h, *args))
+        return out
+
+    def core_calculate(self, elnes_mat, dos_params, core_type="absorption", polar=False, qdir=(0, 0, 1), symops=None,
+                       lai=None):
+        """lai: None or dict(gaussian_width=, lorentzian_width=, lorentzian_scale=, lorentzian_offset=)"""
+        p = CoreParams()
+        self.L.od_core_params_defaults(C.byref(p))
+        p.dos = dos_params
+        p.core_type, p.polar = CORE_TYPE[core_type], int(polar)
+        for i in range(3):
+            p.qdir[i] = float(qdir[i])
+        if lai is not None:
+            p.lai_broadening = 1
+            p.lai_gaussian_width = lai.get("gaussian_width", 0.0)
+            p.lai_lorentzian_width = lai.get("lorentzian_width", 0.0)
+            p.lai_lorentzian_scale = lai.get("lorentzian_scale", 0.0)
+            p.lai_lorentzian_offset = lai.get("lorentzian_offset", 0.0)
+        em = np.asfortranarray(elnes_mat, dtype=np.complex128)
+        norb = em.shape[0]
+        nsym = 0 if symops is None else symops.shape[2]
+        so = None if symops is None else f64(symops)
+        res = CoreResult()
+        self._ck(self.L.od_core_calculate(self.h, C.byref(p), em.ctypes.data_as(c_dp), C.c_int(OD_MEM_HOST), C.c_int(norb), _p(so),
+                                          C.c_int(nsym), C.byref(res)))
+        n = res.nbins
+        out = dict(nbins=n, efermi=res.efermi, emin=res.emin, delta=res.delta_bins, E=np.zeros(n),
+                   weighted_dos=np.zeros((n, self.ns, norb), order="F"))
+        wb = None
+        if res.have_broadened:
+            out["weighted_dos_broadened"] = np.zeros((n, self.ns, norb), order="F")
+            wb = _p(out["weighted_dos_broadened"])
+        self._ck(self.L.od_core_get(self.h, _p(out["E"]), _p(out["weighted_dos"]), wb))
         return out
 
     # ---- bookkeeping

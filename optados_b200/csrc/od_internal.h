@@ -33,6 +33,18 @@ struct Spectra {
   bool have_weighted = false;
 };
 
+// results of the task mirrors (od_tasks.cu)
+struct OpticsRes {
+  int nbins = 0, n_geom = 0;
+  double delta = 0.0;
+  std::vector<double> E, epsilon, conduct, refract, loss_fn, absorp, reflect;
+};
+struct CoreRes {
+  int nbins = 0, ns = 0, norb = 0;
+  double efermi = 0.0;
+  std::vector<double> E, wdos, wdos_broadened;
+};
+
 struct od_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -58,9 +70,11 @@ struct od_ctx {
   DevBuf gslab[2];
 
   // scratch
-  DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, scratch_e, mw_tmp, in_tmp, in_tmp2, moments;
+  DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, scratch_e, mw_tmp, in_tmp, in_tmp2, moments, task_mw;
 
   Spectra dos_res, jdos_res;
+  OpticsRes optics_res;
+  CoreRes core_res;
 };
 
 int od_fail(od_ctx *ctx, int code, const char *fmt, ...);

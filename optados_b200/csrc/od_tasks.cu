@@ -1,0 +1,161 @@
+// od_tasks.cu -- host-side mirrors of two of the reference's tasks, built from the entry points of this library:
+//   optics_calculate  optics.f90:78-155   (interband): make_weights fused into the JDOS pass -> epsilon_2 ->
+//                                         Kramers-Kronig epsilon_1 -> conductivity, refractive index, loss function,
+//                                         absorption, reflection (the last five not for optics_geom = tensor)
+//   core_calculate    core.f90:38-83      Fermi level -> ELNES weights -> weighted DOS -> LAI broadening -> the unit
+//                                         factors of write_core (core.f90:317-323)
+// Same order of operations, same flags, same quirks (sticky dos_nbins Q4, weighted spectrum of the most complex
+// scheme Q14, single-precision literals Q11).  Writers, edge bookkeeping and the intraband (Drude) terms stay with
+// the caller / out of scope.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "od_internal.h"
+
+namespace {
+// optics.f90:68-72
+constexpr double kEps0 = 8.8541878176E-12, kECharge = 1.602176487E-19, kHbar = 1.054571628E-34, kCSpeed = 299792458.0;
+constexpr double kBohr2Ang = 0.52917720859;
+constexpr double kPi = 3.141592653589793238462643383279502884197;
+}  // namespace
+
+// ------------------------------------------------------------------ optics
+extern "C" void od_optics_params_defaults(od_optics_params *p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  od_jdos_params_defaults(&p->jdos);
+  p->geom = OD_GEOM_POLYCRYS;       // parameters.f90: optics_geom default 'polycrystalline'
+  p->qdir[0] = 1.0; p->qdir[1] = 1.0; p->qdir[2] = 1.0;  // parameters.f90: optics_qdir default
+  p->lossfn_gaussian = 0.0;
+}
+
+extern "C" int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const double *optical_mat, int ome_mem, const double *symops,
+                                   int num_symm, od_optics_result *res) {
+  if (!ctx || !p || !res || !optical_mat) return ctx ? od_fail(ctx, OD_ERR_ARG, "od_optics_calculate: null argument") : OD_ERR_ARG;
+  if (!(p->jdos.cell_volume > 0.0)) return od_fail(ctx, OD_ERR_ARG, "od_optics_calculate needs cell_volume");
+  memset(res, 0, sizeof(*res));
+  od_jdos_result jr;
+  // make_weights + jdos_utils_calculate(matrix_weights, weighted_jdos)   (optics.f90:104-107)
+  const int per_volume = p->jdos.dos_per_volume;
+  OD_CHECK(od_jdos_utils_calculate(ctx, &p->jdos, nullptr, 0, OD_MEM_HOST, optical_mat, ome_mem, p->geom, p->qdir, symops, num_symm, &jr));
+  (void)per_volume;
+  const int nbins = jr.nbins, ng = jr.n_geom, ns = ctx->ns;
+  OpticsRes &O = ctx->optics_res;
+  O = OpticsRes();
+  O.nbins = nbins; O.n_geom = ng; O.delta = jr.delta_bins;
+  O.E.resize(nbins);
+  for (int i = 0; i < nbins; ++i) O.E[i] = (double)i * jr.delta_bins;  // jdos_utils.f90:217
+  std::vector<double> wj((size_t)nbins * ns * ng), e2((size_t)nbins * ng), e1((size_t)nbins * ng);
+  OD_CHECK(od_jdos_get_weighted(ctx, wj.data()));
+  OD_CHECK(od_calc_epsilon_2(ctx, wj.data(), nbins, ns, ng, p->jdos.cell_volume, e2.data()));   // optics.f90:495-551
+  OD_CHECK(od_calc_epsilon_1(ctx, O.E.data(), nbins, ng, e2.data(), e1.data()));                // :569-621
+  O.epsilon.assign((size_t)nbins * 2 * ng, 0.0);  // epsilon(nbins, 2, n_geom): (:,1,:) real part, (:,2,:) imaginary part
+  for (int g = 0; g < ng; ++g)
+    for (int i = 0; i < nbins; ++i) {
+      O.epsilon[i + (size_t)nbins * (0 + 2 * g)] = e1[i + (size_t)nbins * g];
+      O.epsilon[i + (size_t)nbins * (1 + 2 * g)] = e2[i + (size_t)nbins * g];
+    }
+  res->nbins = nbins; res->n_geom = ng; res->delta_bins = jr.delta_bins;
+  if (p->geom == OD_GEOM_TENSOR) return OD_OK;  // optics.f90:130
+  // ---- derived quantities of component 1 (optics.f90:722-825)
+  O.conduct.resize((size_t)nbins * 2); O.refract.resize((size_t)nbins * 2); O.absorp.resize(nbins); O.reflect.resize(nbins);
+  for (int i = 0; i < nbins; ++i) {
+    const double E = O.E[i], a = e1[i], b = e2[i];
+    O.conduct[i] = (E * kECharge / kHbar) * kEps0 * b;                      // calc_conduct
+    O.conduct[i + (size_t)nbins] = (E * kECharge / kHbar) * kEps0 * (1.0 - a);
+    const double mod = pow((a * a) + (b * b), 0.5);
+    O.refract[i] = pow(0.5 * (mod + a), 0.5);                               // calc_refract
+    O.refract[i + (size_t)nbins] = pow(0.5 * (mod - a), 0.5);
+    O.absorp[i] = 2 * O.refract[i + (size_t)nbins] * E * kECharge / (kHbar * kCSpeed);  // calc_absorp
+    const double n = O.refract[i], k = O.refract[i + (size_t)nbins];
+    O.reflect[i] = (((n - 1) * (n - 1)) + (k * k)) / (((n + 1) * (n + 1)) + (k * k));     // calc_reflect
+  }
+  const bool lossb = fabs(p->lossfn_gaussian) >= 1.0e-6;  // parameters.f90:371
+  O.loss_fn.assign((size_t)nbins * (lossb ? 2 : 1), 0.0);
+  OD_CHECK(od_calc_loss_fn(ctx, O.E.data(), nbins, e1.data(), e2.data(), p->lossfn_gaussian, O.loss_fn.data(),
+                           lossb ? O.loss_fn.data() + nbins : nullptr));
+  res->have_derived = 1;
+  res->have_loss_fn_broadened = lossb ? 1 : 0;
+  return OD_OK;
+}
+
+static void copy_out(const std::vector<double> &v, double *dst) {
+  if (dst && !v.empty()) memcpy(dst, v.data(), sizeof(double) * v.size());
+}
+
+extern "C" int od_optics_get(od_ctx *ctx, double *E, double *epsilon, double *conduct, double *refract, double *loss_fn, double *absorp,
+                             double *reflect) {
+  if (!ctx) return OD_ERR_ARG;
+  const OpticsRes &O = ctx->optics_res;
+  if (O.nbins == 0) return od_fail(ctx, OD_ERR_STATE, "od_optics_calculate has not been called");
+  if ((conduct || refract || loss_fn || absorp || reflect) && O.conduct.empty())
+    return od_fail(ctx, OD_ERR_STATE, "no derived optical properties for optics_geom = tensor (optics.f90:130)");
+  copy_out(O.E, E); copy_out(O.epsilon, epsilon); copy_out(O.conduct, conduct); copy_out(O.refract, refract);
+  copy_out(O.loss_fn, loss_fn); copy_out(O.absorp, absorp); copy_out(O.reflect, reflect);
+  return OD_OK;
+}
+
+// ------------------------------------------------------------------ core
+extern "C" void od_core_params_defaults(od_core_params *p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  od_dos_params_defaults(&p->dos);
+  p->core_type = OD_CORE_ABSORPTION;  // parameters.f90: core_type default 'absorption'
+  p->polar = 0;                       // core_geom default 'polycrystalline'
+  p->qdir[0] = 0.0; p->qdir[1] = 0.0; p->qdir[2] = 1.0;
+  p->lai_broadening = 0;
+}
+
+extern "C" int od_core_calculate(od_ctx *ctx, od_core_params *p, const double *elnes_mat, int elnes_mem, int norb, const double *symops,
+                                 int num_sym, od_core_result *res) {
+  if (!ctx || !p || !res || !elnes_mat) return ctx ? od_fail(ctx, OD_ERR_ARG, "od_core_calculate: null argument") : OD_ERR_ARG;
+  if (norb < 1) return od_fail(ctx, OD_ERR_ARG, "od_core_calculate: norb = %d", norb);
+  if (!(p->dos.cell_volume > 0.0)) return od_fail(ctx, OD_ERR_ARG, "od_core_calculate needs cell_volume");
+  if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system has not been called");
+  memset(res, 0, sizeof(*res));
+  const int ns = ctx->ns, nb = ctx->nb, nk = ctx->nk;
+  // if (.not. efermi_set) call dos_utils_set_efermi   (core.f90:62)
+  double efermi = 0.0;
+  OD_CHECK(od_dos_utils_set_efermi(ctx, &p->dos, &efermi));
+  // core_prepare_matrix_elements (core.f90:64), weights stay on the device
+  const size_t nmw = (size_t)norb * nb * nk * ns;
+  OD_CHECK(od_buf_ensure(ctx, ctx->task_mw, sizeof(double) * nmw));
+  OD_CHECK(od_core_prepare_matrix_elements(ctx, elnes_mat, elnes_mem, norb, p->polar, p->qdir, symops, num_sym, p->core_type, efermi,
+                                           ctx->task_mw.as<double>(), OD_MEM_DEVICE));
+  // dos_utils_calculate(matrix_weights, weighted_dos) (core.f90:66); dos_nbins is sticky by now (quirk Q4)
+  od_dos_result dr;
+  OD_CHECK(od_dos_utils_calculate(ctx, &p->dos, ctx->task_mw.as<double>(), norb, nb, nk, OD_MEM_DEVICE, &dr));
+  if (!dr.have_weighted) return od_fail(ctx, OD_ERR_STATE, "no weighted DOS came back");
+  const int nbins = dr.nbins;
+  CoreRes &R = ctx->core_res;
+  R = CoreRes();
+  R.nbins = nbins; R.ns = ns; R.norb = norb; R.efermi = efermi;
+  R.E.resize(nbins);
+  for (int i = 0; i < nbins; ++i) R.E[i] = dr.emin + (double)i * dr.delta_bins;
+  const size_t n = (size_t)nbins * ns * norb;
+  R.wdos.resize(n);
+  OD_CHECK(od_dos_get_weighted(ctx, R.wdos.data()));
+  if (p->lai_broadening) {  // core.f90:70-76
+    R.wdos_broadened.resize(n);
+    OD_CHECK(od_core_lai_broadening(ctx, R.E.data(), nbins, ns * norb, efermi, p->lai_gaussian_width, p->lai_lorentzian_width,
+                                    p->lai_lorentzian_scale, p->lai_lorentzian_offset, R.wdos.data(), R.wdos_broadened.data()));
+  }
+  // write_core (core.f90:317-323): Ang^2 and the dimensionless-epsilon_2 factor, single-precision literals (Q11)
+  const double b2 = kBohr2Ang * kBohr2Ang;  // bohr2ang**2
+  const double c = (kECharge * kPi * (double)1E-20f) / (p->dos.cell_volume * (double)1E-30f * kEps0);
+  for (double &v : R.wdos) { v = v * b2; v = v * c; }
+  for (double &v : R.wdos_broadened) { v = v * b2; v = v * c; }
+  res->nbins = nbins; res->emin = dr.emin; res->delta_bins = dr.delta_bins; res->efermi = efermi; res->norb = norb;
+  res->have_broadened = p->lai_broadening ? 1 : 0;
+  return OD_OK;
+}
+
+extern "C" int od_core_get(od_ctx *ctx, double *E, double *weighted_dos, double *weighted_dos_broadened) {
+  if (!ctx) return OD_ERR_ARG;
+  const CoreRes &R = ctx->core_res;
+  if (R.nbins == 0) return od_fail(ctx, OD_ERR_STATE, "od_core_calculate has not been called");
+  if (weighted_dos_broadened && R.wdos_broadened.empty()) return od_fail(ctx, OD_ERR_STATE, "core_LAI_broadening was off");
+  copy_out(R.E, E); copy_out(R.wdos, weighted_dos); copy_out(R.wdos_broadened, weighted_dos_broadened);
+  return OD_OK;
+}

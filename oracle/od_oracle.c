@@ -844,6 +844,24 @@ void odo_calc_loss_fn(const double *epsilon1, const double *epsilon2, const doub
     }
 }
 
+/* optics.f90:722-825 (no intraband): calc_conduct, calc_refract, calc_absorp, calc_reflect of component 1.
+ * No golden file of the reference's test-suite holds these four (parity of this function is unpinned);
+ * they are O(B) closed forms of epsilon, which is pinned. */
+void odo_calc_optics_derived(const double *E, const double *epsilon1, const double *epsilon2, int nbins, double *conduct,
+                             double *refract, double *absorp, double *reflect) {
+  const double epsilon_0 = 8.8541878176E-12, e_charge = 1.602176487E-19, hbar = 1.054571628E-34, c_speed = 299792458.0; /* :68-72 */
+  int N;
+  for (N = 0; N < nbins; ++N) {
+    conduct[N] = (E[N] * e_charge / hbar) * epsilon_0 * epsilon2[N];
+    conduct[N + nbins] = (E[N] * e_charge / hbar) * epsilon_0 * (1.0 - epsilon1[N]);
+    refract[N] = pow(0.5 * ((pow((pow(epsilon1[N], 2.0)) + (pow(epsilon2[N], 2.0)), 0.5)) + epsilon1[N]), 0.5);
+    refract[N + nbins] = pow(0.5 * ((pow((pow(epsilon1[N], 2.0)) + (pow(epsilon2[N], 2.0)), 0.5)) - epsilon1[N]), 0.5);
+    absorp[N] = 2 * refract[N + nbins] * E[N] * e_charge / (hbar * c_speed);
+    reflect[N] = ((pow(refract[N] - 1, 2.0)) + (pow(refract[N + nbins], 2.0))) /
+                 ((pow(refract[N] + 1, 2.0)) + (pow(refract[N + nbins], 2.0)));
+  }
+}
+
 /* core.f90:692-732 core_lorentzian: every bin of weighted_dos(:, col) becomes a Lorentzian whose half width
  * grows linearly above efermi + offset (lifetime broadening); `out` is accumulated into (core.f90:72-75 zeroes it) */
 void odo_core_lorentzian(const double *wdos, const double *E, int nbins, int ncols, double efermi, double lorentzian_width,

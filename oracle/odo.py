@@ -266,6 +266,18 @@ def calc_loss_fn(eps1, eps2, E, lossfn_gaussian=0.0):
     return lf, (lb if br else None)
 
 
+def calc_optics_derived(E, eps1, eps2):
+    """optics.f90:722-825, component 1, no intraband -> dict(conduct (B,2), refract (B,2), absorp, reflect)"""
+    L = lib()
+    E = f64(E)
+    a, b = f64(np.asarray(eps1).reshape(-1)[:E.size]), f64(np.asarray(eps2).reshape(-1)[:E.size])
+    n = E.size
+    out = dict(conduct=np.zeros((n, 2), order="F"), refract=np.zeros((n, 2), order="F"), absorp=np.zeros(n), reflect=np.zeros(n))
+    L.odo_calc_optics_derived(_p(E), _p(a), _p(b), C.c_int(n), _p(out["conduct"]), _p(out["refract"]), _p(out["absorp"]),
+                              _p(out["reflect"]))
+    return out
+
+
 def core_lai_broadening(wdos, E, efermi, gaussian_width=0.0, lorentzian_width=0.0, lorentzian_scale=0.0, lorentzian_offset=0.0):
     """core.f90:70-76: weighted_dos(B, ns, norb) -> weighted_dos_broadened"""
     L = lib()

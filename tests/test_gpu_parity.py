@@ -543,3 +543,71 @@ def test_fixed_wide_on_reference_fixture(ob, odo):
     assert_int(r["intdos_fixed"], ref["intdos"])
     assert abs(r["efermi_fixed"] - ref["efermi"]) < 1e-9
     ctx.close()
+
+
+# ------------------------------------------------------------------ task mirrors
+@pytest.mark.parametrize("geom,btype,test", [("polar", "adaptive", "testopt_optics_polar"), ("tensor", "adaptive", "testopt_optics_tensor"),
+                                             ("unpolar", "linear", "testopt_optics_unpolar")])
+def test_optics_task_golden(ob, odo, geom, btype, test):
+    """od_optics_calculate (optics_calculate, optics.f90:78-155) in one call against the reference's golden files:
+    Si2_epsilon.dat (polar, tensor) and Si2_loss_fn.dat (unpolar); the derived quantities against the oracle."""
+    fx = fixture("si2_optics")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params(btype, dos_spacing=0.1, num_electrons=fx["num_electrons"])
+    ef = ctx.dos_utils_set_efermi(p)
+    r = ctx.optics_calculate(fx["optical_mat"], ef, float(fx["cell_volume"]), btype, geom=geom, qdir=(0.5, 0.5, 0.25), symops=fx["symops"],
+                             jdos_spacing=0.01, jdos_max_energy=30.0, lossfn_gaussian=1.0)
+    G = load_npz("gold_" + test)
+    if geom == "unpolar":
+        g = G["block0"]
+        assert r["loss_fn"].shape == (3000, 2)
+        assert rel_to_peak(r["loss_fn"][:, 0], g[:, 1]) < 1e-9
+        assert rel_to_peak(r["loss_fn"][:, 1], g[:, 2]) < 1e-9
+    else:
+        assert r["n_geom"] == len(G)
+        for c in range(r["n_geom"]):
+            g = G[f"block{c}"]
+            assert np.abs(r["E"] - g[:, 0]).max() < 1e-12
+            scale = np.abs(G["block0"][:, 2]).max()          # off-diagonal tensor components are ~0: compare on the diagonal's scale
+            assert np.abs(r["epsilon"][:, 1, c] - g[:, 2]).max() < 1e-9 * scale, c
+            assert np.abs(r["epsilon"][:, 0, c] - g[:, 1]).max() < 1e-9 * np.abs(G["block0"][:, 1]).max(), c
+    if geom == "tensor":
+        assert "conduct" not in r                              # optics.f90:130
+    else:
+        d = odo.calc_optics_derived(r["E"], r["epsilon"][:, 0, 0], r["epsilon"][:, 1, 0])
+        for k in ("conduct", "refract", "absorp", "reflect"):
+            assert np.abs(r[k] - d[k]).max() <= 1e-13 * np.abs(d[k]).max(), k
+    ctx.close()
+
+
+@pytest.mark.parametrize("test,btype,core_type,polar", [("testopt_core_polarised", "adaptive", "emission", True),
+                                                        ("testopt_core_emisson", "linear", "emission", True),
+                                                        ("testopt_core_all", "linear", "all", False)])
+def test_core_task_golden(ob, odo, test, btype, core_type, polar):
+    """od_core_calculate (core_calculate, core.f90:38-83 + the unit factors of write_core) in one call against both
+    data columns of the reference's Si2_core_edge.dat."""
+    lai = {"testopt_core_polarised": (0.0, 0.2, 0.1), "testopt_core_emisson": (0.5, 0.0, 0.0), "testopt_core_all": (0.8, 0.2, 0.1)}[test]
+    fx = fixture("si2_core")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params(btype, dos_spacing=0.01, num_electrons=fx["num_electrons"], cell_volume=float(fx["cell_volume"]))
+    r = ctx.core_calculate(fx["elnes_mat"], p, core_type=core_type, polar=polar, qdir=(0.5, 0.5, 0.25),
+                           symops=fx["symops"] if polar else None,
+                           lai=dict(gaussian_width=lai[0], lorentzian_width=lai[1], lorentzian_scale=lai[2]))
+    G = load_npz("gold_" + test)
+    ch2l = {1: 0, 2: 1, 3: 1, 4: 1, 5: 2, 6: 2, 7: 2, 8: 2, 9: 2}
+    keys = list(zip(fx["elnes_species"], fx["elnes_rank"], fx["elnes_shell"], [ch2l.get(int(a), 3) for a in fx["elnes_am"]]))
+    edges = []
+    for o, k in enumerate(keys):
+        if edges and edges[-1][0] == k:
+            edges[-1][1].append(o)
+        else:
+            edges.append((k, [o]))
+    assert len(edges) == len(G)
+    for i, (_, orbs) in enumerate(edges):
+        g = G[f"block{i}"]
+        assert g.shape[0] == r["nbins"] and np.abs(r["E"] - g[:, 0]).max() < 1e-10
+        col = sum(r["weighted_dos"][:, 0, o] for o in orbs) / float(len(orbs))
+        colb = sum(r["weighted_dos_broadened"][:, 0, o] for o in orbs) / float(len(orbs))
+        assert rel_to_peak(col, g[:, 1]) < TOL_SPEC, i
+        assert rel_to_peak(colb, g[:, 2]) < TOL_SPEC, i
+    ctx.close()
