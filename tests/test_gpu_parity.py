@@ -611,3 +611,41 @@ def test_core_task_golden(ob, odo, test, btype, core_type, polar):
         assert rel_to_peak(col, g[:, 1]) < TOL_SPEC, i
         assert rel_to_peak(colb, g[:, 2]) < TOL_SPEC, i
     ctx.close()
+
+
+# ------------------------------------------------------------------ size-independent properties at a larger scale
+def test_large_scale_properties(ob, monkeypatch):
+    """A k-slab of BASELINE config 2 (20k k-points x 256 bands x 2 spins = 10M states, 20 000 bins) in several
+    k-point slabs: total weight, monotone integrated DOS, integral of the DOS, and additivity over k-point subsets
+    (the spectrum of the whole set is the sum of the spectra of its two halves), for the adaptive, linear, narrow
+    fixed and wide fixed schemes.  No oracle at this size: these are the properties the domain offers."""
+    monkeypatch.setenv("OD_SLAB_UNITS", str(3 << 20))      # force 4 slabs per call
+    grid, ns, nb, nk = (100, 100, 100), 2, 256, 20000
+    nbins = 20000
+
+    def spectra(k_first, n):
+        ctx = ob.Context(0)
+        ctx.synth_bands(grid, k_first, n, ns, nb, seed=2)
+        out = {}
+        for name, t, br in (("adaptive", "a", ob.broadening()), ("linear", "l", ob.broadening()),
+                            ("fixed_narrow", "f", ob.broadening(fixed_smearing=0.02)), ("fixed_wide", "f", ob.broadening(fixed_smearing=0.3))):
+            out[name] = ctx.calculate_dos(t, -16.0, 42.0 / (nbins - 1), nbins, br=br)[:2]
+        kw = ctx.get_kweights().sum()
+        ctx.close()
+        return out, kw
+
+    whole, kw = spectra(0, nk)
+    a, kwa = spectra(0, nk // 2)
+    b, kwb = spectra(nk // 2, nk - nk // 2)
+    delta = 42.0 / (nbins - 1)
+    total = kw * nb                                       # electrons_per_state = 1 with two spins: weight per spin channel
+    for name, (dos, intdos) in whole.items():
+        assert np.all(np.abs(intdos[-1] - total) < 1e-10 * total), name            # every state inside the grid
+        assert np.all(np.diff(intdos, axis=0) > -1e-12 * total), name
+        assert np.all(np.abs(dos.sum(axis=0) * delta - total) < 2e-4 * total), name      # rectangle rule on the grid
+        assert np.all(dos >= -1e-12 * dos.max()), name
+        sum_dos, sum_int = a[name][0] + b[name][0], a[name][1] + b[name][1]
+        assert rel_to_peak(sum_dos, dos) < 1e-12, name
+        assert rel_to_peak(sum_int, intdos) < 1e-12, name
+    # the fixed schemes have one width for all states: the wide one is the narrow one convolved further; same integral
+    assert np.allclose(whole["fixed_wide"][1][-1], whole["fixed_narrow"][1][-1], rtol=1e-12)
