@@ -284,6 +284,8 @@ typedef struct od_optics_result {
   double delta_bins;      /* E(i) = (i-1)*delta_bins */
   int have_derived;       /* 0 for optics_geom = tensor */
   int have_loss_fn_broadened;
+  double n_eff;           /* sum rule of calc_epsilon_2 (optics.f90:552-563; N_geom = 1 only, else 0) */
+  double n_eff2, n_eff3;  /* first / second sum rule of calc_loss_fn (optics.f90:700-719; with have_derived) */
 } od_optics_result;
 int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const double *optical_mat, int ome_mem, const double *symops,
                         int num_symm, od_optics_result *res);

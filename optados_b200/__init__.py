@@ -63,7 +63,7 @@ class OpticsParams(C.Structure):
 
 class OpticsResult(C.Structure):
     _fields_ = [("nbins", C.c_int), ("n_geom", C.c_int), ("delta_bins", C.c_double), ("have_derived", C.c_int),
-                ("have_loss_fn_broadened", C.c_int)]
+                ("have_loss_fn_broadened", C.c_int), ("n_eff", C.c_double), ("n_eff2", C.c_double), ("n_eff3", C.c_double)]
 
 
 class CoreParams(C.Structure):
@@ -496,7 +496,8 @@ class Context:
         self._ck(self.L.od_optics_calculate(self.h, C.byref(p), om.ctypes.data_as(c_dp), C.c_int(OD_MEM_HOST), _p(so), C.c_int(nsym),
                                             C.byref(res)))
         n, ng = res.nbins, res.n_geom
-        out = dict(nbins=n, n_geom=ng, delta=res.delta_bins, E=np.zeros(n), epsilon=np.zeros((n, 2, ng), order="F"))
+        out = dict(nbins=n, n_geom=ng, delta=res.delta_bins, E=np.zeros(n), epsilon=np.zeros((n, 2, ng), order="F"),
+                   n_eff=res.n_eff, n_eff2=res.n_eff2, n_eff3=res.n_eff3)
         args = [_p(out["E"]), _p(out["epsilon"])]
         if res.have_derived:
             out.update(conduct=np.zeros((n, 2), order="F"), refract=np.zeros((n, 2), order="F"),

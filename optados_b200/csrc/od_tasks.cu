@@ -16,6 +16,7 @@
 namespace {
 // optics.f90:68-72
 constexpr double kEps0 = 8.8541878176E-12, kECharge = 1.602176487E-19, kHbar = 1.054571628E-34, kCSpeed = 299792458.0;
+constexpr double kEMass = 9.10938215E-31;
 constexpr double kBohr2Ang = 0.52917720859;
 constexpr double kPi = 3.141592653589793238462643383279502884197;
 }  // namespace
@@ -37,9 +38,7 @@ extern "C" int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const doubl
   memset(res, 0, sizeof(*res));
   od_jdos_result jr;
   // make_weights + jdos_utils_calculate(matrix_weights, weighted_jdos)   (optics.f90:104-107)
-  const int per_volume = p->jdos.dos_per_volume;
   OD_CHECK(od_jdos_utils_calculate(ctx, &p->jdos, nullptr, 0, OD_MEM_HOST, optical_mat, ome_mem, p->geom, p->qdir, symops, num_symm, &jr));
-  (void)per_volume;
   const int nbins = jr.nbins, ng = jr.n_geom, ns = ctx->ns;
   OpticsRes &O = ctx->optics_res;
   O = OpticsRes();
@@ -57,6 +56,12 @@ extern "C" int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const doubl
       O.epsilon[i + (size_t)nbins * (1 + 2 * g)] = e2[i + (size_t)nbins * g];
     }
   res->nbins = nbins; res->n_geom = ng; res->delta_bins = jr.delta_bins;
+  const double dE = O.E[1] - O.E[0], vol = p->jdos.cell_volume;
+  if (ng == 1) {  // sum rule of calc_epsilon_2 (optics.f90:552-563): the bin index, not the energy, multiplies dE**2
+    double x = 0.0;
+    for (int N = 2; N <= nbins; ++N) x = x + ((N * (dE * dE) * e2[N - 1]) / (kHbar * kHbar));
+    res->n_eff = (x * kEMass * vol * (double)1E-30f * kEps0 * 2) / (kPi);
+  }
   if (p->geom == OD_GEOM_TENSOR) return OD_OK;  // optics.f90:130
   // ---- derived quantities of component 1 (optics.f90:722-825)
   O.conduct.resize((size_t)nbins * 2); O.refract.resize((size_t)nbins * 2); O.absorp.resize(nbins); O.reflect.resize(nbins);
@@ -75,6 +80,14 @@ extern "C" int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const doubl
   O.loss_fn.assign((size_t)nbins * (lossb ? 2 : 1), 0.0);
   OD_CHECK(od_calc_loss_fn(ctx, O.E.data(), nbins, e1.data(), e2.data(), p->lossfn_gaussian, O.loss_fn.data(),
                            lossb ? O.loss_fn.data() + nbins : nullptr));
+  {  // sum rules of calc_loss_fn (optics.f90:700-719)
+    double x = 0.0;
+    for (int N = 2; N <= nbins; ++N) x = x + (N * (dE * dE) * O.loss_fn[N - 1]);
+    res->n_eff2 = x * (kEMass * vol * (double)1E-30f * kEps0 * 2) / (kPi * (kHbar * kHbar));
+    x = 0;
+    for (int N = 2; N <= nbins; ++N) x = x + (O.loss_fn[N - 1] / N);
+    res->n_eff3 = x;
+  }
   res->have_derived = 1;
   res->have_loss_fn_broadened = lossb ? 1 : 0;
   return OD_OK;

@@ -844,6 +844,30 @@ void odo_calc_loss_fn(const double *epsilon1, const double *epsilon2, const doub
     }
 }
 
+/* sum rules (no intraband): N_eff of calc_epsilon_2 (optics.f90:552-563, N_geom = 1 only) and N_eff2 / N_eff3 of
+ * calc_loss_fn (:700-719).  The loop index N (1-based), not the energy, multiplies dE**2; 1E-30 is a
+ * single-precision literal (Q11). */
+void odo_optics_sum_rules(const double *E, const double *epsilon2, const double *loss_fn, int nbins, double cell_volume,
+                          double *N_eff, double *N_eff2, double *N_eff3) {
+  const double epsilon_0 = 8.8541878176E-12, e_mass = 9.10938215E-31, hbar = 1.054571628E-34; /* :68-71 */
+  const double dE = E[1] - E[0];
+  double x;
+  int N;
+  if (epsilon2 && N_eff) {
+    x = 0.0;
+    for (N = 2; N <= nbins; ++N) x = x + ((N * (pow(dE, 2.0)) * epsilon2[N - 1]) / (pow(hbar, 2.0)));
+    *N_eff = (x * e_mass * cell_volume * (double)1E-30f * epsilon_0 * 2) / (ODO_PI);
+  }
+  if (loss_fn && N_eff2 && N_eff3) {
+    x = 0.0;
+    for (N = 2; N <= nbins; ++N) x = x + (N * (pow(dE, 2.0)) * loss_fn[N - 1]);
+    *N_eff2 = x * (e_mass * cell_volume * (double)1E-30f * epsilon_0 * 2) / (ODO_PI * (pow(hbar, 2.0)));
+    x = 0;
+    for (N = 2; N <= nbins; ++N) x = x + (loss_fn[N - 1] / N);
+    *N_eff3 = x;
+  }
+}
+
 /* optics.f90:722-825 (no intraband): calc_conduct, calc_refract, calc_absorp, calc_reflect of component 1.
  * No golden file of the reference's test-suite holds these four (parity of this function is unpinned);
  * they are O(B) closed forms of epsilon, which is pinned. */

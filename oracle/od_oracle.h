@@ -137,6 +137,8 @@ void odo_calc_epsilon_1(const double *epsilon2, const double *E, int nbins, int 
                         double *epsilon1);
 void odo_calc_loss_fn(const double *epsilon1, const double *epsilon2, const double *E, int nbins, int broadening,
                       double lossfn_gaussian, double *loss_fn, double *loss_fn_broadened);
+void odo_optics_sum_rules(const double *E, const double *epsilon2, const double *loss_fn, int nbins, double cell_volume,
+                          double *N_eff, double *N_eff2, double *N_eff3);
 void odo_calc_optics_derived(const double *E, const double *epsilon1, const double *epsilon2, int nbins, double *conduct,
                              double *refract, double *absorp, double *reflect);
 void odo_core_lorentzian(const double *wdos, const double *E, int nbins, int ncols, double efermi, double lorentzian_width,

@@ -266,6 +266,16 @@ def calc_loss_fn(eps1, eps2, E, lossfn_gaussian=0.0):
     return lf, (lb if br else None)
 
 
+def optics_sum_rules(E, eps2, loss_fn, cell_volume):
+    """N_eff (optics.f90:552-563), N_eff2, N_eff3 (:700-719); eps2 / loss_fn: component 1, no intraband"""
+    L = lib()
+    E = f64(E)
+    a, b = f64(np.asarray(eps2).reshape(-1)[:E.size]), f64(np.asarray(loss_fn).reshape(-1)[:E.size])
+    n1, n2, n3 = C.c_double(), C.c_double(), C.c_double()
+    L.odo_optics_sum_rules(_p(E), _p(a), _p(b), C.c_int(E.size), C.c_double(cell_volume), C.byref(n1), C.byref(n2), C.byref(n3))
+    return n1.value, n2.value, n3.value
+
+
 def calc_optics_derived(E, eps1, eps2):
     """optics.f90:722-825, component 1, no intraband -> dict(conduct (B,2), refract (B,2), absorp, reflect)"""
     L = lib()

@@ -273,6 +273,22 @@ def golden_odo(test, seed):
     return out
 
 
+def golden_header_scalars(test, seed):
+    """sum rules printed in the headers of Si2_epsilon.dat / Si2_loss_fn.dat (optics.f90:895, :1030-1031)"""
+    path = f"{REF}/tests/{test}/benchmark.out.default.inp={seed}.odi"
+    out = {}
+    for line in open(path):
+        if not line.lstrip().startswith("#"):
+            break
+        for key, pat in (("N_eff", r"Result of sum rule: Neff\(E\) =\s*([-+\dEe.]+)"),
+                         ("N_eff2", r"Result of first sum rule: Neff\(E\) =\s*([-+\dEe.]+)"),
+                         ("N_eff3", r"Result of second sum rule \(pi/2 = 1.570796327\):\s*([-+\dEe.]+)")):
+            m = re.search(pat, line)
+            if m:
+                out[key] = float(m.group(1))
+    return out
+
+
 def save(name, d):
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **{k: np.asarray(v) for k, v in d.items()})
@@ -302,6 +318,8 @@ def main():
     for t in ["testopt_dos_fixed", "testopt_dos_adaptive", "testopt_dos_linear", "testopt_jdos_fixed_odo",
               "testopt_pdos_string1", "testopt_pdos_string4", "testopt_optics_poly", "testopt_core_absorb"]:
         odo[t] = golden_odo(t, "Si2")
+    for t in ["testopt_optics_polar", "testopt_optics_unpolar"]:
+        odo[t] = golden_header_scalars(t, "Si2")
     with open(os.path.join(OUT, "gold_odo.json"), "w") as f:
         json.dump(odo, f, indent=1, sort_keys=True)
     print("gold_odo.json", odo)

@@ -558,6 +558,14 @@ def test_optics_task_golden(ob, odo, geom, btype, test):
     r = ctx.optics_calculate(fx["optical_mat"], ef, float(fx["cell_volume"]), btype, geom=geom, qdir=(0.5, 0.5, 0.25), symops=fx["symops"],
                              jdos_spacing=0.01, jdos_max_energy=30.0, lossfn_gaussian=1.0)
     G = load_npz("gold_" + test)
+    import json
+    import os
+    hdr = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gold_odo.json"))).get(test, {})
+    if "N_eff" in hdr:       # header of Si2_epsilon.dat (optics.f90:895)
+        assert abs(r["n_eff"] / hdr["N_eff"] - 1.0) < 1e-9
+    if "N_eff2" in hdr:      # header of Si2_loss_fn.dat (optics.f90:1030-1031)
+        assert abs(r["n_eff2"] / hdr["N_eff2"] - 1.0) < 1e-9
+        assert abs(r["n_eff3"] / hdr["N_eff3"] - 1.0) < 1e-9
     if geom == "unpolar":
         g = G["block0"]
         assert r["loss_fn"].shape == (3000, 2)

@@ -157,6 +157,23 @@ def test_optics_unpolar_loss_fn(odo):
     assert rel_to_peak(lb, g[:, 2]) < 1e-11
 
 
+def test_optics_sum_rules(odo):
+    """the sum rules printed in the headers of Si2_epsilon.dat (polar) and Si2_loss_fn.dat (unpolar)"""
+    import json
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gold_odo.json")))
+    fx = fixture("si2_optics")
+    vol = float(fx["cell_volume"])
+    r, e1, e2 = _optics(odo, "polar", "adaptive")
+    lf, _ = odo.calc_loss_fn(e1[:, 0], e2[:, 0], r["E"])
+    n1, _, _ = odo.optics_sum_rules(r["E"], e2[:, 0], lf, vol)
+    assert abs(n1 / G["testopt_optics_polar"]["N_eff"] - 1.0) < 1e-12
+    r, e1, e2 = _optics(odo, "unpolar", "linear")
+    lf, _ = odo.calc_loss_fn(e1[:, 0], e2[:, 0], r["E"], lossfn_gaussian=1.0)
+    _, n2, n3 = odo.optics_sum_rules(r["E"], e2[:, 0], lf, vol)
+    assert abs(n2 / G["testopt_optics_unpolar"]["N_eff2"] - 1.0) < 1e-11
+    assert abs(n3 / G["testopt_optics_unpolar"]["N_eff3"] - 1.0) < 1e-11
+
+
 def test_optics_tensor_epsilon(odo):
     r, e1, e2 = _optics(odo, "tensor", "adaptive")
     G = gold("testopt_optics_tensor")
