@@ -12,19 +12,24 @@
 //      bucket order using shared-memory cursors only.  Sorting by width class as well as by
 //      position makes the 32 records of a warp-group nearly congruent, which is what lets one
 //      lane = one record run without idle lanes.
-//   2. ACCUMULATES: warps pull chunks of 2048 consecutive records.  Within a group of 32 records
+//   2. ACCUMULATES: warps pull chunks of 512 consecutive records.  Within a group of 32 records
 //      LANE = RECORD: every lane walks all bins of the group's common window, lane l starting l
 //      bins in and wrapping round, so that in any one step the 32 lanes touch 32 DIFFERENT bins
 //      of a warp-private shared-memory tile -- plain LDS/STS read-modify-write, no atomics, no
-//      reductions.  Walking consecutive bins lets a lane advance its Gaussian by the recurrence
+//      reductions; windows of >= 64 bins run as two interleaved half-window streams per lane.
+//      Walking consecutive bins lets a lane advance its Gaussian by the recurrence
 //      g(j+1) = g(j) r(j), r(j+1) = r(j) q  (q = exp(-dE^2/w^2)): two multiplies per bin instead
 //      of an exp.  The integrated spectrum is split as Phi(z) = H(z >= 0) + [Phi(z) - H]: the
-//      bracket is as local as the DOS and shares its Gaussian,
-//      Phi - H = -+ (1/2) g' R(|z|),  R = P5/Q6 ~ erfcx(|z|/sqrt 2)  (tools/fit_erfcx.py, 5.4e-15),
-//      one reciprocal per bin; the steps H go to a warp-private step tile once per record and
-//      become a prefix sum at the very end.  The linear scheme evaluates the four doslin pieces
-//      branch-free and selects.  Tiles are flushed to HBM with FP64 reductions only when a warp's
-//      window slides off its 512-bin tile or its chunk ends.
+//      bracket is as local as the DOS and shares its Gaussian; the steps H go to a warp-private
+//      step tile once per record and become a prefix sum at the very end.  The bracket is
+//        - for windows up to 84 bins: -+ (1/2) g' R(|z|), R = P5/Q6 ~ erfcx(|z|/sqrt 2)
+//          (tools/fit_erfcx.py, 5.4e-15), one reciprocal per bin;
+//        - for wider windows (dE/w <= 0.2): the Euler-Maclaurin relation between the lane's running
+//          sum of its own Gaussian values and the integral (see narrow_kernel<.., EM>).
+//      The linear scheme evaluates doslin as two smooth forms with clamped arguments and one select.
+//      JDOS / optics / weighted DOS run the same loops in channel passes (JD), many projectors through
+//      a banded GEMM on the FP64 tensor cores (pdos_gemm_kernel).  Tiles are flushed to HBM with FP64
+//      reductions only when a warp's window slides off its 512-bin tile or its chunk ends.
 //   3. Units whose window is wider than 480 bins (and degenerate ones) go to the dense bin-owner
 //      engine (od_accum.cuh) through a compacted list; the partial spectra are then combined.
 //
@@ -45,23 +50,11 @@
 
 namespace {
 
-#ifndef OD_X_UNROLL
-#define OD_X_UNROLL 1
-#endif
-#ifndef OD_X_ESTRIN
-#define OD_X_ESTRIN 0
-#endif
-#define OD_PRAGMA(x) _Pragma(#x)
-#define OD_UNROLL(n) OD_PRAGMA(unroll n)
-#ifndef OD_X_T
-#define OD_X_T 512
-#define OD_X_WMAX OD_NARROW_WMAX
-#define OD_X_MINB 2
-#endif
-constexpr int NR_T = OD_X_T;        // bins per warp tile
-constexpr int NR_WMAX = OD_X_WMAX;     // widest window (bins) the narrow engine takes (Wc + 1 <= NR_T - cell)
+constexpr int NR_T = 512;        // bins per warp tile
+constexpr int NR_WMAX = OD_NARROW_WMAX;     // widest window (bins) the narrow engine takes (Wc + 1 <= NR_T - cell)
 constexpr int NR_CHUNK = 512;   // records per work item
 constexpr int NR_WARPS = 8;      // warps per CTA
+constexpr int NR_CTAS_PER_SM = 2; // accumulate kernels: 2 x 8 warps per SM (registers and shared memory both allow no more)
 constexpr int NR_NCLS = 10;      // width classes
 constexpr int NR_EM_CLASS = 5;   // first width class (windows > 84 bins) whose integrated DOS runs on the Euler-Maclaurin form
 constexpr int NR_MAXBUCKETS = 52224;  // x 4 B = 204 KB of shared memory in the prepare passes
@@ -343,14 +336,6 @@ struct ErfcxCoef {
 
 // cf points into the kernel parameter block, so the coefficients enter the FMAs as c[0x0][..] operands
 __device__ __forceinline__ double erfcx_ratio(double u, const ErfcxCoef &cf) {
-#if OD_X_ESTRIN
-  const double u2 = u * u, u4 = u2 * u2;
-  const double p01 = fma(cf.P[1], u, cf.P[0]), p23 = fma(cf.P[3], u, cf.P[2]), p45 = fma(cf.P[5], u, cf.P[4]);
-  const double q01 = fma(cf.Q[1], u, cf.Q[0]), q23 = fma(cf.Q[3], u, cf.Q[2]), q45 = fma(cf.Q[5], u, cf.Q[4]) + u2;
-  const double pe = fma(u4, p45, fma(u2, p23, p01));
-  const double qe = fma(u4, q45, fma(u2, q23, q01));
-  return pe * rcp_newton(qe);
-#endif
   double p = cf.P[5];
   p = fma(p, u, cf.P[4]);
   p = fma(p, u, cf.P[3]);
@@ -424,7 +409,7 @@ __device__ __forceinline__ void gauss_direct(double e, double w, double om, doub
 // of the series is 2e-6 del^10 of omega; del = dE/w <= 0.2 in these classes (windows of more than 84 bins), i.e.
 // <= 2e-13.  C is fixed at the start of every segment (walk start, wrap) from the rational erfc.
 template <bool LINEAR, bool JD, bool EM = false>
-__global__ void __launch_bounds__(NR_WARPS * 32, OD_X_MINB) narrow_kernel(NarrowArgs A) {
+__global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(NarrowArgs A) {
   extern __shared__ double2 sh_tiles[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2 *tile = sh_tiles + (size_t)warp * NR_T;
@@ -448,13 +433,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, OD_X_MINB) narrow_kernel(Narrow
       const long long idx = g0 + lane;
       const bool valid = idx < c1;
       // ---- my record (and a prefetch of the one this lane takes in the next group)
-#ifndef OD_X_GDIV
-#define OD_X_GDIV 1
-#endif
-#ifndef OD_X_NOPF
-#define OD_X_NOPF 0
-#endif
-      if (!OD_X_NOPF && idx + 32 < c1) {
+      if (idx + 32 < c1) {
         const char *nx = reinterpret_cast<const char *>(A.recs) + (size_t)(idx + 32) * (LINEAR ? sizeof(LRec) : sizeof(GRec));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
       }
@@ -554,7 +533,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, OD_X_MINB) narrow_kernel(Narrow
       const int H = dual ? (Wc + 1) >> 1 : Wc;
       const int n2 = dual ? Wc - H : 0;
       if (!LINEAR) {
-        const double invw = OD_X_GDIV ? 1.0 / p1 : fast_rcp(p1), del = delta * invw;
+        const double invw = 1.0 / p1, del = delta * invw;  // (the reciprocal by MUFU + Newton measured slower here)
         const double amp = om * invw * OD_INV_SQRT_TWO_PI;
         const double cl = p1 * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
         const double q = exp(-del * del), hd2 = 0.5 * del * del;
@@ -626,7 +605,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, OD_X_MINB) narrow_kernel(Narrow
           double z2 = zB + (double)(lane + H) * del;
           double g2 = amp * exp(-0.5 * z2 * z2), rr2 = exp(-fma(z2, del, hd2));
           int r2 = lane + H;
-OD_UNROLL(OD_X_UNROLL)
+#pragma unroll 1
           for (int t = 0; t < n2; ++t) {
             // capture this step's inputs, then advance the recurrences at once so that the next step's
             // operands are ready long before the rational chains below have drained
@@ -711,7 +690,7 @@ OD_UNROLL(OD_X_UNROLL)
         if (dual) {
           double t2 = tB + (double)(lane + H) * delta;
           int r2 = lane + H;
-OD_UNROLL(OD_X_UNROLL)
+#pragma unroll 1
           for (int t = 0; t < n2; ++t) {
             double2 *q1 = tw + r1, *q2 = tw + r2;
             double2 acc1 = *q1;
@@ -1153,7 +1132,7 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
       B.nrec = n;
       OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
       const long long nch = (n + NR_CHUNK - 1) / NR_CHUNK;
-      const int nb = (int)std::min<long long>((long long)ctx->sm_count * OD_X_MINB, (nch + NR_WARPS - 1) / NR_WARPS);
+      const int nb = (int)std::min<long long>((long long)ctx->sm_count * NR_CTAS_PER_SM, (nch + NR_WARPS - 1) / NR_WARPS);
       if (h == 0) {
         OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         narrow_kernel<false, false, false><<<nb, NR_WARPS * 32, smem, ctx->stream>>>(B);
@@ -1167,7 +1146,7 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
   }
   OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
   const long long nchunks = ((long long)nrec + NR_CHUNK - 1) / NR_CHUNK;
-  const int blocks = (int)std::min<long long>((long long)ctx->sm_count * OD_X_MINB, (nchunks + NR_WARPS - 1) / NR_WARPS);
+  const int blocks = (int)std::min<long long>((long long)ctx->sm_count * NR_CTAS_PER_SM, (nchunks + NR_WARPS - 1) / NR_WARPS);
   if (linear) {
     OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<true, JD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     narrow_kernel<true, JD><<<blocks, NR_WARPS * 32, smem, ctx->stream>>>(A);
