@@ -657,3 +657,22 @@ def test_large_scale_properties(ob, monkeypatch):
         assert rel_to_peak(sum_int, intdos) < 1e-12, name
     # the fixed schemes have one width for all states: the wide one is the narrow one convolved further; same integral
     assert np.allclose(whole["fixed_wide"][1][-1], whole["fixed_narrow"][1][-1], rtol=1e-12)
+
+
+@pytest.mark.parametrize("nbins", [60000, 150000])
+def test_very_fine_grids(ob, odo, nbins):
+    """grids with more bins than the bucket table has 8-bin cells for (the prepare pass then doubles its cell size):
+    adaptive, linear and fixed against the oracle"""
+    ctx = ob.Context(0)
+    grid, ns, nb = (7, 6, 5), 2, 16
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=9)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
+    E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=nbins)
+    for t, smear in (("a", 0.3), ("l", 0.3), ("f", 0.004), ("f", 0.3)):
+        ref = odo.calculate_dos(t, s, odo.make_broadening(fixed_smearing=smear, adaptive_smearing=0.1), E, delta, nthreads=8)
+        dos, intdos, _ = ctx.calculate_dos(t, E[0], delta, n, br=ob.broadening(fixed_smearing=smear, adaptive_smearing=0.1))
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC, (t, smear)
+        assert_int(intdos, ref[1])
+    ctx.close()
