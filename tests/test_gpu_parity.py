@@ -676,3 +676,31 @@ def test_very_fine_grids(ob, odo, nbins):
         assert rel_to_peak(dos, ref[0]) < TOL_SPEC, (t, smear)
         assert_int(intdos, ref[1])
     ctx.close()
+
+
+def test_single_spin_and_unequal_kpoint_weights(ob, odo):
+    """one spin channel (electrons_per_state = 2) and symmetry-reduced-style k-point weights through the narrow
+    engine (rational and Euler-Maclaurin classes), the linear scheme and the wide fixed path"""
+    gen = ob.Context(0)
+    grid, nb = (12, 10, 8), 20
+    nk = grid[0] * grid[1] * grid[2]
+    gen.synth_bands(grid, 0, nk, 1, nb, seed=5)
+    be, bg = gen.get_bands(), gen.get_gradients()
+    gen.close()
+    rng = np.random.default_rng(3)
+    kw = rng.integers(1, 49, size=nk).astype(np.float64)
+    kw /= kw.sum()
+    recip = np.eye(3) * (2 * np.pi / 5.43)
+    s = odo.Sys(be, kw, recip, grid, bg, electrons_per_state=2.0)
+    ctx = ob.Context(0)
+    ctx.set_system(nk, 1, nb, recip, np.array(grid, dtype=np.int32), kw, 2.0)
+    ctx.set_bands(be)
+    ctx.set_gradients(bg)
+    E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=12000)
+    for t, smear in (("a", 0.3), ("l", 0.3), ("f", 0.02), ("f", 0.3)):
+        ref = odo.calculate_dos(t, s, odo.make_broadening(fixed_smearing=smear), E, delta, nthreads=8)
+        dos, intdos, _ = ctx.calculate_dos(t, E[0], delta, n, br=ob.broadening(fixed_smearing=smear))
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC, (t, smear)
+        assert_int(intdos, ref[1])
+        assert abs(intdos[-1, 0] - 2.0 * nb) < 1e-9 * nb
+    ctx.close()
