@@ -227,6 +227,12 @@ int od_dos_get_weighted(od_ctx *ctx, double *weighted_dos);
 /* calc_efermi_from_intdos (dos_utils.f90:798-850) on host arrays */
 double od_calc_efermi_from_intdos(const double *intdos, double emin, double delta_bins, int nbins, int ns,
                                   const double *num_electrons);
+/* dos_utils_calculate_at_e (dos_utils.f90:1531-1648): dos_at_e(3, ns) = rows (fixed, adaptive, linear) of the enabled
+ * schemes (others zero); weighted_dos_at_e(ns, mw_norb) from the most complex enabled scheme; delta_bins is the
+ * reference's module variable of the last energy scale (it only enters through finite_bin_correction). */
+int od_dos_utils_calculate_at_e(od_ctx *ctx, const od_dos_params *p, double energy, double delta_bins,
+                                const double *matrix_weights, int mw_norb, int mw_nb, int mw_nk, int mw_mem,
+                                double *dos_at_e, double *weighted_dos_at_e);
 /* dos_utils_set_efermi (dos_utils.f90:296-388).  For OD_EFERMI_OPTADOS runs od_dos_utils_calculate. */
 int od_dos_utils_set_efermi(od_ctx *ctx, od_dos_params *p, double *efermi);
 

@@ -119,7 +119,7 @@ EXPORTS = [
     "od_timer_start", "od_timer_stop", "od_measure_fp64_peak", "od_count_contributions", "od_host_alloc_pinned",
     "od_host_free_pinned", "od_set_engine",
     "od_calc_epsilon_1", "od_calc_loss_fn", "od_core_lai_broadening",
-    "od_optics_params_defaults", "od_optics_calculate", "od_optics_get", "od_core_params_defaults", "od_core_calculate",
+    "od_dos_utils_calculate_at_e", "od_optics_params_defaults", "od_optics_calculate", "od_optics_get", "od_core_params_defaults", "od_core_calculate",
     "od_core_get",
     "od_io_last_error", "od_read_bands_info", "od_read_bands", "od_cell_calc_lattice", "od_cell_find_mp_grid",
     "od_read_symmetry_ops", "od_read_ome", "od_read_dome", "od_read_pdos_info", "od_read_pdos", "od_read_elnes_info",
@@ -429,6 +429,19 @@ class Context:
             self._ck(self.L.od_dos_get_weighted(self.h, _p(w)))
             out["weighted_dos"] = w
         return out
+
+    def dos_utils_calculate_at_e(self, p, energy, delta_bins, mw=None):
+        """dos_utils_calculate_at_e (dos_utils.f90:1531): -> dos_at_e(3, ns), weighted_dos_at_e(ns, norb) or None"""
+        d = np.zeros((3, self.ns), order="F")
+        w = None
+        norb = mwnb = mwnk = 0
+        if mw is not None:
+            mw = f64(mw)
+            norb, mwnb, mwnk = mw.shape[0], mw.shape[1], mw.shape[2]
+            w = np.zeros((self.ns, norb), order="F")
+        self._ck(self.L.od_dos_utils_calculate_at_e(self.h, C.byref(p), C.c_double(energy), C.c_double(delta_bins), _p(mw), C.c_int(norb),
+                                                    C.c_int(mwnb), C.c_int(mwnk), C.c_int(OD_MEM_HOST), _p(d), _p(w)))
+        return d, w
 
     def dos_utils_set_efermi(self, p):
         ef = C.c_double()

@@ -258,6 +258,31 @@ extern "C" int od_dos_utils_set_efermi(od_ctx *ctx, od_dos_params *p, double *ef
   }
 }
 
+// ------------------------------------------------------------------ dos_utils_calculate_at_e
+// dos_utils.f90:1531-1648: every enabled scheme fills its row of dos_at_e(1:3, ns) = (fixed, adaptive, linear);
+// the weighted values come from the most complex enabled scheme only (same rule as dos_utils_calculate, Q14).
+extern "C" int od_dos_utils_calculate_at_e(od_ctx *ctx, const od_dos_params *p, double energy, double delta_bins,
+                                           const double *matrix_weights, int mw_norb, int mw_nb, int mw_nk, int mw_mem,
+                                           double *dos_at_e, double *weighted_dos_at_e) {
+  if (!ctx || !p || !dos_at_e) return OD_ERR_ARG;
+  if (!(p->linear || p->adaptive || p->fixed)) return od_fail(ctx, OD_ERR_REF, " DOS: No Broadening Set (dos_utils.f90:1545)");
+  if (matrix_weights && !weighted_dos_at_e) return od_fail(ctx, OD_ERR_ARG, "matrix_weights given without weighted_dos_at_e");
+  if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system has not been called");
+  const int ns = ctx->ns;
+  for (int i = 0; i < 3 * ns; ++i) dos_at_e[i] = 0.0;
+  const char types[3] = {'f', 'a', 'l'};
+  const int enabled[3] = {p->fixed, p->adaptive, p->linear};
+  const bool with_w[3] = {matrix_weights && !p->adaptive && !p->linear, matrix_weights && !p->linear, matrix_weights != nullptr};
+  std::vector<double> row((size_t)ns);
+  for (int t = 0; t < 3; ++t) {
+    if (!enabled[t]) continue;
+    OD_CHECK(od_calculate_dos_at_e(ctx, types[t], energy, delta_bins, &p->br, with_w[t] ? matrix_weights : nullptr, mw_norb, mw_nb, mw_nk,
+                                   mw_mem, /*merge=*/1, row.data(), with_w[t] ? weighted_dos_at_e : nullptr));
+    for (int is = 0; is < ns; ++is) dos_at_e[t + 3 * is] = row[is];  // dos_at_e(t, is)
+  }
+  return OD_OK;
+}
+
 // ------------------------------------------------------------------ jdos_utils_calculate
 extern "C" int od_jdos_utils_calculate(od_ctx *ctx, od_jdos_params *p, const double *matrix_weights, int n_geom, int mw_mem,
                                        const double *optical_mat, int ome_mem, int geom, const double qdir[3], const double *symops,

@@ -704,3 +704,25 @@ def test_single_spin_and_unequal_kpoint_weights(ob, odo):
         assert_int(intdos, ref[1])
         assert abs(intdos[-1, 0] - 2.0 * nb) < 1e-9 * nb
     ctx.close()
+
+
+@pytest.mark.parametrize("schemes", [("fixed",), ("fixed", "adaptive"), ("fixed", "adaptive", "linear"), ("linear",)])
+def test_dos_utils_calculate_at_e_driver(ob, odo, schemes):
+    """dos_utils_calculate_at_e (dos_utils.f90:1531-1648): one row of dos_at_e(3, ns) per enabled scheme, the weighted
+    values from the most complex one"""
+    fx = fixture("si2_dos")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    rng = np.random.default_rng(8)
+    mw = np.asfortranarray(rng.random((5, s.nb, s.nk, s.ns)))
+    p = ctx.dos_params(list(schemes), dos_spacing=0.05, num_electrons=fx["num_electrons"])
+    d, w = ctx.dos_utils_calculate_at_e(p, 4.3, 0.05, mw=mw)
+    top = [t for t in ("fixed", "adaptive", "linear") if t in schemes][-1]
+    for row, t in enumerate(("fixed", "adaptive", "linear")):
+        if t in schemes:
+            d_ref, w_ref = odo.calculate_dos_at_e(t[0], s, odo.make_broadening(), 0.05, 4.3, mw)
+            assert np.abs(d[row] - d_ref).max() <= 1e-12 * max(1.0, np.abs(d_ref).max())
+            if t == top:
+                assert np.abs(w - w_ref).max() <= 1e-12 * max(1.0, np.abs(w_ref).max())
+        else:
+            assert not d[row].any()
+    ctx.close()
