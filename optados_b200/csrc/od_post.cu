@@ -84,7 +84,7 @@ __global__ void pair_reduce_kernel(const double *__restrict__ partial, int nseg,
 template <class Op>
 int pair_sum(od_ctx *ctx, const Op &op, const double *d_E, const double *d_val, const double *d_par, int nbins, int ncols, double *d_out) {
   const int jb = (nbins + PP_THREADS - 1) / PP_THREADS;
-  int nseg = (2 * ctx->sm_count + jb * ncols - 1) / (jb * ncols);
+  int nseg = (16 * ctx->sm_count + jb * ncols - 1) / (jb * ncols);  // enough CTAs of 128 threads to fill every SM
   nseg = std::max(1, std::min(nseg, 64));
   int seg_len = (nbins + nseg - 1) / nseg;
   seg_len = ((seg_len + PP_TILE - 1) / PP_TILE) * PP_TILE;
