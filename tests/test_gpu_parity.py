@@ -726,3 +726,25 @@ def test_dos_utils_calculate_at_e_driver(ob, odo, schemes):
         else:
             assert not d[row].any()
     ctx.close()
+
+
+def test_euler_maclaurin_matches_rational(ob, odo, monkeypatch):
+    """integrated DOS of the wide width classes: the Euler-Maclaurin form (default) against the rational erfc per bin
+    (OD_NO_EM=1) and against the oracle, on a grid fine enough that most windows exceed 84 bins"""
+    ctx = ob.Context(0)
+    grid, ns, nb = (16, 12, 10), 2, 24
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=11)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
+    E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=20000)
+    ref = odo.calculate_dos("a", s, odo.make_broadening(), E, delta, nthreads=8)
+    monkeypatch.delenv("OD_NO_EM", raising=False)
+    dos_em, int_em, _ = ctx.calculate_dos("a", E[0], delta, n)
+    monkeypatch.setenv("OD_NO_EM", "1")
+    dos_ra, int_ra, _ = ctx.calculate_dos("a", E[0], delta, n)
+    scale = np.abs(ref[1]).max()
+    assert np.abs(int_em - int_ra).max() < 1e-12 * scale
+    assert np.abs(int_em - ref[1]).max() < 1e-12 * scale and np.abs(int_ra - ref[1]).max() < 1e-12 * scale
+    assert rel_to_peak(dos_em, dos_ra) < 1e-13 and rel_to_peak(dos_em, ref[0]) < 1e-11
+    ctx.close()
