@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nk", type=int, default=0, help="override k-points per GPU (debug only; invalidates the number)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--partition", default="cyclic", choices=["cyclic", "block"],
+                    help="k-point assignment over ranks: cyclic (balanced on the k1-ordered synthetic mesh) or contiguous blocks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -181,7 +183,10 @@ def workload_config(args, n_gpus, nk_total):
     return {"workload": "cfg2: synthetic cosine bands, adaptive + linear DOS with integrated DOS",
             "k_points_total": nk_total, "k_points_per_gpu": nk_total // n_gpus, "bands": NB, "spins": NS,
             "energy_bins": NBINS, "adaptive_smearing": 0.4, "finite_bin_correction": True, "seed": SEED,
-            "sharding": f"k-points, contiguous blocks over {n_gpus} GPU(s), one NCCL allreduce per broadening",
+            "sharding": (f"k-points over {n_gpus} GPU(s), " +
+                         ("cyclic (k = rank + i N): the synthetic mesh is ordered by k1, contiguous blocks would differ by +-12 % in work"
+                          if args.partition == "cyclic" else "contiguous blocks as algor_dist_array") +
+                         ", one NCCL allreduce per broadening"),
             "l2": "inputs (16.4 GB / N per GPU) are larger than the 126 MB L2; no flush needed"}
 
 
@@ -210,7 +215,10 @@ def main():
         dist.broadcast(buf, 0)
         uid = bytes(buf.cpu().numpy().tobytes())
     ctx = ob.Context(local, rank, world, uid)
-    ctx.synth_bands(grid_total, k_first, nk_gpu, NS, NB, lattice_a=LATTICE_A, seed=SEED)
+    if args.partition == "cyclic":     # same counts as algor_dist_array, k = rank + i * world
+        ctx.synth_bands(grid_total, rank, nk_gpu, NS, NB, lattice_a=LATTICE_A, seed=SEED, k_stride=world)
+    else:
+        ctx.synth_bands(grid_total, k_first, nk_gpu, NS, NB, lattice_a=LATTICE_A, seed=SEED)
 
     p = ctx.dos_params(["adaptive", "linear"], dos_nbins=NBINS, num_electrons=(NB / 2.0, NB / 2.0))
 

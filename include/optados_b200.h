@@ -269,6 +269,10 @@ int od_jdos_get_weighted(od_ctx *ctx, double *weighted_jdos);
  * k_first + nk_local) of a grid[0] x grid[1] x grid[2] MP mesh (k3 fastest) and calls od_set_system. */
 int od_synth_bands(od_ctx *ctx, const int grid[3], long long k_first, int nk_local, int ns, int nb,
                    double lattice_a, uint64_t seed);
+/* the same for the k-points k_first, k_first + k_stride, ... (a cyclic partition over ranks: the synthetic mesh is
+ * ordered by k1, so contiguous blocks differ by +-12 % in work at 8 ranks; sums commute, any assignment is valid) */
+int od_synth_bands_strided(od_ctx *ctx, const int grid[3], long long k_first, long long k_stride, int nk_local, int ns,
+                           int nb, double lattice_a, uint64_t seed);
 /* copy the resident arrays of the ctx back to the host (for parity tests against the oracle) */
 int od_get_bands(od_ctx *ctx, double *band_energy_host);
 int od_get_kweights(od_ctx *ctx, double *kpoint_weight_host);

@@ -115,7 +115,7 @@ EXPORTS = [
     "od_calculate_jdos_optics", "od_make_weights", "od_core_prepare_matrix_elements", "od_projection_merge",
     "od_calc_epsilon_2", "od_dos_params_defaults", "od_dos_utils_calculate", "od_dos_get", "od_dos_get_weighted",
     "od_calc_efermi_from_intdos", "od_dos_utils_set_efermi", "od_jdos_params_defaults", "od_jdos_utils_calculate",
-    "od_jdos_get", "od_jdos_get_weighted", "od_synth_bands", "od_get_bands", "od_get_kweights",
+    "od_jdos_get", "od_jdos_get_weighted", "od_synth_bands", "od_synth_bands_strided", "od_get_bands", "od_get_kweights",
     "od_timer_start", "od_timer_stop", "od_measure_fp64_peak", "od_count_contributions", "od_host_alloc_pinned",
     "od_host_free_pinned", "od_set_engine",
     "od_calc_epsilon_1", "od_calc_loss_fn", "od_core_lai_broadening",
@@ -216,10 +216,10 @@ class Context:
         a = np.asfortranarray(optical_mat, dtype=np.complex128)
         self._ck(self.L.od_set_gradients_from_ome(self.h, a.ctypes.data_as(c_dp), OD_MEM_HOST))
 
-    def synth_bands(self, grid, k_first, nk_local, ns, nb, lattice_a=5.43, seed=2):
+    def synth_bands(self, grid, k_first, nk_local, ns, nb, lattice_a=5.43, seed=2, k_stride=1):
         g = np.asarray(grid, dtype=np.int32)
-        self._ck(self.L.od_synth_bands(self.h, g.ctypes.data_as(c_ip), C.c_longlong(k_first), C.c_int(nk_local), C.c_int(ns),
-                                       C.c_int(nb), C.c_double(lattice_a), C.c_uint64(seed)))
+        self._ck(self.L.od_synth_bands_strided(self.h, g.ctypes.data_as(c_ip), C.c_longlong(k_first), C.c_longlong(k_stride),
+                                               C.c_int(nk_local), C.c_int(ns), C.c_int(nb), C.c_double(lattice_a), C.c_uint64(seed)))
         self.nk, self.ns, self.nb = nk_local, ns, nb
 
     def get_bands(self):

@@ -330,14 +330,14 @@ namespace {
 // one CTA per (k-point, spin): E_n = c_n + t_n * sum_i cos(2 pi k_i) (+0.3 eV for spin 2),
 // dE/dk_i = -a t_n sin(2 pi k_i); (E, grad) pairs sorted ascending in E with a bitonic network.
 __global__ void synth_bands_kernel(const double *__restrict__ cn, const double *__restrict__ tn, int nb, int ns, int nk_local,
-                                   long long k_first, int n1, int n2, int n3, double a, double *__restrict__ bands,
-                                   double *__restrict__ grads) {
+                                   long long k_first, long long k_stride, int n1, int n2, int n3, double a,
+                                   double *__restrict__ bands, double *__restrict__ grads) {
   extern __shared__ double sm[];
   const int P = blockDim.x;  // power of two >= nb
   double *sE = sm, *sT = sm + P;
   int *sIdx = reinterpret_cast<int *>(sm + 2 * P);
   const int ik = blockIdx.x, is = blockIdx.y, t = threadIdx.x;
-  const long long kg = k_first + ik;
+  const long long kg = k_first + (long long)ik * k_stride;
   const int i3 = (int)(kg % n3), i2 = (int)((kg / n3) % n2), i1 = (int)(kg / ((long long)n3 * n2));
   const double twopi = 6.283185307179586476925286766559005768394;
   const double k1 = (2.0 * i1 - n1 + 1.0) / (2.0 * n1), k2 = (2.0 * i2 - n2 + 1.0) / (2.0 * n2), k3 = (2.0 * i3 - n3 + 1.0) / (2.0 * n3);
@@ -384,10 +384,15 @@ inline uint64_t splitmix64_next(uint64_t &x) {
 
 extern "C" int od_synth_bands(od_ctx *ctx, const int grid[3], long long k_first, int nk_local, int ns, int nb, double lattice_a,
                               uint64_t seed) {
+  return od_synth_bands_strided(ctx, grid, k_first, 1, nk_local, ns, nb, lattice_a, seed);
+}
+
+extern "C" int od_synth_bands_strided(od_ctx *ctx, const int grid[3], long long k_first, long long k_stride, int nk_local, int ns, int nb,
+                                      double lattice_a, uint64_t seed) {
   if (!ctx || !grid) return OD_ERR_ARG;
-  if (nb < 1 || nb > 1024 || ns < 1 || ns > 2 || nk_local < 1) return od_fail(ctx, OD_ERR_ARG, "bad synthetic dimensions");
+  if (nb < 1 || nb > 1024 || ns < 1 || ns > 2 || nk_local < 1 || k_stride < 1) return od_fail(ctx, OD_ERR_ARG, "bad synthetic dimensions");
   const long long nk_total = (long long)grid[0] * grid[1] * grid[2];
-  if (k_first < 0 || k_first + nk_local > nk_total) return od_fail(ctx, OD_ERR_ARG, "k-point range outside the grid");
+  if (k_first < 0 || k_first + (long long)(nk_local - 1) * k_stride >= nk_total) return od_fail(ctx, OD_ERR_ARG, "k-point range outside the grid");
   OD_CUDA(ctx, cudaSetDevice(ctx->device));
   const double twopi = 6.283185307179586476925286766559005768394;
   double recip[9] = {0};
@@ -411,7 +416,7 @@ extern "C" int od_synth_bands(od_ctx *ctx, const int grid[3], long long k_first,
   while (P < nb) P <<= 1;
   dim3 g(nk_local, ns);
   synth_bands_kernel<<<g, P, (2 * sizeof(double) + sizeof(int)) * P, ctx->stream>>>(ctx->small.as<double>(), ctx->small.as<double>() + nb, nb, ns,
-                                                                                   nk_local, k_first, grid[0], grid[1], grid[2], lattice_a,
+                                                                                   nk_local, k_first, k_stride, grid[0], grid[1], grid[2], lattice_a,
                                                                                    ctx->bands.as<double>(), ctx->grads.as<double>());
   OD_LAUNCH_CHECK(ctx);
   fill_kernel<<<grid_for(ctx, nk_local, 256), 256, 0, ctx->stream>>>(ctx->kweight.as<double>(), (size_t)nk_local, 1.0 / (double)nk_total);

@@ -748,3 +748,25 @@ def test_euler_maclaurin_matches_rational(ob, odo, monkeypatch):
     assert np.abs(int_em - ref[1]).max() < 1e-12 * scale and np.abs(int_ra - ref[1]).max() < 1e-12 * scale
     assert rel_to_peak(dos_em, dos_ra) < 1e-13 and rel_to_peak(dos_em, ref[0]) < 1e-11
     ctx.close()
+
+
+def test_cyclic_kpoint_partition(ob):
+    """od_synth_bands_strided: the k-points rank, rank + N, ... of the synthetic mesh; the partial spectra of the N
+    parts add up to the spectrum of the whole mesh (what bench.py relies on for N > 1)"""
+    grid, ns, nb = (12, 10, 9), 2, 16
+    nk = grid[0] * grid[1] * grid[2]
+    nbins, emin, delta = 4000, -16.0, 42.0 / 3999
+
+    def run(k_first, stride, n):
+        ctx = ob.Context(0)
+        ctx.synth_bands(grid, k_first, n, ns, nb, seed=6, k_stride=stride)
+        out = [ctx.calculate_dos(t, emin, delta, nbins)[:2] for t in ("a", "l")]
+        ctx.close()
+        return out
+
+    whole = run(0, 1, nk)
+    parts = [run(r, 3, len(range(r, nk, 3))) for r in range(3)]
+    for i in range(2):
+        for j in range(2):
+            tot = sum(p[i][j] for p in parts)
+            assert rel_to_peak(tot, whole[i][j]) < 1e-12
