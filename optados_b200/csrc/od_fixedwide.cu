@@ -13,6 +13,9 @@
 // U_p[d] (the reference's gaussian cut-off z^2/2 > 30 and NSWC erf, algorithms.f90:73-91, 252-306, evaluated on
 // the grid offsets d); states whose erf has saturated enter through a prefix sum of m_0.
 // P is chosen so that the truncation 1.09 eta_max^(P+1)/sqrt((P+1)!) is below 1e-13 of the peak (P <= 7).
+// Weighted spectra (PDOS, core-loss, optics) get one more set of moment arrays per weight column, filled with
+// omega_s mw(o, s) eta^p/p!, and JDOS treats a band pair as the "state"; the integrated spectrum exists for the DOS
+// channel only.  Units come from the same producers as the other engines (DosProducer / JdosProducer).
 // Differences from the reference: that truncation, and the cut-off being applied at |E_j - E_c| instead of
 // |E_j - e_s| (a term of exp(-30) = 9.4e-14 of one state's peak).  Work: O(S) + O(B W P) instead of O(S W).
 #include <algorithm>
@@ -35,28 +38,40 @@ struct FwPlan {
   int hg, he;    // half windows (bins) of the Gaussian cut-off and of the unsaturated erf
 };
 
-// moments: M[(p * ns + is) * next + (c + pad)];  below[is] = weight of the states below the padded grid
-__global__ void __launch_bounds__(256) fw_moments_kernel(const double *__restrict__ bands, const double *__restrict__ kw, double eps, int nb,
-                                                         int ns, long long k_first, long long nstates, GridSpec grid, double invw, FwPlan pl,
+// moments: M[((ch * (P+1) + p) * ns + is) * next + (c + pad)], channel 0 = the spectrum itself, channel 1 + o =
+// weight column o;  below[is] = weight of the states below the padded grid (their step covers the whole grid)
+template <class Producer>
+__global__ void __launch_bounds__(256) fw_moments_kernel(Producer prod, int ns, int og, int nch, GridSpec grid, double invw, FwPlan pl,
                                                          double *__restrict__ M, double *__restrict__ below) {
   const double inv_delta = 1.0 / grid.delta;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nstates; t += (long long)gridDim.x * blockDim.x) {
-    const long long ks = t / nb;  // (is + ns * ik_local)
-    const int is = (int)(ks % ns);
-    const long long ik = k_first + ks / ns;
-    const double e = bands[(size_t)k_first * nb * ns + t];  // band_energy(ib, is, ik)
-    const double om = eps * kw[ik];
+  const int z = blockIdx.y, is = z % ns, grp = z / ns;
+  const size_t cstride = (size_t)(pl.P + 1) * ns * pl.next, pstride = (size_t)ns * pl.next;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < prod.units_per_z; u += (long long)gridDim.x * blockDim.x) {
+    RecOut r;
+    r.mode = -1;
+#pragma unroll
+    for (int a = 0; a < OD_MAXW; ++a) r.wt[a] = 0.0;
+    prod(u, z, r);
+    if (r.mode != 0) continue;  // null unit (fixed broadening only produces Gaussian records)
+    const double e = r.e0, om = r.omega;
     const double cf = rint((e - grid.emin) * inv_delta);
-    if (cf < -(double)pl.pad) { atomicAdd(&below[is], om); continue; }  // its step covers the whole grid
-    if (cf >= (double)(grid.nbins + pl.pad)) continue;                 // above everything: no contribution
+    if (cf < -(double)pl.pad) { if (grp == 0 && below) atomicAdd(&below[is], om); continue; }
+    if (cf >= (double)(grid.nbins + pl.pad)) continue;  // above everything: no contribution
     const int c = (int)cf;
     const double eta = (e - (grid.emin + (double)c * grid.delta)) * invw;
     double *m = M + (size_t)is * pl.next + (c + pl.pad);
-    double term = om;
-    atomicAdd(m, term);
-    for (int p = 1; p <= pl.P; ++p) {
-      term *= eta / (double)p;
-      atomicAdd(m + (size_t)p * ns * pl.next, term);
+    double pw[FW_PMAX + 1];  // omega eta^p / p!
+    pw[0] = om;
+    for (int p = 1; p <= pl.P; ++p) pw[p] = pw[p - 1] * (eta / (double)p);
+    if (grp == 0)
+      for (int p = 0; p <= pl.P; ++p) atomicAdd(m + p * pstride, pw[p]);
+    for (int a = 0; a < OD_MAXW; ++a) {
+      const int ch = 1 + grp * og + a;
+      if (a >= og || ch >= nch) break;
+      const double wa = r.wt[a];
+      if (wa == 0.0) continue;
+      double *mc = m + (size_t)ch * cstride;
+      for (int p = 0; p <= pl.P; ++p) atomicAdd(mc + p * pstride, pw[p] * wa);
     }
   }
 }
@@ -93,33 +108,41 @@ __global__ void fw_prefix_kernel(const double *__restrict__ M, int ns, int next,
   }
 }
 
-// dos[j] += sum_{|d| <= hg} sum_p m_p[j - d] T_p[d];  intdos[j] += below + pre[j - he - 1] + sum_{|d| <= he} sum_p m_p[j - d] U_p[d]
-// grid: (bins / 128, ns, nseg): the offsets d are split into segments; results are reduced with FP64 atomics
+// channel ch of spin is:  out[j] += sum_{|d| <= hw} sum_p m_p[j - d] T_p[d];  for channel 0 with an integrated
+// spectrum also  intdos[j] += below + pre[j - he - 1] + sum_{|d| <= he} sum_p m_p[j - d] U_p[d].
+// grid: (bins / 128, ns * nch, nseg): the offsets d are split into segments; results are reduced with FP64 atomics.
+// out_off[ch * ns + is] = offset of that spectrum in `accum`; int_off[is] likewise (or < 0: no integrated spectrum)
 __global__ void __launch_bounds__(128) fw_convolve_kernel(const double *__restrict__ M, const double *__restrict__ pre,
                                                           const double *__restrict__ below, const double *__restrict__ T,
                                                           const double *__restrict__ U, int nbins, int ns, FwPlan pl, int seg_len,
-                                                          double *__restrict__ dos, double *__restrict__ intdos) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x, is = blockIdx.y, seg = blockIdx.z;
+                                                          const long long *__restrict__ out_off, const long long *__restrict__ int_off,
+                                                          double *__restrict__ accum) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y / ns, is = blockIdx.y % ns, seg = blockIdx.z;
   if (j >= nbins) return;
+  const long long ioff = (ch == 0) ? int_off[is] : -1;
+  const bool with_int = ioff >= 0;
   const int nd = 2 * pl.he + 1;
   const int i0 = seg * seg_len, i1 = min(i0 + seg_len, nd);
-  const double *m = M + (size_t)is * pl.next + pl.pad + j;  // m[-d] = m_p[j - d] after adding p * ns * next
   const size_t pstride = (size_t)ns * pl.next;
+  const double *m = M + (size_t)ch * (pl.P + 1) * pstride + (size_t)is * pl.next + pl.pad + j;  // m[p * pstride - d] = m_p[j - d]
   double sd = 0.0, si = 0.0;
   for (int i = i0; i < i1; ++i) {
     const int d = i - pl.he;
+    if (!with_int && (d < -pl.hg - 1 || d > pl.hg + 1)) continue;  // beyond the Gaussian cut-off T is zero
     double a = 0.0, b = 0.0;
     for (int p = 0; p <= pl.P; ++p) {
       const double mv = m[(long long)p * (long long)pstride - d];
       a = fma(mv, T[(size_t)p * nd + i], a);
-      b = fma(mv, U[(size_t)p * nd + i], b);
+      if (with_int) b = fma(mv, U[(size_t)p * nd + i], b);
     }
     sd += a;
     si += b;
   }
-  if (seg == 0) si += below[is] + pre[(size_t)is * pl.next + pl.pad + j - pl.he - 1];  // pad >= he + 1
-  atomicAdd(&dos[(size_t)is * nbins + j], sd);
-  atomicAdd(&intdos[(size_t)is * nbins + j], si);
+  if (sd != 0.0) atomicAdd(&accum[out_off[ch * ns + is] + j], sd);
+  if (with_int) {
+    if (seg == 0) si += below[is] + pre[(size_t)is * pl.next + pl.pad + j - pl.he - 1];  // pad >= he + 1
+    atomicAdd(&accum[ioff + j], si);
+  }
 }
 
 FwPlan make_plan(double w, const GridSpec &grid) {
@@ -142,35 +165,40 @@ FwPlan make_plan(double w, const GridSpec &grid) {
 }  // namespace
 
 // window (bins) of a fixed-width state; the narrow engine takes up to OD_NARROW_WMAX
-bool od_fixedwide_applies(const od_ctx *ctx, const BroadSpec &b, const GridSpec &grid) {
+// gwin: half width of a state's window in units of w (the erf window for DOS, the Gaussian cut-off for JDOS)
+bool od_fixedwide_applies(const od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, double gwin) {
   if (ctx->engine == OD_ENGINE_DENSE || b.type != 0) return false;
   double w = b.fixed_w;
   if (b.fbc && w < b.delta_bins) w = b.delta_bins;
   if (!(w > 0.0)) return false;
-  return 2.0 * FW_ERFWIN * w / grid.delta + 2.0 > (double)OD_NARROW_WMAX;
+  return 2.0 * gwin * w / grid.delta + 2.0 > (double)OD_NARROW_WMAX;
 }
 
 static double fw_width(const BroadSpec &b) { return (b.fbc && b.fixed_w < b.delta_bins) ? b.delta_bins : b.fixed_w; }
 
-int od_fixedwide_begin(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid) {
+static size_t fw_moment_count(const od_ctx *ctx, const FwPlan &pl, int nch) { return (size_t)nch * (pl.P + 1) * ctx->ns * pl.next; }
+
+// nch = 1 + number of weight columns
+int od_fixedwide_begin(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, int nch) {
   const FwPlan pl = make_plan(fw_width(b), grid);
-  const size_t n = (size_t)(pl.P + 1) * ctx->ns * pl.next + 2;
+  const size_t n = fw_moment_count(ctx, pl, nch) + 2;
   OD_CHECK(od_buf_ensure(ctx, ctx->moments, sizeof(double) * n));
   OD_CUDA(ctx, cudaMemsetAsync(ctx->moments.p, 0, sizeof(double) * n, ctx->stream));
   return OD_OK;
 }
 
-int od_fixedwide_accumulate(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, long long k_first, int nk_slab) {
+// units of `prod` (nz = ns * weight groups of `og` columns each for the DOS producer, ns for the JDOS producer)
+template <class Producer>
+static int fw_accumulate(od_ctx *ctx, const Producer &prod, int nz, int og, const BroadSpec &b, const GridSpec &grid, int nch, bool with_int) {
   const double w = fw_width(b);
   const FwPlan pl = make_plan(w, grid);
-  const long long nstates = (long long)ctx->nb * ctx->ns * nk_slab;
-  if (nstates <= 0) return OD_OK;
+  if (prod.units_per_z <= 0) return OD_OK;
   double *M = ctx->moments.as<double>();
-  double *below = M + (size_t)(pl.P + 1) * ctx->ns * pl.next;
-  const int blocks = (int)std::min<long long>((nstates + 255) / 256, (long long)ctx->sm_count * 16);
+  double *below = with_int ? M + fw_moment_count(ctx, pl, nch) : nullptr;
+  const int bx = (int)std::min<long long>((prod.units_per_z + 255) / 256, (long long)ctx->sm_count * 16);
+  dim3 g(bx, nz);
   OD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  fw_moments_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bands.as<double>(), ctx->kweight.as<double>(), ctx->eps, ctx->nb, ctx->ns, k_first,
-                                                     nstates, grid, 1.0 / w, pl, M, below);
+  fw_moments_kernel<Producer><<<g, 256, 0, ctx->stream>>>(prod, ctx->ns, og, nch, grid, 1.0 / w, pl, M, below);
   OD_LAUNCH_CHECK(ctx);
   OD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   OD_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
@@ -180,30 +208,50 @@ int od_fixedwide_accumulate(od_ctx *ctx, const BroadSpec &b, const GridSpec &gri
   return OD_OK;
 }
 
-int od_fixedwide_finish(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, double *accum) {
+int od_fixedwide_accumulate_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, int norb) {
+  const int ngroups = norb > 0 ? (norb + OD_MAXW - 1) / OD_MAXW : 1;
+  return fw_accumulate(ctx, prod, ctx->ns * ngroups, OD_MAXW, prod.b, grid, 1 + norb, true);
+}
+
+int od_fixedwide_accumulate_jdos(od_ctx *ctx, const JdosProducer &prod, const GridSpec &grid, int n_geom) {
+  return fw_accumulate(ctx, prod, ctx->ns, OD_MAXW, prod.b, grid, 1 + n_geom, false);
+}
+
+// out_off[ch * ns + is]: offset of the spectrum of channel ch / spin is in accum; int_off[is]: the integrated spectrum
+// of channel 0, or null
+int od_fixedwide_finish(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, int nch, const long long *out_off, const long long *int_off,
+                        double *accum) {
   const double w = fw_width(b);
   const FwPlan pl = make_plan(w, grid);
   const int ns = ctx->ns, nbins = grid.nbins, nd = 2 * pl.he + 1;
   double *M = ctx->moments.as<double>();
-  double *below = M + (size_t)(pl.P + 1) * ns * pl.next;
-  // tables and prefix live in scratch_a: [T (P+1) nd | U (P+1) nd | pre ns next]
-  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_a, sizeof(double) * (2 * (size_t)(pl.P + 1) * nd + (size_t)ns * pl.next)));
+  double *below = M + fw_moment_count(ctx, pl, nch);
+  // tables, prefix and the offset lists live in scratch_a: [T (P+1) nd | U (P+1) nd | pre ns next | offsets]
+  const size_t ndbl = 2 * (size_t)(pl.P + 1) * nd + (size_t)ns * pl.next;
+  const size_t noff = (size_t)nch * ns + ns;
+  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_a, sizeof(double) * ndbl + sizeof(long long) * noff));
   double *T = ctx->scratch_a.as<double>(), *U = T + (size_t)(pl.P + 1) * nd, *pre = U + (size_t)(pl.P + 1) * nd;
+  long long *d_off = reinterpret_cast<long long *>(pre + (size_t)ns * pl.next);
+  std::vector<long long> h_off(noff);
+  for (size_t i = 0; i < (size_t)nch * ns; ++i) h_off[i] = out_off[i];
+  for (int is = 0; is < ns; ++is) h_off[(size_t)nch * ns + is] = int_off ? int_off[is] : -1;
+  OD_CUDA(ctx, cudaMemcpyAsync(d_off, h_off.data(), sizeof(long long) * noff, cudaMemcpyHostToDevice, ctx->stream));
   OD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   fw_tables_kernel<<<(nd + 127) / 128, 128, 0, ctx->stream>>>(w, grid.delta, pl, T, U);
   OD_LAUNCH_CHECK(ctx);
-  fw_prefix_kernel<<<ns, 32, 0, ctx->stream>>>(M, ns, pl.next, pre);
-  OD_LAUNCH_CHECK(ctx);
+  if (int_off) {
+    fw_prefix_kernel<<<ns, 32, 0, ctx->stream>>>(M, ns, pl.next, pre);
+    OD_LAUNCH_CHECK(ctx);
+  }
   const int jb = (nbins + 127) / 128;
-  int nseg = std::max(1, std::min(64, (4 * ctx->sm_count + jb * ns - 1) / (jb * ns)));
+  int nseg = std::max(1, std::min(64, (4 * ctx->sm_count + jb * ns * nch - 1) / (jb * ns * nch)));
   const int seg_len = (nd + nseg - 1) / nseg;
   nseg = (nd + seg_len - 1) / seg_len;
-  dim3 g(jb, ns, nseg);
-  const size_t n1 = (size_t)nbins * ns;
-  fw_convolve_kernel<<<g, 128, 0, ctx->stream>>>(M, pre, below, T, U, nbins, ns, pl, seg_len, accum, accum + n1);
+  dim3 g(jb, ns * nch, nseg);
+  fw_convolve_kernel<<<g, 128, 0, ctx->stream>>>(M, pre, below, T, U, nbins, ns, pl, seg_len, d_off, d_off + (size_t)nch * ns, accum);
   OD_LAUNCH_CHECK(ctx);
   OD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  OD_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  OD_CUDA(ctx, cudaEventSynchronize(ctx->ev1));  // (h_off is a host vector)
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->prof.accumulate_ms += ms;

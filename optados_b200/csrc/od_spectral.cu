@@ -72,17 +72,25 @@ __global__ void linear_smear_kernel(const double *__restrict__ dos, double *__re
 // ------------------------------------------------------------------ calculate_dos
 #define OD_SLAB_UNITS_DEFAULT (32ll << 20)
 // one k-point slab of one broadening scheme, ADDED into accum = [dos | intdos | weighted_dos]
-static int dos_slab(od_ctx *ctx, char dos_type, const od_broadening *br, const GridSpec &grid, const double *mw_dev, int norb,
-                    int mw_nb, int mw_nk, long long k_first, int nk_slab, const double *grads_dev, int nk_g, double *accum) {
-  const int ns = ctx->ns, nbins = grid.nbins;
+static int dos_producer(od_ctx *ctx, char dos_type, const od_broadening *br, const GridSpec &grid, const double *mw_dev, int norb,
+                        int mw_nb, int mw_nk, long long k_first, int nk_slab, const double *grads_dev, int nk_g, DosProducer *out) {
   DosProducer p;
   p.units_per_z = (long long)ctx->nb * nk_slab;
   p.k_first = k_first;
-  p.nb = ctx->nb; p.ns = ns; p.nk = ctx->nk; p.nk_g = nk_g;
+  p.nb = ctx->nb; p.ns = ctx->ns; p.nk = ctx->nk; p.nk_g = nk_g;
   p.bands = ctx->bands.as<double>(); p.grads = grads_dev; p.kw = ctx->kweight.as<double>();
   p.eps = ctx->eps;
   OD_CHECK(od_make_broadspec(ctx, dos_type, br, grid.delta, /*honor_hybrid=*/false, &p.b));
   p.mw = mw_dev; p.norb = norb; p.mw_nb = mw_nb; p.mw_nk = mw_nk; p.og = OD_MAXW;
+  *out = p;
+  return OD_OK;
+}
+
+static int dos_slab(od_ctx *ctx, char dos_type, const od_broadening *br, const GridSpec &grid, const double *mw_dev, int norb,
+                    int mw_nb, int mw_nk, long long k_first, int nk_slab, const double *grads_dev, int nk_g, double *accum) {
+  const int ns = ctx->ns, nbins = grid.nbins;
+  DosProducer p;
+  OD_CHECK(dos_producer(ctx, dos_type, br, grid, mw_dev, norb, mw_nb, mw_nk, k_first, nk_slab, grads_dev, nk_g, &p));
   const size_t n1 = (size_t)nbins * ns;
   if (ctx->engine != OD_ENGINE_DENSE) return od_narrow_dos(ctx, p, grid, dos_type == 'l', accum);
   if (!mw_dev) {
@@ -134,7 +142,7 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
   std::vector<char> fixedwide((size_t)ntypes, 0);  // fixed broadening with very wide windows: moment expansion
   for (int t = 0; t < ntypes; ++t) {
     OD_CHECK(od_make_broadspec(ctx, types[t], br, delta_bins, false, &bspec[t]));  // validates dos_type
-    fixedwide[t] = (!weighted[t] || !mw_dev) && od_fixedwide_applies(ctx, bspec[t], grid);
+    fixedwide[t] = od_fixedwide_applies(ctx, bspec[t], grid, OD_ERF_CUT * OD_SQRT_TWO);
   }
   const size_t n1 = (size_t)nbins * ns;
   const size_t stride = 2 * n1 + n1 * norb + n1;
@@ -143,9 +151,13 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
   OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * stride * ntypes, ctx->stream));
 
   for (int t = 0; t < ntypes; ++t)
-    if (fixedwide[t]) OD_CHECK(od_fixedwide_begin(ctx, bspec[t], grid));
+    if (fixedwide[t]) OD_CHECK(od_fixedwide_begin(ctx, bspec[t], grid, 1 + (weighted[t] ? norb : 0)));
   auto one_slab = [&](int t, long long k0, int nks, const double *grads_dev, int nk_g) -> int {
-    if (fixedwide[t]) return od_fixedwide_accumulate(ctx, bspec[t], grid, k0, nks);
+    if (fixedwide[t]) {
+      DosProducer p;
+      OD_CHECK(dos_producer(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0, nks, grads_dev, nk_g, &p));
+      return od_fixedwide_accumulate_dos(ctx, p, grid, weighted[t] ? norb : 0);
+    }
     return dos_slab(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0, nks, grads_dev, nk_g, accum + stride * t);
   };
   const bool streamed = ctx->grads_host != nullptr && need_grad;
@@ -202,7 +214,16 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
   for (int t = 0; t < ntypes; ++t) {
     double *acc = accum + stride * t;
     const size_t ntot = 2 * n1 + (weighted[t] ? n1 * norb : 0);
-    if (fixedwide[t]) OD_CHECK(od_fixedwide_finish(ctx, bspec[t], grid, acc));
+    if (fixedwide[t]) {
+      const int nw = weighted[t] ? norb : 0;
+      std::vector<long long> out_off((size_t)(1 + nw) * ns), int_off((size_t)ns);
+      for (int is = 0; is < ns; ++is) {
+        out_off[is] = (long long)is * nbins;
+        int_off[is] = (long long)(n1 + (size_t)is * nbins);
+        for (int o = 0; o < nw; ++o) out_off[(size_t)(1 + o) * ns + is] = (long long)(2 * n1 + (size_t)nbins * (is + (size_t)ns * o));
+      }
+      OD_CHECK(od_fixedwide_finish(ctx, bspec[t], grid, 1 + nw, out_off.data(), int_off.data(), acc));
+    }
     // rank-local epilogue, before the merge like the reference (quirk Q16)
     if (types[t] == 'l' && br->linear_smearing > 0.0) {
       double *tmp = acc + stride - n1;
@@ -469,7 +490,26 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
       p.occ_list = dl;
       p.unocc_list = dl + p.n_occ;
       p.units_per_z = p.pairs_per_k() * ctx->nk;
-      OD_CHECK(od_narrow_jdos(ctx, p, grid, jdos_type == 'l', n_geom, accum));
+      if (od_fixedwide_applies(ctx, p.b, grid, OD_SQRT60)) {
+        // fixed broadening with windows beyond the narrow engine: moment expansion (od_fixedwide.cu), in k-point
+        // slabs of < 2^30 pair slots
+        OD_CHECK(od_fixedwide_begin(ctx, p.b, grid, 1 + n_geom));
+        const long long ppk = p.pairs_per_k(), slab_k = std::max<long long>(1, (1ll << 30) / ppk);
+        for (long long k0 = 0; k0 < ctx->nk; k0 += slab_k) {
+          JdosProducer ps = p;
+          ps.k_first = k0;
+          ps.units_per_z = std::min<long long>(slab_k, ctx->nk - k0) * ppk;
+          OD_CHECK(od_fixedwide_accumulate_jdos(ctx, ps, grid, n_geom));
+        }
+        std::vector<long long> out_off((size_t)(1 + n_geom) * ns);
+        for (int is = 0; is < ns; ++is) {
+          out_off[is] = (long long)is * nbins;
+          for (int a = 0; a < n_geom; ++a) out_off[(size_t)(1 + a) * ns + is] = (long long)(n1 + (size_t)nbins * (is + (size_t)ns * a));
+        }
+        OD_CHECK(od_fixedwide_finish(ctx, p.b, grid, 1 + n_geom, out_off.data(), nullptr, accum));
+      } else {
+        OD_CHECK(od_narrow_jdos(ctx, p, grid, jdos_type == 'l', n_geom, accum));
+      }
     }  // else: no pair anywhere, the spectra stay zero
   } else if (n_geom == 0) OD_CHECK((od_run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   else if (n_geom == 1) OD_CHECK((od_run_dense<1, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));

@@ -26,10 +26,12 @@ int od_optics_coefficients(od_ctx *ctx, int geom, const double qdir[3], const do
 // widest window (bins) the narrow engine takes; wider ones go to the dense engine or, for fixed broadening
 // without weights, to the moment expansion of od_fixedwide.cu
 #define OD_NARROW_WMAX 480
-bool od_fixedwide_applies(const od_ctx *ctx, const BroadSpec &b, const GridSpec &grid);
-int od_fixedwide_begin(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid);
-int od_fixedwide_accumulate(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, long long k_first, int nk_slab);
-int od_fixedwide_finish(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, double *accum);
+bool od_fixedwide_applies(const od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, double gwin);
+int od_fixedwide_begin(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, int nch);
+int od_fixedwide_accumulate_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, int norb);
+int od_fixedwide_accumulate_jdos(od_ctx *ctx, const JdosProducer &prod, const GridSpec &grid, int n_geom);
+int od_fixedwide_finish(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, int nch, const long long *out_off, const long long *int_off,
+                        double *accum);
 
 // narrow (sorted, recurrence) engine for calculate_dos without weights (od_narrow.cu)
 int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bool linear, double *accum);

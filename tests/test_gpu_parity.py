@@ -770,3 +770,55 @@ def test_cyclic_kpoint_partition(ob):
         for j in range(2):
             tot = sum(p[i][j] for p in parts)
             assert rel_to_peak(tot, whole[i][j]) < 1e-12
+
+
+@pytest.mark.parametrize("norb", [3, 19])
+def test_fixed_wide_weighted_dos(ob, odo, norb):
+    """PDOS / core-style weighted DOS with fixed broadening and very wide windows: one more set of Taylor moments per
+    weight column (od_fixedwide.cu); fewer weighted bands than bands, more columns than one producer group"""
+    ctx = ob.Context(0)
+    grid, ns, nb = (7, 6, 5), 2, 16
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=4)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
+    nbins = 8000
+    lo, hi = be.min() + 4.0, be.max() + 5.0              # the grid cuts through the bands at the bottom
+    delta = (hi - lo) / (nbins - 1)
+    E = lo + delta * np.arange(nbins)
+    rng = np.random.default_rng(12)
+    mw = np.asfortranarray(rng.random((norb, nb - 3, nk, ns)))
+    mw[:, 2, :, :] = 0.0                                   # a band without weight (like the occupied bands of core absorption)
+    ref = odo.calculate_dos("f", s, odo.make_broadening(fixed_smearing=0.3), E, delta, mw, nthreads=8)
+    dos, intdos, wdos = ctx.calculate_dos("f", E[0], delta, nbins, br=ob.broadening(fixed_smearing=0.3), mw=mw)
+    assert rel_to_peak(dos, ref[0]) < 1e-11
+    assert_int(intdos, ref[1])
+    assert rel_to_peak(wdos, ref[2]) < 1e-11
+    ctx.close()
+
+
+def test_fixed_wide_jdos_and_optics(ob, odo):
+    """JDOS and fused optical weights with fixed broadening on a fine JDOS grid (windows of ~2300 bins): the moment
+    expansion over band pairs, against the oracle"""
+    ctx = ob.Context(0)
+    grid, ns, nb = (6, 5, 4), 2, 12
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=21)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0, num_electrons=[6.0, 6.0])
+    ef = odo.efermi_insulator(s)
+    E, delta, n = odo.jdos_energy_scale(s, ef, jdos_spacing=0.002, jdos_max_energy=14.0)
+    assert 2 * 7.746 * 0.3 / delta > 480
+    bro, brg = odo.make_broadening(fixed_smearing=0.3), ob.broadening(fixed_smearing=0.3)
+    rng = np.random.default_rng(5)
+    om = np.asfortranarray(rng.normal(0, 0.1, (nb, nb, 3, nk, ns)) + 1j * rng.normal(0, 0.1, (nb, nb, 3, nk, ns)))
+    ref_j, _ = odo.calculate_jdos("f", s, bro, E, delta, ef, scissor_op=0.3, exclude_bands=(2,), nthreads=8)
+    jd, _ = ctx.calculate_jdos("f", delta, n, ef, br=brg, scissor_op=0.3, exclude_bands=(2,))
+    assert rel_to_peak(jd, ref_j) < 1e-11
+    for geom in ("polycrys", "tensor"):
+        mw = odo.make_weights(s, om, geom, ef, qdir=(0.3, 0.5, 0.25))
+        rj, rw = odo.calculate_jdos("f", s, bro, E, delta, ef, mw=mw, nthreads=8)
+        jd, wj = ctx.calculate_jdos_optics("f", delta, n, ef, om, geom, qdir=(0.3, 0.5, 0.25), br=brg)
+        assert rel_to_peak(jd, rj) < 1e-11, geom
+        assert rel_to_peak(wj, rw) < 1e-11, geom
+    ctx.close()
