@@ -12,7 +12,7 @@
 //      bucket order using shared-memory cursors only.  Sorting by width class as well as by
 //      position makes the 32 records of a warp-group nearly congruent, which is what lets one
 //      lane = one record run without idle lanes.
-//   2. ACCUMULATES: warps pull chunks of 512 consecutive records.  Within a group of 32 records
+//   2. ACCUMULATES: warps pull chunks of 256 consecutive records.  Within a group of 32 records
 //      LANE = RECORD: every lane walks all bins of the group's common window, lane l starting l
 //      bins in and wrapping round, so that in any one step the 32 lanes touch 32 DIFFERENT bins
 //      of a warp-private shared-memory tile -- plain LDS/STS read-modify-write, no atomics, no
@@ -52,7 +52,7 @@ namespace {
 
 constexpr int NR_T = 512;        // bins per warp tile
 constexpr int NR_WMAX = OD_NARROW_WMAX;     // widest window (bins) the narrow engine takes (Wc + 1 <= NR_T - cell)
-constexpr int NR_CHUNK = 512;   // records per work item
+constexpr int NR_CHUNK = 256;   // records per work item (512: +1 %, 1024: +3 % on config 2)
 constexpr int NR_WARPS = 8;      // warps per CTA
 constexpr int NR_CTAS_PER_SM = 2; // accumulate kernels: 2 x 8 warps per SM (registers and shared memory both allow no more)
 constexpr int NR_NCLS = 10;      // width classes
