@@ -822,3 +822,27 @@ def test_fixed_wide_jdos_and_optics(ob, odo):
         assert rel_to_peak(jd, rj) < 1e-11, geom
         assert rel_to_peak(wj, rw) < 1e-11, geom
     ctx.close()
+
+
+def test_config2_slab_vs_oracle(ob, odo, monkeypatch):
+    """A k-slab of BASELINE config 2 itself (the 100^3 mesh, 256 bands, 2 spins, 20 000 bins: the window widths, width
+    classes and bucket occupancies of the bench) against the oracle's dense loops: 600 k-points = 307k states, in
+    three k-point slabs, adaptive and linear."""
+    monkeypatch.setenv("OD_SLAB_UNITS", str(110000))
+    ctx = ob.Context(0)
+    grid, ns, nb, nk = (100, 100, 100), 2, 256, 600
+    ctx.synth_bands(grid, 431700, nk, ns, nb, seed=2)         # mid-mesh: the widest windows
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
+    nbins, emin = 20000, -16.0
+    delta = 42.0 / (nbins - 1)
+    E = emin + delta * np.arange(nbins)
+    for t in ("a", "l"):
+        ref = odo.calculate_dos(t, s, odo.make_broadening(), E, delta, nthreads=16)
+        dos, intdos, _ = ctx.calculate_dos(t, emin, delta, nbins)
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC, t
+        assert_int(intdos, ref[1])
+        assert rel_to_peak(dos, ref[0]) < 1e-11 and np.abs(intdos - ref[1]).max() < 1e-12 * np.abs(ref[1]).max(), t
+    p = ctx.profile_get()
+    assert p["contributions"] > 0.4 * p["lane_steps"]          # the narrow engine took it (small slabs: sparse buckets, so below the bench's 0.8)
+    ctx.close()
