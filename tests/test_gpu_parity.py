@@ -846,3 +846,67 @@ def test_config2_slab_vs_oracle(ob, odo, monkeypatch):
     p = ctx.profile_get()
     assert p["contributions"] > 0.4 * p["lane_steps"]          # the narrow engine took it (small slabs: sparse buckets, so below the bench's 0.8)
     ctx.close()
+
+
+def test_config3_slab_vs_oracle(ob, odo):
+    """BASELINE config 3's shape on a k-slab: 200 bands x 64 projectors (weights normalised to one per state), 20 000
+    bins, adaptive: the DMMA contraction against the oracle, and the sum rule sum_o PDOS_o = DOS"""
+    ctx = ob.Context(0)
+    grid, ns, nb, nk, norb = (100, 100, 50), 1, 200, 64, 64
+    ctx.synth_bands(grid, 260000, nk, ns, nb, seed=3)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=2.0)
+    nbins, emin = 20000, be.min() - 5.0
+    delta = (be.max() - be.min() + 10.0) / (nbins - 1)
+    E = emin + delta * np.arange(nbins)
+    rng = np.random.default_rng(3)
+    mw = rng.random((norb, nb, nk, ns))
+    mw = np.asfortranarray(mw / mw.sum(axis=0, keepdims=True))
+    ref = odo.calculate_dos("a", s, odo.make_broadening(), E, delta, mw, nthreads=16)
+    dos, intdos, wdos = ctx.calculate_dos("a", emin, delta, nbins, mw=mw)
+    assert rel_to_peak(dos, ref[0]) < TOL_SPEC and rel_to_peak(wdos, ref[2]) < TOL_SPEC
+    assert_int(intdos, ref[1])
+    assert np.abs(wdos.sum(axis=2) - dos).max() < 1e-12 * dos.max()
+    ctx.close()
+
+
+def test_config4_and_5_slabs_vs_oracle(ob, odo):
+    """BASELINE configs 4 and 5 on k-slabs of their own meshes: 128 bands, all occupied -> unoccupied pairs, 3000-bin
+    JDOS grid with fused polycrystalline / tensor optical weights; 300 bands x 16 core orbitals, ELNES weights
+    (absorption, polycrystalline and polarised), 20 000 bins, adaptive"""
+    rng = np.random.default_rng(4)
+    # ---- config 4
+    ctx = ob.Context(0)
+    grid, ns, nb, nk = (50, 50, 80), 1, 128, 24
+    ctx.synth_bands(grid, 100000, nk, ns, nb, seed=4)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=2.0, num_electrons=[128.0])
+    ef = odo.efermi_insulator(s)
+    E, delta, n = odo.jdos_energy_scale(s, ef, jdos_spacing=0.01, jdos_max_energy=30.0)
+    om = np.asfortranarray(rng.normal(0, 0.1, (nb, nb, 3, nk, ns)) + 1j * rng.normal(0, 0.1, (nb, nb, 3, nk, ns)))
+    for geom in ("polycrys", "tensor"):
+        mw = odo.make_weights(s, om, geom, ef)
+        rj, rw = odo.calculate_jdos("a", s, odo.make_broadening(), E, delta, ef, mw=mw, nthreads=16)
+        jd, wj = ctx.calculate_jdos_optics("a", delta, n, ef, om, geom)
+        assert rel_to_peak(jd, rj) < TOL_SPEC and rel_to_peak(wj, rw) < TOL_SPEC, geom
+    ctx.close()
+    # ---- config 5
+    ctx = ob.Context(0)
+    grid, ns, nb, nk, norb = (60, 50, 100), 1, 300, 40, 16
+    ctx.synth_bands(grid, 150000, nk, ns, nb, seed=5)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=2.0, num_electrons=[300.0])
+    ef = odo.efermi_insulator(s)
+    el = np.asfortranarray(rng.normal(0, 0.01, (norb, nb, 3, nk, ns)) + 1j * rng.normal(0, 0.01, (norb, nb, 3, nk, ns)))
+    nbins, emin = 20000, be.min() - 5.0
+    delta = (be.max() - be.min() + 10.0) / (nbins - 1)
+    E = emin + delta * np.arange(nbins)
+    for polar in (False, True):
+        mw_ref = odo.core_prepare_matrix_elements(s, el, "absorption", ef, polar=polar, qdir=(0.5, 0.5, 0.25))
+        mw = ctx.core_prepare_matrix_elements(el, "absorption", ef, polar=polar, qdir=(0.5, 0.5, 0.25))
+        assert np.abs(mw - mw_ref).max() <= 1e-12 * np.abs(mw_ref).max()
+        ref = odo.calculate_dos("a", s, odo.make_broadening(), E, delta, mw_ref, nthreads=16)
+        dos, intdos, wdos = ctx.calculate_dos("a", emin, delta, nbins, mw=mw)
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC and rel_to_peak(wdos, ref[2]) < TOL_SPEC, polar
+        assert_int(intdos, ref[1])
+    ctx.close()
