@@ -176,7 +176,7 @@ def run_reference(args, rank, world, local, dist):
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, args.gpus, nk_full * (args.gpus if args.scaling == "weak" else 1)),
             "cpu_baseline": {"value": value, "unit": "contributions/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "contributions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n_gpus, nk_total):
@@ -190,7 +190,26 @@ def workload_config(args, n_gpus, nk_total):
             "l2": "inputs (16.4 GB / N per GPU) are larger than the 126 MB L2; no flush needed"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print to stdout on their own (torch's NCCL process group announces "NCCL version ..." there): everything
+    # but the JSON line goes to stderr, so that stdout carries exactly one line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank, world, local, dist = dist_setup(args)
     if args.impl == "reference":
@@ -333,7 +352,7 @@ def main():
                 "dense_equivalent_evaluations_per_s": 2.0 * float(nk_total) * NB * NS * NBINS / (ms_step * 1e-3),
                 "contributions_per_step": contrib_total, "wall_ms_per_step": wall / args.steps * 1e3,
                 "efermi_adaptive": r.get("efermi_adaptive"), "efermi_linear": r.get("efermi_linear")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     barrier(dist)
     if dist is not None:
