@@ -910,3 +910,27 @@ def test_config4_and_5_slabs_vs_oracle(ob, odo):
         assert rel_to_peak(dos, ref[0]) < TOL_SPEC and rel_to_peak(wdos, ref[2]) < TOL_SPEC, polar
         assert_int(intdos, ref[1])
     ctx.close()
+
+
+def test_narrow_engine_on_a_grid_that_cuts_through_the_bands(ob, odo):
+    """windows clipped by both ends of the energy grid (states below, inside and above it): the lane walks then start
+    inside the Gaussians (segment constants of the Euler-Maclaurin form away from the tails), steps of states below the
+    grid must still reach the integrated DOS"""
+    ctx = ob.Context(0)
+    grid, ns, nb = (16, 12, 10), 2, 24
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=13)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
+    nbins = 9000
+    lo, hi = be.min() + 7.0, be.max() - 11.0
+    delta = (hi - lo) / (nbins - 1)
+    E = lo + delta * np.arange(nbins)
+    for t in ("a", "l", "f"):
+        bro, brg = odo.make_broadening(fixed_smearing=0.04), ob.broadening(fixed_smearing=0.04)
+        ref = odo.calculate_dos(t, s, bro, E, delta, nthreads=8)
+        dos, intdos, _ = ctx.calculate_dos(t, E[0], delta, nbins, br=brg)
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC, t
+        assert_int(intdos, ref[1])
+        assert intdos[0].min() > 0.1 * nb                    # a good part of the states lies below the grid
+    ctx.close()
