@@ -3,7 +3,7 @@ NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr
 CSRC      := optados_b200/csrc
-SRCS      := $(CSRC)/od_ctx.cu $(CSRC)/od_spectral.cu $(CSRC)/od_weights.cu $(CSRC)/od_drivers.cu $(CSRC)/od_util.cu $(CSRC)/od_narrow.cu $(CSRC)/od_post.cu $(CSRC)/od_fixedwide.cu $(CSRC)/od_tasks.cu
+SRCS      := $(CSRC)/od_ctx.cu $(CSRC)/od_spectral.cu $(CSRC)/od_weights.cu $(CSRC)/od_drivers.cu $(CSRC)/od_util.cu $(CSRC)/od_narrow.cu $(CSRC)/od_post.cu $(CSRC)/od_fixedwide.cu $(CSRC)/od_tasks.cu $(CSRC)/od_analysis.cu
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/optados_b200.h
 OBJS      := $(SRCS:.cu=.o) $(CSRC)/od_io.o
 LIB       := optados_b200/lib/liboptados_b200.so

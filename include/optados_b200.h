@@ -17,6 +17,12 @@
  *     library copies it to HBM; OD_MEM_DEVICE: a device pointer the library uses in place and
  *     that must stay valid until the next od_set_* of the same array or od_ctx_destroy).
  *     Output arrays are always host memory unless the name says _device.
+ *   - OD_MEM_HOST inputs are copied with cudaMemcpyAsync on the ctx stream.  From PAGEABLE memory (an ordinary
+ *     Fortran array) the source has been read when the call returns; from PINNED memory the copy may still be in
+ *     flight, so a pinned input must stay valid and untouched until the next blocking call on the ctx (any
+ *     calculate / get call, or od_synchronize).
+ *   - no global state: everything lives in the ctx, with one exception -- the table of NCCL entry points bound with
+ *     dlopen on first use (process-wide, read-only afterwards).
  *   - calls are blocking and not re-entrant per ctx.  There is no CPU fallback: without a CUDA
  *     device od_ctx_create fails.
  *   - one ctx = one GPU = one k-point shard (the reference's "node", algorithms.f90:309).  With
@@ -79,10 +85,13 @@ int od_profile_get(od_ctx *ctx, double *accumulate_ms, double *prepare_ms, doubl
 /* device-side stopwatch on the ctx stream (CUDA events): start, ... library calls ..., stop -> ms */
 int od_timer_start(od_ctx *ctx);
 int od_timer_stop(od_ctx *ctx, double *elapsed_ms);
-/* sustained FP64 FMA throughput of this GPU (all SMs, dependent-chain-free DFMA loop of about
- * `seconds`), in TFLOP/s (2 flops per FMA) -- the denominator of the FP64 roofline, measured in place
- * because MEASURED_PEAKS.json carries no FP64 entry */
+/* sustained FP64 throughput of this GPU's FP64 pipe (all SMs, about `seconds` of dependent-chain-free DFMA and DMMA
+ * loops, the larger of the two), in TFLOP/s (2 flops per FMA) -- the denominator of the FP64 roofline, measured in
+ * place because MEASURED_PEAKS.json carries no FP64 entry */
 int od_measure_fp64_peak(od_ctx *ctx, double seconds, double *tflops);
+/* mode 0: the larger of a DFMA loop and a DMMA (mma.sync m16n8k8 f64) loop = the FP64 pipe peak (what
+ * od_measure_fp64_peak returns); 1: the DFMA loop alone; 2: the DMMA loop alone */
+int od_measure_fp64_peak_mode(od_ctx *ctx, double seconds, int mode, double *tflops);
 /* in-window (unit, bin) contributions of a calculate_dos pass on this rank, the unit of the
  * throughput metric: gaussian W = floor(2 sqrt(60) w / dE) + 1,
  * linear W = floor(2 (e0 - e4) / dE) + 1, each clipped to the grid */
@@ -236,6 +245,26 @@ int od_dos_utils_calculate_at_e(od_ctx *ctx, const od_dos_params *p, double ener
 /* dos_utils_set_efermi (dos_utils.f90:296-388).  For OD_EFERMI_OPTADOS runs od_dos_utils_calculate. */
 int od_dos_utils_set_efermi(od_ctx *ctx, od_dos_params *p, double *efermi);
 
+/* dos_utils_compute_bandgap (dos_utils.f90:457-750).  Every rank passes its block [k_first, k_first + nk_local) of the
+ * nk_global k-points (ignored without a communicator); the (vbm, cbm) slices are gathered and scanned in the
+ * reference's order, so multiplicities and k-point numbers (1-based, -1 = never set) do not depend on the number of
+ * ranks.  num_electrons(nspins) only enters the weighted average.  Also sets the vbm_energy / cbm_energy the
+ * core-loss chemical shift uses (core.f90:533-535). */
+typedef struct od_bandgap_result {
+  double vbm_energy, cbm_energy, thermal_bandgap;   /* <- TBg */
+  long long thermal_vbm_k, thermal_cbm_k;           /* equal = direct gap (only meaningful without multiplicity) */
+  int vbm_multiplicity[2], cbm_multiplicity[2], optical_multiplicity[2];
+  double optical_bandgap[2], average_bandgap[2];    /* <- OBg, <- ABg */
+  double weighted_average;                          /* <- wAB (nspins > 1) */
+  int thermal_multiplicity;                         /* "Multiple Band Minima and Maxima -- Gap unknown" */
+} od_bandgap_result;
+int od_dos_utils_compute_bandgap(od_ctx *ctx, double efermi, const double *num_electrons, long long nk_global,
+                                 long long k_first, od_bandgap_result *res);
+/* dos_utils_compute_band_energies (dos_utils.f90:853-924): band_energy_dos(3) = calc_band_energies (:753-795) of the
+ * fixed / adaptive / linear DOS of the last od_dos_utils_calculate (0 where not computed; <- BEF/BEA/BEL),
+ * band_energy_castep = sum of the occupied eigenvalues, SUM-reduced over the ranks (<- BEC) */
+int od_dos_utils_compute_band_energies(od_ctx *ctx, double efermi, double band_energy_dos[3], double *band_energy_castep);
+
 typedef struct od_jdos_params {
   int fixed, adaptive, linear;
   od_broadening br;
@@ -314,6 +343,11 @@ typedef struct od_core_params {
   double qdir[3];         /* core_qdir */
   int lai_broadening;     /* core_LAI_broadening */
   double lai_gaussian_width, lai_lorentzian_width, lai_lorentzian_scale, lai_lorentzian_offset;
+  int set_efermi_zero;          /* write_core: E_shift = E - efermi (core.f90:490-494) */
+  double core_chemical_shift;   /* Mizoguchi shift; -1 = off (parameters.f90:267).  write_core prints E + shift - cbm_energy
+                                 * (core.f90:533-535) with the MODULE variable cbm_energy of od_dos_utils: core_calculate never
+                                 * calls dos_utils_compute_bandgap, so it is 0 unless od_dos_utils_compute_bandgap ran on this
+                                 * ctx before (a dos task in the same run) -- reproduced as is */
 } od_core_params;
 void od_core_params_defaults(od_core_params *p);
 typedef struct od_core_result {
@@ -323,7 +357,8 @@ typedef struct od_core_result {
 } od_core_result;
 int od_core_calculate(od_ctx *ctx, od_core_params *p, const double *elnes_mat, int elnes_mem, int norb, const double *symops,
                       int num_sym, od_core_result *res);
-/* E(nbins), weighted_dos(nbins, ns, norb) and its LAI-broadened copy, both in the units write_core prints */
+/* E(nbins) as write_core prints it (E_shift: set_efermi_zero, core_chemical_shift), weighted_dos(nbins, ns, norb) and its
+ * LAI-broadened copy, both in the units write_core prints */
 int od_core_get(od_ctx *ctx, double *E, double *weighted_dos, double *weighted_dos_broadened);
 
 /* ---------------------------------------------------------------- O(B^2) post-processing ------ */

@@ -69,7 +69,16 @@ class OpticsResult(C.Structure):
 class CoreParams(C.Structure):
     _fields_ = [("dos", DosParams), ("core_type", C.c_int), ("polar", C.c_int), ("qdir", C.c_double * 3),
                 ("lai_broadening", C.c_int), ("lai_gaussian_width", C.c_double), ("lai_lorentzian_width", C.c_double),
-                ("lai_lorentzian_scale", C.c_double), ("lai_lorentzian_offset", C.c_double)]
+                ("lai_lorentzian_scale", C.c_double), ("lai_lorentzian_offset", C.c_double),
+                ("set_efermi_zero", C.c_int), ("core_chemical_shift", C.c_double)]
+
+
+class BandgapResult(C.Structure):
+    _fields_ = [("vbm_energy", C.c_double), ("cbm_energy", C.c_double), ("thermal_bandgap", C.c_double),
+                ("thermal_vbm_k", C.c_longlong), ("thermal_cbm_k", C.c_longlong),
+                ("vbm_multiplicity", C.c_int * 2), ("cbm_multiplicity", C.c_int * 2), ("optical_multiplicity", C.c_int * 2),
+                ("optical_bandgap", C.c_double * 2), ("average_bandgap", C.c_double * 2),
+                ("weighted_average", C.c_double), ("thermal_multiplicity", C.c_int)]
 
 
 class CoreResult(C.Structure):
@@ -116,11 +125,11 @@ EXPORTS = [
     "od_calc_epsilon_2", "od_dos_params_defaults", "od_dos_utils_calculate", "od_dos_get", "od_dos_get_weighted",
     "od_calc_efermi_from_intdos", "od_dos_utils_set_efermi", "od_jdos_params_defaults", "od_jdos_utils_calculate",
     "od_jdos_get", "od_jdos_get_weighted", "od_synth_bands", "od_synth_bands_strided", "od_get_bands", "od_get_kweights",
-    "od_timer_start", "od_timer_stop", "od_measure_fp64_peak", "od_count_contributions", "od_host_alloc_pinned",
+    "od_timer_start", "od_timer_stop", "od_measure_fp64_peak", "od_measure_fp64_peak_mode", "od_count_contributions", "od_host_alloc_pinned",
     "od_host_free_pinned", "od_set_engine",
     "od_calc_epsilon_1", "od_calc_loss_fn", "od_core_lai_broadening",
     "od_dos_utils_calculate_at_e", "od_optics_params_defaults", "od_optics_calculate", "od_optics_get", "od_core_params_defaults", "od_core_calculate",
-    "od_core_get",
+    "od_core_get", "od_dos_utils_compute_bandgap", "od_dos_utils_compute_band_energies",
     "od_io_last_error", "od_read_bands_info", "od_read_bands", "od_cell_calc_lattice", "od_cell_find_mp_grid",
     "od_read_symmetry_ops", "od_read_ome", "od_read_dome", "od_read_pdos_info", "od_read_pdos", "od_read_elnes_info",
     "od_read_elnes",
@@ -521,12 +530,34 @@ class Context:
         self._ck(self.L.od_optics_get(self.h, *args))
         return out
 
+    def compute_bandgap(self, efermi, num_electrons=None, nk_global=0, k_first=0):
+        """dos_utils_compute_bandgap (dos_utils.f90:457-750) -> dict"""
+        b = BandgapResult()
+        ne = None if num_electrons is None else f64(np.asarray(num_electrons, dtype=np.float64))
+        self._ck(self.L.od_dos_utils_compute_bandgap(self.h, C.c_double(efermi), _p(ne), C.c_longlong(nk_global),
+                                                     C.c_longlong(k_first), C.byref(b)))
+        ns = self.ns
+        return dict(thermal_vbm=b.vbm_energy, thermal_cbm=b.cbm_energy, thermal_bandgap=b.thermal_bandgap,
+                    thermal_vbm_k=b.thermal_vbm_k, thermal_cbm_k=b.thermal_cbm_k,
+                    vbm_multiplicity=list(b.vbm_multiplicity)[:ns], cbm_multiplicity=list(b.cbm_multiplicity)[:ns],
+                    optical_multiplicity=list(b.optical_multiplicity)[:ns], optical_bandgap=list(b.optical_bandgap)[:ns],
+                    average_bandgap=list(b.average_bandgap)[:ns], weighted_average=b.weighted_average,
+                    thermal_multiplicity=bool(b.thermal_multiplicity))
+
+    def compute_band_energies(self, efermi):
+        """dos_utils_compute_band_energies (dos_utils.f90:853-924) -> (dict(fixed=, adaptive=, linear=), from_bands)"""
+        be = (C.c_double * 3)()
+        ec = C.c_double()
+        self._ck(self.L.od_dos_utils_compute_band_energies(self.h, C.c_double(efermi), be, C.byref(ec)))
+        return dict(fixed=be[0], adaptive=be[1], linear=be[2]), ec.value
+
     def core_calculate(self, elnes_mat, dos_params, core_type="absorption", polar=False, qdir=(0, 0, 1), symops=None,
-                       lai=None):
+                       lai=None, set_efermi_zero=False, core_chemical_shift=-1.0):
         """lai: None or dict(gaussian_width=, lorentzian_width=, lorentzian_scale=, lorentzian_offset=)"""
         p = CoreParams()
         self.L.od_core_params_defaults(C.byref(p))
         p.dos = dos_params
+        p.set_efermi_zero, p.core_chemical_shift = int(set_efermi_zero), float(core_chemical_shift)
         p.core_type, p.polar = CORE_TYPE[core_type], int(polar)
         for i in range(3):
             p.qdir[i] = float(qdir[i])
@@ -607,9 +638,10 @@ class Context:
         self._ck(self.L.od_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
-    def measure_fp64_peak(self, seconds=0.3):
+    def measure_fp64_peak(self, seconds=0.3, mode=0):
+        """mode 0: the FP64 pipe peak (max of the DFMA and the DMMA loop); 1: DFMA loop; 2: DMMA loop"""
         t = C.c_double()
-        self._ck(self.L.od_measure_fp64_peak(self.h, C.c_double(seconds), C.byref(t)))
+        self._ck(self.L.od_measure_fp64_peak_mode(self.h, C.c_double(seconds), C.c_int(mode), C.byref(t)))
         return t.value
 
     def count_contributions(self, dos_type, emin, delta_bins, nbins, br=None):

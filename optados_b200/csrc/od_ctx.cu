@@ -21,6 +21,12 @@ int od_fail(od_ctx *ctx, int code, const char *fmt, ...) {
   return code;
 }
 
+namespace {
+__global__ void poison_kernel(int *p, size_t n, int v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+}  // namespace
+
 int od_buf_ensure(od_ctx *ctx, DevBuf &b, size_t bytes) {
   if (b.owned && b.bytes >= bytes && b.p) return OD_OK;
   if (b.owned && b.p) cudaFree(b.p);
@@ -30,6 +36,12 @@ int od_buf_ensure(od_ctx *ctx, DevBuf &b, size_t bytes) {
   if (bytes == 0) bytes = 8;
   OD_CUDA(ctx, cudaMalloc(&b.p, bytes));
   b.bytes = bytes;
+  // tests only: OD_DEBUG_POISON=<int> fills every fresh allocation with that 32-bit pattern, so that code which reads a
+  // buffer it never wrote (or that a re-allocation emptied) fails loudly instead of passing on a recycled address
+  if (const char *poison = getenv("OD_DEBUG_POISON")) {
+    poison_kernel<<<256, 256, 0, ctx ? ctx->stream : nullptr>>>(static_cast<int *>(b.p), bytes / sizeof(int), atoi(poison));
+    OD_CUDA(ctx, cudaStreamSynchronize(ctx ? ctx->stream : nullptr));
+  }
   return OD_OK;
 }
 
@@ -149,6 +161,8 @@ extern "C" int od_ctx_destroy(od_ctx *ctx) {
   for (DevBuf *b : bufs) od_buf_release(*b);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  if (ctx->t0) cudaEventDestroy(ctx->t0);
+  if (ctx->t1) cudaEventDestroy(ctx->t1);
   for (int i = 0; i < 2; ++i) {
     od_buf_release(ctx->gslab[i]);
     if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);

@@ -107,6 +107,8 @@ extern "C" int od_dos_utils_calculate(od_ctx *ctx, od_dos_params *p, const doubl
   S = Spectra();
   S.nbins = nbins;
   S.ns = ns;
+  S.emin = emin;
+  S.delta = delta;
   const char types[3] = {'f', 'a', 'l'};
   const int enabled[3] = {p->fixed, p->adaptive, p->linear};
   // weighted spectrum only with the most complex enabled scheme (dos_utils.f90:179-208)

@@ -27,6 +27,7 @@ struct Profile {
 // results of the task drivers (the reference's module-global dos_*/intdos_*/jdos_* arrays)
 struct Spectra {
   int nbins = 0, ns = 0, norb = 0;
+  double emin = 0.0, delta = 0.0;         // E(i) = emin + (i-1)*delta
   std::vector<double> dos[3], intdos[3];  // index 0 fixed, 1 adaptive, 2 linear
   bool have[3] = {false, false, false};
   std::vector<double> weighted;
@@ -42,13 +43,14 @@ struct OpticsRes {
 struct CoreRes {
   int nbins = 0, ns = 0, norb = 0;
   double efermi = 0.0;
-  std::vector<double> E, wdos, wdos_broadened;
+  std::vector<double> E, E_shift, wdos, wdos_broadened;
 };
 
 struct od_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;  // od_timer_start / od_timer_stop
   int rank = 0, nranks = 1;
   void *comm = nullptr;  // ncclComm_t
   std::string err;
@@ -73,6 +75,7 @@ struct od_ctx {
   DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, scratch_e, mw_tmp, in_tmp, in_tmp2, moments, task_mw;
 
   Spectra dos_res, jdos_res;
+  double vbm_energy = 0.0, cbm_energy = 0.0;  // od_dos_utils module variables set by compute_bandgap (dos_utils.f90:55-56)
   OpticsRes optics_res;
   CoreRes core_res;
 };

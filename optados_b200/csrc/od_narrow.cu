@@ -745,9 +745,8 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
 // those are 8 contiguous ranges (one per width class).  One CTA = one work item (bin tile, orbital tile, record
 // segment): K-chunks of 32 records are expanded into a dense G[32][64] tile in shared memory (Gaussian by the
 // same two-multiply recurrence along bins, linear by the branch-free doslin pieces), their weight rows are
-// gathered (coalesced, 8 * BN bytes per record) into W[32][BN], and every thread keeps a register tile of
-// (64 * BN / 256) accumulators: 4 shared-memory loads feed 16 DFMAs.  FP64 DMMA tensor cores are not used: on
-// B200 their peak equals the DFMA peak this loop already runs on.
+// gathered (coalesced, 8 * BN bytes per record) into W[32][BN], and the product runs on the FP64 tensor cores
+// (DMMA m16n8k8, see pdos_gemm_kernel below).
 constexpr int PG_BM = 64, PG_KC = 32, PG_SEG = 2048;
 
 
@@ -1158,19 +1157,25 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
   return OD_OK;
 }
 
+// bins per position cell for a grid: the smallest power of two >= 8 whose bucket table fits the prepare passes'
+// shared memory; 0 = the grid is too large for the narrow engine (the callers then use the dense engine)
+int narrow_cell_for(int nbins, int ns) {
+  for (int cell = 8; cell <= 128; cell *= 2) {
+    const int bpad = ((nbins + NR_T + cell - 1) / cell) * cell;
+    if ((long long)NR_NCLS * ns * (bpad / cell) <= NR_MAXBUCKETS) return cell;
+  }
+  return 0;
+}
+
 // carve the scratch buffers for a grid / unit count / number of channel arrays
 int narrow_scratch(od_ctx *ctx, const GridSpec &grid, int ns, long long total_units, int nchan_arrays, Scratch &S) {
   PrepSpec &ps = S.ps;
   ps.grid = grid;
-  ps.cell = 8;
-  for (;;) {
-    ps.bpad = ((grid.nbins + NR_T + ps.cell - 1) / ps.cell) * ps.cell;
-    ps.ncells = ns * ps.bpad / ps.cell;
-    ps.nbuckets = NR_NCLS * ps.ncells;
-    if (ps.nbuckets <= NR_MAXBUCKETS) break;
-    ps.cell *= 2;
-  }
-  if (ps.cell > 128) return od_fail(ctx, OD_ERR_ARG, "narrow engine: energy grid too large (%d bins)", grid.nbins);
+  ps.cell = narrow_cell_for(grid.nbins, ns);
+  if (ps.cell == 0) return od_fail(ctx, OD_ERR_ARG, "narrow engine: energy grid too large (%d bins)", grid.nbins);
+  ps.bpad = ((grid.nbins + NR_T + ps.cell - 1) / ps.cell) * ps.cell;
+  ps.ncells = ns * ps.bpad / ps.cell;
+  ps.nbuckets = NR_NCLS * ps.ncells;
   S.nout = (size_t)ns * ps.bpad + NR_T;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -1213,6 +1218,8 @@ int collect_stats(od_ctx *ctx, const Scratch &S) {
 }
 
 }  // namespace
+
+bool od_narrow_grid_fits(int nbins, int ns) { return narrow_cell_for(nbins, ns) != 0; }
 
 // Narrow pipeline for calculate_dos.  accum = [dos(B,ns) | intdos(B,ns) | weighted_dos(B,ns,norb)], zeroed by the
 // caller.  With matrix_weights (prod_in.mw != null) the sorted records are walked once more per pair of weight

@@ -92,7 +92,7 @@ static int dos_slab(od_ctx *ctx, char dos_type, const od_broadening *br, const G
   DosProducer p;
   OD_CHECK(dos_producer(ctx, dos_type, br, grid, mw_dev, norb, mw_nb, mw_nk, k_first, nk_slab, grads_dev, nk_g, &p));
   const size_t n1 = (size_t)nbins * ns;
-  if (ctx->engine != OD_ENGINE_DENSE) return od_narrow_dos(ctx, p, grid, dos_type == 'l', accum);
+  if (ctx->engine != OD_ENGINE_DENSE && od_narrow_grid_fits(nbins, ns)) return od_narrow_dos(ctx, p, grid, dos_type == 'l', accum);
   if (!mw_dev) {
     std::vector<long long> dest(ns * 2);
     for (int is = 0; is < ns; ++is) {
@@ -452,18 +452,17 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
     dest[(size_t)is * nacc] = (long long)is * nbins;
     for (int a = 0; a < n_geom; ++a) dest[(size_t)is * nacc + 1 + a] = (long long)(n1 + (size_t)nbins * (is + (size_t)ns * a));
   }
-  // the exclude list lives in ctx->small, which the narrow engine also uses: it gets its own copy
+  // the exclude list lives in ctx->small, which the narrow engine also uses: it gets its own copy.  ONE allocation of
+  // the final size first (od_buf_ensure does not preserve contents when it grows a buffer), then the copy.
   if (ctx->engine != OD_ENGINE_DENSE) {
+    const int nb = ctx->nb;
+    const size_t excl_bytes = (sizeof(int) * (size_t)num_exclude_bands + 15) & ~(size_t)15;
+    OD_CHECK(od_buf_ensure(ctx, ctx->in_tmp2, excl_bytes + sizeof(int) * 4 * (size_t)nb));
     if (num_exclude_bands > 0) {
-      OD_CHECK(od_buf_ensure(ctx, ctx->in_tmp2, sizeof(int) * (size_t)num_exclude_bands));
       OD_CUDA(ctx, cudaMemcpyAsync(ctx->in_tmp2.p, exclude_bands, sizeof(int) * (size_t)num_exclude_bands, cudaMemcpyHostToDevice, ctx->stream));
       p.exclude = ctx->in_tmp2.as<int>();
     }
     // candidate band lists: a pair (ib, jb) needs E_ib < efermi and E_jb >= efermi at the same (k, spin)
-    const int nb = ctx->nb;
-    const size_t excl_bytes = (sizeof(int) * (size_t)num_exclude_bands + 15) & ~(size_t)15;
-    OD_CHECK(od_buf_ensure(ctx, ctx->in_tmp2, excl_bytes + sizeof(int) * 4 * (size_t)nb));
-    if (num_exclude_bands > 0) p.exclude = ctx->in_tmp2.as<int>();  // (the buffer may have moved)
     int *flags = reinterpret_cast<int *>(ctx->in_tmp2.as<char>() + excl_bytes);
     OD_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)nb, ctx->stream));
     const size_t nstates = (size_t)nb * ns * ctx->nk;
@@ -507,8 +506,14 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
           for (int a = 0; a < n_geom; ++a) out_off[(size_t)(1 + a) * ns + is] = (long long)(n1 + (size_t)nbins * (is + (size_t)ns * a));
         }
         OD_CHECK(od_fixedwide_finish(ctx, p.b, grid, 1 + n_geom, out_off.data(), nullptr, accum));
-      } else {
+      } else if (od_narrow_grid_fits(nbins, ns)) {
         OD_CHECK(od_narrow_jdos(ctx, p, grid, jdos_type == 'l', n_geom, accum));
+      } else {  // a grid beyond the narrow engine's bucket table: the dense engine over all nb x nb slots
+        p.occ_list = p.unocc_list = nullptr;
+        p.units_per_z = (long long)nb * nb * ctx->nk;
+        if (n_geom == 0) OD_CHECK((od_run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+        else if (n_geom == 1) OD_CHECK((od_run_dense<1, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
+        else OD_CHECK((od_run_dense<6, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
       }
     }  // else: no pair anywhere, the spectra stay zero
   } else if (n_geom == 0) OD_CHECK((od_run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));

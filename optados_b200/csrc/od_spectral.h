@@ -33,6 +33,9 @@ int od_fixedwide_accumulate_jdos(od_ctx *ctx, const JdosProducer &prod, const Gr
 int od_fixedwide_finish(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, int nch, const long long *out_off, const long long *int_off,
                         double *accum);
 
+// does the bucket table of the narrow engine fit for this grid?  (~650k bins per spin channel at most; finer grids run on
+// the dense engine, as the reference accepts any dos_nbins / jdos_nbins)
+bool od_narrow_grid_fits(int nbins, int ns);
 // narrow (sorted, recurrence) engine for calculate_dos without weights (od_narrow.cu)
 int od_narrow_dos(od_ctx *ctx, const DosProducer &prod, const GridSpec &grid, bool linear, double *accum);
 // narrow engine for calculate_jdos: accum = [jdos(B,ns) | weighted_jdos(B,ns,n_geom)]

@@ -118,6 +118,8 @@ extern "C" void od_core_params_defaults(od_core_params *p) {
   p->polar = 0;                       // core_geom default 'polycrystalline'
   p->qdir[0] = 0.0; p->qdir[1] = 0.0; p->qdir[2] = 1.0;
   p->lai_broadening = 0;
+  p->set_efermi_zero = 0;
+  p->core_chemical_shift = -1.0;  // parameters.f90:267
 }
 
 extern "C" int od_core_calculate(od_ctx *ctx, od_core_params *p, const double *elnes_mat, int elnes_mem, int norb, const double *symops,
@@ -146,6 +148,11 @@ extern "C" int od_core_calculate(od_ctx *ctx, od_core_params *p, const double *e
   R.nbins = nbins; R.ns = ns; R.norb = norb; R.efermi = efermi;
   R.E.resize(nbins);
   for (int i = 0; i < nbins; ++i) R.E[i] = dr.emin + (double)i * dr.delta_bins;
+  R.E_shift = R.E;  // write_core's abscissa (core.f90:490-494, :533-535); the LAI broadening below works on E itself
+  if (p->set_efermi_zero)
+    for (double &e : R.E_shift) e = e - efermi;
+  if (p->core_chemical_shift != -1.0)
+    for (int i = 0; i < nbins; ++i) R.E_shift[i] = R.E[i] + p->core_chemical_shift - ctx->cbm_energy;
   const size_t n = (size_t)nbins * ns * norb;
   R.wdos.resize(n);
   OD_CHECK(od_dos_get_weighted(ctx, R.wdos.data()));
@@ -169,6 +176,6 @@ extern "C" int od_core_get(od_ctx *ctx, double *E, double *weighted_dos, double 
   const CoreRes &R = ctx->core_res;
   if (R.nbins == 0) return od_fail(ctx, OD_ERR_STATE, "od_core_calculate has not been called");
   if (weighted_dos_broadened && R.wdos_broadened.empty()) return od_fail(ctx, OD_ERR_STATE, "core_LAI_broadening was off");
-  copy_out(R.E, E); copy_out(R.wdos, weighted_dos); copy_out(R.wdos_broadened, weighted_dos_broadened);
+  copy_out(R.E_shift, E); copy_out(R.wdos, weighted_dos); copy_out(R.wdos_broadened, weighted_dos_broadened);
   return OD_OK;
 }

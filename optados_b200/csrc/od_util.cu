@@ -7,8 +7,6 @@
 #include "od_spectral.h"
 
 namespace {
-cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
-
 // 8 independent FMA chains per thread: enough ILP to saturate the FP64 pipe at 4+ warps per SMSP
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -21,6 +19,29 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
   }
   const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
   if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
+}
+
+// The same pipe through the FP64 tensor-core instruction (DMMA m16n8k8, 4 independent accumulator sets per warp): 1024
+// FMAs per instruction.  On B200 this reaches the pipe's 64 FMA / clock / SM (37.1 TFLOP/s at 1965 MHz); the DFMA loop
+// above issues every 2.18 cycles instead of 2 (register-operand read ports) and reads 34.2.
+__global__ void __launch_bounds__(256) fp64_dmma_peak_kernel(double *out, int iters, const double *gin) {
+  const double a0 = gin[threadIdx.x & 7], a1 = gin[(threadIdx.x + 1) & 7], a2 = gin[(threadIdx.x + 2) & 7], a3 = gin[(threadIdx.x + 3) & 7];
+  const double b0 = gin[(threadIdx.x + 4) & 7], b1 = gin[(threadIdx.x + 5) & 7];
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = 0.0;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+d"(c[4 * j]), "+d"(c[4 * j + 1]), "+d"(c[4 * j + 2]), "+d"(c[4 * j + 3])
+                   : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  if (s == 12345.678) out[8] = s;
 }
 
 __global__ void count_contrib_kernel(DosProducer prod, GridSpec grid, double *__restrict__ out /* [gridDim.x] */) {
@@ -53,44 +74,61 @@ __global__ void count_contrib_kernel(DosProducer prod, GridSpec grid, double *__
 extern "C" int od_timer_start(od_ctx *ctx) {
   if (!ctx) return OD_ERR_ARG;
   OD_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!g_t0) { OD_CUDA(ctx, cudaEventCreate(&g_t0)); OD_CUDA(ctx, cudaEventCreate(&g_t1)); }
-  OD_CUDA(ctx, cudaEventRecord(g_t0, ctx->stream));
+  if (!ctx->t0) { OD_CUDA(ctx, cudaEventCreate(&ctx->t0)); OD_CUDA(ctx, cudaEventCreate(&ctx->t1)); }
+  OD_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
   return OD_OK;
 }
 
 extern "C" int od_timer_stop(od_ctx *ctx, double *elapsed_ms) {
-  if (!ctx || !elapsed_ms || !g_t0) return OD_ERR_ARG;
-  OD_CUDA(ctx, cudaEventRecord(g_t1, ctx->stream));
-  OD_CUDA(ctx, cudaEventSynchronize(g_t1));
+  if (!ctx || !elapsed_ms || !ctx->t0) return OD_ERR_ARG;
+  OD_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+  OD_CUDA(ctx, cudaEventSynchronize(ctx->t1));
   float ms = 0.f;
-  OD_CUDA(ctx, cudaEventElapsedTime(&ms, g_t0, g_t1));
+  OD_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->t0, ctx->t1));
   *elapsed_ms = ms;
+  return OD_OK;
+}
+
+// mode 0: the larger of the two loops (the pipe peak); 1: the DFMA loop only; 2: the DMMA loop only
+static int measure_fp64(od_ctx *ctx, double seconds, int mode, double *tflops) {
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  OD_CHECK(od_buf_ensure(ctx, ctx->small, 256));
+  OD_CUDA(ctx, cudaMemsetAsync(ctx->small.p, 0, 256, ctx->stream));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  double best = 0.0;
+  for (int which = 0; which < 2; ++which) {
+    if (mode == 1 && which == 1) continue;
+    if (mode == 2 && which == 0) continue;
+    int iters = 2000;
+    double elapsed_total = 0.0;
+    for (int rep = 0; rep < 64 && elapsed_total < seconds * 0.5e3; ++rep) {
+      OD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+      if (which == 0) fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->small.as<double>(), iters, 0.999999, 1e-7);
+      else fp64_dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->small.as<double>() + 8, iters, ctx->small.as<double>());
+      OD_LAUNCH_CHECK(ctx);
+      OD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+      OD_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      elapsed_total += ms;
+      // FMAs: 64 per thread and iteration in the DFMA loop; 4 x 1024 per warp and iteration in the DMMA loop
+      const double fma = which == 0 ? 64.0 * (double)iters * blocks * threads : 4096.0 * (double)iters * blocks * (threads / 32);
+      if (rep > 0) best = std::max(best, 2.0 * fma / (ms * 1e-3) / 1e12);
+      if (ms < 20.f) iters *= 2;
+    }
+  }
+  *tflops = best;
   return OD_OK;
 }
 
 extern "C" int od_measure_fp64_peak(od_ctx *ctx, double seconds, double *tflops) {
   if (!ctx || !tflops) return OD_ERR_ARG;
-  OD_CUDA(ctx, cudaSetDevice(ctx->device));
-  OD_CHECK(od_buf_ensure(ctx, ctx->small, 64));
-  const int blocks = ctx->sm_count * 8, threads = 256;
-  int iters = 2000;
-  double best = 0.0;
-  double elapsed_total = 0.0;
-  for (int rep = 0; rep < 64 && elapsed_total < seconds * 1e3; ++rep) {
-    OD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->small.as<double>(), iters, 0.999999, 1e-7);
-    OD_LAUNCH_CHECK(ctx);
-    OD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    OD_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    elapsed_total += ms;
-    const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
-    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
-    if (ms < 20.f) iters *= 2;
-  }
-  *tflops = best;
-  return OD_OK;
+  return measure_fp64(ctx, seconds, 0, tflops);
+}
+
+extern "C" int od_measure_fp64_peak_mode(od_ctx *ctx, double seconds, int mode, double *tflops) {
+  if (!ctx || !tflops || mode < 0 || mode > 2) return OD_ERR_ARG;
+  return measure_fp64(ctx, seconds, mode, tflops);
 }
 
 extern "C" int od_count_contributions(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins,

@@ -102,7 +102,6 @@ int od_optics_coefficients(od_ctx *ctx, int geom, const double optics_qdir[3], c
         ea[pa[g]] = 1.0; eb[pb[g]] = 1.0;
         double tmp[6] = {0, 0, 0, 0, 0, 0};
         add_outer(tmp, ea, eb, 1.0);
-        if (pa[g] != pb[g]) for (int k = 3; k < 6; ++k) tmp[k] *= 1.0;  // Re(M_a conj(M_b)) = P_ab exactly
         for (int k = 0; k < 6; ++k) coef->c[g][k] = tmp[k];
       }
     } else {

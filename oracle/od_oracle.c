@@ -505,6 +505,104 @@ double odo_efermi_insulator(const odo_system *sys, const double *num_electrons) 
   return vbm + 0.5 * (cbm - vbm);
 }
 
+/* dos_utils.f90:457-750.  The (vbm, cbm) slices are built per (spin, k) exactly as :507-519 (first band above
+ * efermi and the one below it; -200 when no band lies above), then scanned in the order of :606-646 -- spins
+ * outermost, ONE running thermal_vbm / thermal_cbm shared by both spins, multiplicities per spin. */
+int odo_compute_bandgap(const odo_system *sys, double efermi, const double *num_electrons, odo_bandgap *out) {
+  const int nk = sys->nk, ns = sys->ns, nb = sys->nb;
+  double *bandgap = (double *)malloc(sizeof(double) * 2 * (size_t)ns * nk);
+  int is, ik, ib;
+  double thermal_cbm = DBL_MAX, thermal_vbm = -DBL_MAX, kpoint_bandgap;
+  if (!bandgap) return 1;
+  for (ik = 0; ik < 2 * ns * nk; ++ik) bandgap[ik] = -200.00; /* :504 */
+  for (is = 0; is < ns; ++is)
+    for (ik = 0; ik < nk; ++ik)
+      for (ib = 0; ib < nb; ++ib)
+        if (BE(sys, ib, is, ik) > efermi) { /* :513 */
+          /* ib = 0 reads band_energy(0,...) in the reference (out of bounds); keep the -200 marker */
+          if (ib > 0) bandgap[0 + 2 * (is + (size_t)ns * ik)] = BE(sys, ib - 1, is, ik);
+          bandgap[1 + 2 * (is + (size_t)ns * ik)] = BE(sys, ib, is, ik);
+          break;
+        }
+  out->thermal_vbm_k = -1;
+  out->thermal_cbm_k = -1;
+  for (is = 0; is < 2; ++is) {
+    out->vbm_multiplicity[is] = out->cbm_multiplicity[is] = out->optical_multiplicity[is] = 1;
+    out->optical_bandgap[is] = DBL_MAX;
+    out->average_bandgap[is] = 0.0;
+  }
+  for (is = 0; is < ns; ++is)
+    for (ik = 0; ik < nk; ++ik) {
+      const double v = bandgap[0 + 2 * (is + (size_t)ns * ik)], c = bandgap[1 + 2 * (is + (size_t)ns * ik)];
+      if (v >= thermal_vbm) { /* :609 */
+        if (fabs(v - thermal_vbm) < DBL_EPSILON) {
+          out->vbm_multiplicity[is] += 1;
+        } else {
+          thermal_vbm = v;
+          out->vbm_multiplicity[is] = 1;
+          out->thermal_vbm_k = ik + 1;
+        }
+      }
+      if (c <= thermal_cbm) { /* :623 */
+        if (fabs(c - thermal_cbm) < DBL_EPSILON) {
+          out->cbm_multiplicity[is] += 1;
+        } else {
+          thermal_cbm = c;
+          out->cbm_multiplicity[is] = 1;
+          out->thermal_cbm_k = ik + 1;
+        }
+      }
+      kpoint_bandgap = c - v; /* :634 */
+      if (kpoint_bandgap <= out->optical_bandgap[is]) {
+        if (fabs(kpoint_bandgap - out->optical_bandgap[is]) < DBL_EPSILON) {
+          out->optical_multiplicity[is] += 1;
+        } else {
+          out->optical_bandgap[is] = kpoint_bandgap;
+          out->optical_multiplicity[is] = 1;
+        }
+      }
+      out->average_bandgap[is] = out->average_bandgap[is] + (c - v); /* :647 */
+    }
+  for (is = 0; is < ns; ++is) out->average_bandgap[is] = out->average_bandgap[is] / nk; /* :652 */
+  out->thermal_vbm = thermal_vbm;
+  out->thermal_cbm = thermal_cbm;
+  out->thermal_bandgap = thermal_cbm - thermal_vbm;
+  out->thermal_multiplicity = 0;
+  for (is = 0; is < ns; ++is)
+    if (out->vbm_multiplicity[is] != 1 || out->cbm_multiplicity[is] != 1) out->thermal_multiplicity = 1;
+  out->weighted_average = 0.0;
+  if (ns > 1) /* :713-715 */
+    out->weighted_average = (out->average_bandgap[0] * num_electrons[0] + out->average_bandgap[1] * num_electrons[1]) /
+                            (num_electrons[0] + num_electrons[1]);
+  free(bandgap);
+  return 0;
+}
+
+/* dos_utils.f90:753-795 */
+double odo_calc_band_energies(const double *dos, const double *E, int nbins, int ns, double delta_bins, double efermi) {
+  double gband = 0.0;
+  int is, idos;
+  for (is = 0; is < ns; ++is)
+    for (idos = 0; idos < nbins; ++idos) {
+      if (E[idos] <= efermi)
+        gband = gband + dos[idos + (size_t)nbins * is] * E[idos] * delta_bins;
+      else
+        break;
+    }
+  return gband;
+}
+
+/* dos_utils.f90:900-908 */
+double odo_band_energy_from_bands(const odo_system *sys, double efermi) {
+  double eband = 0.0;
+  int ik, is, ib;
+  for (ik = 0; ik < sys->nk; ++ik)
+    for (is = 0; is < sys->ns; ++is)
+      for (ib = 0; ib < sys->nb; ++ib)
+        if (BE(sys, ib, is, ik) <= efermi) eband = eband + BE(sys, ib, is, ik) * sys->electrons_per_state * sys->kpoint_weight[ik];
+  return eband;
+}
+
 /* jdos_utils.f90:193-218 */
 void odo_jdos_energy_scale(double max_band_energy, double efermi, double jdos_spacing,
                            double *jdos_max_energy, int *jdos_nbins, double *delta_bins) {

@@ -161,6 +161,21 @@ void odo_projection_merge(const double *pdos_weights, const int *mask, int norb_
 /* electronic.f90:280-291 : band_gradient(ib,:,ik,is) = Re(optical_mat(ib,ib,:,ik,is)) */
 void odo_gradient_from_ome(const double *optical_mat, int nb, int nk, int ns, double *band_gradient);
 
+/* dos_utils_compute_bandgap (dos_utils.f90:457-750): root's analysis of the (vbm, cbm) slice of every (k, spin).
+ * k indices are 1-based like the reference's printout; -1 = never set. */
+typedef struct odo_bandgap {
+  double thermal_vbm, thermal_cbm, thermal_bandgap; /* vbm_energy, cbm_energy (:651-653) */
+  int thermal_vbm_k, thermal_cbm_k;
+  int vbm_multiplicity[2], cbm_multiplicity[2], optical_multiplicity[2];
+  double optical_bandgap[2], average_bandgap[2];
+  double weighted_average;  /* :713-715, nspins > 1 only */
+  int thermal_multiplicity; /* :664-667 */
+} odo_bandgap;
+int odo_compute_bandgap(const odo_system *sys, double efermi, const double *num_electrons, odo_bandgap *out);
+/* calc_band_energies (dos_utils.f90:753-795) and the "From CASTEP" sum of dos_utils_compute_band_energies (:900-908) */
+double odo_calc_band_energies(const double *dos, const double *E, int nbins, int ns, double delta_bins, double efermi);
+double odo_band_energy_from_bands(const odo_system *sys, double efermi);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,14 @@ class System(C.Structure):
                 ("electrons_per_state", C.c_double)]
 
 
+class Bandgap(C.Structure):
+    _fields_ = [("thermal_vbm", C.c_double), ("thermal_cbm", C.c_double), ("thermal_bandgap", C.c_double),
+                ("thermal_vbm_k", C.c_int), ("thermal_cbm_k", C.c_int),
+                ("vbm_multiplicity", C.c_int * 2), ("cbm_multiplicity", C.c_int * 2), ("optical_multiplicity", C.c_int * 2),
+                ("optical_bandgap", C.c_double * 2), ("average_bandgap", C.c_double * 2),
+                ("weighted_average", C.c_double), ("thermal_multiplicity", C.c_int)]
+
+
 class Broadening(C.Structure):
     _fields_ = [("adaptive_smearing", C.c_double), ("fixed_smearing", C.c_double),
                 ("linear_smearing", C.c_double), ("finite_bin_correction", C.c_int),
@@ -53,6 +61,8 @@ def lib():
         L.odo_doslin.argtypes = [C.c_double] * 6 + [c_dp, c_ip]
         L.odo_calc_efermi_from_intdos.restype = C.c_double
         L.odo_efermi_insulator.restype = C.c_double
+        L.odo_calc_band_energies.restype = C.c_double
+        L.odo_band_energy_from_bands.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -183,6 +193,35 @@ def calc_efermi_from_intdos(intdos, E, num_electrons):
 
 def efermi_insulator(sys):
     return lib().odo_efermi_insulator(C.byref(sys.c), _p(sys.num_electrons))
+
+
+def compute_bandgap(sys, efermi):
+    """dos_utils_compute_bandgap (dos_utils.f90:457-750) -> dict"""
+    b = Bandgap()
+    ne = f64(sys.num_electrons if sys.num_electrons is not None else np.ones(sys.ns))
+    rc = lib().odo_compute_bandgap(C.byref(sys.c), C.c_double(efermi), _p(ne), C.byref(b))
+    if rc:
+        raise RuntimeError("oracle compute_bandgap failed")
+    ns = sys.ns
+    return dict(thermal_vbm=b.thermal_vbm, thermal_cbm=b.thermal_cbm, thermal_bandgap=b.thermal_bandgap,
+                thermal_vbm_k=b.thermal_vbm_k, thermal_cbm_k=b.thermal_cbm_k,
+                vbm_multiplicity=list(b.vbm_multiplicity)[:ns], cbm_multiplicity=list(b.cbm_multiplicity)[:ns],
+                optical_multiplicity=list(b.optical_multiplicity)[:ns], optical_bandgap=list(b.optical_bandgap)[:ns],
+                average_bandgap=list(b.average_bandgap)[:ns], weighted_average=b.weighted_average,
+                thermal_multiplicity=bool(b.thermal_multiplicity))
+
+
+def calc_band_energies(dos, E, delta_bins, efermi):
+    """calc_band_energies (dos_utils.f90:753-795)"""
+    dos = f64(dos)
+    E = f64(E)
+    return lib().odo_calc_band_energies(_p(dos), _p(E), C.c_int(E.size), C.c_int(dos.shape[1]), C.c_double(delta_bins),
+                                        C.c_double(efermi))
+
+
+def band_energy_from_bands(sys, efermi):
+    """the 'From CASTEP' band energy of dos_utils_compute_band_energies (dos_utils.f90:900-908)"""
+    return lib().odo_band_energy_from_bands(C.byref(sys.c), C.c_double(efermi))
 
 
 def jdos_energy_scale(sys, efermi, jdos_spacing=0.01, jdos_max_energy=-1.0, max_band_energy=None):

@@ -264,12 +264,41 @@ def golden_table(test, seed):
 
 
 def golden_odo(test, seed):
+    """every tagged number of a golden .odo (the `<- XXX` lines the reference's own test harness greps for):
+    Fermi energies (EfA/EfF/EfL), band gaps (TBg, OBg, ABg, wAB: dos_utils.f90:457-750), band energies
+    (BEA/BEF/BEL/BEC: :853-924), DOS at the Fermi level (DEA/DEF/DEL: :391-455) and the occupations (Occ: :841-846)"""
     path = f"{REF}/tests/{test}/benchmark.out.default.inp={seed}.odi"
     out = {}
+    num = r"[-+]?\d+\.\d+(?:[Ee][-+]?\d+)?"
     for line in open(path):
         m = re.search(r"Fermi energy \((\w+) broadening\) :\s*([-\d.]+)", line)
         if m:
             out["efermi_" + m.group(1).lower()] = float(m.group(2))
+        m = re.search(r"<- (\w+) \|", line)
+        if not m:
+            continue
+        tag = m.group(1)
+        body = line[:m.start()]
+        if tag in ("OBg", "ABg"):
+            mm = re.search(r"Spin :\s*(\d+)\s*:\s*(" + num + ")", body)
+            out.setdefault(tag, []).append(float(mm.group(2)))
+        elif tag in ("DEA", "DEF", "DEL"):
+            mm = re.search(r"DOS at Fermi Energy :\s*(" + num + ")", body)
+            out.setdefault(tag, []).append(float(mm.group(1)))
+        elif tag == "Occ":
+            mm = re.search(r"occupation between\s*(" + num + r")\s*and\s*(" + num + ")", body)
+            out.setdefault(tag, []).append([float(mm.group(1)), float(mm.group(2))])
+        elif tag in ("TBg", "wAB", "BEA", "BEF", "BEL", "BEC"):
+            mm = re.findall(num, body)
+            out[tag] = float(mm[-1])
+    # multiplicities and the direct / indirect verdict printed beside the thermal gap
+    txt = open(path).read()
+    mm = re.findall(r"Spin :\s*(\d+)\s*:\s*(\d+)\s+(\d+)\s", txt)
+    if mm:
+        out["vbm_cbm_multiplicity"] = [[int(a[1]), int(a[2])] for a in mm]
+    for key in ("Direct Gap", "Indirect Gap", "Gap unknown"):
+        if key in txt:
+            out["gap_kind"] = key
     return out
 
 
@@ -301,6 +330,11 @@ def main():
     save("fx_si2_dos", fixture("Si2_DOS", "Si2", {"dome", "pdos", "cell"}))
     save("fx_si2_core", fixture("Si2_core", "Si2", {"dome", "elnes", "cell"}))
     save("fx_nage_core", fixture("NaGe_core_chemical_shift", "NaGe", {"dome", "elnes", "cell"}))
+    # testopt_dos_fixed ships its own 10-k-point, 23-band Si2.bands (no gradients)
+    b = read_bands(f"{REF}/tests/testopt_dos_fixed/Si2.bands")
+    rl, rc, vol = calc_lattice(b["real_lattice_bohr"])
+    b.update(real_lattice=rl, recip_lattice=np.asfortranarray(rc), cell_volume=vol, kpoint_grid_dim=find_mp_grid(b["kpoint_r"]))
+    save("fx_si2_fixed", b)
 
     dat_tests = {
         "testopt_dos_adaptive_dat": "Si2", "testopt_dos_adaptive_no_spin": "Si2",

@@ -621,6 +621,113 @@ def test_core_task_golden(ob, odo, test, btype, core_type, polar):
     ctx.close()
 
 
+def test_core_chemical_shift_golden_nage(ob, odo):
+    """testopt_core_chemical_shift through od_core_calculate: NaGe, the one fixture of the reference with a non-symmetric
+    reciprocal lattice (2x2x2 mesh), adaptive_smearing 0.2, LAI 1.0 / 0.5 / 0.1, core_chemical_shift 11142.275222 with
+    cbm_energy = 0 (core_calculate never runs the band-gap analysis, core.f90:38-83, :533-535).  Tolerance: the oracle
+    itself sits 2.7e-11 of peak from this golden (tests/test_oracle_golden.py explains why); vs the oracle: TOL_SPEC."""
+    fx = fixture("nage_core")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    p = ctx.dos_params("adaptive", dos_spacing=0.1, num_electrons=fx["num_electrons"], cell_volume=float(fx["cell_volume"]),
+                       br=ob.broadening(adaptive_smearing=0.2))
+    r = ctx.core_calculate(fx["elnes_mat"], p, core_type="absorption", polar=False,
+                           lai=dict(gaussian_width=1.0, lorentzian_width=0.5, lorentzian_scale=0.1), core_chemical_shift=11142.275222)
+    G = load_npz("gold_testopt_core_chemical_shift")
+    ch2l = {1: 0, 2: 1, 3: 1, 4: 1, 5: 2, 6: 2, 7: 2, 8: 2, 9: 2}
+    keys = list(zip(fx["elnes_species"], fx["elnes_rank"], fx["elnes_shell"], [ch2l.get(int(a), 3) for a in fx["elnes_am"]]))
+    edges = []
+    for o, k in enumerate(keys):
+        if edges and edges[-1][0] == k:
+            edges[-1][1].append(o)
+        else:
+            edges.append((k, [o]))
+    assert len(edges) == len(G) == 17
+    # the oracle on the same (sticky, quirk Q4) grid
+    bro = odo.make_broadening(adaptive_smearing=0.2)
+    first = odo.dos_utils_calculate(s, "adaptive", dos_spacing=0.1, br=bro)
+    assert abs(r["efermi"] - first["efermi"]) < 1e-9
+    mw = odo.core_prepare_matrix_elements(s, fx["elnes_mat"], "absorption", first["efermi"])
+    E, delta, n = odo.dos_energy_scale(s, 0.1, dos_nbins=first["nbins"])
+    wd = odo.calculate_dos("a", s, bro, E, delta, mw)[2]
+    c = (1.602176487E-19 * 3.141592653589793238462643383279502884197 * float(np.float32(1e-20))) / (
+        s.cell_volume * float(np.float32(1e-30)) * 8.8541878176E-12)
+    wd = wd * 0.52917720859 ** 2 * c
+    assert r["nbins"] == n and np.abs(r["E"] - (E + 11142.275222)).max() < 1e-9
+    assert rel_to_peak(r["weighted_dos"], wd) < TOL_SPEC
+    for i, (_, orbs) in enumerate(edges):
+        g = G[f"block{i}"]
+        assert g.shape[0] == r["nbins"] and np.abs(r["E"] - g[:, 0]).max() < 1e-9
+        col = sum(r["weighted_dos"][:, 0, o] for o in orbs) / float(len(orbs))
+        colb = sum(r["weighted_dos_broadened"][:, 0, o] for o in orbs) / float(len(orbs))
+        assert rel_to_peak(col, g[:, 1]) < 5e-11, i
+        assert rel_to_peak(colb, g[:, 2]) < 5e-11, i
+    # a band-gap analysis on the same ctx sets the module's cbm_energy, which write_core then subtracts
+    bg = ctx.compute_bandgap(r["efermi"], fx["num_electrons"])
+    r2 = ctx.core_calculate(fx["elnes_mat"], p, core_type="absorption", core_chemical_shift=11142.275222)
+    assert np.abs(r2["E"] - (r["E"] - bg["thermal_cbm"])).max() < 1e-9
+    ctx.close()
+
+
+@pytest.mark.parametrize("test,fxname,btype,tag", [("testopt_dos_adaptive", "si2_optics", "adaptive", "BEA"),
+                                                   ("testopt_dos_linear", "si2_optics", "linear", "BEL"),
+                                                   ("testopt_dos_fixed", "si2_fixed", "fixed", "BEF")])
+def test_bandgap_and_band_energies(ob, odo, test, fxname, btype, tag):
+    """dos_utils_compute_bandgap / dos_utils_compute_band_energies against the oracle (exact: same
+    scan order) and the tagged numbers of the reference's .odo goldens (f15.10 / f12.4 / f8.4)."""
+    import json
+    import os
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gold_odo.json")))[test]
+    fx = fixture(fxname)
+    ctx, s = gpu_ctx(ob, fx, odo, gradient=None if fxname == "si2_fixed" else "auto")
+    p = ctx.dos_params(btype, dos_spacing=0.1, num_electrons=fx["num_electrons"])
+    r = ctx.dos_utils_calculate(p)
+    ef = r["efermi_" + btype]
+    assert abs(ef - G["efermi_" + btype]) < 5.1e-5
+    bg, ref = ctx.compute_bandgap(ef, fx["num_electrons"]), odo.compute_bandgap(s, ef)
+    for k in ("thermal_vbm", "thermal_cbm", "thermal_bandgap", "thermal_vbm_k", "thermal_cbm_k", "vbm_multiplicity", "cbm_multiplicity",
+              "optical_multiplicity", "optical_bandgap", "average_bandgap", "weighted_average", "thermal_multiplicity"):
+        assert bg[k] == ref[k], k
+    assert abs(bg["thermal_bandgap"] - G["TBg"]) < 5.1e-11
+    for is_ in range(s.ns):
+        assert abs(bg["optical_bandgap"][is_] - G["OBg"][is_]) < 5.1e-11
+        assert abs(bg["average_bandgap"][is_] - G["ABg"][is_]) < 5.1e-11
+        assert [bg["vbm_multiplicity"][is_], bg["cbm_multiplicity"][is_]] == G["vbm_cbm_multiplicity"][is_]
+    if s.ns > 1:
+        assert abs(bg["weighted_average"] - G["wAB"]) < 5.1e-11
+    be, bec = ctx.compute_band_energies(ef)
+    assert abs(be[btype] - odo.calc_band_energies(r["dos_" + btype], r["E"], r["delta"], ef)) < 1e-11
+    assert abs(be[btype] - G[tag]) < 5.1e-5
+    assert abs(bec - odo.band_energy_from_bands(s, ef)) < 1e-11 and abs(bec - G["BEC"]) < 5.1e-5
+    d_at_e = ctx.dos_utils_calculate_at_e(p, ef, r["delta"])[0]
+    for is_ in range(s.ns):
+        assert abs(d_at_e[{"fixed": 0, "adaptive": 1, "linear": 2}[btype], is_] - G["DE" + btype[0].upper()][is_]) < 5.1e-5
+    ctx.close()
+
+
+def test_bandgap_ties_and_missing_bands(ob, odo):
+    """the sequential tie counting of the band-gap scan (one running VBM / CBM shared by both spins, multiplicities per
+    spin) and the -200 markers of (k, spin) columns without a band above the Fermi level (dos_utils.f90:504)"""
+    nb, ns, nk = 6, 2, 40
+    rng = np.random.default_rng(3)
+    be = np.sort(rng.uniform(-2.0, 2.0, (nb, ns, nk)), axis=0)
+    be[2, :, :] = np.minimum(be[2, :, :], -0.1)
+    be[3, :, :] = np.maximum(be[3, :, :], 0.3)
+    be = np.sort(be, axis=0)
+    be[2, 0, 5] = be[2, 0, 17] = be[2, 1, 8] = -0.1     # three-fold degenerate VBM across k and spin
+    be[3, 1, 30] = be[3, 1, 31] = 0.3                    # two-fold CBM in spin 2
+    be[:, 0, 12] = np.linspace(-3.0, -1.0, nb)           # a column entirely below the Fermi level
+    be = np.asfortranarray(be)
+    kw = np.full(nk, 1.0 / nk)
+    ctx = ob.Context(0)
+    ctx.set_system(nk, ns, nb, np.eye(3), (4, 5, 2), kw, 1.0)
+    ctx.set_bands(be)
+    s = odo.Sys(be, kw, np.eye(3), (4, 5, 2), None, electrons_per_state=1.0, num_electrons=[3.0, 3.0])
+    bg, ref = ctx.compute_bandgap(0.0, [3.0, 3.0]), odo.compute_bandgap(s, 0.0)
+    assert bg == ref
+    assert ref["thermal_multiplicity"]
+    ctx.close()
+
+
 # ------------------------------------------------------------------ size-independent properties at a larger scale
 def test_large_scale_properties(ob, monkeypatch):
     """A k-slab of BASELINE config 2 (20k k-points x 256 bands x 2 spins = 10M states, 20 000 bins) in several
@@ -675,6 +782,55 @@ def test_very_fine_grids(ob, odo, nbins):
         dos, intdos, _ = ctx.calculate_dos(t, E[0], delta, n, br=ob.broadening(fixed_smearing=smear, adaptive_smearing=0.1))
         assert rel_to_peak(dos, ref[0]) < TOL_SPEC, (t, smear)
         assert_int(intdos, ref[1])
+    ctx.close()
+
+
+def test_grid_beyond_the_narrow_engine_falls_back_to_dense(ob, odo):
+    """a grid with more bins than the narrow engine's bucket table can hold (~650k per spin channel) used to
+    be a hard error; the reference accepts any dos_nbins / jdos_nbins, so the dense engine takes these"""
+    ctx = ob.Context(0)
+    grid, ns, nb = (3, 3, 2), 2, 6
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=13)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0, num_electrons=[3.0, 3.0])
+    E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=700000)
+    for t in ("a", "l"):
+        ref = odo.calculate_dos(t, s, odo.make_broadening(adaptive_smearing=0.02), E, delta, nthreads=8)
+        dos, intdos, _ = ctx.calculate_dos(t, E[0], delta, n, br=ob.broadening(adaptive_smearing=0.02))
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC, t
+        assert_int(intdos, ref[1])
+    ef = odo.efermi_insulator(s)
+    Ej, dj, nj = odo.jdos_energy_scale(s, ef, jdos_spacing=2e-5, jdos_max_energy=14.0)
+    assert nj == 700000
+    rj, _ = odo.calculate_jdos("a", s, odo.make_broadening(adaptive_smearing=0.02), Ej, dj, ef, nthreads=8)
+    jd, _ = ctx.calculate_jdos("a", dj, nj, ef, br=ob.broadening(adaptive_smearing=0.02))
+    assert rel_to_peak(jd, rj) < TOL_SPEC
+    ctx.close()
+
+
+def test_exclude_bands_on_a_fresh_context_with_poisoned_allocations(ob, odo, monkeypatch):
+    """the narrow JDOS path copied exclude_bands into a buffer and then grew that buffer, which
+    frees and reallocates without keeping the contents.  Every fresh allocation is filled with band index 3 here
+    (OD_DEBUG_POISON), so a list that was lost would exclude band 3 instead of band 2."""
+    monkeypatch.setenv("OD_DEBUG_POISON", "3")
+    ctx = ob.Context(0)
+    grid, ns, nb = (8, 6, 5), 1, 10
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=17)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=2.0, num_electrons=[10.0])
+    ef = odo.efermi_insulator(s)
+    E, delta, n = odo.jdos_energy_scale(s, ef, jdos_spacing=0.005, jdos_max_energy=14.0)
+    jd, _ = ctx.calculate_jdos("a", delta, n, ef, exclude_bands=(2,))          # the FIRST jdos call of this ctx
+    ref, _ = odo.calculate_jdos("a", s, odo.make_broadening(), E, delta, ef, exclude_bands=(2,), nthreads=8)
+    ref3, _ = odo.calculate_jdos("a", s, odo.make_broadening(), E, delta, ef, exclude_bands=(3,), nthreads=8)
+    assert rel_to_peak(ref3, ref) > 1e-3
+    assert rel_to_peak(jd, ref) < TOL_SPEC
+    for t in ("l", "f"):       # and once more per scheme with a longer list (the buffer grows again)
+        jd, _ = ctx.calculate_jdos(t, delta, n, ef, exclude_bands=(2, 4, 1), br=ob.broadening(fixed_smearing=0.03))
+        ref, _ = odo.calculate_jdos(t, s, odo.make_broadening(fixed_smearing=0.03), E, delta, ef, exclude_bands=(2, 4, 1), nthreads=8)
+        assert rel_to_peak(jd, ref) < TOL_SPEC, t
     ctx.close()
 
 
@@ -933,4 +1089,78 @@ def test_narrow_engine_on_a_grid_that_cuts_through_the_bands(ob, odo):
         assert rel_to_peak(dos, ref[0]) < TOL_SPEC, t
         assert_int(intdos, ref[1])
         assert intdos[0].min() > 0.1 * nb                    # a good part of the states lies below the grid
+    ctx.close()
+
+
+# ------------------------------------------------------------------ lattice orientation (every fixture and every
+# synthetic test had a symmetric reciprocal matrix, so a row/column swap could not fail)
+NONSYM_RECIP = np.array([[1.2, -0.6, 0.6], [0.0, 1.2, -1.2], [0.0, 0.0, 1.2]])   # rows = reciprocal vectors, not symmetric
+
+
+def _nonsym_ctx(ob, odo, grid, ns, nb, seed, scale=1.0, num_electrons=None):
+    """device-generated cosine bands, then the cell is swapped for a non-symmetric, non-orthogonal reciprocal lattice on an
+    anisotropic k-grid (any (E, gradient, lattice) triple is a valid input of the path; tests/test_oracle_lattice.py pins
+    the oracle's index order on the same lattice against a literal numpy restatement of dos_utils.f90:1210-1216, :1355-1367)"""
+    ctx = ob.Context(0)
+    nk = grid[0] * grid[1] * grid[2]
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=seed)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    recip = NONSYM_RECIP * scale
+    ctx.set_system(nk, ns, nb, recip, grid, None, 1.0)
+    s = odo.Sys(be, kw, recip, grid, bg, electrons_per_state=1.0, num_electrons=num_electrons)
+    return ctx, s
+
+
+@pytest.mark.parametrize("dos_type", ["a", "l", "f"])
+def test_nonsymmetric_lattice_dos(ob, odo, dos_type):
+    ctx, s = _nonsym_ctx(ob, odo, (21, 10, 6), 2, 20, seed=51)
+    E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=5000)
+    bro, brg = odo.make_broadening(fixed_smearing=0.03), ob.broadening(fixed_smearing=0.03)
+    ref = odo.calculate_dos(dos_type, s, bro, E, delta, nthreads=8)
+    # the transposed lattice gives a different spectrum on this cell: the comparison below can fail
+    st = odo.Sys(s.band_energy, s.kpoint_weight, s.recip_lattice.T, s.kpoint_grid_dim, s.band_gradient, electrons_per_state=1.0)
+    if dos_type != "f":
+        ref_t = odo.calculate_dos(dos_type, st, bro, E, delta, nthreads=8)
+        assert rel_to_peak(ref_t[0], ref[0]) > 1e-3
+    for eng in ("auto", "dense"):
+        ctx.set_engine(eng)
+        dos, intdos, _ = ctx.calculate_dos(dos_type, E[0], delta, n, br=brg)
+        assert rel_to_peak(dos, ref[0]) < TOL_SPEC, eng
+        assert_int(intdos, ref[1])
+    ctx.set_engine("auto")
+    for e_at in (E[n // 3], E[n // 2]):
+        d, _ = ctx.calculate_dos_at_e(dos_type, e_at, delta, br=brg)
+        rd, _ = odo.calculate_dos_at_e(dos_type, s, bro, delta, e_at)
+        assert np.abs(d - rd).max() <= 1e-10 * max(np.abs(rd).max(), 1e-300)
+    ctx.close()
+
+
+@pytest.mark.parametrize("jtype", ["a", "l"])
+def test_nonsymmetric_lattice_jdos_and_optics(ob, odo, jtype):
+    grid, ns, nb = (12, 7, 5), 2, 16
+    ctx, s = _nonsym_ctx(ob, odo, grid, ns, nb, seed=52, num_electrons=[8.0, 8.0])
+    nk = s.nk
+    ef = odo.efermi_insulator(s)
+    E, delta, n = odo.jdos_energy_scale(s, ef, jdos_spacing=0.005, jdos_max_energy=12.0)
+    bro, brg = odo.make_broadening(), ob.broadening()
+    rng = np.random.default_rng(7)
+    om = np.asfortranarray(rng.normal(0, 0.1, (nb, nb, 3, nk, ns)) + 1j * rng.normal(0, 0.1, (nb, nb, 3, nk, ns)))
+    # a symmetry list that is NOT closed under transposition (a 4-fold rotation without its inverse): a transposed
+    # crystal_symmetry_operations(:, :, isym) in make_weights (optics.f90:213-244) changes the polar and tensor weights
+    c4 = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    symops = np.asfortranarray(np.stack([np.eye(3), c4], axis=2))
+    for geom in ("polar", "tensor", "unpolar"):
+        q = (0.3, 0.5, 0.25)
+        mw = odo.make_weights(s, om, geom, ef, qdir=q, symops=symops)
+        mw_t = odo.make_weights(s, om, geom, ef, qdir=q, symops=np.asfortranarray(symops.transpose(1, 0, 2)))
+        if geom != "unpolar":
+            assert np.abs(mw - mw_t).max() > 1e-3 * np.abs(mw).max()
+        rj, rw = odo.calculate_jdos(jtype, s, bro, E, delta, ef, mw=mw, nthreads=8)
+        for eng in ("auto", "dense"):
+            ctx.set_engine(eng)
+            jd, wj = ctx.calculate_jdos_optics(jtype, delta, n, ef, om, geom, qdir=q, symops=symops, br=brg)
+            assert rel_to_peak(jd, rj) < TOL_SPEC, (geom, eng)
+            assert rel_to_peak(wj, rw) < TOL_SPEC, (geom, eng)
+        mw_g = ctx.make_weights(om, geom, ef, qdir=q, symops=symops)
+        assert np.abs(mw_g - mw).max() <= 1e-12 * np.abs(mw).max()
     ctx.close()
