@@ -50,6 +50,7 @@ def parse():
                     help="k-point assignment over ranks: cyclic (balanced on the k1-ordered synthetic mesh) or contiguous blocks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank spectrum comparison (N > 1)")
     return ap.parse_args()
 
 
@@ -333,6 +334,27 @@ def main():
         ob.host_free_pinned(h_be)
         ob.host_free_pinned(h_bg)
 
+    # ---- multi-rank parity of the LIBRARY (not the oracle): rank 0 runs the whole mesh on one communicator-less ctx and
+    #      compares the spectra the N ranks produced through od_dos_utils_calculate + the NCCL merge with it
+    parity = None
+    if world > 1 and not args.no_parity:
+        r_multi = step()                       # collective: every rank calls it
+        if rank == 0:
+            ctx1 = ob.Context(local)
+            ctx1.synth_bands(grid_total, 0, nk_total, NS, NB, lattice_a=LATTICE_A, seed=SEED)
+            p1 = ctx1.dos_params(["adaptive", "linear"], dos_nbins=NBINS, num_electrons=(NB / 2.0, NB / 2.0))
+            r_one = ctx1.dos_utils_calculate(p1)
+            ctx1.close()
+            parity = {"reference": "the same library on ONE GPU over all k-points, no communicator",
+                      "nbins_equal": bool(r_one["nbins"] == r_multi["nbins"] and r_one["emin"] == r_multi["emin"])}
+            for k in ("dos_adaptive", "dos_linear"):
+                parity["max_rel_" + k] = float(np.abs(r_multi[k] - r_one[k]).max() / np.abs(r_one[k]).max())
+            for k in ("intdos_adaptive", "intdos_linear"):
+                parity["max_rel_" + k] = float(np.abs(r_multi[k] - r_one[k]).max() / np.abs(r_one[k]).max())
+            parity["efermi_abs_diff"] = float(max(abs(r_multi["efermi_adaptive"] - r_one["efermi_adaptive"]),
+                                                  abs(r_multi["efermi_linear"] - r_one["efermi_linear"])))
+        barrier(dist)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): restated reference loop on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -348,7 +370,7 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, world, nk_total), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "multi_gpu_parity": parity, "gpu_launches": int(launches), "clocks": sampler.summary(),
                 "dense_equivalent_evaluations_per_s": 2.0 * float(nk_total) * NB * NS * NBINS / (ms_step * 1e-3),
                 "contributions_per_step": contrib_total, "wall_ms_per_step": wall / args.steps * 1e3,
                 "efermi_adaptive": r.get("efermi_adaptive"), "efermi_linear": r.get("efermi_linear")}

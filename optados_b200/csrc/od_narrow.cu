@@ -56,7 +56,6 @@ constexpr int NR_CHUNK = 256;   // records per work item (512: +1 %, 1024: +3 % 
 constexpr int NR_WARPS = 8;      // warps per CTA
 constexpr int NR_CTAS_PER_SM = 2; // accumulate kernels: 2 x 8 warps per SM (registers and shared memory both allow no more)
 constexpr int NR_NCLS = 10;      // width classes
-constexpr int NR_EM_CLASS = 5;   // first width class (windows > 84 bins) whose integrated DOS runs on the Euler-Maclaurin form
 constexpr int NR_MAXBUCKETS = 52224;  // x 4 B = 204 KB of shared memory in the prepare passes
 constexpr int NR_PREP_THREADS = 1024;
 constexpr unsigned KEY_WIDE = 0xFFFFFFFEu, KEY_DROP = 0xFFFFFFFFu;
@@ -366,6 +365,8 @@ struct NarrowArgs {
   unsigned long long *stats;             // [0] lane-steps spent, [1] in-window (record, bin) pairs
   ErfcxCoef cf;
   double *out_dos, *out_int, *out_step;  // [ns * bpad + NR_T]; JD mode: out_dos / out_int are the two channels
+  double *out_dos_em, *out_corr;         // Gaussian DOS, Euler-Maclaurin groups: their DOS and the correction sums
+  int no_em;                             // OD_NO_EM=1: rational erfc for every group (tests)
   // JD (JDOS / optics) mode: channel pass `chan` accumulates K*m0 and K*m1 with (m0, m1) =
   // (1, wt[0]) for chan 0 and (wt[2 chan - 1], wt[2 chan]) after that; wts[rec * ng + a]
   const double *wts;
@@ -378,15 +379,20 @@ struct NarrowArgs {
   long long k_first;
 };
 
-__device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, const NarrowArgs &A, int lane) {
+// tile -> HBM.  mode 0: (dos, local part of the integrated DOS, steps) / the two JD channels; mode 1: the
+// Euler-Maclaurin pair (dos_em, corr)
+__device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, int mode, const NarrowArgs &A, int lane) {
+  double *o0 = mode ? A.out_dos_em : A.out_dos, *o1 = mode ? A.out_corr : A.out_int;
   for (int i = lane; i < used; i += 32) {
     const double2 v = tile[i];
-    const double s = stile[i];
-    if (v.x != 0.0) atomicAdd(&A.out_dos[base + i], v.x);
-    if (v.y != 0.0) atomicAdd(&A.out_int[base + i], v.y);
-    if (s != 0.0) atomicAdd(&A.out_step[base + i], s);
+    if (v.x != 0.0) atomicAdd(&o0[base + i], v.x);
+    if (v.y != 0.0) atomicAdd(&o1[base + i], v.y);
     tile[i] = make_double2(0.0, 0.0);
-    stile[i] = 0.0;
+    if (!mode) {
+      const double s = stile[i];
+      if (s != 0.0) atomicAdd(&A.out_step[base + i], s);
+      stile[i] = 0.0;
+    }
   }
   __syncwarp();
 }
@@ -401,24 +407,118 @@ __device__ __forceinline__ void gauss_direct(double e, double w, double om, doub
   s = (j < cabs) ? h : -h;
 }
 
-// EM (Gaussian DOS + integrated DOS, width classes >= NR_EM_CLASS only): the integrated spectrum of a lane's
-// record is advanced along its walk by the Euler-Maclaurin relation between a sum and an integral,
-//   omega Phi(z_j) = C + dE S_j - g_j K(z_j),   S_j = sum of the record's Gaussian values since the start of the
-//   segment,   K(z) = dE/2 + w z (q0 + q1 z^2 + q2 z^4 + q3 z^6)   (the del^2 .. del^8 correction terms),
-// instead of one rational erfc per bin: 13 FP64 operations per bin instead of 21 + a reciprocal.  The next term
-// of the series is 2e-6 del^10 of omega; del = dE/w <= 0.2 in these classes (windows of more than 84 bins), i.e.
-// <= 2e-13.  C is fixed at the start of every segment (walk start, wrap) from the rational erfc.
-template <bool LINEAR, bool JD, bool EM = false>
+// Euler-Maclaurin form of the integrated Gaussian (tools/em_table.py prints the table and the del thresholds):
+//   omega Phi(z_j) = dE S_j - g_j [dE/2 + w z_j W(z_j^2)],   z W(z^2) = - sum_{k=1..NT} B_2k/(2k)! del^2k He_{2k-1}(z)
+// with S_j the inclusive sum of the record's Gaussian values from the bottom of its window.  Summed over records the
+// first term is a prefix sum of the DOS these records produce, so the kernel only accumulates g and g z w W(z^2) per bin
+// (10 FP64 operations for NT = 4, 13 for NT = 7, against 21 + a reciprocal for the rational erfc) and combine_kernel
+// does the prefix sum once per call.  Truncation: <= 3e-12 of omega for del <= 0.2568 (NT = 4) / 0.5348 (NT = 7).
+constexpr double EM_DEL4 = 0.2568, EM_DEL7 = 0.5348;
+__constant__ double c_emT[7][7] = {
+    {-8.33333333333333287e-02, 0, 0, 0, 0, 0, 0},
+    {-4.16666666666666661e-03, 1.38888888888888894e-03, 0, 0, 0, 0, 0},
+    {-4.96031746031746004e-04, 3.30687830687830669e-04, -3.30687830687830710e-05, 0, 0, 0, 0},
+    {-8.68055555555555589e-05, 8.68055555555555589e-05, -1.73611111111111111e-05, 8.26719576719576754e-07, 0, 0, 0},
+    {-1.97285353535353552e-05, 2.63047138047138036e-05, -7.89141414141414141e-06, 7.51563251563251527e-07, -2.08767569878681002e-08, 0, 0},
+    {-5.49291564916564902e-06, 9.15485941527608198e-06, -3.66194376611043296e-06, 5.23134823730061852e-07, -2.90630457627812118e-08,
+     5.28419013868749322e-10, 0},
+    {-1.80844907407407414e-06, 3.61689814814814829e-06, -1.80844907407407414e-06, 3.44466490299823656e-07, -2.87055408583186369e-08,
+     1.04383784939340501e-09, -1.33825365306846789e-11}};
+
+// c[m] = w * sum_{k > m} T[k][m] del^(2k+2): coefficient of z^(2m+1) in w z W(z^2)
+template <int NT>
+__device__ __forceinline__ void em_coeffs(double del, double w, double (&c)[NT]) {
+  const double d2 = del * del;
+  double pw[NT];
+  pw[0] = d2 * w;
+#pragma unroll
+  for (int k = 1; k < NT; ++k) pw[k] = pw[k - 1] * d2;
+#pragma unroll
+  for (int m = 0; m < NT; ++m) {
+    double a = 0.0;
+#pragma unroll
+    for (int k = NT - 1; k >= m; --k) a = fma(c_emT[k][m], pw[k], a);
+    c[m] = a;
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ double em_zw(double z, const double (&c)[NT]) {
+  const double u = z * z;
+  double w = c[NT - 1];
+#pragma unroll
+  for (int m = NT - 2; m >= 0; --m) w = fma(w, u, c[m]);
+  return z * w;
+}
+
+// one Gaussian group on the Euler-Maclaurin path: acc.x += g, acc.y += g z w W(z^2)
+template <int NT>
+__device__ __forceinline__ void em_walk(double2 *tw, int lane, int Wc, double del, double w, double q, double zB, double gB, double rB,
+                                        double amp, double hd2) {
+  double c[NT];
+  em_coeffs<NT>(del, w, c);
+  double z1 = zB + (double)lane * del;
+  double g1 = amp * exp(-0.5 * z1 * z1), rr1 = exp(-fma(z1, del, hd2));
+  int r1 = lane;
+  const bool dual = Wc >= 64;
+  const int H = dual ? (Wc + 1) >> 1 : Wc;
+  const int n2 = dual ? Wc - H : 0;
+  if (dual) {
+    double z2 = zB + (double)(lane + H) * del;
+    double g2 = amp * exp(-0.5 * z2 * z2), rr2 = exp(-fma(z2, del, hd2));
+    int r2 = lane + H;
+#pragma unroll 1
+    for (int t = 0; t < n2; ++t) {
+      const double c1 = g1, c2 = g2;
+      const double t1 = em_zw<NT>(z1, c), t2 = em_zw<NT>(z2, c);
+      double2 *q1 = tw + r1, *q2 = tw + r2;
+      g1 *= rr1; rr1 *= q; z1 += del; ++r1;
+      g2 *= rr2; rr2 *= q; z2 += del; ++r2;
+      if (r2 == Wc) { r2 = 0; g2 = gB; rr2 = rB; z2 = zB; }
+      double2 acc1 = *q1;
+      double2 acc2 = *q2;
+      acc1.x += c1; acc1.y = fma(c1, t1, acc1.y);
+      acc2.x += c2; acc2.y = fma(c2, t2, acc2.y);
+      *q1 = acc1;
+      *q2 = acc2;
+      __syncwarp();
+    }
+  }
+#pragma unroll 1
+  for (int t = n2; t < H; ++t) {
+    double2 acc = tw[r1];
+    acc.x += g1;
+    acc.y = fma(g1, em_zw<NT>(z1, c), acc.y);
+    tw[r1] = acc;
+    g1 *= rr1; rr1 *= q; z1 += del;
+    ++r1;
+    if (r1 == Wc) { r1 = 0; g1 = gB; rr1 = rB; z1 = zB; }
+    __syncwarp();
+  }
+}
+
+constexpr int NR_NLV = 64;                                    // levels of the in-chunk counting sort
+constexpr int NR_SORT_INTS = 72;                              // per warp: 65 counters (+ padding) ...
+constexpr int NR_SORT_BYTES = NR_SORT_INTS * 4 + NR_CHUNK;    // ... and the sorted order (one byte per record)
+static_assert(NR_CHUNK == 256, "the in-chunk sort keeps 8 records per lane and one-byte local indices");
+
+template <bool LINEAR, bool JD>
 __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(NarrowArgs A) {
   extern __shared__ double2 sh_tiles[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2 *tile = sh_tiles + (size_t)warp * NR_T;
   double *stile = reinterpret_cast<double *>(sh_tiles + (size_t)NR_WARPS * NR_T) + (size_t)warp * NR_T;
+  unsigned char *sort_area = reinterpret_cast<unsigned char *>(reinterpret_cast<double *>(sh_tiles + (size_t)NR_WARPS * NR_T) + (size_t)NR_WARPS * NR_T) +
+                             (size_t)warp * NR_SORT_BYTES;
+  int *cnt = reinterpret_cast<int *>(sort_area);
+  unsigned char *order = sort_area + NR_SORT_INTS * 4;
   for (int i = lane; i < NR_T; i += 32) { tile[i] = make_double2(0.0, 0.0); stile[i] = 0.0; }
   __syncwarp();
-  int base = 0, used = 0;
+  int base = 0, used = 0, tmode = 0;
   const double delta = A.grid.delta, emin = A.grid.emin;
   const long long nchunks = (A.nrec + NR_CHUNK - 1) / NR_CHUNK;
+  constexpr size_t RECB = LINEAR ? sizeof(LRec) : sizeof(GRec);
+  constexpr size_t TAILB = LINEAR ? 48 : 24;  // byte offset of (klo, cpos | wlen << 16) in a record
 
   for (;;) {
     unsigned long long ch = 0;
@@ -426,15 +526,71 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
     ch = __shfl_sync(0xffffffffu, ch, 0);
     if ((long long)ch >= nchunks) break;
     const long long c0 = (long long)ch * NR_CHUNK;
-    const long long c1 = min(c0 + (long long)NR_CHUNK, A.nrec);
+    const int n = (int)min((long long)NR_CHUNK, A.nrec - c0);
     unsigned long long st_steps = 0, st_useful = 0;
 
-    for (long long g0 = c0; g0 < c1; g0 += 32) {
-      const long long idx = g0 + lane;
-      const bool valid = idx < c1;
+    // ---- regroup the chunk.  The records of a chunk come from one or a few (width class, 8-bin cell) buckets, in no
+    //      particular order inside a bucket, and every group of 32 walks the UNION of its records' windows: a counting
+    //      sort on (window start, window length), quantised to 64 levels -- nlk start levels x 64 / nlk length levels, nlk
+    //      chosen so that the 8 groups tile the chunk's (start, length) rectangle in roughly square pieces -- makes the
+    //      windows of a group nearly congruent (lane efficiency 0.80 -> ~0.9 at config 2).
+    {
+      const char *rb = reinterpret_cast<const char *>(A.recs) + (size_t)c0 * RECB + TAILB;
+      int klo_j[8], wl_j[8];
+      int kmin = 0x7fffffff, kmax = -0x7fffffff, wmin = 0x7fffffff, wmax = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int li = j * 32 + lane;
+        int2 t = make_int2(0, 0);
+        if (li < n) t = *reinterpret_cast<const int2 *>(rb + (size_t)li * RECB);
+        klo_j[j] = t.x;
+        wl_j[j] = (int)((unsigned)t.y >> 16);
+        if (li < n) { kmin = min(kmin, t.x); kmax = max(kmax, t.x); wmin = min(wmin, wl_j[j]); wmax = max(wmax, wl_j[j]); }
+      }
+      kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+      wmin = __reduce_min_sync(0xffffffffu, wmin); wmax = __reduce_max_sync(0xffffffffu, wmax);
+      const int dk = kmax - kmin + 1, dw = wmax - wmin + 1;
+      const long long r8 = 8ll * dk;
+      const int nlk = r8 < 2ll * dw ? 1 : (r8 < 8ll * dw ? 2 : (r8 < 32ll * dw ? 4 : 8));
+      const int nlw = NR_NLV / nlk;
+      const float fk = (float)nlk / (float)dk, fw = (float)nlw / (float)dw;
+      cnt[lane] = 0; cnt[lane + 32] = 0;
+      if (lane == 0) cnt[64] = 0;
+      __syncwarp();
+      int lvl_j[8], pos_j[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kl = min(nlk - 1, (int)((float)(klo_j[j] - kmin) * fk)), wl = min(nlw - 1, (int)((float)(wl_j[j] - wmin) * fw));
+        lvl_j[j] = kl * nlw + wl;
+        pos_j[j] = 0;
+        if (j * 32 + lane < n) pos_j[j] = atomicAdd(&cnt[lvl_j[j]], 1);
+      }
+      __syncwarp();
+      {
+        const int a0 = cnt[2 * lane], a1 = cnt[2 * lane + 1];
+        int incl = a0 + a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        __syncwarp();
+        cnt[2 * lane] = incl - a0 - a1;
+        cnt[2 * lane + 1] = incl - a1;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j * 32 + lane < n) order[cnt[lvl_j[j]] + pos_j[j]] = (unsigned char)(j * 32 + lane);
+      __syncwarp();
+    }
+
+    for (int g0 = 0; g0 < n; g0 += 32) {
+      const bool valid = g0 + lane < n;
+      const long long idx = c0 + (valid ? (int)order[g0 + lane] : 0);
       // ---- my record (and a prefetch of the one this lane takes in the next group)
-      if (idx + 32 < c1) {
-        const char *nx = reinterpret_cast<const char *>(A.recs) + (size_t)(idx + 32) * (LINEAR ? sizeof(LRec) : sizeof(GRec));
+      if (g0 + 32 + lane < n) {
+        const char *nx = reinterpret_cast<const char *>(A.recs) + (size_t)(c0 + order[g0 + 32 + lane]) * RECB;
         asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
       }
       double e0 = 0, p1 = 1, p2 = 0, p3 = 0, p4 = 0, om = 0;
@@ -508,10 +664,30 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         }
         continue;
       }
-      if (gl < base || gl + Wc + 1 > base + NR_T) {
-        flush_tile(tile, stile, base, used, A, lane);
+      const double E0 = emin + (double)(jb - a) * delta;  // energy of relative bin 0
+
+      // ---- Gaussian DOS: which form of the integrated spectrum does this group take?
+      double invw = 1.0, del = 0.0, zB = 0.0;
+      int emode = 0;  // 0: rational erfc (bracket + steps); 4 / 7: Euler-Maclaurin with that many terms
+      if (!LINEAR) {
+        invw = 1.0 / p1;  // (the reciprocal by MUFU + Newton measured slower here)
+        del = delta * invw;
+        zB = (E0 - e0) * invw;
+        if (!JD && !A.no_em) {
+          // every lane must start its walk where Phi is still ~0 (a window clipped by the bottom of the grid does
+          // not) and sit inside the series' range of validity
+          const double dmax = __hiloint2double((int)__reduce_max_sync(0xffffffffu, (unsigned)__double2hiint(valid ? del : 0.0)), 0);
+          const bool ok = __all_sync(0xffffffffu, !valid || zB <= -8.0);
+          // dmax is del rounded DOWN to its high word: compare against thresholds lowered by one part in 2^20
+          if (ok && dmax <= EM_DEL7 * (1.0 - 1e-6)) emode = dmax <= EM_DEL4 * (1.0 - 1e-6) ? 4 : 7;
+        }
+      }
+      const int want_mode = emode ? 1 : 0;
+      if (gl < base || gl + Wc + 1 > base + NR_T || want_mode != tmode) {
+        flush_tile(tile, stile, base, used, tmode, A, lane);
         base = gl & ~(A.cell - 1);
         used = 0;
+        tmode = want_mode;
       }
       const int off = gl - base;
       used = max(used, off + Wc + 1);
@@ -521,10 +697,9 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
 
       // ---- the steps H: one add per record into the warp-private step tile.  Several records of a
       //      group usually share their centre bin, so this one place uses shared-memory atomics.
-      if (!JD && valid) atomicAdd(stile + off + cabs, om);
+      if (!JD && !emode && valid) atomicAdd(stile + off + cabs, om);
       __syncwarp();
 
-      const double E0 = emin + (double)(jb - a) * delta;  // energy of relative bin 0
       // Two streams per lane when the window allows it (Wc >= 64): stream 1 walks bins lane .. lane+H-1
       // and never wraps, stream 2 starts H = ceil(Wc/2) bins further on and wraps once.  At any step the
       // two 32-bin footprints are >= 32 bins apart (cyclically), so all 64 accesses hit different bins;
@@ -533,74 +708,18 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       const int H = dual ? (Wc + 1) >> 1 : Wc;
       const int n2 = dual ? Wc - H : 0;
       if (!LINEAR) {
-        const double invw = 1.0 / p1, del = delta * invw;  // (the reciprocal by MUFU + Newton measured slower here)
         const double amp = om * invw * OD_INV_SQRT_TWO_PI;
-        const double cl = p1 * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
         const double q = exp(-del * del), hd2 = 0.5 * del * del;
-        const double zB = (E0 - e0) * invw;
         const double gB = amp * exp(-0.5 * zB * zB), rB = exp(-fma(zB, del, hd2));
+        if (!JD && emode) {
+          if (emode == 4) em_walk<4>(tw, lane, Wc, del, p1, q, zB, gB, rB, amp, hd2);
+          else em_walk<7>(tw, lane, Wc, del, p1, q, zB, gB, rB, amp, hd2);
+          continue;
+        }
+        const double cl = p1 * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
         double z1 = zB + (double)lane * del;
         double g1 = amp * exp(-0.5 * z1 * z1), rr1 = exp(-fma(z1, del, hd2));
         int r1 = lane;
-        if (EM && !JD) {
-          // K(z) = dE/2 + z W(z^2); coefficients of W from the Euler-Maclaurin terms del^2/12, -del^4/720,
-          // del^6/30240, -del^8/1209600 applied to the 1st, 3rd, 5th and 7th derivative of phi (= -He_n phi)
-          const double d2 = del * del, d4 = d2 * d2, d6 = d4 * d2, d8 = d4 * d4;
-          const double wq3 = p1 * (d8 * (1.0 / 1209600.0));
-          const double wq2 = p1 * (-d6 * (1.0 / 30240.0) - d8 * (21.0 / 1209600.0));
-          const double wq1 = p1 * (d4 * (1.0 / 720.0) + d6 * (10.0 / 30240.0) + d8 * (105.0 / 1209600.0));
-          const double wq0 = p1 * (-d2 * (1.0 / 12.0) - d4 * (3.0 / 720.0) - d6 * (15.0 / 30240.0) - d8 * (105.0 / 1209600.0));
-          const double hdE = 0.5 * delta;
-          auto Wpoly = [&](double u) { return fma(fma(fma(wq3, u, wq2), u, wq1), u, wq0); };
-          // segment constant: C = omega Phi(z0) - g0 (dE/2 - z0 W(z0^2)), Phi from the rational erfc
-          auto seg_const = [&](double z0, double g0) {
-            const double hh = (g0 * cl) * erfcx_ratio(fabs(z0), A.cf);
-            const double phi0 = z0 < 0.0 ? hh : om - hh;
-            return phi0 - g0 * (hdE - z0 * Wpoly(z0 * z0));
-          };
-          const double CB = seg_const(zB, gB);
-          double C1 = seg_const(z1, g1), S1 = 0.0;
-          if (dual) {
-            double z2 = zB + (double)(lane + H) * del;
-            double g2 = amp * exp(-0.5 * z2 * z2), rr2 = exp(-fma(z2, del, hd2));
-            double C2 = seg_const(z2, g2), S2 = 0.0;
-            int r2 = lane + H;
-#pragma unroll 1
-            for (int t = 0; t < n2; ++t) {
-              const double c1 = g1, c2 = g2, y1 = z1, y2 = z2;
-              double2 *q1 = tw + r1, *q2 = tw + r2;
-              const double b1 = (r1 >= cabs) ? C1 - om : C1, b2 = (r2 >= cabs) ? C2 - om : C2;
-              S1 += c1; S2 += c2;
-              g1 *= rr1; rr1 *= q; z1 += del; ++r1;
-              g2 *= rr2; rr2 *= q; z2 += del; ++r2;
-              double2 acc1 = *q1;
-              double2 acc2 = *q2;
-              const double k1 = fma(y1, Wpoly(y1 * y1), hdE), k2 = fma(y2, Wpoly(y2 * y2), hdE);
-              acc1.x += c1;
-              acc1.y += fma(-c1, k1, fma(delta, S1, b1));
-              acc2.x += c2;
-              acc2.y += fma(-c2, k2, fma(delta, S2, b2));
-              *q1 = acc1;
-              *q2 = acc2;
-              if (r2 == Wc) { r2 = 0; g2 = gB; rr2 = rB; z2 = zB; S2 = 0.0; C2 = CB; }
-              __syncwarp();
-            }
-          }
-#pragma unroll 1
-          for (int t = n2; t < H; ++t) {
-            double2 acc = tw[r1];
-            S1 += g1;
-            const double b1 = (r1 >= cabs) ? C1 - om : C1;
-            acc.x += g1;
-            acc.y += fma(-g1, fma(z1, Wpoly(z1 * z1), hdE), fma(delta, S1, b1));
-            tw[r1] = acc;
-            g1 *= rr1; rr1 *= q; z1 += del;
-            ++r1;
-            if (r1 == Wc) { r1 = 0; g1 = gB; rr1 = rB; z1 = zB; S1 = 0.0; C1 = CB; }
-            __syncwarp();
-          }
-          continue;
-        }
         if (dual) {
           double z2 = zB + (double)(lane + H) * del;
           double g2 = amp * exp(-0.5 * z2 * z2), rr2 = exp(-fma(z2, del, hd2));
@@ -734,7 +853,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
     for (int o = 16; o > 0; o >>= 1) st_useful += __shfl_xor_sync(0xffffffffu, st_useful, o);
     if (lane == 0) { atomicAdd(&A.stats[0], st_steps * 32ull); atomicAdd(&A.stats[1], st_useful); }
     // consecutive chunks of one warp are usually far apart on the grid: flush now
-    flush_tile(tile, stile, base, used, A, lane);
+    flush_tile(tile, stile, base, used, tmode, A, lane);
     used = 0;
   }
 }
@@ -990,9 +1109,11 @@ struct WideListProducer {
   }
 };
 
-// out(j, is): dos += narrow dos; intdos += narrow local part + inclusive prefix sum of the step histogram
+// out(j, is): dos += narrow dos (both families of groups); intdos += the local part of the rational-erfc groups + the
+// inclusive prefix sum of their step histogram + the Euler-Maclaurin groups' dE (prefix(dos_em)_j - dos_em_j / 2) - corr_j
 __global__ void __launch_bounds__(1024) combine_kernel(const double *__restrict__ n_dos, const double *__restrict__ n_int,
-                                                       const double *__restrict__ stephist, int nbins, int bpad,
+                                                       const double *__restrict__ stephist, const double *__restrict__ n_dos_em,
+                                                       const double *__restrict__ n_corr, double delta, int nbins, int bpad,
                                                        double *__restrict__ dos, double *__restrict__ intdos) {
   __shared__ double sh[1024];
   __shared__ double carry;
@@ -1001,7 +1122,8 @@ __global__ void __launch_bounds__(1024) combine_kernel(const double *__restrict_
   __syncthreads();
   for (int b0 = 0; b0 < nbins; b0 += 1024) {
     const int j = b0 + threadIdx.x;
-    const double v = (j < nbins) ? stephist[(size_t)is * bpad + j] : 0.0;
+    const double dem = (j < nbins) ? n_dos_em[(size_t)is * bpad + j] : 0.0;
+    const double v = (j < nbins) ? fma(delta, dem, stephist[(size_t)is * bpad + j]) : 0.0;
     sh[threadIdx.x] = v;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -1011,8 +1133,8 @@ __global__ void __launch_bounds__(1024) combine_kernel(const double *__restrict_
       __syncthreads();
     }
     if (j < nbins) {
-      dos[(size_t)is * nbins + j] += n_dos[(size_t)is * bpad + j];
-      intdos[(size_t)is * nbins + j] += n_int[(size_t)is * bpad + j] + (carry + sh[threadIdx.x]);
+      dos[(size_t)is * nbins + j] += n_dos[(size_t)is * bpad + j] + dem;
+      intdos[(size_t)is * nbins + j] += n_int[(size_t)is * bpad + j] - n_corr[(size_t)is * bpad + j] - 0.5 * delta * dem + (carry + sh[threadIdx.x]);
     }
     __syncthreads();
     if (threadIdx.x == 1023) carry += sh[1023];
@@ -1044,7 +1166,7 @@ inline void set_eager(JdosProducer &p) { p.eager = 1; }
 
 template <class Producer>
 int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear, unsigned *h_nrec, unsigned long long h_wide[2],
-                   long long *wide_stride, unsigned *h_em_split = nullptr) {
+                   long long *wide_stride) {
   Producer prod = prod_in;
   prod.b.fast_corners = 1;  // both passes; wide units are re-made by the dense engine with the reference's arithmetic
   Producer prod_keys = prod;  // pass A only needs the windows: no weight columns, no optical matrix elements
@@ -1063,8 +1185,6 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   OD_LAUNCH_CHECK(ctx);
   OD_CUDA(ctx, cudaMemcpyAsync(h_wide, S.wide, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
   OD_CUDA(ctx, cudaMemcpyAsync(h_nrec, S.base + ps.nbuckets, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-  if (h_em_split)  // first record of width class NR_EM_CLASS (records are sorted by class, then cell)
-    OD_CUDA(ctx, cudaMemcpyAsync(h_em_split, S.base + (size_t)NR_EM_CLASS * ps.ncells, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *wide_stride = (long long)std::max(h_wide[0], h_wide[1]);
   const size_t rec_bytes = linear ? sizeof(LRec) : sizeof(GRec);
@@ -1095,7 +1215,7 @@ struct MwGather {
 
 template <bool JD>
 int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int col0, int col1, double *out0, double *out1,
-                  const MwGather *gather = nullptr, long long em_split = -1) {
+                  const MwGather *gather = nullptr) {
   NarrowArgs A;
   A.recs = ctx->recs.p;
   A.nrec = (long long)nrec;
@@ -1108,6 +1228,9 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
   A.out_dos = out0;
   A.out_int = out1;
   A.out_step = S.stephist;
+  A.out_dos_em = JD ? nullptr : S.chan + 2 * S.nout;  // DOS: chan = [dos | int | dos_em | corr]
+  A.out_corr = JD ? nullptr : S.chan + 3 * S.nout;
+  A.no_em = getenv("OD_NO_EM") ? 1 : 0;
   A.wts = S.ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
   A.ng = S.ps.ng;
   A.col0 = col0;
@@ -1118,31 +1241,7 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
     A.mw = gather->mw; A.norb = gather->norb; A.mw_nb = gather->mw_nb; A.mw_nk = gather->mw_nk; A.nb = gather->nb;
     A.k_first = gather->k_first;
   }
-  const size_t smem = (sizeof(double2) + sizeof(double)) * NR_T * NR_WARPS;
-  if (!JD && !linear && em_split >= 0 && em_split <= (long long)nrec && !getenv("OD_NO_EM")) {
-    // Gaussian DOS: records of the narrow width classes with the rational erfc per bin, the wide classes (sorted
-    // behind them) with the Euler-Maclaurin form of the integrated spectrum
-    const long long part[2][2] = {{0, em_split}, {em_split, (long long)nrec}};
-    for (int h = 0; h < 2; ++h) {
-      const long long n = part[h][1] - part[h][0];
-      if (n <= 0) continue;
-      NarrowArgs B = A;
-      B.recs = static_cast<const char *>(A.recs) + (size_t)part[h][0] * sizeof(GRec);
-      B.nrec = n;
-      OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
-      const long long nch = (n + NR_CHUNK - 1) / NR_CHUNK;
-      const int nb = (int)std::min<long long>((long long)ctx->sm_count * NR_CTAS_PER_SM, (nch + NR_WARPS - 1) / NR_WARPS);
-      if (h == 0) {
-        OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        narrow_kernel<false, false, false><<<nb, NR_WARPS * 32, smem, ctx->stream>>>(B);
-      } else {
-        OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        narrow_kernel<false, false, true><<<nb, NR_WARPS * 32, smem, ctx->stream>>>(B);
-      }
-      OD_LAUNCH_CHECK(ctx);
-    }
-    return OD_OK;
-  }
+  const size_t smem = (sizeof(double2) + sizeof(double)) * NR_T * NR_WARPS + (size_t)NR_SORT_BYTES * NR_WARPS;
   OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
   const long long nchunks = ((long long)nrec + NR_CHUNK - 1) / NR_CHUNK;
   const int blocks = (int)std::min<long long>((long long)ctx->sm_count * NR_CTAS_PER_SM, (nchunks + NR_WARPS - 1) / NR_WARPS);
@@ -1233,7 +1332,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   if (total >= (1ll << 32) || prod.units_per_z >= (1ll << 31))
     return od_fail(ctx, OD_ERR_ARG, "narrow engine: more than 2^31 units per spin channel in one call");
   Scratch S;
-  OD_CHECK(narrow_scratch(ctx, grid, ns, total, 2, S));
+  OD_CHECK(narrow_scratch(ctx, grid, ns, total, 4, S));  // [dos | local intdos | dos of the Euler-Maclaurin groups | their corrections]
   S.ps.gwin = NR_ERFWIN;
   S.ps.with_int = 1;
   S.ps.linear_pass = 0;  // calculate_dos ignores hybrid_linear (quirk Q8): a linear pass has no Gaussian records
@@ -1246,13 +1345,13 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   unsigned long long h_wide[2] = {0, 0};
   long long wide_stride = 0;
   tp.start(ctx->stream);
-  unsigned h_em_split = 0;
-  OD_CHECK(narrow_prepare(ctx, prod, S, linear, &h_nrec, h_wide, &wide_stride, &h_em_split));
+  OD_CHECK(narrow_prepare(ctx, prod, S, linear, &h_nrec, h_wide, &wide_stride));
   tp.stop(ctx->stream);
   ta.start(ctx->stream);
-  if (h_nrec > 0) OD_CHECK(narrow_launch<false>(ctx, S, linear, h_nrec, -2, -2, ndos, nint, nullptr, linear ? -1 : (long long)h_em_split));
+  if (h_nrec > 0) OD_CHECK(narrow_launch<false>(ctx, S, linear, h_nrec, -2, -2, ndos, nint, nullptr));
   const size_t n1 = (size_t)nbins * ns;
-  combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, nbins, S.ps.bpad, accum, accum + n1);
+  combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, S.chan + 2 * S.nout, S.chan + 3 * S.nout, grid.delta, nbins, S.ps.bpad,
+                                                accum, accum + n1);
   OD_LAUNCH_CHECK(ctx);
   int wpasses = 0;
   if (h_nrec > 0 && norb >= 8) {

@@ -709,22 +709,25 @@ def test_bandgap_ties_and_missing_bands(ob, odo):
     spin) and the -200 markers of (k, spin) columns without a band above the Fermi level (dos_utils.f90:504)"""
     nb, ns, nk = 6, 2, 40
     rng = np.random.default_rng(3)
-    be = np.sort(rng.uniform(-2.0, 2.0, (nb, ns, nk)), axis=0)
-    be[2, :, :] = np.minimum(be[2, :, :], -0.1)
-    be[3, :, :] = np.maximum(be[3, :, :], 0.3)
-    be = np.sort(be, axis=0)
+    be = np.concatenate([np.sort(rng.uniform(-2.0, -0.2, (3, ns, nk)), axis=0), np.sort(rng.uniform(0.4, 2.0, (3, ns, nk)), axis=0)])
     be[2, 0, 5] = be[2, 0, 17] = be[2, 1, 8] = -0.1     # three-fold degenerate VBM across k and spin
     be[3, 1, 30] = be[3, 1, 31] = 0.3                    # two-fold CBM in spin 2
-    be[:, 0, 12] = np.linspace(-3.0, -1.0, nb)           # a column entirely below the Fermi level
-    be = np.asfortranarray(be)
     kw = np.full(nk, 1.0 / nk)
     ctx = ob.Context(0)
     ctx.set_system(nk, ns, nb, np.eye(3), (4, 5, 2), kw, 1.0)
-    ctx.set_bands(be)
-    s = odo.Sys(be, kw, np.eye(3), (4, 5, 2), None, electrons_per_state=1.0, num_electrons=[3.0, 3.0])
-    bg, ref = ctx.compute_bandgap(0.0, [3.0, 3.0]), odo.compute_bandgap(s, 0.0)
-    assert bg == ref
-    assert ref["thermal_multiplicity"]
+    for missing in (False, True):
+        if missing:
+            be[:, 0, 12] = np.linspace(-3.0, -1.0, nb)   # a column entirely below the Fermi level
+        bef = np.asfortranarray(be)
+        ctx.set_bands(bef)
+        s = odo.Sys(bef, kw, np.eye(3), (4, 5, 2), None, electrons_per_state=1.0, num_electrons=[3.0, 3.0])
+        bg, ref = ctx.compute_bandgap(0.0, [3.0, 3.0]), odo.compute_bandgap(s, 0.0)
+        assert bg == ref
+        assert ref["thermal_multiplicity"] and ref["vbm_multiplicity"] == [2, 2]
+        if not missing:
+            assert ref["cbm_multiplicity"] == [1, 2] and ref["thermal_cbm"] == 0.3 and ref["thermal_vbm"] == -0.1
+        else:   # the reference's -200 marker wins the CBM search and gives a zero "gap" at that k-point (as the reference)
+            assert ref["thermal_cbm"] == -200.0 and ref["optical_bandgap"][0] == 0.0
     ctx.close()
 
 
