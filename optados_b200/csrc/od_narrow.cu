@@ -44,6 +44,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "od_internal.h"
 #include "od_spectral.h"
@@ -451,57 +452,19 @@ __device__ __forceinline__ double em_zw(double z, const double (&c)[NT]) {
   return z * w;
 }
 
-// one Gaussian group on the Euler-Maclaurin path: acc.x += g, acc.y += g z w W(z^2)
-template <int NT>
-__device__ __forceinline__ void em_walk(double2 *tw, int lane, int Wc, double del, double w, double q, double zB, double gB, double rB,
-                                        double amp, double hd2) {
-  double c[NT];
-  em_coeffs<NT>(del, w, c);
-  double z1 = zB + (double)lane * del;
-  double g1 = amp * exp(-0.5 * z1 * z1), rr1 = exp(-fma(z1, del, hd2));
-  int r1 = lane;
-  const bool dual = Wc >= 64;
-  const int H = dual ? (Wc + 1) >> 1 : Wc;
-  const int n2 = dual ? Wc - H : 0;
-  if (dual) {
-    double z2 = zB + (double)(lane + H) * del;
-    double g2 = amp * exp(-0.5 * z2 * z2), rr2 = exp(-fma(z2, del, hd2));
-    int r2 = lane + H;
-#pragma unroll 1
-    for (int t = 0; t < n2; ++t) {
-      const double c1 = g1, c2 = g2;
-      const double t1 = em_zw<NT>(z1, c), t2 = em_zw<NT>(z2, c);
-      double2 *q1 = tw + r1, *q2 = tw + r2;
-      g1 *= rr1; rr1 *= q; z1 += del; ++r1;
-      g2 *= rr2; rr2 *= q; z2 += del; ++r2;
-      if (r2 == Wc) { r2 = 0; g2 = gB; rr2 = rB; z2 = zB; }
-      double2 acc1 = *q1;
-      double2 acc2 = *q2;
-      acc1.x += c1; acc1.y = fma(c1, t1, acc1.y);
-      acc2.x += c2; acc2.y = fma(c2, t2, acc2.y);
-      *q1 = acc1;
-      *q2 = acc2;
-      __syncwarp();
-    }
-  }
-#pragma unroll 1
-  for (int t = n2; t < H; ++t) {
-    double2 acc = tw[r1];
-    acc.x += g1;
-    acc.y = fma(g1, em_zw<NT>(z1, c), acc.y);
-    tw[r1] = acc;
-    g1 *= rr1; rr1 *= q; z1 += del;
-    ++r1;
-    if (r1 == Wc) { r1 = 0; g1 = gB; rr1 = rB; z1 = zB; }
-    __syncwarp();
-  }
-}
-
 constexpr int NR_NLV = 64;                                    // levels of the in-chunk counting sort
 constexpr int NR_SORT_INTS = 72;                              // per warp: 65 counters (+ padding) ...
 constexpr int NR_SORT_BYTES = NR_SORT_INTS * 4 + NR_CHUNK;    // ... and the sorted order (one byte per record)
 static_assert(NR_CHUNK == 256, "the in-chunk sort keeps 8 records per lane and one-byte local indices");
 
+// Accumulation.  A warp takes a chunk of 256 consecutive records, regroups them (below) and walks them in groups of
+// 64: LANE = TWO RECORDS (A = sorted position g0 + lane, B = g0 + 32 + lane).  Every lane walks all Wc bins of the
+// group's common window, lane l starting l bins in and wrapping round, so that in any one step the 32 lanes touch 32
+// DIFFERENT bins of the warp-private tile: one LDS.128 / STS.128 read-modify-write per lane and step carries the
+// contributions of both of its records.  (One record per lane, the round-1 layout, moved 32 B of shared memory per
+// contribution: with the integrated spectrum down to 10 FP64 operations per bin the kernel then ran at 72 % of the
+// shared-memory wavefront peak and 53 % of the FP64 pipe; two records per lane halve the wavefronts and give every lane
+// two independent recurrences, which is also what the short windows of the linear scheme were missing.)
 template <bool LINEAR, bool JD>
 __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(NarrowArgs A) {
   extern __shared__ double2 sh_tiles[];
@@ -519,21 +482,22 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
   const long long nchunks = (A.nrec + NR_CHUNK - 1) / NR_CHUNK;
   constexpr size_t RECB = LINEAR ? sizeof(LRec) : sizeof(GRec);
   constexpr size_t TAILB = LINEAR ? 48 : 24;  // byte offset of (klo, cpos | wlen << 16) in a record
+  constexpr unsigned FULL = 0xffffffffu;
 
   for (;;) {
     unsigned long long ch = 0;
     if (lane == 0) ch = atomicAdd(A.next_chunk, 1ull);
-    ch = __shfl_sync(0xffffffffu, ch, 0);
+    ch = __shfl_sync(FULL, ch, 0);
     if ((long long)ch >= nchunks) break;
     const long long c0 = (long long)ch * NR_CHUNK;
     const int n = (int)min((long long)NR_CHUNK, A.nrec - c0);
     unsigned long long st_steps = 0, st_useful = 0;
 
     // ---- regroup the chunk.  The records of a chunk come from one or a few (width class, 8-bin cell) buckets, in no
-    //      particular order inside a bucket, and every group of 32 walks the UNION of its records' windows: a counting
-    //      sort on (window start, window length), quantised to 64 levels -- nlk start levels x 64 / nlk length levels, nlk
-    //      chosen so that the 8 groups tile the chunk's (start, length) rectangle in roughly square pieces -- makes the
-    //      windows of a group nearly congruent (lane efficiency 0.80 -> ~0.9 at config 2).
+    //      particular order inside a bucket, and every group walks the UNION of its records' windows: a counting sort on
+    //      (window start, window length), quantised to 64 levels -- nlk start levels x 64 / nlk length levels, nlk chosen
+    //      so that the groups tile the chunk's (start, length) rectangle in roughly square pieces -- makes the windows of
+    //      a group nearly congruent (lane efficiency 0.80 -> 0.9 at config 2).
     {
       const char *rb = reinterpret_cast<const char *>(A.recs) + (size_t)c0 * RECB + TAILB;
       int klo_j[8], wl_j[8];
@@ -547,11 +511,11 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         wl_j[j] = (int)((unsigned)t.y >> 16);
         if (li < n) { kmin = min(kmin, t.x); kmax = max(kmax, t.x); wmin = min(wmin, wl_j[j]); wmax = max(wmax, wl_j[j]); }
       }
-      kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
-      wmin = __reduce_min_sync(0xffffffffu, wmin); wmax = __reduce_max_sync(0xffffffffu, wmax);
+      kmin = __reduce_min_sync(FULL, kmin); kmax = __reduce_max_sync(FULL, kmax);
+      wmin = __reduce_min_sync(FULL, wmin); wmax = __reduce_max_sync(FULL, wmax);
       const int dk = kmax - kmin + 1, dw = wmax - wmin + 1;
-      const long long r8 = 8ll * dk;
-      const int nlk = r8 < 2ll * dw ? 1 : (r8 < 8ll * dw ? 2 : (r8 < 32ll * dw ? 4 : 8));
+      const long long r4 = 4ll * dk;  // 4 groups of 64 per chunk
+      const int nlk = r4 < 2ll * dw ? 1 : (r4 < 8ll * dw ? 2 : 4);
       const int nlw = NR_NLV / nlk;
       const float fk = (float)nlk / (float)dk, fw = (float)nlw / (float)dw;
       cnt[lane] = 0; cnt[lane + 32] = 0;
@@ -571,7 +535,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         int incl = a0 + a1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          const int t = __shfl_up_sync(FULL, incl, o);
           if (lane >= o) incl += t;
         }
         __syncwarp();
@@ -585,100 +549,129 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       __syncwarp();
     }
 
-    for (int g0 = 0; g0 < n; g0 += 32) {
-      const bool valid = g0 + lane < n;
-      const long long idx = c0 + (valid ? (int)order[g0 + lane] : 0);
-      // ---- my record (and a prefetch of the one this lane takes in the next group)
-      if (g0 + 32 + lane < n) {
-        const char *nx = reinterpret_cast<const char *>(A.recs) + (size_t)(c0 + order[g0 + 32 + lane]) * RECB;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-      }
-      double e0 = 0, p1 = 1, p2 = 0, p3 = 0, p4 = 0, om = 0;
-      int klo = 0x3fffffff, wlen = 0, cpos = 0;
-      if (valid) {
-        if (LINEAR) {
-          const LRec r = reinterpret_cast<const LRec *>(A.recs)[idx];
-          e0 = r.e0; p1 = r.e1; p2 = r.e2; p3 = r.e3; p4 = r.e4; om = r.om; klo = r.klo; wlen = r.wlen; cpos = r.cpos;
-        } else {
-          const GRec r = reinterpret_cast<const GRec *>(A.recs)[idx];
-          e0 = r.e; p1 = r.w; om = r.om; klo = r.klo; wlen = r.wlen; cpos = r.cpos;
+    for (int g0 = 0; g0 < n; g0 += 64) {
+      // ---- my two records (and a prefetch of the two this lane takes in the next group)
+      bool valid[2];
+      long long idx[2];
+      double e0[2], p1[2], p2[2], p3[2], p4[2], om[2];
+      int klo[2], wlen[2], cpos[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int pos = g0 + 32 * s + lane;
+        valid[s] = pos < n;
+        idx[s] = c0 + (valid[s] ? (int)order[pos] : 0);
+        if (pos + 64 < n) {
+          const char *nx = reinterpret_cast<const char *>(A.recs) + (size_t)(c0 + order[pos + 64]) * RECB;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+        }
+        e0[s] = 0; p1[s] = 1; p2[s] = p3[s] = p4[s] = 0; om[s] = 0;
+        klo[s] = 0x3fffffff; wlen[s] = 0; cpos[s] = 0;
+        if (valid[s]) {
+          if (LINEAR) {
+            const LRec r = reinterpret_cast<const LRec *>(A.recs)[idx[s]];
+            e0[s] = r.e0; p1[s] = r.e1; p2[s] = r.e2; p3[s] = r.e3; p4[s] = r.e4; om[s] = r.om; klo[s] = r.klo; wlen[s] = r.wlen; cpos[s] = r.cpos;
+          } else {
+            const GRec r = reinterpret_cast<const GRec *>(A.recs)[idx[s]];
+            e0[s] = r.e; p1[s] = r.w; om[s] = r.om; klo[s] = r.klo; wlen[s] = r.wlen; cpos[s] = r.cpos;
+          }
         }
       }
-      double m0 = 1.0, m1 = 0.0;  // JD channel multipliers
-      if (JD && valid) {
-        const double *w = nullptr;
-        if (A.runit) {
-          const unsigned u = A.runit[idx];
-          const unsigned ikl = u / (unsigned)A.nb, ib = u - ikl * (unsigned)A.nb;
-          const long long ik = A.k_first + ikl;
-          const int is = klo >= A.bpad ? 1 : 0;
-          if (ik < A.mw_nk && (int)ib < A.mw_nb)  // dos_utils.f90:1268-1269
-            w = A.mw + (size_t)A.norb * (ib + (size_t)A.mw_nb * (ik + (size_t)A.mw_nk * is));
-        } else if (A.wts) {
-          w = A.wts + (size_t)idx * A.ng;
+      double m0[2] = {1.0, 1.0}, m1[2] = {0.0, 0.0};  // JD channel multipliers
+      if (JD) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (!valid[s]) continue;
+          const double *w = nullptr;
+          if (A.runit) {
+            const unsigned u = A.runit[idx[s]];
+            const unsigned ikl = u / (unsigned)A.nb, ib = u - ikl * (unsigned)A.nb;
+            const long long ik = A.k_first + ikl;
+            const int is = klo[s] >= A.bpad ? 1 : 0;
+            if (ik < A.mw_nk && (int)ib < A.mw_nb)  // dos_utils.f90:1268-1269
+              w = A.mw + (size_t)A.norb * (ib + (size_t)A.mw_nb * (ik + (size_t)A.mw_nk * is));
+          } else if (A.wts) {
+            w = A.wts + (size_t)idx[s] * A.ng;
+          }
+          m0[s] = A.col0 == -1 ? 1.0 : ((A.col0 >= 0 && w) ? w[A.col0] : 0.0);
+          m1[s] = A.col1 == -1 ? 1.0 : ((A.col1 >= 0 && w) ? w[A.col1] : 0.0);
         }
-        m0 = A.col0 == -1 ? 1.0 : ((A.col0 >= 0 && w) ? w[A.col0] : 0.0);
-        m1 = A.col1 == -1 ? 1.0 : ((A.col1 >= 0 && w) ? w[A.col1] : 0.0);
       }
       // ---- the group's common window [gl, gl + Wc)
-      const int gl = __reduce_min_sync(0xffffffffu, klo);
-      const int gh = __reduce_max_sync(0xffffffffu, valid ? klo + wlen - 1 : -0x3fffffff);
+      const int gl = __reduce_min_sync(FULL, min(klo[0], klo[1]));
+      const int gh = __reduce_max_sync(FULL, max(valid[0] ? klo[0] + wlen[0] - 1 : -0x3fffffff, valid[1] ? klo[1] + wlen[1] - 1 : -0x3fffffff));
       int Wc = gh - gl + 1;
       if (Wc < 32) Wc = 32;
-      const int spin_off = (klo >= A.bpad && valid) ? A.bpad : 0;  // ns <= 2
-      const int jb = valid ? klo - spin_off : 0;                    // my first bin on the grid
-      const int a = valid ? klo - gl : 0;                           // my window starts at relative bin a
-      const int cabs = a + cpos;                                    // first relative bin at / above my centre
+      int jb[2], a[2], cabs[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int spin_off = (klo[s] >= A.bpad && valid[s]) ? A.bpad : 0;  // ns <= 2
+        jb[s] = valid[s] ? klo[s] - spin_off : 0;                           // my first bin on the grid
+        a[s] = valid[s] ? klo[s] - gl : 0;                                  // my window starts at relative bin a
+        cabs[s] = a[s] + cpos[s];                                           // first relative bin at / above my centre
+      }
       // The fast loop starts every lane's recurrence a few bins BELOW its own window (relative bin
       // `lane`, and bin 0 after the wrap): harmless while that start is not so deep in the tail that
       // exp underflows.  Gaussian only; del <= 8 by construction, so this only trips on sparse data.
       bool irregular = Wc + 1 > NR_T - A.cell;  // (+1: the step of a centre just above the window)
-      if (!LINEAR) irregular = irregular || (valid && (double)a * delta > 25.0 * p1);
-      irregular = __any_sync(0xffffffffu, irregular);
+      if (!LINEAR) irregular = irregular || (valid[0] && (double)a[0] * delta > 25.0 * p1[0]) || (valid[1] && (double)a[1] * delta > 25.0 * p1[1]);
+      irregular = __any_sync(FULL, irregular);
 
       if (irregular) {
         // sparse data, a group that straddles the two spin channels, ...: record by record, lanes over
         // bins, straight to HBM.
-        for (int l = 0; l < 32; ++l) {
-          const int k_l = __shfl_sync(0xffffffffu, klo, l), w_l = __shfl_sync(0xffffffffu, wlen, l), c_l = __shfl_sync(0xffffffffu, cpos, l);
-          const int jb_l = __shfl_sync(0xffffffffu, jb, l);
-          const double a0 = __shfl_sync(0xffffffffu, e0, l), a1 = __shfl_sync(0xffffffffu, p1, l), a2 = __shfl_sync(0xffffffffu, p2, l);
-          const double a3 = __shfl_sync(0xffffffffu, p3, l), a4 = __shfl_sync(0xffffffffu, p4, l), ao = __shfl_sync(0xffffffffu, om, l);
-          const double b0 = __shfl_sync(0xffffffffu, m0, l), b1 = __shfl_sync(0xffffffffu, m1, l);
-          if (w_l == 0) continue;
-          if (!JD && lane == 0 && jb_l + c_l < A.grid.nbins) atomicAdd(&A.out_step[k_l + c_l], ao);
-          for (int r = lane; r < w_l; r += 32) {
-            const double Ej = emin + (double)(jb_l + r) * delta;
-            double d, s;
-            if (LINEAR) {
-              double cum; int bad = 0;
-              d = od_doslin(a0, a1, a2, a3, a4, Ej, &cum, &bad) * ao;
-              s = ((r < c_l) ? cum : cum - 1.0) * ao;
-            } else {
-              gauss_direct(a0, a1, ao, Ej, r, c_l, A.cf, d, s);
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll 1
+          for (int l = 0; l < 32; ++l) {
+            const int k_l = __shfl_sync(FULL, klo[s], l), w_l = __shfl_sync(FULL, wlen[s], l), c_l = __shfl_sync(FULL, cpos[s], l);
+            const int jb_l = __shfl_sync(FULL, jb[s], l);
+            const double a0 = __shfl_sync(FULL, e0[s], l), a1 = __shfl_sync(FULL, p1[s], l), a2 = __shfl_sync(FULL, p2[s], l);
+            const double a3 = __shfl_sync(FULL, p3[s], l), a4 = __shfl_sync(FULL, p4[s], l), ao = __shfl_sync(FULL, om[s], l);
+            const double b0 = __shfl_sync(FULL, m0[s], l), b1 = __shfl_sync(FULL, m1[s], l);
+            if (w_l == 0) continue;
+            if (!JD && lane == 0 && jb_l + c_l < A.grid.nbins) atomicAdd(&A.out_step[k_l + c_l], ao);
+            for (int r = lane; r < w_l; r += 32) {
+              const double Ej = emin + (double)(jb_l + r) * delta;
+              double d, sv;
+              if (LINEAR) {
+                double cum; int bad = 0;
+                d = od_doslin(a0, a1, a2, a3, a4, Ej, &cum, &bad) * ao;
+                sv = ((r < c_l) ? cum : cum - 1.0) * ao;
+              } else {
+                gauss_direct(a0, a1, ao, Ej, r, c_l, A.cf, d, sv);
+              }
+              if (JD) { sv = d * b1; d = d * b0; }
+              if (d != 0.0) atomicAdd(&A.out_dos[k_l + r], d);
+              if (sv != 0.0) atomicAdd(&A.out_int[k_l + r], sv);
             }
-            if (JD) { s = d * b1; d = d * b0; }
-            if (d != 0.0) atomicAdd(&A.out_dos[k_l + r], d);
-            if (s != 0.0) atomicAdd(&A.out_int[k_l + r], s);
           }
-        }
         continue;
       }
-      const double E0 = emin + (double)(jb - a) * delta;  // energy of relative bin 0
+      // energy of relative bin 0 (the same for both records up to rounding; each record uses its own copy so that an
+      // invalid slot cannot disturb the valid one)
+      double E0[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) E0[s] = emin + (double)(jb[s] - a[s]) * delta;
+      if (!valid[0]) E0[0] = E0[1];
+      if (!valid[1]) E0[1] = E0[0];
 
       // ---- Gaussian DOS: which form of the integrated spectrum does this group take?
-      double invw = 1.0, del = 0.0, zB = 0.0;
+      double invw[2] = {1.0, 1.0}, del[2] = {0.0, 0.0}, zB[2] = {0.0, 0.0};
       int emode = 0;  // 0: rational erfc (bracket + steps); 4 / 7: Euler-Maclaurin with that many terms
       if (!LINEAR) {
-        invw = 1.0 / p1;  // (the reciprocal by MUFU + Newton measured slower here)
-        del = delta * invw;
-        zB = (E0 - e0) * invw;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          invw[s] = 1.0 / p1[s];  // (the reciprocal by MUFU + Newton measured slower here)
+          del[s] = delta * invw[s];
+          zB[s] = (E0[s] - e0[s]) * invw[s];
+        }
         if (!JD && !A.no_em) {
-          // every lane must start its walk where Phi is still ~0 (a window clipped by the bottom of the grid does
+          // every record must start its walk where Phi is still ~0 (a window clipped by the bottom of the grid does
           // not) and sit inside the series' range of validity
-          const double dmax = __hiloint2double((int)__reduce_max_sync(0xffffffffu, (unsigned)__double2hiint(valid ? del : 0.0)), 0);
-          const bool ok = __all_sync(0xffffffffu, !valid || zB <= -8.0);
-          // dmax is del rounded DOWN to its high word: compare against thresholds lowered by one part in 2^20
+          const double dl = fmax(valid[0] ? del[0] : 0.0, valid[1] ? del[1] : 0.0);
+          const double dmax = __hiloint2double((int)__reduce_max_sync(FULL, (unsigned)__double2hiint(dl)), 0);
+          const bool ok = __all_sync(FULL, (!valid[0] || zB[0] <= -8.0) && (!valid[1] || zB[1] <= -8.0));
+          // dmax is del rounded DOWN to its high word: compare against thresholds lowered by one part in 10^6
           if (ok && dmax <= EM_DEL7 * (1.0 - 1e-6)) emode = dmax <= EM_DEL4 * (1.0 - 1e-6) ? 4 : 7;
         }
       }
@@ -691,84 +684,97 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       }
       const int off = gl - base;
       used = max(used, off + Wc + 1);
-      st_steps += (unsigned)Wc;
-      st_useful += (unsigned)wlen;
+      st_steps += (unsigned)Wc * ((valid[0] ? 1u : 0u) + (valid[1] ? 1u : 0u));
+      st_useful += (unsigned)(wlen[0] + wlen[1]);
       double2 *tw = tile + off;
 
       // ---- the steps H: one add per record into the warp-private step tile.  Several records of a
       //      group usually share their centre bin, so this one place uses shared-memory atomics.
-      if (!JD && !emode && valid) atomicAdd(stile + off + cabs, om);
+      if (!JD && !emode) {
+        if (valid[0]) atomicAdd(stile + off + cabs[0], om[0]);
+        if (valid[1]) atomicAdd(stile + off + cabs[1], om[1]);
+      }
       __syncwarp();
 
-      // Two streams per lane when the window allows it (Wc >= 64): stream 1 walks bins lane .. lane+H-1
-      // and never wraps, stream 2 starts H = ceil(Wc/2) bins further on and wraps once.  At any step the
-      // two 32-bin footprints are >= 32 bins apart (cyclically), so all 64 accesses hit different bins;
-      // the two dependent chains per lane double the ILP and halve the per-bin loop / wrap overhead.
-      const bool dual = Wc >= 64;
-      const int H = dual ? (Wc + 1) >> 1 : Wc;
-      const int n2 = dual ? Wc - H : 0;
+      int r = lane;
       if (!LINEAR) {
-        const double amp = om * invw * OD_INV_SQRT_TWO_PI;
-        const double q = exp(-del * del), hd2 = 0.5 * del * del;
-        const double gB = amp * exp(-0.5 * zB * zB), rB = exp(-fma(zB, del, hd2));
+        double amp[2], q[2], gB[2], rB[2], z[2], g[2], rr[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          amp[s] = om[s] * invw[s] * OD_INV_SQRT_TWO_PI;
+          const double hd2 = 0.5 * del[s] * del[s];
+          q[s] = exp(-del[s] * del[s]);
+          gB[s] = amp[s] * exp(-0.5 * zB[s] * zB[s]);
+          rB[s] = exp(-fma(zB[s], del[s], hd2));
+          z[s] = zB[s] + (double)lane * del[s];
+          g[s] = amp[s] * exp(-0.5 * z[s] * z[s]);
+          rr[s] = exp(-fma(z[s], del[s], hd2));
+        }
+        // Every walk below is split in two: Wc - 31 steps in which no lane can reach the end of the window (lane l starts
+        // at bin l), then 31 steps in which exactly one lane per step wraps round to bin 0.  The restart values are 6
+        // doubles; as predicated moves inside one loop they were 13 of 47 instructions of EVERY step.
+        const int nmain = Wc - 31;
         if (!JD && emode) {
-          if (emode == 4) em_walk<4>(tw, lane, Wc, del, p1, q, zB, gB, rB, amp, hd2);
-          else em_walk<7>(tw, lane, Wc, del, p1, q, zB, gB, rB, amp, hd2);
+          auto em_run = [&](auto NTc) {
+            constexpr int NT = decltype(NTc)::value;
+            double cA[NT], cB[NT];
+            em_coeffs<NT>(del[0], p1[0], cA);
+            em_coeffs<NT>(del[1], p1[1], cB);
+            auto step = [&](auto WRAP) {
+              if (decltype(WRAP)::value) {
+                if (r == Wc) { r = 0; g[0] = gB[0]; rr[0] = rB[0]; z[0] = zB[0]; g[1] = gB[1]; rr[1] = rB[1]; z[1] = zB[1]; }
+              }
+              const double gA = g[0], gb = g[1];
+              const double tA = em_zw<NT>(z[0], cA), tb = em_zw<NT>(z[1], cB);
+              double2 *qp = tw + r;
+              g[0] *= rr[0]; rr[0] *= q[0]; z[0] += del[0];
+              g[1] *= rr[1]; rr[1] *= q[1]; z[1] += del[1];
+              ++r;
+              double2 acc = *qp;
+              acc.x += gA + gb;
+              acc.y += fma(gA, tA, gb * tb);
+              *qp = acc;
+              __syncwarp();
+            };
+#pragma unroll 1
+            for (int t = 0; t < nmain; ++t) step(std::false_type{});
+#pragma unroll 1
+            for (int t = 0; t < 31; ++t) step(std::true_type{});
+          };
+          if (emode == 4) em_run(std::integral_constant<int, 4>{});
+          else em_run(std::integral_constant<int, 7>{});
           continue;
         }
-        const double cl = p1 * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
-        double z1 = zB + (double)lane * del;
-        double g1 = amp * exp(-0.5 * z1 * z1), rr1 = exp(-fma(z1, del, hd2));
-        int r1 = lane;
-        if (dual) {
-          double z2 = zB + (double)(lane + H) * del;
-          double g2 = amp * exp(-0.5 * z2 * z2), rr2 = exp(-fma(z2, del, hd2));
-          int r2 = lane + H;
-#pragma unroll 1
-          for (int t = 0; t < n2; ++t) {
-            // capture this step's inputs, then advance the recurrences at once so that the next step's
-            // operands are ready long before the rational chains below have drained
-            const double u1 = fabs(z1), u2 = fabs(z2), c1 = g1, c2 = g2;
-            double2 *q1 = tw + r1, *q2 = tw + r2;
-            const bool f1 = r1 >= cabs, f2 = r2 >= cabs;
-            g1 *= rr1; rr1 *= q; z1 += del; ++r1;
-            g2 *= rr2; rr2 *= q; z2 += del; ++r2;
-            if (r2 == Wc) { r2 = 0; g2 = gB; rr2 = rB; z2 = zB; }
-            double2 acc1 = *q1;
-            double2 acc2 = *q2;
-            if (JD) {
-              acc1.x = fma(c1, m0, acc1.x); acc1.y = fma(c1, m1, acc1.y);
-              acc2.x = fma(c2, m0, acc2.x); acc2.y = fma(c2, m1, acc2.y);
-            } else {
-              const double h1 = (c1 * cl) * erfcx_ratio(u1, A.cf);
-              const double h2 = (c2 * cl) * erfcx_ratio(u2, A.cf);
-              acc1.x += c1;
-              acc1.y += flip_sign_if(h1, f1);
-              acc2.x += c2;
-              acc2.y += flip_sign_if(h2, f2);
-            }
-            *q1 = acc1;
-            *q2 = acc2;
-            __syncwarp();
+        const double clA = p1[0] * 1.2533141373155002512, clB = p1[1] * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
+        auto step = [&](auto WRAP) {
+          if (decltype(WRAP)::value) {
+            if (r == Wc) { r = 0; g[0] = gB[0]; rr[0] = rB[0]; z[0] = zB[0]; g[1] = gB[1]; rr[1] = rB[1]; z[1] = zB[1]; }
           }
-        }
-        // single stream: the whole window when Wc < 64, else the odd leftover bin of stream 1
-#pragma unroll 1
-        for (int t = n2; t < H; ++t) {
-          double2 acc = tw[r1];
+          // capture this step's inputs, then advance the recurrences at once so that the next step's
+          // operands are ready long before the rational chains below have drained
+          const double uA = fabs(z[0]), uB = fabs(z[1]), gA = g[0], gb = g[1];
+          double2 *qp = tw + r;
+          const bool fA = r >= cabs[0], fB = r >= cabs[1];
+          g[0] *= rr[0]; rr[0] *= q[0]; z[0] += del[0];
+          g[1] *= rr[1]; rr[1] *= q[1]; z[1] += del[1];
+          ++r;
+          double2 acc = *qp;
           if (JD) {
-            acc.x = fma(g1, m0, acc.x); acc.y = fma(g1, m1, acc.y);
+            acc.x += fma(gA, m0[0], gb * m0[1]);
+            acc.y += fma(gA, m1[0], gb * m1[1]);
           } else {
-            const double h = (g1 * cl) * erfcx_ratio(fabs(z1), A.cf);
-            acc.x += g1;
-            acc.y += flip_sign_if(h, r1 >= cabs);
+            const double hA = (gA * clA) * erfcx_ratio(uA, A.cf);
+            const double hB = (gb * clB) * erfcx_ratio(uB, A.cf);
+            acc.x += gA + gb;
+            acc.y += flip_sign_if(hA, fA) + flip_sign_if(hB, fB);
           }
-          tw[r1] = acc;
-          g1 *= rr1; rr1 *= q; z1 += del;
-          ++r1;
-          if (r1 == Wc) { r1 = 0; g1 = gB; rr1 = rB; z1 = zB; }
+          *qp = acc;
           __syncwarp();
-        }
+        };
+#pragma unroll 1
+        for (int t = 0; t < nmain; ++t) step(std::false_type{});
+#pragma unroll 1
+        for (int t = 0; t < 31; ++t) step(std::true_type{});
       } else {
         // doslin (dos_utils.f90:1391-1528) in x = e_use - e4 = dd - |E_j - e0| (the mirror of :1469), with
         // aa = e3-e4 <= bb = e2-e4 <= cc = e1-e4 <= dd = e0-e4.  The five branches collapse into two smooth
@@ -776,82 +782,76 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         //   x <  bb:  D = x - aa/2 + p^2/(2 aa),          I = x^2/2 - aa x/2 + aa^2/6 - p^3/(6 aa)
         //   x >= bb:  D = hh - y^2/(2 (cc-bb)),           I = hh x + k30 + y^3/(6 (cc-bb))
         // (pieces 1|2 and 3|4 of the reference; identical polynomials, continuity at aa / cc used once).
-        const double aa = p3 - p4, bb = p2 - p4, cc = p1 - p4, dd = e0 - p4;
-        const double hh = 0.5 * (cc + bb - aa), haa = 0.5 * aa;
         constexpr double third = 1.0 / 3.0, sixth = 1.0 / 6.0, tiny = 1e-280;
-        const double cb = cc - bb;
-        const double full = (cc - aa) * cc + (aa * aa - cb * cb) * third;
-        const double sc = valid ? om * fast_rcp(full + (cc + bb - aa) * (dd - cc)) : 0.0;  // alpha * omega
-        const double inv2a = aa > tiny ? 0.5 * fast_rcp(aa) : 0.0, inv2cb = cb > tiny ? 0.5 * fast_rcp(cb) : 0.0;
-        const double i6a = inv2a * third, i6cb = inv2cb * third;
-        const double a2_6 = aa * aa * sixth;
-        const double k30 = 0.5 * (aa * aa * third - cc * bb) - cb * cb * sixth;
-        const double tB = E0 - e0;  // E_j - e0 at relative bin 0
-        const double scm0 = sc * m0, scm1 = sc * m1;
+        double aa[2], bb[2], cc[2], dd[2], hh[2], haa[2], inv2a[2], inv2cb[2], i6a[2], i6cb[2], a2_6[2], k30[2], sc[2], tB[2], tt[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          aa[s] = p3[s] - p4[s]; bb[s] = p2[s] - p4[s]; cc[s] = p1[s] - p4[s]; dd[s] = e0[s] - p4[s];
+          hh[s] = 0.5 * (cc[s] + bb[s] - aa[s]); haa[s] = 0.5 * aa[s];
+          const double cb = cc[s] - bb[s];
+          const double full = (cc[s] - aa[s]) * cc[s] + (aa[s] * aa[s] - cb * cb) * third;
+          sc[s] = valid[s] ? om[s] * fast_rcp(full + (cc[s] + bb[s] - aa[s]) * (dd[s] - cc[s])) : 0.0;  // alpha * omega
+          inv2a[s] = aa[s] > tiny ? 0.5 * fast_rcp(aa[s]) : 0.0;
+          inv2cb[s] = cb > tiny ? 0.5 * fast_rcp(cb) : 0.0;
+          i6a[s] = inv2a[s] * third; i6cb[s] = inv2cb[s] * third;
+          a2_6[s] = aa[s] * aa[s] * sixth;
+          k30[s] = 0.5 * (aa[s] * aa[s] * third - cc[s] * bb[s]) - cb * cb * sixth;
+          tB[s] = E0[s] - e0[s];  // E_j - e0 at relative bin 0
+          tt[s] = tB[s] + (double)lane * delta;
+        }
         auto clamp0 = [](double v) {  // max(v, +0) on the sign / exponent word: negative -> < 2^-1022
           return __hiloint2double(max(__double2hiint(v), 0), __double2loint(v));
         };
-        auto lin_eval = [&](double t, double &D, double &I) {
-          const double x = clamp0(dd - fabs(t));  // bins outside (e4, 2 e0 - e4): x -> +0, D = I = 0
-          const double p = clamp0(aa - x), y = clamp0(cc - x);
+        auto lin_eval = [&](int s, double t, double &D, double &I) {
+          const double x = clamp0(dd[s] - fabs(t));  // bins outside (e4, 2 e0 - e4): x -> +0, D = I = 0
+          const double p = clamp0(aa[s] - x), y = clamp0(cc[s] - x);
           const double pp = p * p, yy = y * y;
-          const double Dlo = fma(pp, inv2a, x - haa), Dhi = fma(-yy, inv2cb, hh);
-          const bool lo = x < bb;
+          const double Dlo = fma(pp, inv2a[s], x - haa[s]), Dhi = fma(-yy, inv2cb[s], hh[s]);
+          const bool lo = x < bb[s];
           D = lo ? Dlo : Dhi;
           if (!JD) {
-            const double Ilo = fma(-(pp * p), i6a, fma(x, fma(x, 0.5, -haa), a2_6));
-            const double Ihi = fma(yy * y, i6cb, fma(hh, x, k30));
+            const double Ilo = fma(-(pp * p), i6a[s], fma(x, fma(x, 0.5, -haa[s]), a2_6[s]));
+            const double Ihi = fma(yy * y, i6cb[s], fma(hh[s], x, k30[s]));
             I = lo ? Ilo : Ihi;
           }
         };
-        double t1 = tB + (double)lane * delta;
-        int r1 = lane;
-        if (dual) {
-          double t2 = tB + (double)(lane + H) * delta;
-          int r2 = lane + H;
-#pragma unroll 1
-          for (int t = 0; t < n2; ++t) {
-            double2 *q1 = tw + r1, *q2 = tw + r2;
-            double2 acc1 = *q1;
-            double2 acc2 = *q2;
-            double D1, I1 = 0, D2, I2 = 0;
-            lin_eval(t1, D1, I1);
-            lin_eval(t2, D2, I2);
-            if (JD) {
-              acc1.x = fma(D1, scm0, acc1.x); acc1.y = fma(D1, scm1, acc1.y);
-              acc2.x = fma(D2, scm0, acc2.x); acc2.y = fma(D2, scm1, acc2.y);
-            } else {
-              acc1.x = fma(D1, sc, acc1.x); acc1.y = fma(I1, flip_sign_if(sc, r1 >= cabs), acc1.y);
-              acc2.x = fma(D2, sc, acc2.x); acc2.y = fma(I2, flip_sign_if(sc, r2 >= cabs), acc2.y);
-            }
-            *q1 = acc1;
-            *q2 = acc2;
-            t1 += delta; ++r1;
-            t2 += delta; ++r2;
-            if (r2 == Wc) { r2 = 0; t2 = tB; }
-            __syncwarp();
+        const double scm0A = sc[0] * m0[0], scm1A = sc[0] * m1[0], scm0B = sc[1] * m0[1], scm1B = sc[1] * m1[1];
+        // the sign of the local part flips where the walk passes the record's centre: d = cabs - 1 - r goes negative there,
+        // so the flip is the sign bit of a counter (one add and one logic operation per record and step)
+        int dA = cabs[0] - 1 - r, dB = cabs[1] - 1 - r;
+        const int nmain = Wc - 31;
+        auto step = [&](auto WRAP) {
+          if (decltype(WRAP)::value) {
+            if (r == Wc) { r = 0; tt[0] = tB[0]; tt[1] = tB[1]; dA = cabs[0] - 1; dB = cabs[1] - 1; }
           }
-        }
-#pragma unroll 1
-        for (int t = n2; t < H; ++t) {
-          double2 acc = tw[r1];
-          double D, I = 0;
-          lin_eval(t1, D, I);
+          double2 *qp = tw + r;
+          double2 acc = *qp;
+          double DA, IA = 0, DB, IB = 0;
+          lin_eval(0, tt[0], DA, IA);
+          lin_eval(1, tt[1], DB, IB);
           if (JD) {
-            acc.x = fma(D, scm0, acc.x); acc.y = fma(D, scm1, acc.y);
+            acc.x += fma(DA, scm0A, DB * scm0B);
+            acc.y += fma(DA, scm1A, DB * scm1B);
           } else {
-            acc.x = fma(D, sc, acc.x); acc.y = fma(I, flip_sign_if(sc, r1 >= cabs), acc.y);
+            const double sA = __hiloint2double(__double2hiint(sc[0]) ^ (dA & 0x80000000), __double2loint(sc[0]));
+            const double sB = __hiloint2double(__double2hiint(sc[1]) ^ (dB & 0x80000000), __double2loint(sc[1]));
+            acc.x += fma(DA, sc[0], DB * sc[1]);
+            acc.y += fma(IA, sA, IB * sB);
           }
-          tw[r1] = acc;
-          t1 += delta;
-          ++r1;
-          if (r1 == Wc) { r1 = 0; t1 = tB; }
+          *qp = acc;
+          tt[0] += delta; tt[1] += delta;
+          ++r; --dA; --dB;
           __syncwarp();
-        }
+        };
+#pragma unroll 1
+        for (int t = 0; t < nmain; ++t) step(std::false_type{});
+#pragma unroll 1
+        for (int t = 0; t < 31; ++t) step(std::true_type{});
       }
     }
-    for (int o = 16; o > 0; o >>= 1) st_useful += __shfl_xor_sync(0xffffffffu, st_useful, o);
-    if (lane == 0) { atomicAdd(&A.stats[0], st_steps * 32ull); atomicAdd(&A.stats[1], st_useful); }
+    for (int o = 16; o > 0; o >>= 1) st_useful += __shfl_xor_sync(FULL, st_useful, o);
+    for (int o = 16; o > 0; o >>= 1) st_steps += __shfl_xor_sync(FULL, st_steps, o);
+    if (lane == 0) { atomicAdd(&A.stats[0], st_steps); atomicAdd(&A.stats[1], st_useful); }
     // consecutive chunks of one warp are usually far apart on the grid: flush now
     flush_tile(tile, stile, base, used, tmode, A, lane);
     used = 0;

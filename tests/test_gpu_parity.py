@@ -1003,7 +1003,7 @@ def test_config2_slab_vs_oracle(ob, odo, monkeypatch):
         assert_int(intdos, ref[1])
         assert rel_to_peak(dos, ref[0]) < 1e-11 and np.abs(intdos - ref[1]).max() < 1e-12 * np.abs(ref[1]).max(), t
     p = ctx.profile_get()
-    assert p["contributions"] > 0.4 * p["lane_steps"]          # the narrow engine took it (small slabs: sparse buckets, so below the bench's 0.8)
+    assert p["contributions"] > 0.25 * p["lane_steps"]         # the narrow engine took it (small slabs: 2 records per bucket, so far below the bench's 0.9)
     ctx.close()
 
 
