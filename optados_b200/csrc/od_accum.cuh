@@ -61,7 +61,7 @@ __device__ __forceinline__ void od_rec_window(const RecOut &r, const GridSpec &g
 template <int NW, bool INT, class Producer>
 __global__ void __launch_bounds__(OD_TILE)
 od_dense_kernel(Producer prod, GridSpec grid, long long chunk_units, double *__restrict__ partial,
-                int *__restrict__ bad_flag) {
+                int *__restrict__ bad_flag, const unsigned long long *__restrict__ dev_units = nullptr) {
   constexpr int NACC = 1 + (INT ? 1 : 0) + NW;
   __shared__ double s_e0[OD_TILE], s_p1[OD_TILE], s_p2[OD_TILE], s_p3[OD_TILE], s_p4[OD_TILE], s_om[OD_TILE];
   __shared__ double s_wt[NW > 0 ? NW : 1][OD_TILE];
@@ -73,9 +73,17 @@ od_dense_kernel(Producer prod, GridSpec grid, long long chunk_units, double *__r
   const int j = blockIdx.x * OD_TILE + tid;                 // my bin
   const int wlo = blockIdx.x * OD_TILE + warp * 32, whi = wlo + 31;  // my warp's bins
   const double Ej = grid.emin + (double)j * grid.delta;      // dos_utils.f90:996
+  // dev_units: the unit count is only known on the device (the wide list of the narrow engine, [0] / [1] per spin): the
+  // chunking is then derived here, and a launch over an empty list returns at once (od_reduce_partials skips it too)
+  long long upz = prod.units_per_z;
+  if (dev_units) {
+    upz = (long long)max(dev_units[0], dev_units[1]);
+    if (upz == 0) return;
+    chunk_units = ((upz + gridDim.y - 1) / gridDim.y + OD_TILE - 1) / OD_TILE * OD_TILE;
+  }
   const long long u0 = (long long)blockIdx.y * chunk_units;
   long long u1 = u0 + chunk_units;
-  if (u1 > prod.units_per_z) u1 = prod.units_per_z;
+  if (u1 > upz) u1 = upz;
 
   double acc_d = 0.0, acc_i = 0.0;
   double acc_w[NW > 0 ? NW : 1];
@@ -153,10 +161,12 @@ od_dense_kernel(Producer prod, GridSpec grid, long long chunk_units, double *__r
 
 // out[dest[z*nacc+a] + j] (+)= sum_c partial[((c*nz+z)*nacc+a)*nbins + j], chunks summed in order.
 static __global__ void od_reduce_partials(const double *__restrict__ partial, int nchunks, int nz, int nacc, int nbins,
-                                   const long long *__restrict__ dest, double *__restrict__ out) {
+                                   const long long *__restrict__ dest, double *__restrict__ out,
+                                   const unsigned long long *__restrict__ dev_units = nullptr) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int za = blockIdx.y;  // z*nacc + a
   if (j >= nbins) return;
+  if (dev_units && max(dev_units[0], dev_units[1]) == 0) return;
   const long long d = dest[za];
   if (d < 0) return;
   double s = 0.0;

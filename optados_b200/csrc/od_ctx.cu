@@ -157,10 +157,12 @@ extern "C" int od_ctx_destroy(od_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(ctx->comm));
   DevBuf *bufs[] = {&ctx->kweight, &ctx->bands, &ctx->grads, &ctx->partial, &ctx->accum, &ctx->small, &ctx->recs,
-                    &ctx->keys, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->scratch_d, &ctx->scratch_e, &ctx->mw_tmp, &ctx->in_tmp, &ctx->in_tmp2, &ctx->moments, &ctx->task_mw};
+                    &ctx->keys, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->scratch_d, &ctx->scratch_e, &ctx->mw_tmp, &ctx->in_tmp, &ctx->in_tmp2, &ctx->moments, &ctx->task_mw, &ctx->flags, &ctx->stats_dev, &ctx->dest_dev};
   for (DevBuf *b : bufs) od_buf_release(*b);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  for (const od_ctx::PendingTime &t : ctx->pending_times) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->t0) cudaEventDestroy(ctx->t0);
   if (ctx->t1) cudaEventDestroy(ctx->t1);
   for (int i = 0; i < 2; ++i) {
@@ -168,6 +170,7 @@ extern "C" int od_ctx_destroy(od_ctx *ctx) {
     if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
   }
+  if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -192,15 +195,78 @@ extern "C" int od_synchronize(od_ctx *ctx) {
   return OD_OK;
 }
 
+int od_flags_ready(od_ctx *ctx) {
+  if (ctx->flags.p && ctx->stats_dev.p) return OD_OK;
+  OD_CHECK(od_buf_ensure(ctx, ctx->flags, sizeof(int) * 4));
+  OD_CHECK(od_buf_ensure(ctx, ctx->stats_dev, sizeof(unsigned long long) * 2));
+  OD_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * 4, ctx->stream));
+  OD_CUDA(ctx, cudaMemsetAsync(ctx->stats_dev.p, 0, sizeof(unsigned long long) * 2, ctx->stream));
+  return OD_OK;
+}
+
+int od_check_deferred(od_ctx *ctx) {
+  if (!ctx->flags.p) return OD_OK;
+  int h[4] = {0, 0, 0, 0};
+  OD_CUDA(ctx, cudaMemcpyAsync(h, ctx->flags.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[0]) {
+    OD_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * 4, ctx->stream));
+    return od_fail(ctx, OD_ERR_DOSLIN, "doslin: input arguments incorrect (dos_utils.f90:1431/1514)");
+  }
+  return OD_OK;
+}
+
+int od_time_begin(od_ctx *ctx, int kind, size_t *slot) {
+  od_ctx::PendingTime t;
+  for (cudaEvent_t *e : {&t.e0, &t.e1}) {
+    if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else OD_CUDA(ctx, cudaEventCreate(e));
+  }
+  t.kind = kind;
+  OD_CUDA(ctx, cudaEventRecord(t.e0, ctx->stream));
+  ctx->pending_times.push_back(t);
+  *slot = ctx->pending_times.size() - 1;
+  return OD_OK;
+}
+
+int od_time_end(od_ctx *ctx, size_t slot) {
+  OD_CUDA(ctx, cudaEventRecord(ctx->pending_times[slot].e1, ctx->stream));
+  return OD_OK;
+}
+
+int od_times_resolve(od_ctx *ctx) {
+  for (const od_ctx::PendingTime &t : ctx->pending_times) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess)
+      (t.kind == 0 ? ctx->prof.prepare_ms : ctx->prof.accumulate_ms) += ms;
+    ctx->event_pool.push_back(t.e0);
+    ctx->event_pool.push_back(t.e1);
+  }
+  ctx->pending_times.clear();
+  return OD_OK;
+}
+
 extern "C" int od_profile_reset(od_ctx *ctx) {
   if (!ctx) return OD_ERR_ARG;
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  OD_CHECK(od_times_resolve(ctx));
   ctx->prof = Profile();
+  if (ctx->stats_dev.p) OD_CUDA(ctx, cudaMemsetAsync(ctx->stats_dev.p, 0, sizeof(unsigned long long) * 2, ctx->stream));
   return OD_OK;
 }
 
 extern "C" int od_profile_get(od_ctx *ctx, double *accumulate_ms, double *prepare_ms, double *contributions, double *lane_steps,
                               long long *accumulate_launches) {
   if (!ctx) return OD_ERR_ARG;
+  OD_CUDA(ctx, cudaSetDevice(ctx->device));
+  OD_CHECK(od_times_resolve(ctx));
+  if (ctx->stats_dev.p) {
+    unsigned long long h[2] = {0, 0};
+    OD_CUDA(ctx, cudaMemcpyAsync(h, ctx->stats_dev.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof.lane_steps = (double)h[0];
+    ctx->prof.contributions = (double)h[1];
+  }
   if (accumulate_ms) *accumulate_ms = ctx->prof.accumulate_ms;
   if (prepare_ms) *prepare_ms = ctx->prof.prepare_ms;
   if (contributions) *contributions = ctx->prof.contributions;
@@ -391,6 +457,20 @@ __global__ void minmax_kernel(const double *__restrict__ a, size_t n, double *__
     if (l == 0) { out[2 * blockIdx.x] = lo; out[2 * blockIdx.x + 1] = hi; }
   }
 }
+
+// (min, -max) of the per-CTA pairs, so that one MIN allreduce serves both (dos_utils.f90:968-977)
+__global__ void __launch_bounds__(256) minmax_final_kernel(const double *__restrict__ part, int nparts, double *__restrict__ out2) {
+  double lo = DBL_MAX, hi = -DBL_MAX;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) { lo = fmin(lo, part[2 * i]); hi = fmax(hi, part[2 * i + 1]); }
+  __shared__ double slo[256], shi[256];
+  slo[threadIdx.x] = lo; shi[threadIdx.x] = hi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { slo[threadIdx.x] = fmin(slo[threadIdx.x], slo[threadIdx.x + o]); shi[threadIdx.x] = fmax(shi[threadIdx.x], shi[threadIdx.x + o]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out2[0] = slo[0]; out2[1] = -shi[0]; }
+}
 }  // namespace
 
 extern "C" int od_band_minmax(od_ctx *ctx, double *mn, double *mx) {
@@ -400,24 +480,17 @@ extern "C" int od_band_minmax(od_ctx *ctx, double *mn, double *mx) {
   const size_t n = (size_t)ctx->nb * ctx->ns * ctx->nk;
   const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
   OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(double) * 2 * (size_t)blocks + 64));
-  minmax_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bands.as<double>(), n, ctx->small.as<double>());
+  double *part = ctx->small.as<double>(), *out2 = part + 2 * (size_t)blocks;
+  minmax_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bands.as<double>(), n, part);
   OD_LAUNCH_CHECK(ctx);
-  std::vector<double> h(2 * (size_t)blocks);
-  OD_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->small.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  minmax_final_kernel<<<1, 256, 0, ctx->stream>>>(part, blocks, out2);
+  OD_LAUNCH_CHECK(ctx);
+  // comms_reduce MIN / MAX + bcast (dos_utils.f90:968-977): one MIN allreduce of (min, -max) on the device
+  OD_CHECK(od_allreduce_device(ctx, out2, 2, 'm'));
+  double v[2] = {0.0, 0.0};
+  OD_CUDA(ctx, cudaMemcpyAsync(v, out2, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
   OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  double lo = DBL_MAX, hi = -DBL_MAX;
-  for (int b = 0; b < blocks; ++b) {
-    lo = std::min(lo, h[2 * b]);
-    hi = std::max(hi, h[2 * b + 1]);
-  }
-  // comms_reduce MIN / MAX + bcast (dos_utils.f90:968-977)
-  if (ctx->nranks > 1) {
-    double v[2] = {lo, -hi};
-    OD_CHECK(od_allreduce(ctx, v, 2, 'm'));
-    lo = v[0];
-    hi = -v[1];
-  }
-  *mn = lo;
-  *mx = hi;
+  *mn = v[0];
+  *mx = -v[1];
   return OD_OK;
 }

@@ -121,15 +121,26 @@ extern "C" int od_dos_utils_calculate(od_ctx *ctx, od_dos_params *p, const doubl
     if (enabled[t]) { tl[nt] = types[t]; wl[nt] = wt[t]; idx[nt] = t; ++nt; }
   double *accum = nullptr;
   size_t stride = 0;
-  OD_CHECK(od_dos_accumulate(ctx, nt, tl, wl, emin, delta, nbins, &p->br, mw_dev, mw_norb, mw_nb, mw_nk, /*merge=*/1, &accum, &stride));
+  // one merge, one device -> host transfer and one synchronisation for all schemes
+  const size_t per = 2 * n1 + (calc_weighted ? n1 * (size_t)mw_norb : 0);
+  if (ctx->host_stage_bytes < sizeof(double) * per * nt) {
+    if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
+    ctx->host_stage = nullptr;
+    ctx->host_stage_bytes = 0;
+    OD_CUDA(ctx, cudaHostAlloc(&ctx->host_stage, sizeof(double) * per * nt, cudaHostAllocDefault));
+    ctx->host_stage_bytes = sizeof(double) * per * nt;
+  }
+  double *hs = static_cast<double *>(ctx->host_stage);
+  OD_CHECK(od_dos_accumulate(ctx, nt, tl, wl, emin, delta, nbins, &p->br, mw_dev, mw_norb, mw_nb, mw_nk, /*merge=*/1, &accum, &stride, hs));
+  if (stride != per) return od_fail(ctx, OD_ERR_STATE, "internal: spectrum block of %zu doubles, expected %zu", stride, per);
   for (int i = 0; i < nt; ++i) {
     const int t = idx[i];
-    double *acc = accum + stride * i;
-    OD_CHECK(pull(ctx, S.dos[t], acc, n1));
-    OD_CHECK(pull(ctx, S.intdos[t], acc + n1, n1));
+    const double *acc = hs + stride * i;
+    S.dos[t].assign(acc, acc + n1);
+    S.intdos[t].assign(acc + n1, acc + 2 * n1);
     S.have[t] = true;
     if (wt[t]) {
-      OD_CHECK(pull(ctx, S.weighted, acc + 2 * n1, n1 * mw_norb));
+      S.weighted.assign(acc + 2 * n1, acc + 2 * n1 + n1 * mw_norb);
       S.have_weighted = true;
       S.norb = mw_norb;
     }

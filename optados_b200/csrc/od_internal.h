@@ -72,6 +72,14 @@ struct od_ctx {
   DevBuf gslab[2];
 
   // scratch
+  DevBuf flags;      // int[4]: [0] doslin `stop` conditions met by kernels that are not followed by a host synchronisation
+  DevBuf stats_dev;  // unsigned long long[2]: lane-steps / in-window pairs of the narrow engine since the last profile reset
+  DevBuf dest_dev;
+  void *host_stage = nullptr;  // pinned staging for the results of the task drivers
+  size_t host_stage_bytes = 0;
+  struct PendingTime { cudaEvent_t e0, e1; int kind; };  // kind 0: prepare, 1: accumulate
+  std::vector<PendingTime> pending_times;
+  std::vector<cudaEvent_t> event_pool;
   DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, scratch_e, mw_tmp, in_tmp, in_tmp2, moments, task_mw;
 
   Spectra dos_res, jdos_res;
@@ -120,5 +128,14 @@ GridGeom od_grid_geom(const od_ctx *ctx, double adaptive_smearing);
 
 // allreduce on a DEVICE buffer (no-op when nranks == 1)
 int od_allreduce_device(od_ctx *ctx, double *dbuf, size_t n, char op);
+// ctx->flags / ctx->stats_dev allocated and zeroed
+int od_flags_ready(od_ctx *ctx);
+// after a host synchronisation: report (and clear) what kernels flagged since the last check
+int od_check_deferred(od_ctx *ctx);
+// device stopwatch without a synchronisation: bracket a region with od_time_begin / od_time_end; the elapsed times are
+// added to ctx->prof when od_profile_get (or od_times_resolve) is called
+int od_time_begin(od_ctx *ctx, int kind, size_t *slot);
+int od_time_end(od_ctx *ctx, size_t slot);
+int od_times_resolve(od_ctx *ctx);
 // make deferred gradients resident (paths that do not stream)
 int od_grads_resident(od_ctx *ctx);

@@ -359,7 +359,7 @@ __device__ __forceinline__ double flip_sign_if(double v, bool flip) {
 
 struct NarrowArgs {
   const void *recs;
-  long long nrec;
+  const unsigned *nrec_dev;  // number of records, left on the device by the prepare passes
   GridSpec grid;
   int bpad, cell;
   unsigned long long *next_chunk;
@@ -479,7 +479,8 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
   __syncwarp();
   int base = 0, used = 0, tmode = 0;
   const double delta = A.grid.delta, emin = A.grid.emin;
-  const long long nchunks = (A.nrec + NR_CHUNK - 1) / NR_CHUNK;
+  const long long nrec = (long long)*A.nrec_dev;
+  const long long nchunks = (nrec + NR_CHUNK - 1) / NR_CHUNK;
   constexpr size_t RECB = LINEAR ? sizeof(LRec) : sizeof(GRec);
   constexpr size_t TAILB = LINEAR ? 48 : 24;  // byte offset of (klo, cpos | wlen << 16) in a record
   constexpr unsigned FULL = 0xffffffffu;
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
     ch = __shfl_sync(FULL, ch, 0);
     if ((long long)ch >= nchunks) break;
     const long long c0 = (long long)ch * NR_CHUNK;
-    const int n = (int)min((long long)NR_CHUNK, A.nrec - c0);
+    const int n = (int)min((long long)NR_CHUNK, nrec - c0);
     unsigned long long st_steps = 0, st_useful = 0;
 
     // ---- regroup the chunk.  The records of a chunk come from one or a few (width class, 8-bin cell) buckets, in no
@@ -1100,7 +1101,7 @@ struct WideListProducer {
   Inner inner;
   const unsigned *list;
   long long stride;
-  unsigned long long count[2];
+  const unsigned long long *count;  // device: wide units of spin 1 / 2
   __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
     r.mode = -1;
     const int is = z % inner.ns;  // z may also carry an orbital group (dense weighted DOS)
@@ -1143,19 +1144,22 @@ __global__ void __launch_bounds__(1024) combine_kernel(const double *__restrict_
 }
 
 // JD mode: out[dest(c) + is*nbins + j] += channel array c
+struct ChanDest {  // destination offsets of up to 8 channel arrays, passed by value (no staging copy, no synchronisation)
+  long long d[8];
+};
 __global__ void combine_channels_kernel(const double *__restrict__ chan, size_t chan_stride, int nchan, int nbins, int bpad, int ns,
-                                        const long long *__restrict__ dest, double *__restrict__ out) {
+                                        ChanDest dest, double *__restrict__ out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y / ns, is = blockIdx.y % ns;
-  if (j >= nbins || c >= nchan || dest[c] < 0) return;
-  out[dest[c] + (size_t)is * nbins + j] += chan[(size_t)c * chan_stride + (size_t)is * bpad + j];
+  if (j >= nbins || c >= nchan || dest.d[c] < 0) return;
+  out[dest.d[c] + (size_t)is * nbins + j] += chan[(size_t)c * chan_stride + (size_t)is * bpad + j];
 }
 
 struct Scratch {
   PrepSpec ps;
   size_t nout;
   unsigned *keys, *table, *colsum, *base;
-  unsigned long long *wide;  // [0..1] wide counts, [2..3] wide cursors, [4] next_chunk, [5..6] stats
+  unsigned long long *wide;  // [0..1] wide counts, [2..3] wide cursors, [4] next_chunk
   double *stephist, *chan;   // chan: 2 * npass arrays of nout doubles (DOS: dos, int)
 };
 
@@ -1164,9 +1168,10 @@ inline void strip_weights(JdosProducer &p) { p.mw = nullptr; p.ome = nullptr; }
 inline void set_eager(DosProducer &) {}
 inline void set_eager(JdosProducer &p) { p.eager = 1; }
 
+// Both prepare passes, without a host synchronisation: the number of records (S.base[nbuckets]) and of wide units
+// (S.wide[0..1]) stay on the device, the record buffers are sized for the worst case (every unit narrow / every unit wide).
 template <class Producer>
-int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear, unsigned *h_nrec, unsigned long long h_wide[2],
-                   long long *wide_stride) {
+int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear, long long *wide_stride) {
   Producer prod = prod_in;
   prod.b.fast_corners = 1;  // both passes; wide units are re-made by the dense engine with the reference's arithmetic
   Producer prod_keys = prod;  // pass A only needs the windows: no weight columns, no optical matrix elements
@@ -1175,6 +1180,13 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   const PrepSpec &ps = S.ps;
   const int prows = ctx->sm_count;  // one prepare CTA per SM; pass A and pass B MUST use the same grid
   const size_t hist_smem = sizeof(unsigned) * ps.nbuckets;
+  const size_t units = (size_t)prod.units_per_z * prod.ns;
+  *wide_stride = prod.units_per_z;
+  const size_t rec_bytes = linear ? sizeof(LRec) : sizeof(GRec);
+  OD_CHECK(od_buf_ensure(ctx, ctx->recs, rec_bytes * units + 256));
+  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_b, sizeof(unsigned) * units + 256));
+  if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * units * ps.ng + 256));
+  if (ps.want_unit) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_e, sizeof(unsigned) * units + 256));
   OD_CUDA(ctx, cudaMemsetAsync(S.wide, 0, sizeof(unsigned long long) * 5, ctx->stream));
   OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
   prep_hist_kernel<Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod_keys, ps, S.keys, S.table, S.wide);
@@ -1183,15 +1195,6 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   OD_LAUNCH_CHECK(ctx);
   scan_kernel<<<1, 1024, 0, ctx->stream>>>(S.colsum, ps.nbuckets, S.base);
   OD_LAUNCH_CHECK(ctx);
-  OD_CUDA(ctx, cudaMemcpyAsync(h_wide, S.wide, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
-  OD_CUDA(ctx, cudaMemcpyAsync(h_nrec, S.base + ps.nbuckets, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  *wide_stride = (long long)std::max(h_wide[0], h_wide[1]);
-  const size_t rec_bytes = linear ? sizeof(LRec) : sizeof(GRec);
-  OD_CHECK(od_buf_ensure(ctx, ctx->recs, rec_bytes * (size_t)*h_nrec + 256));
-  OD_CHECK(od_buf_ensure(ctx, ctx->scratch_b, sizeof(unsigned) * (size_t)*wide_stride * prod.ns + 256));
-  if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * (size_t)*h_nrec * ps.ng + 256));
-  if (ps.want_unit) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_e, sizeof(unsigned) * (size_t)*h_nrec + 256));
   double *wts = ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
   unsigned *runit = ps.want_unit ? ctx->scratch_e.as<unsigned>() : nullptr;
   if (linear) {
@@ -1214,16 +1217,16 @@ struct MwGather {
 };
 
 template <bool JD>
-int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int col0, int col1, double *out0, double *out1,
+int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, int col0, int col1, double *out0, double *out1,
                   const MwGather *gather = nullptr) {
   NarrowArgs A;
   A.recs = ctx->recs.p;
-  A.nrec = (long long)nrec;
+  A.nrec_dev = S.base + S.ps.nbuckets;
   A.grid = S.ps.grid;
   A.bpad = S.ps.bpad;
   A.cell = S.ps.cell;
   A.next_chunk = S.wide + 4;
-  A.stats = S.wide + 5;
+  A.stats = ctx->stats_dev.as<unsigned long long>();
   for (int i = 0; i < 6; ++i) { A.cf.P[i] = h_P[i]; A.cf.Q[i] = h_Q[i]; }
   A.out_dos = out0;
   A.out_int = out1;
@@ -1243,8 +1246,7 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, unsigned nrec, int
   }
   const size_t smem = (sizeof(double2) + sizeof(double)) * NR_T * NR_WARPS + (size_t)NR_SORT_BYTES * NR_WARPS;
   OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
-  const long long nchunks = ((long long)nrec + NR_CHUNK - 1) / NR_CHUNK;
-  const int blocks = (int)std::min<long long>((long long)ctx->sm_count * NR_CTAS_PER_SM, (nchunks + NR_WARPS - 1) / NR_WARPS);
+  const int blocks = ctx->sm_count * NR_CTAS_PER_SM;  // persistent; the record count is read on the device
   if (linear) {
     OD_CUDA(ctx, cudaFuncSetAttribute(narrow_kernel<true, JD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     narrow_kernel<true, JD><<<blocks, NR_WARPS * 32, smem, ctx->stream>>>(A);
@@ -1276,6 +1278,7 @@ int narrow_scratch(od_ctx *ctx, const GridSpec &grid, int ns, long long total_un
   ps.ncells = ns * ps.bpad / ps.cell;
   ps.nbuckets = NR_NCLS * ps.ncells;
   S.nout = (size_t)ns * ps.bpad + NR_T;
+  OD_CHECK(od_flags_ready(ctx));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   const size_t o_csum = take(sizeof(unsigned) * ps.nbuckets);
@@ -1298,24 +1301,6 @@ int narrow_scratch(od_ctx *ctx, const GridSpec &grid, int ns, long long total_un
   return OD_OK;
 }
 
-struct EventTimer {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  EventTimer() { cudaEventCreate(&e0); cudaEventCreate(&e1); }
-  ~EventTimer() { cudaEventDestroy(e0); cudaEventDestroy(e1); }
-  void start(cudaStream_t s) { cudaEventRecord(e0, s); }
-  void stop(cudaStream_t s) { cudaEventRecord(e1, s); }
-  double ms() { float m = 0.f; cudaEventSynchronize(e1); cudaEventElapsedTime(&m, e0, e1); return m; }
-};
-
-int collect_stats(od_ctx *ctx, const Scratch &S) {
-  unsigned long long h_stats[2] = {0, 0};
-  OD_CUDA(ctx, cudaMemcpyAsync(h_stats, S.wide + 5, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
-  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->prof.lane_steps += (double)h_stats[0];
-  ctx->prof.contributions += (double)h_stats[1];
-  return OD_OK;
-}
-
 }  // namespace
 
 bool od_narrow_grid_fits(int nbins, int ns) { return narrow_cell_for(nbins, ns) != 0; }
@@ -1323,6 +1308,7 @@ bool od_narrow_grid_fits(int nbins, int ns) { return narrow_cell_for(nbins, ns) 
 // Narrow pipeline for calculate_dos.  accum = [dos(B,ns) | intdos(B,ns) | weighted_dos(B,ns,norb)], zeroed by the
 // caller.  With matrix_weights (prod_in.mw != null) the sorted records are walked once more per pair of weight
 // columns (the Gaussian recurrence / doslin evaluation is cheap; the weights are gathered by unit index).
+// No host synchronisation on the path without weights: record and wide-unit counts stay on the device.
 int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid, bool linear, double *accum) {
   DosProducer prod = prod_in;
   prod.mw = nullptr;  // the prepare passes and the DOS pass do not need the weights
@@ -1340,21 +1326,19 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   S.ps.want_unit = norb > 0;
   double *ndos = S.chan, *nint = S.chan + S.nout;
 
-  EventTimer tp, ta;
-  unsigned h_nrec = 0;
-  unsigned long long h_wide[2] = {0, 0};
   long long wide_stride = 0;
-  tp.start(ctx->stream);
-  OD_CHECK(narrow_prepare(ctx, prod, S, linear, &h_nrec, h_wide, &wide_stride));
-  tp.stop(ctx->stream);
-  ta.start(ctx->stream);
-  if (h_nrec > 0) OD_CHECK(narrow_launch<false>(ctx, S, linear, h_nrec, -2, -2, ndos, nint, nullptr));
+  size_t tp = 0, ta = 0;
+  OD_CHECK(od_time_begin(ctx, 0, &tp));
+  OD_CHECK(narrow_prepare(ctx, prod, S, linear, &wide_stride));
+  OD_CHECK(od_time_end(ctx, tp));
+  OD_CHECK(od_time_begin(ctx, 1, &ta));
+  OD_CHECK(narrow_launch<false>(ctx, S, linear, -2, -2, ndos, nint, nullptr));
   const size_t n1 = (size_t)nbins * ns;
   combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, S.chan + 2 * S.nout, S.chan + 3 * S.nout, grid.delta, nbins, S.ps.bpad,
                                                 accum, accum + n1);
   OD_LAUNCH_CHECK(ctx);
   int wpasses = 0;
-  if (h_nrec > 0 && norb >= 8) {
+  if (norb >= 8) {
     // many projectors: banded GEMM over (bin tile, orbital tile, record segment) work items
     const PrepSpec &ps = S.ps;
     std::vector<unsigned> hbase((size_t)ps.nbuckets + 1);
@@ -1400,41 +1384,40 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
       OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // items is a host vector
       wpasses = 1;
     }
-  } else if (h_nrec > 0 && norb > 0) {
+  } else if (norb > 0) {
     // weighted spectrum: columns (2c, 2c+1) per pass, K * matrix_weights(o, ib, ik, is) (dos_utils.f90:1271)
     MwGather gth;
     gth.mw = prod_in.mw; gth.norb = norb; gth.mw_nb = prod_in.mw_nb; gth.mw_nk = prod_in.mw_nk; gth.nb = prod_in.nb;
     gth.k_first = prod_in.k_first;
-    OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(long long) * 2));
     for (int c = 0; 2 * c < norb; ++c, ++wpasses) {
       OD_CUDA(ctx, cudaMemsetAsync(S.chan, 0, sizeof(double) * 2 * S.nout, ctx->stream));
-      OD_CHECK(narrow_launch<true>(ctx, S, linear, h_nrec, 2 * c, 2 * c + 1 < norb ? 2 * c + 1 : -2, ndos, nint, &gth));
-      const long long dest[2] = {(long long)(2 * n1 + n1 * (size_t)(2 * c)), 2 * c + 1 < norb ? (long long)(2 * n1 + n1 * (size_t)(2 * c + 1)) : -1};
-      OD_CUDA(ctx, cudaMemcpyAsync(ctx->small.p, dest, sizeof(dest), cudaMemcpyHostToDevice, ctx->stream));
+      OD_CHECK(narrow_launch<true>(ctx, S, linear, 2 * c, 2 * c + 1 < norb ? 2 * c + 1 : -2, ndos, nint, &gth));
+      ChanDest dest;
+      for (long long &d : dest.d) d = -1;
+      dest.d[0] = (long long)(2 * n1 + n1 * (size_t)(2 * c));
+      if (2 * c + 1 < norb) dest.d[1] = (long long)(2 * n1 + n1 * (size_t)(2 * c + 1));
       dim3 g((nbins + 255) / 256, 2 * ns);
-      combine_channels_kernel<<<g, 256, 0, ctx->stream>>>(S.chan, S.nout, 2, nbins, S.ps.bpad, ns, ctx->small.as<long long>(), accum);
+      combine_channels_kernel<<<g, 256, 0, ctx->stream>>>(S.chan, S.nout, 2, nbins, S.ps.bpad, ns, dest, accum);
       OD_LAUNCH_CHECK(ctx);
-      OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // dest is a stack array
     }
   }
-  ta.stop(ctx->stream);
+  OD_CHECK(od_time_end(ctx, ta));
 
-  // ---- the wide units through the dense engine (adds into accum)
-  if (wide_stride > 0) {
+  // ---- the wide units through the dense engine (adds into accum); their count is only known on the device
+  {
     WideListProducer<DosProducer> wp;
     wp.units_per_z = wide_stride;
     wp.inner = prod_in;
     wp.list = ctx->scratch_b.as<unsigned>();
     wp.stride = wide_stride;
-    wp.count[0] = h_wide[0];
-    wp.count[1] = h_wide[1];
+    wp.count = S.wide;
     if (norb == 0) {
       std::vector<long long> dest(ns * 2);
       for (int is = 0; is < ns; ++is) {
         dest[is * 2 + 0] = (long long)is * nbins;
         dest[is * 2 + 1] = (long long)(n1 + (size_t)is * nbins);
       }
-      OD_CHECK((od_run_dense<0, true, WideListProducer<DosProducer>>(ctx, wp, grid, ns, dest, accum)));
+      OD_CHECK((od_run_dense_dev<0, true, WideListProducer<DosProducer>>(ctx, wp, grid, ns, dest, accum, S.wide)));
     } else {
       const int ngroups = (norb + OD_MAXW - 1) / OD_MAXW, nz = ns * ngroups;
       constexpr int NACC = 2 + OD_MAXW;
@@ -1451,13 +1434,11 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
             if (o < norb) dest[(size_t)z * NACC + 2 + a] = (long long)(2 * n1 + (size_t)nbins * (is + (size_t)ns * o));
           }
         }
-      OD_CHECK((od_run_dense<OD_MAXW, true, WideListProducer<DosProducer>>(ctx, wp, grid, nz, dest, accum)));
+      OD_CHECK((od_run_dense_dev<OD_MAXW, true, WideListProducer<DosProducer>>(ctx, wp, grid, nz, dest, accum, S.wide)));
     }
   }
-  OD_CHECK(collect_stats(ctx, S));
-  ctx->prof.prepare_ms += tp.ms();
-  ctx->prof.accumulate_ms += ta.ms();
-  ctx->prof.accumulate_launches += (h_nrec > 0) ? 1 + wpasses : 0;
+  ctx->prof.accumulate_launches += 1 + wpasses;
+  if (ctx->pending_times.size() > 4096) OD_CHECK(od_times_resolve(ctx));
   return OD_OK;
 }
 
@@ -1465,7 +1446,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
 // from the optical matrix elements by the producer).  accum = [jdos(B,ns) | weighted_jdos(B,ns,n_geom)], zeroed
 // by the caller.  Pair slots are processed in k-point slabs of < 2^30 slots.
 int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &grid, bool linear, int n_geom, double *accum) {
-  const int ns = prod_in.ns, nbins = grid.nbins, nb = prod_in.nb;
+  const int ns = prod_in.ns, nbins = grid.nbins;
   const long long ppk = prod_in.pairs_per_k();  // pair slots per k-point
   const long long nk = prod_in.units_per_z / ppk;
   // pair slots per k-slab: small enough that the bucket-order scatter of one slab stays L2-friendly (see the DOS
@@ -1485,54 +1466,45 @@ int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &gri
     JdosProducer prod = prod_in;
     prod.k_first = prod_in.k_first + k0;
     prod.units_per_z = std::min(slab_k, nk - k0) * ppk;
-    EventTimer tp, ta;
-    unsigned h_nrec = 0;
-    unsigned long long h_wide[2] = {0, 0};
     long long wide_stride = 0;
-    tp.start(ctx->stream);
-    OD_CHECK(narrow_prepare(ctx, prod, S, linear, &h_nrec, h_wide, &wide_stride));
-    tp.stop(ctx->stream);
-    ta.start(ctx->stream);
-    if (h_nrec > 0)
-      for (int c = 0; c < npass; ++c) {  // (jdos, w1) (w2, w3) (w4, w5) (w6, -)
-        const int col0 = c == 0 ? -1 : 2 * c - 1, col1 = 2 * c < n_geom ? 2 * c : -2;
-        OD_CHECK(narrow_launch<true>(ctx, S, linear, h_nrec, col0, col1, S.chan + (size_t)(2 * c) * S.nout,
-                                     S.chan + (size_t)(2 * c + 1) * S.nout));
-      }
-    ta.stop(ctx->stream);
-    if (wide_stride > 0) {
+    size_t tp = 0, ta = 0;
+    OD_CHECK(od_time_begin(ctx, 0, &tp));
+    OD_CHECK(narrow_prepare(ctx, prod, S, linear, &wide_stride));
+    OD_CHECK(od_time_end(ctx, tp));
+    OD_CHECK(od_time_begin(ctx, 1, &ta));
+    for (int c = 0; c < npass; ++c) {  // (jdos, w1) (w2, w3) (w4, w5) (w6, -)
+      const int col0 = c == 0 ? -1 : 2 * c - 1, col1 = 2 * c < n_geom ? 2 * c : -2;
+      OD_CHECK(narrow_launch<true>(ctx, S, linear, col0, col1, S.chan + (size_t)(2 * c) * S.nout, S.chan + (size_t)(2 * c + 1) * S.nout));
+    }
+    OD_CHECK(od_time_end(ctx, ta));
+    {
       WideListProducer<JdosProducer> wp;
       wp.units_per_z = wide_stride;
       wp.inner = prod;
       wp.list = ctx->scratch_b.as<unsigned>();
       wp.stride = wide_stride;
-      wp.count[0] = h_wide[0];
-      wp.count[1] = h_wide[1];
+      wp.count = S.wide;
       const int nacc = 1 + n_geom;
       std::vector<long long> dest((size_t)ns * nacc);
       for (int is = 0; is < ns; ++is) {
         dest[(size_t)is * nacc] = (long long)is * nbins;
         for (int a = 0; a < n_geom; ++a) dest[(size_t)is * nacc + 1 + a] = (long long)(n1 + (size_t)nbins * (is + (size_t)ns * a));
       }
-      if (n_geom == 0) OD_CHECK((od_run_dense<0, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum)));
-      else if (n_geom == 1) OD_CHECK((od_run_dense<1, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum)));
-      else OD_CHECK((od_run_dense<6, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum)));
+      if (n_geom == 0) OD_CHECK((od_run_dense_dev<0, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum, S.wide)));
+      else if (n_geom == 1) OD_CHECK((od_run_dense_dev<1, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum, S.wide)));
+      else OD_CHECK((od_run_dense_dev<6, false, WideListProducer<JdosProducer>>(ctx, wp, grid, ns, dest, accum, S.wide)));
     }
-    OD_CHECK(collect_stats(ctx, S));
-    OD_CUDA(ctx, cudaMemsetAsync(S.wide + 5, 0, sizeof(unsigned long long) * 2, ctx->stream));
-    ctx->prof.prepare_ms += tp.ms();
-    ctx->prof.accumulate_ms += ta.ms();
-    ctx->prof.accumulate_launches += (h_nrec > 0) ? npass : 0;
+    ctx->prof.accumulate_launches += npass;
+    // the next slab's prepare resets S.wide and overwrites the lists: stream order keeps the dense pass above ahead of it
   }
   // channel arrays -> [jdos | weighted_jdos]: array 0 = jdos, array a (a >= 1) = geometry component a
-  std::vector<long long> dest(2 * npass, -1);
-  dest[0] = 0;
-  for (int a = 1; a <= n_geom; ++a) dest[a] = (long long)(n1 + (size_t)nbins * ns * (a - 1));
-  OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(long long) * dest.size()));
-  OD_CUDA(ctx, cudaMemcpyAsync(ctx->small.p, dest.data(), sizeof(long long) * dest.size(), cudaMemcpyHostToDevice, ctx->stream));
+  ChanDest dest;
+  for (long long &d : dest.d) d = -1;
+  dest.d[0] = 0;
+  for (int a = 1; a <= n_geom; ++a) dest.d[a] = (long long)(n1 + (size_t)nbins * ns * (a - 1));
   dim3 g((nbins + 255) / 256, 2 * npass * ns);
-  combine_channels_kernel<<<g, 256, 0, ctx->stream>>>(S.chan, S.nout, 2 * npass, nbins, S.ps.bpad, ns, ctx->small.as<long long>(), accum);
+  combine_channels_kernel<<<g, 256, 0, ctx->stream>>>(S.chan, S.nout, 2 * npass, nbins, S.ps.bpad, ns, dest, accum);
   OD_LAUNCH_CHECK(ctx);
-  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->pending_times.size() > 4096) OD_CHECK(od_times_resolve(ctx));
   return OD_OK;
 }

@@ -123,10 +123,14 @@ static int dos_slab(od_ctx *ctx, char dos_type, const od_broadening *br, const G
 // Several broadening schemes over the rank's k-points in ONE sweep of k-point slabs.  With deferred (host)
 // gradients the slabs are uploaded on a second stream into two buffers while the kernels work on the
 // previous slab; otherwise there is a single slab.  accum_t = accum_base + t * stride:
-// [dos(B,ns) | intdos(B,ns) | weighted_dos(B,ns,norb) if weighted[t] | scratch(B,ns)]
+// [dos(B,ns) | intdos(B,ns) | weighted_dos(B,ns,norb)], all schemes contiguous, followed by one status word and a
+// scratch array.  merge: ONE sum-allreduce over [all schemes | status] (dos_utils_merge, dos_utils.f90:1013-1053, for
+// every scheme at once); the status word makes a rank-local failure an error on EVERY rank instead of a hang in the
+// collective.  host_out (may be null): the merged block is copied there (ntypes * stride doubles) in one transfer,
+// with the synchronisation and the deferred-error check of the call.
 int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *weighted, double emin, double delta_bins, int nbins,
                       const od_broadening *br, const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_base,
-                      size_t *accum_stride) {
+                      size_t *accum_stride, double *host_out) {
   bool need_grad = false;
   for (int t = 0; t < ntypes; ++t) need_grad = need_grad || types[t] != 'f';
   OD_CHECK(check_ready(ctx, need_grad));
@@ -145,11 +149,14 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
     fixedwide[t] = od_fixedwide_applies(ctx, bspec[t], grid, OD_ERF_CUT * OD_SQRT_TWO);
   }
   const size_t n1 = (size_t)nbins * ns;
-  const size_t stride = 2 * n1 + n1 * norb + n1;
-  OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * stride * ntypes));
+  const size_t stride = 2 * n1 + n1 * norb;
+  const size_t nall = stride * ntypes;  // + 1 status word + n1 scratch
+  OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * (nall + 1 + n1)));
   double *accum = ctx->accum.as<double>();
-  OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * stride * ntypes, ctx->stream));
+  OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * (nall + 1), ctx->stream));
 
+  // everything rank-local runs inside this lambda: its return code travels in the status word of the merge
+  auto local = [&]() -> int {
   for (int t = 0; t < ntypes; ++t)
     if (fixedwide[t]) OD_CHECK(od_fixedwide_begin(ctx, bspec[t], grid, 1 + (weighted[t] ? norb : 0)));
   auto one_slab = [&](int t, long long k0, int nks, const double *grads_dev, int nk_g) -> int {
@@ -213,8 +220,7 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
 
   for (int t = 0; t < ntypes; ++t) {
     double *acc = accum + stride * t;
-    const size_t ntot = 2 * n1 + (weighted[t] ? n1 * norb : 0);
-    if (fixedwide[t]) {
+      if (fixedwide[t]) {
       const int nw = weighted[t] ? norb : 0;
       std::vector<long long> out_off((size_t)(1 + nw) * ns), int_off((size_t)ns);
       for (int is = 0; is < ns; ++is) {
@@ -226,7 +232,7 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
     }
     // rank-local epilogue, before the merge like the reference (quirk Q16)
     if (types[t] == 'l' && br->linear_smearing > 0.0) {
-      double *tmp = acc + stride - n1;
+      double *tmp = accum + nall + 1;
       dim3 g((nbins + 127) / 128, ns);
       linear_smear_kernel<<<g, 128, 0, ctx->stream>>>(acc, tmp, nbins, ns, emin, delta_bins, br->linear_smearing);
       OD_LAUNCH_CHECK(ctx);
@@ -236,10 +242,29 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
       numerical_intdos_kernel<<<1, 32, 0, ctx->stream>>>(acc, acc + n1, nbins, ns, delta_bins);
       OD_LAUNCH_CHECK(ctx);
     }
-    if (merge) OD_CHECK(od_allreduce_device(ctx, acc, ntot, 's'));  // dos_utils_merge (dos_utils.f90:1041-1043)
   }
+  return OD_OK;
+  };
+  const int rc_local = local();
+  const std::string err_local = ctx->err;
+  if (merge && ctx->nranks > 1) {
+    if (rc_local != 0) {
+      const double one = 1.0;
+      cudaMemcpyAsync(accum + nall, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    OD_CHECK(od_allreduce_device(ctx, accum, nall + 1, 's'));  // dos_utils_merge (dos_utils.f90:1041-1043), all schemes at once
+  }
+  if (rc_local != 0 && !(merge && ctx->nranks > 1 && host_out)) return rc_local;
   *accum_base = accum;
   *accum_stride = stride;
+  if (host_out) {
+    OD_CUDA(ctx, cudaMemcpyAsync(host_out, accum, sizeof(double) * nall, cudaMemcpyDeviceToHost, ctx->stream));
+    double status = 0.0;
+    OD_CUDA(ctx, cudaMemcpyAsync(&status, accum + nall, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    OD_CHECK(od_check_deferred(ctx));  // (synchronises)
+    if (rc_local != 0) { ctx->err = err_local; return rc_local; }
+    if (status != 0.0) return od_fail(ctx, OD_ERR_STATE, "calculate_dos failed on %d other rank(s) of the communicator", (int)status);
+  }
   return OD_OK;
 }
 
@@ -247,7 +272,7 @@ int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delt
                             const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_out) {
   const bool weighted = mw_dev != nullptr;
   size_t stride = 0;
-  return od_dos_accumulate(ctx, 1, &dos_type, &weighted, emin, delta_bins, nbins, br, mw_dev, norb, mw_nb, mw_nk, merge, accum_out, &stride);
+  return od_dos_accumulate(ctx, 1, &dos_type, &weighted, emin, delta_bins, nbins, br, mw_dev, norb, mw_nb, mw_nk, merge, accum_out, &stride, nullptr);
 }
 
 extern "C" int od_calculate_dos(od_ctx *ctx, char dos_type, double emin, double delta_bins, int nbins, const od_broadening *br,
@@ -272,8 +297,7 @@ extern "C" int od_calculate_dos(od_ctx *ctx, char dos_type, double emin, double 
   OD_CUDA(ctx, cudaMemcpyAsync(intdos, accum + n1, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
   if (matrix_weights)
     OD_CUDA(ctx, cudaMemcpyAsync(weighted_dos, accum + 2 * n1, sizeof(double) * n1 * mw_norb, cudaMemcpyDeviceToHost, ctx->stream));
-  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return OD_OK;
+  return od_check_deferred(ctx);  // synchronises; doslin `stop` conditions met by the wide-window pass surface here
 }
 
 // ------------------------------------------------------------------ calculate_dos_at_e
@@ -529,8 +553,7 @@ static int jdos_copy_out(od_ctx *ctx, const double *accum, int nbins, int n_geom
   OD_CUDA(ctx, cudaMemcpyAsync(jdos, accum, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
   if (wjdos && n_geom > 0)
     OD_CUDA(ctx, cudaMemcpyAsync(wjdos, accum + n1, sizeof(double) * n1 * n_geom, cudaMemcpyDeviceToHost, ctx->stream));
-  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return OD_OK;
+  return od_check_deferred(ctx);  // synchronises
 }
 
 extern "C" int od_calculate_jdos(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br, double efermi,

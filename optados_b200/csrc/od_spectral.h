@@ -14,7 +14,7 @@ int od_calculate_dos_device(od_ctx *ctx, char dos_type, double emin, double delt
 // several broadening schemes in one sweep over k-point slabs (streams deferred gradients); see od_spectral.cu
 int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *weighted, double emin, double delta_bins, int nbins,
                       const od_broadening *br, const double *mw_dev, int norb, int mw_nb, int mw_nk, int merge, double **accum_base,
-                      size_t *accum_stride);
+                      size_t *accum_stride, double *host_out);
 // *accum_out -> [jdos(B,ns) | weighted_jdos(B,ns,n_geom)]
 int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int nbins, const od_broadening *br, double efermi,
                              double scissor_op, const int *exclude_bands, int num_exclude_bands, const double *mw_dev,
@@ -32,6 +32,30 @@ int od_fixedwide_accumulate_dos(od_ctx *ctx, const DosProducer &prod, const Grid
 int od_fixedwide_accumulate_jdos(od_ctx *ctx, const JdosProducer &prod, const GridSpec &grid, int n_geom);
 int od_fixedwide_finish(od_ctx *ctx, const BroadSpec &b, const GridSpec &grid, int nch, const long long *out_off, const long long *int_off,
                         double *accum);
+
+// The same launch for a unit list whose length is only known on the device (dev_units[0 / 1] = units of spin 1 / 2; the
+// wide list of the narrow engine): no host synchronisation; a doslin `stop` condition is OR-ed into ctx->flags and
+// reported by od_check_deferred after the caller's next synchronisation.  prod.units_per_z must be an UPPER BOUND.
+template <int NW, bool INT, class Producer>
+int od_run_dense_dev(od_ctx *ctx, const Producer &prod, const GridSpec &grid, int nz, const std::vector<long long> &dest, double *accum,
+                     const unsigned long long *dev_units) {
+  constexpr int NACC = 1 + (INT ? 1 : 0) + NW;
+  const int ntiles = (grid.nbins + OD_TILE - 1) / OD_TILE;
+  const long long nchunks = std::max<long long>(1, std::min<long long>(256, ((long long)ctx->sm_count * 16 + (long long)ntiles * nz - 1) / ((long long)ntiles * nz)));
+  const size_t pbytes = sizeof(double) * (size_t)nchunks * nz * NACC * grid.nbins;
+  OD_CHECK(od_buf_ensure(ctx, ctx->partial, pbytes));
+  OD_CHECK(od_buf_ensure(ctx, ctx->dest_dev, sizeof(long long) * dest.size()));
+  OD_CUDA(ctx, cudaMemcpyAsync(ctx->dest_dev.p, dest.data(), sizeof(long long) * dest.size(), cudaMemcpyHostToDevice, ctx->stream));
+  OD_CHECK(od_flags_ready(ctx));
+  dim3 g(ntiles, (unsigned)nchunks, nz);
+  od_dense_kernel<NW, INT, Producer><<<g, OD_TILE, 0, ctx->stream>>>(prod, grid, 0, ctx->partial.as<double>(), ctx->flags.as<int>(), dev_units);
+  OD_LAUNCH_CHECK(ctx);
+  dim3 rg((grid.nbins + 255) / 256, nz * NACC);
+  od_reduce_partials<<<rg, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), (int)nchunks, nz, NACC, grid.nbins,
+                                                  ctx->dest_dev.as<long long>(), accum, dev_units);
+  OD_LAUNCH_CHECK(ctx);
+  return OD_OK;
+}
 
 // does the bucket table of the narrow engine fit for this grid?  (~650k bins per spin channel at most; finer grids run on
 // the dense engine, as the reference accepts any dos_nbins / jdos_nbins)

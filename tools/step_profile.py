@@ -27,3 +27,20 @@ for t in ("a", "l"):
           f"lane efficiency {p['contributions'] / p['lane_steps']:.3f}  in-window (engine) {p['contributions'] / reps:.4g}  "
           f"in-window (metric) {c:.4g}  accumulate rate {p['contributions'] / reps / (p['accumulate_ms'] / reps * 1e-3):.4g} /s")
 ctx.close()
+
+# fixed cost per call: a 2000-k-point problem through the driver (energy scale, both schemes, merge, Fermi analysis)
+import time
+ctx = ob.Context(0)
+ctx.synth_bands((100, 100, 100), 0, 2000, 2, 256, seed=2)
+p = ctx.dos_params(["adaptive", "linear"], dos_nbins=20000, num_electrons=(128.0, 128.0))
+for _ in range(3):
+    p.dos_nbins = 20000
+    ctx.dos_utils_calculate(p)
+ctx.synchronize()
+t0 = time.perf_counter()
+for _ in range(20):
+    p.dos_nbins = 20000
+    ctx.dos_utils_calculate(p)
+ctx.synchronize()
+print(f"2000 k-points, adaptive + linear through od_dos_utils_calculate: {(time.perf_counter() - t0) / 20 * 1e3:.3f} ms per step (wall)")
+ctx.close()
