@@ -50,6 +50,7 @@ def parse():
                     help="k-point assignment over ranks: cyclic (balanced on the k1-ordered synthetic mesh) or contiguous blocks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs 3-5 block")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank spectrum comparison (N > 1)")
     return ap.parse_args()
 
@@ -274,8 +275,10 @@ def main():
     contrib_total = sum_over_ranks(dist, contrib_local, local)
     value = contrib_total / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (accumulation), FP64-bound
-    fp64_peak = ctx.measure_fp64_peak(0.4)
+    # ---- roofline, FP64-bound.  `frac`: the accumulation kernels alone (CUDA events around their launches);
+    #      `frac_step`: the WHOLE timed step (prepare passes, merges, Fermi analysis included) against the same peak.
+    fp64_peak = ctx.measure_fp64_peak(0.6)          # FP64 pipe peak: the larger of a DFMA and a DMMA loop
+    fp64_dfma = ctx.measure_fp64_peak(0.3, mode=1)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -283,24 +286,34 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     acc_ms = prof["accumulate_ms"] / max(1, args.steps)                       # per step, all accumulate launches
+    prep_ms = prof["prepare_ms"] / max(1, args.steps)
     flops_step = contrib_a_local * FLOPS_ADAPTIVE + (contrib_local - contrib_a_local) * FLOPS_LINEAR
     achieved_tf = flops_step / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
+    step_tf = sum_over_ranks(dist, flops_step, local) / (ms_step * 1e-3) / 1e12 / world     # per GPU
     states = float(nk_gpu) * NB * NS
     hbm_gbs = 2.0 * states * BYTES_PER_STATE / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
-    traffic = None
-    try:   # DRAM bytes of the accumulation kernels from the committed ncu capture, scaled to this step's units
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        per_unit = sum(tr[k]["dram_bytes_read"] + tr[k]["dram_bytes_write"] for k in ("narrow_kernel<0,0>", "narrow_kernel<1,0>"))
-        traffic = per_unit / tr["units_per_profiled_launch"] * states
+    traffic, kernels = None, None
+    try:   # per-kernel ncu figures of one k-point slab (tools/ncu_summary.py -> profiles/r02_kernels.json), scaled to this step's units
+        kj = json.load(open(os.path.join(ROOT, "profiles", "r02_kernels.json")))
+        kernels = {k: {"fp64_pipe_pct": v["fp64_pipe_pct"], "ms_per_launch": v["ms"], "dram_bytes_per_unit": v["dram_bytes"] / v["units"]}
+                   for k, v in kj["kernels"].items()}
+        traffic = sum(v["dram_bytes"] / v["units"] for v in kj["kernels"].values()) * states
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
-                "traffic_note": "DRAM bytes per step of all accumulation launches (ncu dram__bytes_read+write, profiles/r01_traffic.json)",
-                "peak_source": "measured in this run: od_measure_fp64_peak (DFMA loop, all SMs); MEASURED_PEAKS.json has no FP64 entry",
-                "kernel": "accumulation kernels (adaptive + linear), CUDA events on the library stream",
+                "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
+                "frac_step": step_tf / fp64_peak if fp64_peak > 0 else None, "achieved_step": step_tf,
+                "traffic": traffic,
+                "traffic_note": "DRAM bytes per step of ALL kernels of the step, prepare passes included (ncu dram__bytes_read+write per unit, "
+                                "profiles/r02_kernels.json, x this rank's units); algorithmic input: 32 B per state and scheme",
+                "peak_source": "measured in this run: od_measure_fp64_peak = max(DFMA loop, DMMA m16n8k8 loop) on all SMs; "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "peak_dfma_loop": fp64_dfma,
+                "kernel": "accumulation kernels (narrow_kernel<0,0> adaptive + narrow_kernel<1,0> linear), CUDA events on the library stream",
                 "kernel_ms_per_step": acc_ms, "kernel_share_of_step": acc_ms / ms_step if ms_step > 0 else None,
+                "prepare_ms_per_step": prep_ms, "kernels_ncu": kernels,
                 "algorithmic_flops_per_contribution": {"adaptive+intdos": FLOPS_ADAPTIVE, "linear": FLOPS_LINEAR},
+                "lane_efficiency": prof["contributions"] / prof["lane_steps"] if prof.get("lane_steps") else None,
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
 
@@ -365,17 +378,48 @@ def main():
                "sample": f"{nk_sample} of {nk_gpu} k-points (same nb, ns, bins, seed), dense reference loop, {dt:.1f} s",
                "dense_evaluations_per_s": dense}
 
+    # ---- the other BASELINE configurations (3: PDOS, 4: JDOS + optics, 5: core-loss): not bench lines, but driver-visible
+    #      numbers with their own roofline fractions and a k-slab parity figure against the oracle
+    configs = None
+    ctx.close()
+    ctx = None
+    if not args.no_configs:
+        import gc
+        gc.collect()
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("od_bench_configs", os.path.join(ROOT, "tools", "bench_configs.py"))
+        bc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bc)
+        env = bc.Env(local=local, rank=rank, world=world,
+                     make_ctx=lambda: ob.Context(local, rank, world, uid) if world > 1 else ob.Context(local),
+                     max_over_ranks=lambda x: max_over_ranks(dist, x, local), sum_over_ranks=lambda x: sum_over_ranks(dist, x, local),
+                     barrier=lambda: barrier(dist), fp64_peak=fp64_peak, hbm_peak=hbm_peak, reps=2, parity=True)
+        configs = {}
+        for name in ("cfg3", "cfg4", "cfg5"):
+            try:
+                configs[name] = bc.RUNNERS[name](env)
+            except Exception as e:     # a config that does not fit / fails must not take the headline down with it
+                configs[name] = {"error": repr(e)}
+            try:
+                import torch
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
+            barrier(dist)
+
     if rank == 0:
         line = {"metric": "in-window broadened (k,band,E) contributions/s", "value": value, "unit": "contributions/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, world, nk_total), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "configs": configs,
                 "multi_gpu_parity": parity, "gpu_launches": int(launches), "clocks": sampler.summary(),
                 "dense_equivalent_evaluations_per_s": 2.0 * float(nk_total) * NB * NS * NBINS / (ms_step * 1e-3),
                 "contributions_per_step": contrib_total, "wall_ms_per_step": wall / args.steps * 1e3,
                 "efermi_adaptive": r.get("efermi_adaptive"), "efermi_linear": r.get("efermi_linear")}
         emit(line)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     barrier(dist)
     if dist is not None:
         dist.destroy_process_group()

@@ -70,7 +70,12 @@ __global__ void linear_smear_kernel(const double *__restrict__ dos, double *__re
 }  // namespace
 
 // ------------------------------------------------------------------ calculate_dos
-#define OD_SLAB_UNITS_DEFAULT (32ll << 20)
+// k-point slabs (measured on B200, config 2, see profiles/r02_summary.md): the accumulation kernels like long record
+// arrays (fewer launch tails, fuller buckets: 62.8 / 58.4 / 57.2 ms per step at 16M / 32M / 48M units), the scatter of
+// the 64-byte linear records likes short ones (its write frontier has to stay mergeable in the L2: 25.4 / 30.7 / 42.5 ms).
+// So a slab is 48M units and the linear scheme walks it in sub-slabs of 24M.
+#define OD_SLAB_UNITS_DEFAULT (48ll << 20)
+#define OD_LINEAR_SLAB_UNITS_DEFAULT (24ll << 20)
 // one k-point slab of one broadening scheme, ADDED into accum = [dos | intdos | weighted_dos]
 static int dos_producer(od_ctx *ctx, char dos_type, const od_broadening *br, const GridSpec &grid, const double *mw_dev, int norb,
                         int mw_nb, int mw_nk, long long k_first, int nk_slab, const double *grads_dev, int nk_g, DosProducer *out) {
@@ -165,13 +170,19 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
       OD_CHECK(dos_producer(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0, nks, grads_dev, nk_g, &p));
       return od_fixedwide_accumulate_dos(ctx, p, grid, weighted[t] ? norb : 0);
     }
+    if (types[t] == 'l') {
+      const long long lin_units = getenv("OD_LINEAR_SLAB_UNITS") ? atoll(getenv("OD_LINEAR_SLAB_UNITS")) : OD_LINEAR_SLAB_UNITS_DEFAULT;
+      const int sub_nk = (int)std::max<long long>(1, lin_units / ((long long)nb * ns));
+      for (int s0 = 0; s0 < nks; s0 += sub_nk)
+        OD_CHECK(dos_slab(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0 + s0, std::min(sub_nk, nks - s0),
+                          grads_dev ? grads_dev + (size_t)nb * 3 * s0 : nullptr, nk_g, accum + stride * t));
+      return OD_OK;
+    }
     return dos_slab(ctx, types[t], br, grid, weighted[t] ? mw_dev : nullptr, norb, mw_nb, mw_nk, k0, nks, grads_dev, nk_g, accum + stride * t);
   };
   const bool streamed = ctx->grads_host != nullptr && need_grad;
   if (!streamed) {
-    // resident inputs: k-point slabs of ~32M units.  The bucket-order scatter of one slab then has a write
-    // frontier the L2 can merge into full lines (measured on B200, config 2: prepare 115 -> 54 ms per step),
-    // at the price of a short tail per accumulation launch; OD_SLAB_UNITS overrides for experiments.
+    // resident inputs: k-point slabs (see OD_SLAB_UNITS_DEFAULT above); OD_SLAB_UNITS overrides for experiments.
     long long slab_units = getenv("OD_SLAB_UNITS") ? atoll(getenv("OD_SLAB_UNITS")) : OD_SLAB_UNITS_DEFAULT;
     const int slab_nk = (int)std::max<long long>(1, std::min<long long>(nk, slab_units / ((long long)nb * ns)));
     for (long long k0 = 0; k0 < nk; k0 += slab_nk) {
