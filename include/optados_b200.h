@@ -316,6 +316,11 @@ typedef struct od_optics_params {
   int geom;               /* OD_GEOM_* */
   double qdir[3];         /* optics_qdir */
   double lossfn_gaussian; /* optics_lossfn_broadening: FWHM in eV, < 1e-6 = off (parameters.f90:367-371) */
+  int intraband;          /* optics_intraband (parameters.f90:361): add the Drude term of the bands crossing the Fermi level */
+  double drude_broadening;/* optics_drude_broadening in 1/s, default 1e14 (parameters.f90:364) */
+  double dos_delta_bins;  /* intraband only: the od_dos_utils module variable delta_bins that calculate_dos_at_e applies its
+                           * finite_bin_correction with (dos_utils.f90:1746) -- the grid spacing of the last DOS calculation of
+                           * the run (od_dos_result.delta_bins), 0 if there was none */
 } od_optics_params;
 void od_optics_params_defaults(od_optics_params *p);
 typedef struct od_optics_result {
@@ -325,11 +330,15 @@ typedef struct od_optics_result {
   int have_loss_fn_broadened;
   double n_eff;           /* sum rule of calc_epsilon_2 (optics.f90:552-563; N_geom = 1 only, else 0) */
   double n_eff2, n_eff3;  /* first / second sum rule of calc_loss_fn (optics.f90:700-719; with have_derived) */
+  int n_parts;            /* 1, or 3 with optics_intraband: epsilon(nbins, 2, n_geom, n_parts) = interband, intraband, total */
+  int n_loss_fn;          /* columns of loss_fn: 1 (+1 broadened), with intraband 3 (+1 broadened total) (optics.f90:632-644) */
 } od_optics_result;
 int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const double *optical_mat, int ome_mem, const double *symops,
                         int num_symm, od_optics_result *res);
-/* any pointer may be NULL: E(nbins), epsilon(nbins, 2, n_geom) with (:,1,:) = eps1 and (:,2,:) = eps2,
- * conduct(nbins,2), refract(nbins,2), loss_fn(nbins, 1 or 2), absorp(nbins), reflect(nbins) */
+/* any pointer may be NULL: E(nbins), epsilon(nbins, 2, n_geom, n_parts) with (:,1,:,:) = eps1 and (:,2,:,:) = eps2,
+ * conduct(nbins,2), refract(nbins,2), loss_fn(nbins, n_loss_fn), absorp(nbins), reflect(nbins).
+ * The intraband branches (optics.f90:517-549, :586-617, :632-697, :736-743, :769-778) are restated with their quirks
+ * (the Drude term added once per spin, E e carried by the total epsilon_2, 0/0 at E = 0 in calc_refract). */
 int od_optics_get(od_ctx *ctx, double *E, double *epsilon, double *conduct, double *refract, double *loss_fn,
                   double *absorp, double *reflect);
 

@@ -58,12 +58,14 @@ class JdosResult(C.Structure):
 
 
 class OpticsParams(C.Structure):
-    _fields_ = [("jdos", JdosParams), ("geom", C.c_int), ("qdir", C.c_double * 3), ("lossfn_gaussian", C.c_double)]
+    _fields_ = [("jdos", JdosParams), ("geom", C.c_int), ("qdir", C.c_double * 3), ("lossfn_gaussian", C.c_double),
+                ("intraband", C.c_int), ("drude_broadening", C.c_double), ("dos_delta_bins", C.c_double)]
 
 
 class OpticsResult(C.Structure):
     _fields_ = [("nbins", C.c_int), ("n_geom", C.c_int), ("delta_bins", C.c_double), ("have_derived", C.c_int),
-                ("have_loss_fn_broadened", C.c_int), ("n_eff", C.c_double), ("n_eff2", C.c_double), ("n_eff3", C.c_double)]
+                ("have_loss_fn_broadened", C.c_int), ("n_eff", C.c_double), ("n_eff2", C.c_double), ("n_eff3", C.c_double),
+                ("n_parts", C.c_int), ("n_loss_fn", C.c_int)]
 
 
 class CoreParams(C.Structure):
@@ -498,7 +500,10 @@ class Context:
 
     # ---- task mirrors (optics_calculate, core_calculate)
     def optics_calculate(self, optical_mat, efermi, cell_volume, broadening_type="adaptive", geom="polycrys", qdir=(1, 1, 1),
-                         symops=None, jdos_spacing=0.01, jdos_max_energy=-1.0, scissor_op=0.0, lossfn_gaussian=0.0, br=None):
+                         symops=None, jdos_spacing=0.01, jdos_max_energy=-1.0, scissor_op=0.0, lossfn_gaussian=0.0, br=None,
+                         intraband=False, drude_broadening=1.0e14, dos_delta_bins=0.0):
+        """optics_calculate (optics.f90:78-155).  With intraband=True epsilon comes back as (nbins, 2, n_geom, 3) =
+        interband / intraband / total and loss_fn has 3 (+1 broadened) columns."""
         p = OpticsParams()
         self.L.od_optics_params_defaults(C.byref(p))
         p.jdos.fixed = p.jdos.adaptive = p.jdos.linear = 0
@@ -509,6 +514,7 @@ class Context:
         if br is not None:
             p.jdos.br = br
         p.geom, p.lossfn_gaussian = GEOM[geom], lossfn_gaussian
+        p.intraband, p.drude_broadening, p.dos_delta_bins = int(intraband), float(drude_broadening), float(dos_delta_bins)
         for i in range(3):
             p.qdir[i] = float(qdir[i])
         om = np.asfortranarray(optical_mat, dtype=np.complex128)
@@ -518,12 +524,13 @@ class Context:
         self._ck(self.L.od_optics_calculate(self.h, C.byref(p), om.ctypes.data_as(c_dp), C.c_int(OD_MEM_HOST), _p(so), C.c_int(nsym),
                                             C.byref(res)))
         n, ng = res.nbins, res.n_geom
-        out = dict(nbins=n, n_geom=ng, delta=res.delta_bins, E=np.zeros(n), epsilon=np.zeros((n, 2, ng), order="F"),
+        eps_shape = (n, 2, ng) if res.n_parts == 1 else (n, 2, ng, res.n_parts)
+        out = dict(nbins=n, n_geom=ng, delta=res.delta_bins, E=np.zeros(n), epsilon=np.zeros(eps_shape, order="F"),
                    n_eff=res.n_eff, n_eff2=res.n_eff2, n_eff3=res.n_eff3)
         args = [_p(out["E"]), _p(out["epsilon"])]
         if res.have_derived:
             out.update(conduct=np.zeros((n, 2), order="F"), refract=np.zeros((n, 2), order="F"),
-                       loss_fn=np.zeros((n, 2 if res.have_loss_fn_broadened else 1), order="F"), absorp=np.zeros(n), reflect=np.zeros(n))
+                       loss_fn=np.zeros((n, res.n_loss_fn), order="F"), absorp=np.zeros(n), reflect=np.zeros(n))
             args += [_p(out[k]) for k in ("conduct", "refract", "loss_fn", "absorp", "reflect")]
         else:
             args += [None] * 5

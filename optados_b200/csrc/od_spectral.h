@@ -23,6 +23,9 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
 // contracted optics coefficients (optics.f90:213-435), see od_weights.cu
 int od_optics_coefficients(od_ctx *ctx, int geom, const double qdir[3], const double *symops, int num_symm, OpticsCoef *coef);
 
+// dos_matrix_weights(N_geom, nb, nk, ns) = the diagonal of make_weights (optics.f90:110-119), device in / device out
+int od_optics_diag_weights(od_ctx *ctx, const double *ome_dev, const OpticsCoef &coef, double *out_dev);
+
 // widest window (bins) the narrow engine takes; wider ones go to the dense engine or, for fixed broadening
 // without weights, to the moment expansion of od_fixedwide.cu
 #define OD_NARROW_WMAX 480

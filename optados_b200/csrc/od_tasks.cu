@@ -5,13 +5,13 @@
 //   core_calculate    core.f90:38-83      Fermi level -> ELNES weights -> weighted DOS -> LAI broadening -> the unit
 //                                         factors of write_core (core.f90:317-323)
 // Same order of operations, same flags, same quirks (sticky dos_nbins Q4, weighted spectrum of the most complex
-// scheme Q14, single-precision literals Q11).  Writers, edge bookkeeping and the intraband (Drude) terms stay with
-// the caller / out of scope.
+// scheme Q14, single-precision literals Q11), including the intraband (Drude) terms (optics_intraband).
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "od_internal.h"
+#include "od_spectral.h"
 
 namespace {
 // optics.f90:68-72
@@ -29,6 +29,110 @@ extern "C" void od_optics_params_defaults(od_optics_params *p) {
   p->geom = OD_GEOM_POLYCRYS;       // parameters.f90: optics_geom default 'polycrystalline'
   p->qdir[0] = 1.0; p->qdir[1] = 1.0; p->qdir[2] = 1.0;  // parameters.f90: optics_qdir default
   p->lossfn_gaussian = 0.0;
+  p->intraband = 0;               // parameters.f90:361
+  p->drude_broadening = 1.0e14;   // parameters.f90:364
+  p->dos_delta_bins = 0.0;
+}
+
+// optics_intraband = T: the weighted DOS at the Fermi level of the diagonal matrix elements (optics.f90:110-121) and the
+// Drude terms it feeds in calc_epsilon_2 (:517-549), calc_epsilon_1 (:586-617), calc_loss_fn (:632-719), calc_conduct
+// (:736-743) and calc_refract (:769-778).  wj = weighted_jdos(nbins, ns, ng), e1 = the interband epsilon_1 (Kramers-Kronig
+// of the interband epsilon_2, which the Drude terms do not enter).  Root-only O(B) arithmetic in the reference: host code.
+static int optics_intraband(od_ctx *ctx, od_optics_params *p, const double *optical_mat, int ome_mem, const double *symops, int num_symm,
+                            const std::vector<double> &wj, const std::vector<double> &e1, od_optics_result *res) {
+  OpticsRes &O = ctx->optics_res;
+  const int nbins = O.nbins, ng = O.n_geom, ns = ctx->ns, nb = ctx->nb, nk = ctx->nk;
+  const double vol = p->jdos.cell_volume, gam = p->drude_broadening, dE = O.E[1] - O.E[0];
+  // dos_matrix_weights(N, ib, ik, is) = matrix_weights(ib, ib, ik, is, N), formed from the matrix elements on the device
+  OpticsCoef coef;
+  OD_CHECK(od_optics_coefficients(ctx, p->geom, p->qdir, symops, num_symm, &coef));
+  const double *ome_dev = ome_mem == OD_MEM_DEVICE ? optical_mat : ctx->in_tmp.as<double>();  // staged by od_jdos_utils_calculate
+  OD_CHECK(od_buf_ensure(ctx, ctx->task_mw, sizeof(double) * (size_t)ng * nb * nk * ns));
+  OD_CHECK(od_optics_diag_weights(ctx, ome_dev, coef, ctx->task_mw.as<double>()));
+  od_dos_params dp;
+  od_dos_params_defaults(&dp);
+  dp.fixed = p->jdos.fixed; dp.adaptive = p->jdos.adaptive; dp.linear = p->jdos.linear; dp.br = p->jdos.br;
+  std::vector<double> dos_at_e(3 * (size_t)ns), wdae((size_t)ns * ng, 0.0);
+  OD_CHECK(od_dos_utils_calculate_at_e(ctx, &dp, p->jdos.efermi, p->dos_delta_bins, ctx->task_mw.as<double>(), ng, nb, nk, OD_MEM_DEVICE,
+                                       dos_at_e.data(), wdae.data()));
+  const double c20 = (double)1E-20f, c30 = (double)1E-30f, c10 = (double)1E-10f;  // single-precision literals (Q11)
+  const double eps2c = (kECharge * kPi * c20) / (vol * c30 * kEps0);
+  std::vector<double> intra((size_t)ng, 0.0);
+  for (int g = 0; g < ng; ++g) {
+    for (int is = 0; is < ns; ++is) intra[g] = intra[g] + wdae[is + (size_t)ns * g];
+    intra[g] = intra[g] * kECharge / (vol * c10 * kEps0);
+  }
+  res->n_parts = 3;
+  O.epsilon.assign((size_t)nbins * 2 * ng * 3, 0.0);  // epsilon(nbins, 2, n_geom, 3)
+  auto EP = [&](int i, int c, int g, int t) -> double & { return O.epsilon[(size_t)i + (size_t)nbins * (c + 2 * (g + (size_t)ng * t))]; };
+  for (int g = 0; g < ng; ++g) {
+    for (int is = 0; is < ns; ++is)  // the spin loop encloses the Drude term too (:536-547)
+      for (int i = 1; i < nbins; ++i) {
+        const double E = O.E[i];
+        EP(i, 1, g, 0) = EP(i, 1, g, 0) + eps2c * wj[i + (size_t)nbins * (is + (size_t)ns * g)];
+        EP(i, 1, g, 1) = EP(i, 1, g, 1) + ((intra[g] * (kECharge * kECharge) * kHbar * gam) / (((E * kECharge) * (E * kECharge)) + ((gam * kHbar) * (gam * kHbar))));
+        EP(i, 1, g, 2) = EP(i, 1, g, 2) + EP(i, 1, g, 1) + EP(i, 1, g, 0) * E * kECharge;
+      }
+    for (int i = 0; i < nbins; ++i) {
+      const double E = O.E[i];
+      EP(i, 0, g, 0) = e1[i + (size_t)nbins * g];
+      EP(i, 0, g, 1) = 1.0 - (intra[g] / ((E * E) + (((gam * kHbar) / kECharge) * ((gam * kHbar) / kECharge))));
+      EP(i, 0, g, 2) = EP(i, 0, g, 0) + EP(i, 0, g, 1) - 1.0;
+    }
+  }
+  if (ng == 1) {  // :552-563
+    double x = 0.0;
+    for (int N = 2; N <= nbins; ++N) x = x + ((N * (dE * dE) * EP(N - 1, 1, 0, 2)) / ((kHbar * kHbar) * O.E[N - 1] * kECharge));
+    res->n_eff = (x * kEMass * vol * c30 * kEps0 * 2) / (kPi);
+  }
+  if (p->geom == OD_GEOM_TENSOR) return OD_OK;
+  const bool lossb = fabs(p->lossfn_gaussian) >= 1.0e-6;
+  const int ncol = lossb ? 4 : 3;
+  O.loss_fn.assign((size_t)nbins * ncol, 0.0);
+  for (int i = 0; i < nbins; ++i) {
+    double a = EP(i, 0, 0, 0), b = EP(i, 1, 0, 0);
+    O.loss_fn[i] = b / (a * a + b * b);
+    if (i > 0) {
+      a = EP(i, 0, 0, 1); b = EP(i, 1, 0, 1) / (O.E[i] * kECharge);
+      O.loss_fn[i + (size_t)nbins] = b / (a * a + b * b);
+      a = EP(i, 0, 0, 2); b = EP(i, 1, 0, 2) / (O.E[i] * kECharge);
+      O.loss_fn[i + 2 * (size_t)nbins] = b / (a * a + b * b);
+    }
+  }
+  if (lossb) {  // the Gaussian broadening of the TOTAL loss function (:683-697) is the O(B^2) pass of od_calc_loss_fn (GPU), fed
+                // with a spectrum whose -Im(1 / eps) is column 3: eps = (0, 1 / L) gives b / (a a + b b) = L; eps = (1, 0) gives 0
+    std::vector<double> a((size_t)nbins), b((size_t)nbins), tmp((size_t)nbins);
+    for (int i = 0; i < nbins; ++i) {
+      const double L = O.loss_fn[i + 2 * (size_t)nbins];
+      a[i] = L != 0.0 ? 0.0 : 1.0;
+      b[i] = L != 0.0 ? 1.0 / L : 0.0;
+    }
+    OD_CHECK(od_calc_loss_fn(ctx, O.E.data(), nbins, a.data(), b.data(), p->lossfn_gaussian, tmp.data(), O.loss_fn.data() + 3 * (size_t)nbins));
+  }
+  {
+    double x = 0.0;
+    for (int N = 2; N <= nbins; ++N) x = x + (N * (dE * dE) * O.loss_fn[N - 1 + 2 * (size_t)nbins]);
+    res->n_eff2 = x * (kEMass * vol * c30 * kEps0 * 2) / (kPi * (kHbar * kHbar));
+    x = 0;
+    for (int N = 2; N <= nbins; ++N) x = x + (O.loss_fn[N - 1 + 2 * (size_t)nbins] / N);
+    res->n_eff3 = x;
+  }
+  O.conduct.resize((size_t)nbins * 2); O.refract.resize((size_t)nbins * 2); O.absorp.resize(nbins); O.reflect.resize(nbins);
+  for (int i = 0; i < nbins; ++i) {
+    const double E = O.E[i], e1i = EP(i, 0, 0, 0), e1t = EP(i, 0, 0, 2), e2t = EP(i, 1, 0, 2);
+    O.conduct[i] = kEps0 * e2t / kHbar;
+    O.conduct[i + (size_t)nbins] = (E * kECharge / kHbar) * kEps0 * (1.0 - e1t);
+    const double r = e2t / (E * kECharge);  // 0 / 0 at E = 0, as in the reference
+    O.refract[i] = pow(0.5 * (pow((e1t * e1t) + (r * r), 0.5) + e1i), 0.5);
+    O.refract[i + (size_t)nbins] = pow(0.5 * (pow((e1i * e1i) + (r * r), 0.5) - e1i), 0.5);
+    O.absorp[i] = 2 * O.refract[i + (size_t)nbins] * E * kECharge / (kHbar * kCSpeed);
+    const double n = O.refract[i], k = O.refract[i + (size_t)nbins];
+    O.reflect[i] = (((n - 1) * (n - 1)) + (k * k)) / (((n + 1) * (n + 1)) + (k * k));
+  }
+  res->have_derived = 1;
+  res->have_loss_fn_broadened = lossb ? 1 : 0;
+  res->n_loss_fn = ncol;
+  return OD_OK;
 }
 
 extern "C" int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const double *optical_mat, int ome_mem, const double *symops,
@@ -56,7 +160,9 @@ extern "C" int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const doubl
       O.epsilon[i + (size_t)nbins * (1 + 2 * g)] = e2[i + (size_t)nbins * g];
     }
   res->nbins = nbins; res->n_geom = ng; res->delta_bins = jr.delta_bins;
+  res->n_parts = 1;
   const double dE = O.E[1] - O.E[0], vol = p->jdos.cell_volume;
+  if (p->intraband) return optics_intraband(ctx, p, optical_mat, ome_mem, symops, num_symm, wj, e1, res);
   if (ng == 1) {  // sum rule of calc_epsilon_2 (optics.f90:552-563): the bin index, not the energy, multiplies dE**2
     double x = 0.0;
     for (int N = 2; N <= nbins; ++N) x = x + ((N * (dE * dE) * e2[N - 1]) / (kHbar * kHbar));
@@ -90,6 +196,7 @@ extern "C" int od_optics_calculate(od_ctx *ctx, od_optics_params *p, const doubl
   }
   res->have_derived = 1;
   res->have_loss_fn_broadened = lossb ? 1 : 0;
+  res->n_loss_fn = lossb ? 2 : 1;
   return OD_OK;
 }
 

@@ -152,6 +152,22 @@ __global__ void make_weights_kernel(const double *__restrict__ ome, const double
   }
 }
 
+// the diagonal of make_weights as dos_matrix_weights(N_geom, nb, nk, ns) (optics.f90:110-119): factor = 1 on the diagonal
+// whatever the occupation (:261-266)
+__global__ void optics_diag_weights_kernel(const double *__restrict__ ome, int nb, int nk, int ns, OpticsCoef coef, double *__restrict__ out) {
+  const size_t nb2 = (size_t)nb * nb;
+  const size_t total = (size_t)nb * nk * ns;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(t % nb);
+    const size_t ks = t / nb;  // ik + nk*is
+    double P[6];
+    od_ome_products(ome, n + (size_t)nb * n + nb2 * 3 * ks, nb2, P);
+    for (int g = 0; g < coef.n_geom; ++g)
+      out[g + (size_t)coef.n_geom * t] = coef.c[g][0] * P[0] + coef.c[g][1] * P[1] + coef.c[g][2] * P[2] + coef.c[g][3] * P[3] +
+                                         coef.c[g][4] * P[4] + coef.c[g][5] * P[5];
+  }
+}
+
 // one thread per (orb, ib, ik, is)
 __global__ void core_weights_kernel(const double *__restrict__ elnes, const double *__restrict__ bands, int norb, int nb, int nk,
                                     int ns, double efermi, int core_type, OpticsCoef coef, double *__restrict__ mw) {
@@ -232,6 +248,13 @@ extern "C" int od_make_weights(od_ctx *ctx, const double *optical_mat, int ome_m
                                                                        ctx->nk, ctx->ns, efermi, scissor_op, coef, out);
   OD_LAUNCH_CHECK(ctx);
   return finish_out(ctx, out, matrix_weights, nel * coef.n_geom, out_mem);
+}
+
+int od_optics_diag_weights(od_ctx *ctx, const double *ome_dev, const OpticsCoef &coef, double *out_dev) {
+  const size_t nel = (size_t)ctx->nb * ctx->nk * ctx->ns;
+  optics_diag_weights_kernel<<<grid_for(ctx, nel, 256), 256, 0, ctx->stream>>>(ome_dev, ctx->nb, ctx->nk, ctx->ns, coef, out_dev);
+  OD_LAUNCH_CHECK(ctx);
+  return OD_OK;
 }
 
 extern "C" int od_core_prepare_matrix_elements(od_ctx *ctx, const double *elnes_mat, int elnes_mem, int norb, int polar,

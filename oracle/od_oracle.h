@@ -176,6 +176,13 @@ int odo_compute_bandgap(const odo_system *sys, double efermi, const double *num_
 double odo_calc_band_energies(const double *dos, const double *E, int nbins, int ns, double delta_bins, double efermi);
 double odo_band_energy_from_bands(const odo_system *sys, double efermi);
 
+/* the intraband (Drude) branches of optics.f90 (calc_epsilon_2 / _1, calc_loss_fn, sum rules, calc_conduct, calc_refract,
+ * calc_absorp, calc_reflect); see od_oracle.c.  Unpinned: the Al4 fixtures of the reference's suite are incomplete. */
+void odo_optics_intraband(const double *wjdos, const double *weighted_dos_at_e, const double *E, int nbins, int ns, int n_geom,
+                          double cell_volume, double drude_broadening, int lossfn_broadening, double lossfn_gaussian, int derived,
+                          double *epsilon, double *loss_fn, double *conduct, double *refract, double *absorp, double *reflect,
+                          double *N_eff, double *N_eff2, double *N_eff3);
+
 #ifdef __cplusplus
 }
 #endif

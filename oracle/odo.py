@@ -327,6 +327,25 @@ def calc_optics_derived(E, eps1, eps2):
     return out
 
 
+def optics_intraband(wjdos, weighted_dos_at_e, E, cell_volume, drude_broadening=1.0e14, lossfn_gaussian=0.0, derived=True):
+    """the intraband branches of optics.f90 (see odo_optics_intraband in od_oracle.c; unpinned: no complete Al4 fixture)"""
+    L = lib()
+    wj = f64(wjdos)
+    n, ns, ng = wj.shape
+    wd = f64(weighted_dos_at_e)
+    E = f64(E)
+    lossb = abs(lossfn_gaussian) >= 1e-6
+    out = dict(epsilon=np.zeros((n, 2, ng, 3), order="F"), loss_fn=np.zeros((n, 4 if lossb else 3), order="F"),
+               conduct=np.zeros((n, 2), order="F"), refract=np.zeros((n, 2), order="F"), absorp=np.zeros(n), reflect=np.zeros(n))
+    ne, ne2, ne3 = C.c_double(), C.c_double(), C.c_double()
+    L.odo_optics_intraband(_p(wj), _p(wd), _p(E), C.c_int(n), C.c_int(ns), C.c_int(ng), C.c_double(cell_volume),
+                           C.c_double(drude_broadening), C.c_int(int(lossb)), C.c_double(lossfn_gaussian), C.c_int(int(derived)),
+                           _p(out["epsilon"]), _p(out["loss_fn"]), _p(out["conduct"]), _p(out["refract"]), _p(out["absorp"]),
+                           _p(out["reflect"]), C.byref(ne), C.byref(ne2), C.byref(ne3))
+    out.update(n_eff=ne.value, n_eff2=ne2.value, n_eff3=ne3.value)
+    return out
+
+
 def core_lai_broadening(wdos, E, efermi, gaussian_width=0.0, lorentzian_width=0.0, lorentzian_scale=0.0, lorentzian_offset=0.0):
     """core.f90:70-76: weighted_dos(B, ns, norb) -> weighted_dos_broadened"""
     L = lib()

@@ -588,6 +588,43 @@ def test_optics_task_golden(ob, odo, geom, btype, test):
     ctx.close()
 
 
+@pytest.mark.parametrize("geom,btype,lossb", [("polycrys", "adaptive", 0.0), ("polar", "fixed", 0.8), ("tensor", "adaptive", 0.0)])
+def test_optics_intraband_vs_oracle(ob, odo, geom, btype, lossb):
+    """optics_intraband = T (the Drude term of a metal): od_optics_calculate against the oracle's restatement of the
+    intraband branches of optics.f90 on the spin-polarised Si2 fixture with the Fermi level moved into the conduction
+    bands.  Oracle-pinned only: the reference's three intraband tests need Al4.ome_fmt.bz2, which its checkout lacks."""
+    fx = fixture("si2_optics")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    ef = float(np.sort(s.band_energy.ravel())[s.band_energy.size * 2 // 3])      # bands cross this level
+    q = (0.5, 0.5, 0.25)
+    first = ctx.dos_utils_calculate(ctx.dos_params(btype, dos_spacing=0.1, num_electrons=fx["num_electrons"]))
+    r = ctx.optics_calculate(fx["optical_mat"], ef, s.cell_volume, btype, geom=geom, qdir=q, symops=fx["symops"], jdos_max_energy=30.0,
+                             lossfn_gaussian=lossb, intraband=True, drude_broadening=2.0e14, dos_delta_bins=first["delta"])
+    # the oracle: make_weights -> jdos -> weighted DOS at E_F of the diagonal -> intraband formulas
+    mw = odo.make_weights(s, fx["optical_mat"], geom, ef, qdir=q, symops=fx["symops"])
+    ref = odo.jdos_utils_calculate(s, ef, btype, jdos_spacing=0.01, jdos_max_energy=30.0, mw=mw)
+    idx = np.arange(s.nb)
+    dmw = np.asfortranarray(np.transpose(mw[idx, idx, :, :, :], (3, 0, 1, 2)))       # dos_matrix_weights(N, ib, ik, is)
+    _, wdae = odo.calculate_dos_at_e(btype[0], s, odo.make_broadening(), first["delta"], ef, dmw)
+    o = odo.optics_intraband(ref["wjdos"], wdae, ref["E"], s.cell_volume, drude_broadening=2.0e14, lossfn_gaussian=lossb,
+                             derived=geom != "tensor")
+    assert r["epsilon"].shape == o["epsilon"].shape
+    for part in range(3):
+        for c in range(2):
+            assert rel_to_peak(r["epsilon"][:, c, :, part], o["epsilon"][:, c, :, part]) < TOL_SPEC, (part, c)
+    assert np.abs(r["epsilon"][:, 1, 0, 1]).max() > 0.0          # there is a Drude term
+    if geom != "tensor":
+        for k in ("loss_fn", "conduct", "refract", "absorp", "reflect"):
+            a, b = np.asarray(r[k]), np.asarray(o[k])
+            assert np.array_equal(np.isnan(a), np.isnan(b)), k          # bin 1 (E = 0): 0 / 0 in calc_refract, as the reference
+            m = ~np.isnan(b)
+            assert np.abs(a[m] - b[m]).max() <= 1e-9 * np.abs(b[m]).max(), k
+        assert abs(r["n_eff2"] - o["n_eff2"]) <= 1e-9 * abs(o["n_eff2"]) and abs(r["n_eff3"] - o["n_eff3"]) <= 1e-9 * abs(o["n_eff3"])
+    if geom != "tensor":
+        assert abs(r["n_eff"] - o["n_eff"]) <= 1e-9 * abs(o["n_eff"])
+    ctx.close()
+
+
 @pytest.mark.parametrize("test,btype,core_type,polar", [("testopt_core_polarised", "adaptive", "emission", True),
                                                         ("testopt_core_emisson", "linear", "emission", True),
                                                         ("testopt_core_all", "linear", "all", False)])
