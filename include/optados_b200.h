@@ -435,6 +435,50 @@ int od_read_elnes_info(const char *path, char fmt, od_elnes_info *info);
 int od_read_elnes(const char *path, char fmt, const od_elnes_info *info, int *species_no, int *rank_in_species, int *shell,
                   int *am_channel, double *elnes_mat);
 
+/* ---------------------------------------------------------------- the file contract (host) ---- */
+/* SURVEY.md section 8(f) rank 4.  od_param_read = param_read (parameters.f90:138-465) with its tokenizer (:837-1470):
+ * lower-cased lines, `!` / `#` comments, keyword at column 1 followed by `=`, `:` or a blank, every line must be
+ * consumed ("Unrecognised keyword(s) in input file").  Defaults as the reference sets them. */
+typedef struct od_odi {
+  int iprint, legacy_file_format;
+  int dos, pdos, pdis, jdos, optics, core, compare_dos, compare_jdos;      /* task (parameters.f90:164-197) */
+  int fixed, adaptive, linear;                                             /* broadening (:205-224) */
+  double adaptive_smearing, fixed_smearing, linear_smearing;
+  int efermi_choice;                                                       /* OD_EFERMI_* (:254-259, param_get_efermi) */
+  double efermi_user;
+  int compute_band_energy, compute_band_gap;
+  double core_chemical_shift;                                              /* -1 = off */
+  int finite_bin_correction, numerical_intdos, hybrid_linear;
+  double hybrid_linear_grad_tol;
+  int set_efermi_zero, dos_per_volume;
+  int have_dos_min_energy, have_dos_max_energy;
+  double dos_min_energy, dos_max_energy, dos_spacing;
+  int dos_nbins;
+  char projectors_string[256];                                             /* pdos : ... */
+  double jdos_max_energy, jdos_spacing;
+  int num_exclude_bands;
+  int exclude_bands[256];
+  char optics_geom[32];
+  double scissor_op, optics_qdir[3];
+  int optics_intraband;
+  double optics_drude_broadening;
+  int optics_lossfn_broadening;
+  double optics_lossfn_gaussian;
+  char core_geom[32], core_type[32];
+  double core_qdir[3];
+  int core_lai_broadening;
+  double lai_gaussian_width, lai_lorentzian_width, lai_lorentzian_scale, lai_lorentzian_offset;
+} od_odi;
+void od_odi_defaults(od_odi *p);
+int od_param_read(const char *odi_path, od_odi *p);
+/* message of the last failing od_param_read / od_run_seed of this thread */
+const char *od_run_last_error(void);
+/* <dir>/<seed>.odi + the CASTEP outputs it asks for (<seed>.bands; dome / ome / pdos / elnes files as *_bin, legacy or
+ * formatted *_fmt; <seed>-out.cell) -> <seed>.odo and the reference's .dat files in <dir>, tasks in the reference's order
+ * (optados.f90:120-222) on the GPU of ctx.  pdos_write's projector headers, write_dos / write_jdos E21.13 tables,
+ * write_epsilon / write_loss_fn / ... and write_core blocks as the reference lays them out; .agr files are not written. */
+int od_run_seed(od_ctx *ctx, const char *dir, const char *seedname);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,29 @@ class CoreParams(C.Structure):
                 ("set_efermi_zero", C.c_int), ("core_chemical_shift", C.c_double)]
 
 
+class Odi(C.Structure):
+    """od_odi: the parsed .odi (param_read, parameters.f90:138-465)"""
+    _fields_ = [("iprint", C.c_int), ("legacy_file_format", C.c_int),
+                ("dos", C.c_int), ("pdos", C.c_int), ("pdis", C.c_int), ("jdos", C.c_int), ("optics", C.c_int), ("core", C.c_int),
+                ("compare_dos", C.c_int), ("compare_jdos", C.c_int),
+                ("fixed", C.c_int), ("adaptive", C.c_int), ("linear", C.c_int),
+                ("adaptive_smearing", C.c_double), ("fixed_smearing", C.c_double), ("linear_smearing", C.c_double),
+                ("efermi_choice", C.c_int), ("efermi_user", C.c_double),
+                ("compute_band_energy", C.c_int), ("compute_band_gap", C.c_int), ("core_chemical_shift", C.c_double),
+                ("finite_bin_correction", C.c_int), ("numerical_intdos", C.c_int), ("hybrid_linear", C.c_int),
+                ("hybrid_linear_grad_tol", C.c_double), ("set_efermi_zero", C.c_int), ("dos_per_volume", C.c_int),
+                ("have_dos_min_energy", C.c_int), ("have_dos_max_energy", C.c_int),
+                ("dos_min_energy", C.c_double), ("dos_max_energy", C.c_double), ("dos_spacing", C.c_double), ("dos_nbins", C.c_int),
+                ("projectors_string", C.c_char * 256), ("jdos_max_energy", C.c_double), ("jdos_spacing", C.c_double),
+                ("num_exclude_bands", C.c_int), ("exclude_bands", C.c_int * 256),
+                ("optics_geom", C.c_char * 32), ("scissor_op", C.c_double), ("optics_qdir", C.c_double * 3),
+                ("optics_intraband", C.c_int), ("optics_drude_broadening", C.c_double),
+                ("optics_lossfn_broadening", C.c_int), ("optics_lossfn_gaussian", C.c_double),
+                ("core_geom", C.c_char * 32), ("core_type", C.c_char * 32), ("core_qdir", C.c_double * 3),
+                ("core_lai_broadening", C.c_int), ("lai_gaussian_width", C.c_double), ("lai_lorentzian_width", C.c_double),
+                ("lai_lorentzian_scale", C.c_double), ("lai_lorentzian_offset", C.c_double)]
+
+
 class BandgapResult(C.Structure):
     _fields_ = [("vbm_energy", C.c_double), ("cbm_energy", C.c_double), ("thermal_bandgap", C.c_double),
                 ("thermal_vbm_k", C.c_longlong), ("thermal_cbm_k", C.c_longlong),
@@ -132,6 +155,7 @@ EXPORTS = [
     "od_calc_epsilon_1", "od_calc_loss_fn", "od_core_lai_broadening",
     "od_dos_utils_calculate_at_e", "od_optics_params_defaults", "od_optics_calculate", "od_optics_get", "od_core_params_defaults", "od_core_calculate",
     "od_core_get", "od_dos_utils_compute_bandgap", "od_dos_utils_compute_band_energies",
+    "od_odi_defaults", "od_param_read", "od_run_last_error", "od_run_seed",
     "od_io_last_error", "od_read_bands_info", "od_read_bands", "od_cell_calc_lattice", "od_cell_find_mp_grid",
     "od_read_symmetry_ops", "od_read_ome", "od_read_dome", "od_read_pdos_info", "od_read_pdos", "od_read_elnes_info",
     "od_read_elnes",
@@ -158,6 +182,26 @@ def dist_array(num_elements, num_nodes):
     if rc:
         raise OptadosB200Error(rc, "Fewer kpoints than nodes. Reduce the number of nodes used!")
     return list(per)
+
+
+def param_read(path):
+    """param_read (parameters.f90:138-465) of one .odi file -> dict (host only: no GPU needed)"""
+    L = load()
+    L.od_run_last_error.restype = C.c_char_p
+    p = Odi()
+    rc = L.od_param_read(str(path).encode(), C.byref(p))
+    if rc:
+        raise OptadosB200Error(rc, L.od_run_last_error().decode())
+    out = {}
+    for name, ctype in Odi._fields_:
+        v = getattr(p, name)
+        if isinstance(v, bytes):
+            v = v.decode()
+        elif hasattr(v, "__len__"):
+            v = list(v)
+        out[name] = v
+    out["exclude_bands"] = out["exclude_bands"][:out["num_exclude_bands"]]
+    return out
 
 
 def get_unique_id():
@@ -590,6 +634,13 @@ class Context:
             wb = _p(out["weighted_dos_broadened"])
         self._ck(self.L.od_core_get(self.h, _p(out["E"]), _p(out["weighted_dos"]), wb))
         return out
+
+    def run_seed(self, directory, seedname):
+        """the reference's file contract: <directory>/<seedname>.odi + CASTEP outputs -> .odo and .dat files (od_run_seed)"""
+        self.L.od_run_last_error.restype = C.c_char_p
+        rc = self.L.od_run_seed(self.h, str(directory).encode(), str(seedname).encode())
+        if rc:
+            raise OptadosB200Error(rc, self.L.od_run_last_error().decode() or self.L.od_last_error(self.h).decode())
 
     # ---- bookkeeping
     def kernel_launches(self):

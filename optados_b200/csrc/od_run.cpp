@@ -1,0 +1,1243 @@
+// od_run.cpp -- SURVEY.md section 8(f) rank 4: the reference's FILE CONTRACT end to end, as host C++ above the C ABI.
+//
+//   od_param_read   <seed>.odi            -> od_odi        (param_read, parameters.f90:138-465 + its tokenizer :837-1470)
+//   od_run_seed     a directory with <seed>.odi, <seed>.bands and whatever the tasks ask for (dome / ome / pdos / elnes
+//                   files in binary, legacy or formatted form, <seed>-out.cell) -> <seed>.odo and the .dat files the
+//                   reference writes: <seed>.<type>.dat (dos.f90:150-251), <seed>.j<type>.dat (jdos.f90:75-145),
+//                   <seed>.pdos.dat / .pdos.proj-XXXX-YYYY.dat (pdos.F90:94-252), <seed>_epsilon.dat, _loss_fn.dat,
+//                   _conductivity.dat, _refractive_index.dat, _absorption.dat, _reflection.dat (optics.f90:828-1494),
+//                   <seed>_core_edge.dat (core.f90:170-653)
+// Tasks run in the reference's order (optados.f90:120-222: pdos, core, dos, optics, jdos) with its shared state: efermi_set,
+// the sticky dos_nbins (quirk Q4), "already calculated dos, so returning" (dos_utils.f90:141-147), the module variables
+// vbm_energy / cbm_energy.  All spectra come from the GPU through the same entry points the Fortran shim binds.
+//
+// Not reproduced: the xmgrace .agr files, the parameter echo and timing lines of the .odo (the .odo written here carries
+// the analysis blocks with the reference's `<- XXX` tags, which is what its test harness greps), pdispersion, od2od.
+// Numbers are written with the reference's edit descriptors where it uses them (E21.13, es14.7, f-formats); its
+// list-directed writes (`write(unit,*) x, y, z`) become 3 x ES26.17E3: the same values to 17 digits, not the same bytes.
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/optados_b200.h"
+
+namespace {
+thread_local std::string g_run_err;
+int run_fail(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_run_err = buf;
+  return OD_ERR_IO;
+}
+
+std::string lower(std::string s) {
+  for (char &c : s) c = (char)tolower((unsigned char)c);
+  return s;
+}
+std::string ltrim(const std::string &s) {
+  size_t i = 0;
+  while (i < s.size() && (s[i] == ' ' || s[i] == '\t')) ++i;
+  return s.substr(i);
+}
+std::string rtrim(std::string s) {
+  while (!s.empty() && (s.back() == ' ' || s.back() == '\t' || s.back() == '\r' || s.back() == '\n')) s.pop_back();
+  return s;
+}
+bool file_exists(const std::string &p) {
+  FILE *f = fopen(p.c_str(), "rb");
+  if (!f) return false;
+  fclose(f);
+  return true;
+}
+
+// ---------------------------------------------------------------- the .odi tokenizer (parameters.f90:837-966)
+struct Odi {
+  std::vector<std::string> lines;  // lower-cased, comment-stripped, left-adjusted; a consumed line becomes blank
+  std::string err;
+
+  bool load(const std::string &path) {
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) { err = "Error: Problem opening input file " + path; return false; }
+    char buf[4096];
+    while (fgets(buf, sizeof(buf), f)) {
+      std::string d = ltrim(lower(rtrim(buf)));
+      if (d.empty() || d[0] == '!' || d[0] == '#') continue;
+      const size_t c = d.find_first_of("!#");
+      if (c != std::string::npos) d = d.substr(0, c);
+      lines.push_back(d);
+    }
+    fclose(f);
+    return true;
+  }
+  // the value string of `keyword` (keyword at column 1, followed by '=', ':' or ' '); the line is consumed
+  bool get(const char *keyword, std::string &value, bool consume = true) {
+    const size_t kl = strlen(keyword);
+    bool found = false;
+    for (std::string &l : lines) {
+      if (l.compare(0, kl, keyword) != 0) continue;
+      const char nx = l.size() > kl ? l[kl] : ' ';
+      if (nx != '=' && nx != ':' && nx != ' ') continue;
+      if (found) { err = std::string("Error: Found keyword ") + keyword + " more than once in input file"; return false; }
+      found = true;
+      std::string d = ltrim(l.substr(kl));
+      if (consume) l.clear();
+      if (!d.empty() && (d[0] == '=' || d[0] == ':')) d = ltrim(d.substr(1));
+      value = rtrim(d);
+    }
+    return found;
+  }
+  bool get_logical(const char *k, int &v) {
+    std::string s;
+    if (!get(k, s)) return false;
+    if (s.find('t') != std::string::npos) v = 1;
+    else if (s.find('f') != std::string::npos) v = 0;
+    else err = std::string("Error: Problem reading logical keyword ") + k;
+    return true;
+  }
+  bool get_real(const char *k, double &v) {
+    std::string s;
+    if (!get(k, s)) return false;
+    char *e = nullptr;
+    std::string t = s;
+    for (char &c : t) if (c == 'd') c = 'e';  // Fortran exponent letter
+    const double x = strtod(t.c_str(), &e);
+    if (e == t.c_str()) err = std::string("Error: Problem reading keyword ") + k;
+    else v = x;
+    return true;
+  }
+  bool get_int(const char *k, int &v) {
+    double x = 0.0;
+    if (!get_real(k, x)) return false;
+    v = (int)x;
+    return true;
+  }
+  bool get_vec3(const char *k, double v[3]) {
+    std::string s;
+    if (!get(k, s)) return false;
+    for (char &c : s) if (c == ',') c = ' ';
+    if (sscanf(s.c_str(), "%lf %lf %lf", &v[0], &v[1], &v[2]) != 3) err = std::string("Error: Problem reading keyword ") + k;
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------- Fortran edit descriptors
+// Ew.d: 0.dddddE+ee (three-digit exponents drop the E, as gfortran does)
+std::string fE(double x, int w, int d) {
+  char buf[64];
+  std::string out;
+  if (std::isnan(x)) out = "NaN";
+  else if (std::isinf(x)) out = x < 0 ? "-Infinity" : "Infinity";
+  else {
+    snprintf(buf, sizeof(buf), "%.*e", d - 1, fabs(x));  // D.DDDDe+XX with d significant digits
+    std::string m(buf);
+    const size_t e = m.find('e');
+    std::string digits = m.substr(0, 1) + m.substr(2, e - 2);
+    int ex = atoi(m.c_str() + e + 1) + 1;
+    if (x == 0.0) ex = 0;
+    char eb[16];
+    if (abs(ex) < 100) snprintf(eb, sizeof(eb), "E%c%02d", ex < 0 ? '-' : '+', abs(ex));
+    else snprintf(eb, sizeof(eb), "%c%03d", ex < 0 ? '-' : '+', abs(ex));
+    out = std::string(std::signbit(x) && x != 0.0 ? "-" : "") + "0." + digits + eb;
+  }
+  if ((int)out.size() < w) out = std::string(w - out.size(), ' ') + out;
+  return out;
+}
+// ESw.d: D.ddddE+ee
+std::string fES(double x, int w, int d, int ew = 2) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%.*E", d, x);
+  std::string m(buf);
+  const size_t e = m.find('E');
+  if (e != std::string::npos) {
+    const int ex = atoi(m.c_str() + e + 1);
+    char eb[16];
+    snprintf(eb, sizeof(eb), "E%c%0*d", ex < 0 ? '-' : '+', ew, abs(ex));
+    m = m.substr(0, e) + eb;
+  }
+  if ((int)m.size() < w) m = std::string(w - m.size(), ' ') + m;
+  return m;
+}
+std::string fF(double x, int w, int d) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%*.*f", w, d, x);
+  return buf;
+}
+// a list-directed real: 17 significant digits
+std::string fL(double x) { return fES(x, 26, 16, 3); }
+
+const char *kPeriodic[109] = {"H", "He", "Li", "Be", "B", "C", "N", "O", "F", "Ne", "Na", "Mg", "Al", "Si", "P", "S", "Cl", "Ar", "K", "Ca", "Sc", "Ti",
+                              "V", "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn", "Ga", "Ge", "As", "Se", "Br", "Kr", "Rb", "Sr", "Y", "Zr", "Nb", "Mo", "Tc",
+                              "Ru", "Rh", "Pd", "Ag", "Cd", "In", "Sn", "Sb", "Te", "I", "Xe", "Cs", "Ba", "La", "Ce", "Pr", "Nd", "Pm", "Sm", "Eu", "Gd",
+                              "Tb", "Dy", "Ho", "Er", "Tm", "Yb", "Lu", "Hf", "Ta", "W", "Re", "Os", "Ir", "Pt", "Au", "Hg", "Tl", "Pb", "Bi", "Po", "At",
+                              "Rn", "Fr", "Ra", "Ac", "Th", "Pa", "U", "Np", "Pu", "Am", "Cm", "Bk", "Cf", "Es", "Fm", "Md", "No", "Lr", "Rf", "Db", "Sg",
+                              "Bh", "Hs", "Mt"};
+}  // namespace
+
+extern "C" const char *od_run_last_error(void) { return g_run_err.c_str(); }
+
+extern "C" void od_odi_defaults(od_odi *p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->iprint = 1;
+  p->adaptive_smearing = 0.4; p->fixed_smearing = 0.3; p->linear_smearing = 0.0;  // parameters.f90:245-252
+  p->efermi_choice = OD_EFERMI_OPTADOS; p->efermi_user = -990.0;
+  p->compute_band_energy = 1; p->compute_band_gap = 1;
+  p->core_chemical_shift = -1.0;
+  p->finite_bin_correction = 1;
+  p->hybrid_linear_grad_tol = 0.01;
+  p->dos_min_energy = -1.0; p->dos_max_energy = -1.0;       // :296-301: "not set"
+  p->dos_spacing = -1.0; p->dos_nbins = -1;                 // :303-308
+  p->jdos_max_energy = -1.0; p->jdos_spacing = 0.01;        // :318-322
+  strcpy(p->optics_geom, "polycrys");
+  p->optics_drude_broadening = 1.0e14;
+  strcpy(p->core_geom, "polycrys");
+  strcpy(p->core_type, "absorption");
+  p->lai_lorentzian_scale = 0.1;
+}
+
+// param_read (parameters.f90:138-465)
+extern "C" int od_param_read(const char *path, od_odi *p) {
+  if (!path || !p) return OD_ERR_ARG;
+  od_odi_defaults(p);
+  Odi in;
+  if (!in.load(path)) return run_fail("%s", in.err.c_str());
+  std::string s;
+  in.get_int("iprint", p->iprint);
+  in.get_logical("legacy_file_format", p->legacy_file_format);
+  if (in.get("energy_unit", s) && s.find("ev") == std::string::npos && s.find("ry") == std::string::npos && s.find("ha") == std::string::npos)
+    return run_fail("Error: value of energy_unit not recognised in param_read");
+  if (in.get("task", s)) {  // :164-197 (a vector of task strings)
+    for (char &c : s) if (c == ',') c = ' ';
+    size_t pos = 0;
+    while (pos < s.size()) {
+      while (pos < s.size() && s[pos] == ' ') ++pos;
+      size_t e = s.find(' ', pos);
+      if (e == std::string::npos) e = s.size();
+      const std::string t = s.substr(pos, e - pos);
+      pos = e;
+      if (t.empty()) continue;
+      if (t.find("optics") != std::string::npos) p->optics = 1;
+      else if (t.find("core") != std::string::npos) p->core = 1;
+      else if (t.find("compare_jdos") != std::string::npos) p->jdos = p->compare_jdos = 1;
+      else if (t.find("jdos") != std::string::npos) p->jdos = 1;
+      else if (t.find("pdos") != std::string::npos) p->pdos = 1;
+      else if (t.find("pdispersion") != std::string::npos) p->pdis = 1;
+      else if (t.find("compare_dos") != std::string::npos) p->dos = p->compare_dos = 1;
+      else if (t.find("dos") != std::string::npos) p->dos = 1;
+      else if (t.find("none") != std::string::npos) p->dos = p->pdos = p->jdos = p->optics = p->core = 0;
+      else if (t.find("all") != std::string::npos) p->dos = p->pdos = p->jdos = p->optics = p->core = 1;
+      else return run_fail("Error: value of task unrecognised in param_read");
+    }
+  }
+  if ((p->compare_dos || p->compare_jdos) && (p->pdos || p->core || p->optics))
+    return run_fail("Error: compare_dos/compare_jdos are not comptable with pdos, core or optics tasks");
+  if (p->pdis && (p->optics || p->core || p->jdos || p->pdos || p->dos))
+    return run_fail("Error: projected bandstructure not compatible with any other tasks");
+  if (in.get("broadening", s)) {  // :205-219
+    if (s.find("fixed") != std::string::npos) p->fixed = 1;
+    else if (s.find("adaptive") != std::string::npos) p->adaptive = 1;
+    else if (s.find("linear") != std::string::npos) p->linear = 1;
+    else if (s.find("quad") != std::string::npos) return run_fail("quad broadening is not implemented in the reference either");
+    else return run_fail("Error: value of broadening unrecognised in param_read");
+  }
+  if (p->compare_dos || p->compare_jdos) p->fixed = p->adaptive = p->linear = 1;
+  if (!p->pdis && !(p->fixed || p->adaptive || p->linear)) p->adaptive = 1;
+  in.get("kpoint_mp_grid", s);
+  if (in.get("length_unit", s) && s != "ang" && s != "bohr") return run_fail("Error: value of length_unit not recognised in param_read");
+  in.get_real("adaptive_smearing", p->adaptive_smearing);
+  in.get_real("fixed_smearing", p->fixed_smearing);
+  in.get_real("linear_smearing", p->linear_smearing);
+  if (p->pdis) p->efermi_choice = OD_EFERMI_FILE;
+  if (in.get("efermi", s)) {  // param_get_efermi :969-1018
+    if (s == "optados") p->efermi_choice = OD_EFERMI_OPTADOS;
+    else if (s == "file") p->efermi_choice = OD_EFERMI_FILE;
+    else if (s == "insulator") p->efermi_choice = OD_EFERMI_INSULATOR;
+    else {
+      char *e = nullptr;
+      p->efermi_user = strtod(s.c_str(), &e);
+      if (e == s.c_str()) return run_fail("Error: Problem reading keyword efermi");
+      p->efermi_choice = OD_EFERMI_USER;
+    }
+  }
+  in.get_logical("compute_band_energy", p->compute_band_energy);
+  in.get_real("core_chemical_shift", p->core_chemical_shift);
+  in.get_logical("finite_bin_correction", p->finite_bin_correction);
+  in.get_logical("numerical_intdos", p->numerical_intdos);
+  in.get_logical("hybrid_linear", p->hybrid_linear);
+  in.get_real("hybrid_linear_grad_tol", p->hybrid_linear_grad_tol);
+  if (p->pdis) p->set_efermi_zero = 1;
+  in.get_logical("set_efermi_zero", p->set_efermi_zero);
+  in.get_logical("dos_per_volume", p->dos_per_volume);
+  p->have_dos_min_energy = in.get_real("dos_min_energy", p->dos_min_energy) ? 1 : 0;
+  p->have_dos_max_energy = in.get_real("dos_max_energy", p->dos_max_energy) ? 1 : 0;
+  in.get_real("dos_spacing", p->dos_spacing);
+  in.get_int("dos_nbins", p->dos_nbins);
+  if (p->pdos) {
+    in.get("pdos", s);
+    snprintf(p->projectors_string, sizeof(p->projectors_string), "%s", s.c_str());
+    if (s.empty()) return run_fail("pdos requested but pdos is not specified");
+  }
+  in.get_real("jdos_max_energy", p->jdos_max_energy);
+  in.get_real("jdos_spacing", p->jdos_spacing);
+  if (in.get("exclude_bands", s)) {  // param_get_range_vector :1380-1470: "1,3-5 7"
+    p->num_exclude_bands = 0;
+    std::string d = s;
+    size_t i = 0;
+    auto skip = [&]() { while (i < d.size() && (d[i] == ' ' || d[i] == ',')) ++i; };
+    skip();
+    while (i < d.size()) {
+      char *e = nullptr;
+      const long a = strtol(d.c_str() + i, &e, 10);
+      if (e == d.c_str() + i) return run_fail("Error parsing keyword exclude_bands");
+      i = e - d.c_str();
+      while (i < d.size() && d[i] == ' ') ++i;
+      long b = a;
+      if (i < d.size() && d[i] == '-') {
+        ++i;
+        b = strtol(d.c_str() + i, &e, 10);
+        if (e == d.c_str() + i) return run_fail("Error parsing keyword exclude_bands incorrect range");
+        i = e - d.c_str();
+      }
+      for (long v = std::min(a, b); v <= std::max(a, b); ++v) {
+        if (p->num_exclude_bands >= (int)(sizeof(p->exclude_bands) / sizeof(int))) return run_fail("too many exclude_bands");
+        if (v < 1) return run_fail("Error: exclude_bands must contain positive numbers");
+        p->exclude_bands[p->num_exclude_bands++] = (int)v;
+      }
+      skip();
+    }
+    if (p->num_exclude_bands < 1) return run_fail("Error: problem reading exclude_bands");
+  }
+  if (p->core_chemical_shift > 0.0) p->compute_band_gap = 1;
+  in.get_logical("compute_band_gap", p->compute_band_gap);
+  in.get("devel_flag", s);
+  if (in.get("output_format", s) && s.find("xmgrace") == std::string::npos && s.find("gnuplot") == std::string::npos)
+    return run_fail("Error: value of output_format not recognised in param_read");
+  if (in.get("optics_geom", s)) {
+    if (s.find("polar") == std::string::npos && s.find("polycrys") == std::string::npos && s.find("tensor") == std::string::npos)
+      return run_fail("Error: value of optics_geom not recognised in param_read");
+    snprintf(p->optics_geom, sizeof(p->optics_geom), "%s", s.c_str());
+  }
+  in.get_real("scissor_op", p->scissor_op);
+  {
+    const bool found = in.get_vec3("optics_qdir", p->optics_qdir);
+    const std::string g(p->optics_geom);
+    if (g.find("polar") != std::string::npos && !found && p->optics)
+      return run_fail("Error: polarised or unpolarised optics geometry requested but optics_qdir is not set");
+    if ((g.find("polycrys") != std::string::npos || g.find("tensor") != std::string::npos) && found)
+      return run_fail("Error: polycrystalline optics geometry or full dielectric tensor requested but optics_qdir is set");
+  }
+  in.get_logical("optics_intraband", p->optics_intraband);
+  in.get_real("optics_drude_broadening", p->optics_drude_broadening);
+  p->optics_lossfn_broadening = in.get_real("optics_lossfn_broadening", p->optics_lossfn_gaussian) ? 1 : 0;
+  if (p->optics_lossfn_gaussian < 0.0) return run_fail("Error: optics_lossfn_broadening must be positive");
+  if (fabs(p->optics_lossfn_gaussian) < 1.0e-6) p->optics_lossfn_broadening = 0;
+  if (in.get("core_geom", s)) {
+    if (s.find("polycrys") == std::string::npos && s.find("polar") == std::string::npos)
+      return run_fail("Error: value of core_geom not recognised in param_read");
+    snprintf(p->core_geom, sizeof(p->core_geom), "%s", s.c_str());
+  }
+  if (in.get("core_type", s)) {
+    if (s != "absorption" && s != "emission" && s != "all") return run_fail("Error: value of core_type not recognised in param_read");
+    snprintf(p->core_type, sizeof(p->core_type), "%s", s.c_str());
+  }
+  {
+    const bool found = in.get_vec3("core_qdir", p->core_qdir);
+    const std::string g(p->core_geom);
+    if (g.find("polar") != std::string::npos && !found && p->core) return run_fail("Error: polarised core geometry requested but core_qdir is not set");
+    if (g.find("polycrys") != std::string::npos && found) return run_fail("Error: polycrystalline core geometry requested but core_qdir is set");
+  }
+  in.get_logical("core_lai_broadening", p->core_lai_broadening);
+  in.get_real("lai_gaussian_width", p->lai_gaussian_width);
+  in.get_real("lai_lorentzian_width", p->lai_lorentzian_width);
+  in.get_real("lai_lorentzian_scale", p->lai_lorentzian_scale);
+  in.get_real("lai_lorentzian_offset", p->lai_lorentzian_offset);
+  if (p->lai_gaussian_width < 0.0 || p->lai_lorentzian_width < 0.0 || p->lai_lorentzian_scale < 0.0 || p->lai_lorentzian_offset < 0.0)
+    return run_fail("Error: LAI widths must be positive");
+  if (!in.err.empty()) return run_fail("%s", in.err.c_str());
+  for (const std::string &l : in.lines)  // :403-412
+    if (!rtrim(l).empty()) return run_fail("Unrecognised keyword(s) in input file: %s", l.c_str());
+  // parameters.f90:451-461: neither dos_spacing nor dos_nbins -> the SINGLE precision literal 0.005
+  if (p->dos_spacing < 0.0 && p->dos_nbins < 0) p->dos_spacing = (double)0.005f;
+  return OD_OK;
+}
+
+// ================================================================ the run
+namespace {
+struct Run {
+  od_ctx *ctx;
+  std::string dir, seed, base;
+  od_odi P;
+  od_bands_info bi;
+  int nk = 0, ns = 0, nb = 0;
+  std::vector<double> band_energy, kpoint_r, kweight, grads, ome;
+  double real_lattice[9], recip[9], cell_volume = 0.0;
+  int kgrid[3];
+  std::vector<double> symops;
+  int num_symm = 0;
+  bool have_grads = false, have_ome = false, efermi_set = false, dos_done = false;
+  double efermi = 0.0;
+  od_dos_params dosp;
+  od_dos_result dosr;
+  FILE *odo = nullptr;
+  // species of the cell file (PDOS)
+  std::vector<std::string> species_label;
+  std::vector<int> species_count;
+
+  std::string path(const char *ext) const { return base + ext; }
+  int ck(int rc) {
+    if (rc != OD_OK && g_run_err.empty()) g_run_err = od_last_error(ctx);
+    return rc;
+  }
+  void olog(const char *fmt, ...) {
+    if (!odo) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(odo, fmt, ap);
+    va_end(ap);
+    fputc('\n', odo);
+  }
+};
+
+#define RCHECK(expr)                  \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != OD_OK) return rc__;   \
+  } while (0)
+
+od_broadening broadening_of(const od_odi &P) {
+  od_broadening b;
+  od_broadening_defaults(&b);
+  b.adaptive_smearing = P.adaptive_smearing; b.fixed_smearing = P.fixed_smearing; b.linear_smearing = P.linear_smearing;
+  b.finite_bin_correction = P.finite_bin_correction; b.numerical_intdos = P.numerical_intdos;
+  b.hybrid_linear = P.hybrid_linear; b.hybrid_linear_grad_tol = P.hybrid_linear_grad_tol;
+  return b;
+}
+
+// elec_read_band_gradient (electronic.f90:170-299): the velocity file if there is one, else the diagonal of the optical
+// matrix elements.  Formats: *_bin, the formatted twin *_fmt (what the reference's test-suite ships), or the legacy names.
+int load_ome(Run &R) {
+  if (R.have_ome) return OD_OK;
+  const size_t n = (size_t)R.nb * R.nb * 3 * R.nk * R.ns * 2;
+  R.ome.resize(n);
+  int rc = OD_ERR_IO;
+  if (R.P.legacy_file_format && file_exists(R.path(".cst_ome"))) rc = od_read_ome(R.path(".cst_ome").c_str(), 'l', R.nb, R.nk, R.ns, R.ome.data());
+  else if (file_exists(R.path(".ome_bin"))) rc = od_read_ome(R.path(".ome_bin").c_str(), 'b', R.nb, R.nk, R.ns, R.ome.data());
+  else if (file_exists(R.path(".ome_fmt"))) rc = od_read_ome(R.path(".ome_fmt").c_str(), 't', R.nb, R.nk, R.ns, R.ome.data());
+  else return run_fail("Error: Problem opening ome_bin file in read_band_optical_mat (%s.ome_bin / .ome_fmt)", R.base.c_str());
+  if (rc != OD_OK) return run_fail("%s", od_io_last_error());
+  R.have_ome = true;
+  return OD_OK;
+}
+
+int load_gradients(Run &R) {
+  if (R.have_grads) return OD_OK;
+  const size_t n = (size_t)R.nb * 3 * R.nk * R.ns;
+  int rc = OD_OK;
+  if (R.P.legacy_file_format && file_exists(R.path(".cst_vel"))) {
+    R.grads.resize(n);
+    rc = od_read_dome(R.path(".cst_vel").c_str(), 'l', R.nb, R.nk, R.ns, R.grads.data());
+  } else if (file_exists(R.path(".dome_bin"))) {
+    R.grads.resize(n);
+    rc = od_read_dome(R.path(".dome_bin").c_str(), 'b', R.nb, R.nk, R.ns, R.grads.data());
+  } else if (file_exists(R.path(".dome_fmt"))) {
+    R.grads.resize(n);
+    rc = od_read_dome(R.path(".dome_fmt").c_str(), 't', R.nb, R.nk, R.ns, R.grads.data());
+  } else {
+    RCHECK(load_ome(R));
+    RCHECK(R.ck(od_set_gradients_from_ome(R.ctx, R.ome.data(), OD_MEM_HOST)));  // electronic.f90:276-291 on the device
+    R.have_grads = true;
+    return OD_OK;
+  }
+  if (rc != OD_OK) return run_fail("%s", od_io_last_error());
+  RCHECK(R.ck(od_set_gradients(R.ctx, R.grads.data(), OD_MEM_HOST)));
+  RCHECK(R.ck(od_synchronize(R.ctx)));
+  R.have_grads = true;
+  return OD_OK;
+}
+
+bool need_grads(const od_odi &P) { return P.adaptive || P.linear; }
+
+void fill_dos_params(Run &R) {
+  od_dos_params &d = R.dosp;
+  od_dos_params_defaults(&d);
+  d.fixed = R.P.fixed; d.adaptive = R.P.adaptive; d.linear = R.P.linear;
+  d.br = broadening_of(R.P);
+  d.dos_spacing = R.P.dos_spacing;
+  d.dos_nbins = R.P.dos_nbins;
+  d.have_dos_min_energy = R.P.have_dos_min_energy; d.have_dos_max_energy = R.P.have_dos_max_energy;
+  d.dos_min_energy = R.P.dos_min_energy; d.dos_max_energy = R.P.dos_max_energy;
+  d.efermi_choice = R.P.efermi_choice; d.efermi_user = R.P.efermi_user; d.efermi_castep = R.bi.efermi_castep;
+  d.nspins_electrons = R.ns;
+  d.num_electrons[0] = R.bi.num_electrons[0]; d.num_electrons[1] = R.bi.num_electrons[1];
+  d.dos_per_volume = R.P.dos_per_volume; d.cell_volume = R.cell_volume;
+}
+
+// the Fermi analysis block of dos_utils_calculate (dos_utils.f90:231-263) as the reference prints it
+void log_fermi(Run &R, const od_dos_result &r_in) {
+  od_dos_result r = r_in;
+  const int n = r.nbins, ns = R.ns;
+  std::vector<double> dos((size_t)n * ns), idos((size_t)n * ns);
+  R.olog(" +------------------------ Fermi Energy Analysis ------------------------------+");
+  const char types[3] = {'f', 'a', 'l'};
+  const char *names[3] = {"Fixed", "Adaptive", "Linear"};
+  const char *tags[3] = {"EfF", "EfA", "EfL"};
+  const int have[3] = {R.P.fixed, R.P.adaptive, R.P.linear};
+  for (int t = 0; t < 3; ++t) {
+    if (!have[t] || R.P.efermi_choice != OD_EFERMI_OPTADOS) continue;
+    if (od_dos_get(R.ctx, types[t], dos.data(), idos.data()) != OD_OK) continue;
+    const double ef_t = od_calc_efermi_from_intdos(idos.data(), r.emin, r.delta_bins, n, ns, R.bi.num_electrons);
+    // calc_efermi_from_intdos's occupation line (dos_utils.f90:841-846)
+    double nel = 0.0;
+    for (int is = 0; is < ns; ++is) nel += R.bi.num_electrons[is];
+    auto S = [&](int i1) { double s = 0.0; for (int is = 0; is < ns; ++is) s += idos[(size_t)(i1 - 1) + (size_t)n * is]; return s; };
+    int idx;
+    for (idx = 1; idx <= n; ++idx) if (S(idx) > nel + 0.0001 / 2.0) break;
+    if (idx > n) idx = n;
+    const double sref = idx >= 2 ? S(idx - 1) : 0.0;
+    int i;
+    for (i = idx; i >= 1; --i) if (S(i) < sref - 0.0001 / 2.0) break;
+    if (i < 1) i = 1;
+    for (int is = 0; is < ns; ++is)
+      R.olog(" |%20s%1d%20s%10.5f%4s %10.5f   <- Occ |", "Spin Component : ", is + 1, " occupation between ", idos[(size_t)(i - 1) + (size_t)n * is], "and",
+             idos[(size_t)(idx - 1) + (size_t)n * is]);
+    char nm[64];
+    snprintf(nm, sizeof(nm), " Fermi energy (%s broadening) : ", names[t]);
+    R.olog(" |%46s%8.4f eV%12s<- %s |", nm, ef_t, "", tags[t]);
+  }
+  R.olog(" +----------------------------------------------------------------------------+");
+}
+
+// dos_utils_calculate without weights: "Already calculated dos, so returning" (dos_utils.f90:141-147)
+int ensure_dos(Run &R) {
+  if (R.dos_done) return OD_OK;
+  if (need_grads(R.P)) RCHECK(load_gradients(R));
+  RCHECK(R.ck(od_dos_utils_calculate(R.ctx, &R.dosp, nullptr, 0, 0, 0, OD_MEM_HOST, &R.dosr)));
+  R.dos_done = true;
+  log_fermi(R, R.dosr);
+  return OD_OK;
+}
+
+// dos_utils_set_efermi (dos_utils.f90:296-388)
+int set_efermi(Run &R) {
+  if (R.efermi_set) return OD_OK;
+  R.olog(" +--------------------------- Setting Fermi Energy  --------------------------+");
+  switch (R.P.efermi_choice) {
+    case OD_EFERMI_FILE:
+      R.efermi = R.bi.efermi_castep;
+      R.olog(" |%46s%8.4f eV%12s  <- EfC", " Set fermi energy from file : ", R.efermi, "");
+      break;
+    case OD_EFERMI_USER:
+      R.efermi = R.P.efermi_user;
+      R.olog(" |%46s%8.4f eV%12s  <- EfU", " Fermi energy from user : ", R.efermi, "");
+      break;
+    case OD_EFERMI_INSULATOR:
+      RCHECK(R.ck(od_dos_utils_set_efermi(R.ctx, &R.dosp, &R.efermi)));
+      R.olog(" |%46s%8.4f eV%12s  <- EfI", " Fermi energy assuming insulator : ", R.efermi, "");
+      break;
+    default:
+      RCHECK(ensure_dos(R));
+      if (R.P.fixed) R.efermi = R.dosr.efermi_fixed;
+      if (R.P.linear) R.efermi = R.dosr.efermi_linear;
+      if (R.P.adaptive) R.efermi = R.dosr.efermi_adaptive;
+      R.olog(" |%46s%8.4f eV%12s<- EfD |", " Fermi energy from DOS : ", R.efermi, "");
+  }
+  R.olog(" +----------------------------------------------------------------------------+");
+  R.efermi_set = true;
+  return OD_OK;
+}
+
+void dat_header(FILE *f, const char *what, const char *btype, int ns, bool intdos, bool per_volume) {
+  const char *du = per_volume ? "(electrons per eV/A^3)" : "(electrons per eV)", *iu = per_volume ? "(electrons per A^3)" : "(electrons)";
+  fprintf(f, " ##############################################################################\n #\n");
+  fprintf(f, " #                  O p t a D O S   o u t p u t   f i l e \n #\n");
+  fprintf(f, " #    %s using %s broadening\n", what, btype);
+  fprintf(f, " #  Generated by optados_b200\n # Column        Data\n #    1        Energy (eV)\n");
+  if (ns > 1) {
+    fprintf(f, " #    2        Up-spin DOS %s\n #    3        Down-spin DOS %s\n", du, du);
+    if (intdos) fprintf(f, " #    4        Up-spin Integrated DOS %s\n #    5        Down-spin Integrated DOS %s\n", iu, iu);
+  } else {
+    fprintf(f, " #    2        DOS %s\n", du);
+    if (intdos) fprintf(f, " #    3        Integrated DOS %s\n", iu);
+  }
+  fprintf(f, " #\n ##############################################################################\n");
+}
+
+// ---------------------------------------------------------------- task: dos (dos.f90:48-148)
+int task_dos(Run &R) {
+  R.olog("");
+  R.olog(" +============================================================================+");
+  R.olog(" +                              Density of States                             +");
+  R.olog(" +============================================================================+");
+  RCHECK(ensure_dos(R));
+  RCHECK(set_efermi(R));
+  const int n = R.dosr.nbins, ns = R.ns;
+  // dos_utils_compute_dos_at_efermi (dos_utils.f90:391-455)
+  {
+    std::vector<double> d(3 * (size_t)ns);
+    RCHECK(R.ck(od_dos_utils_calculate_at_e(R.ctx, &R.dosp, R.efermi, R.dosr.delta_bins, nullptr, 0, 0, 0, OD_MEM_HOST, d.data(), nullptr)));
+    R.olog(" +----------------------- DOS at Fermi Energy Analysis -----------------------+");
+    R.olog(" |%46s%8.4f eV%12s       |", " Fermi energy used : ", R.efermi, "");
+    const char *nm[3] = {"Fixed", "Adaptive", "Linear"}, *tag[3] = {"DEF", "DEA", "DEL"};
+    const int en[3] = {R.P.fixed, R.P.adaptive, R.P.linear};
+    for (int t = 0; t < 3; ++t) {
+      if (!en[t]) continue;
+      R.olog(" | From %s broadening", nm[t]);
+      for (int is = 0; is < ns; ++is)
+        R.olog(" |%20s%1d%25s%8.4f eln/cell      <- %s |", "Spin Component : ", is + 1, "  DOS at Fermi Energy : ", d[t + 3 * (size_t)is], tag[t]);
+      R.olog(" +----------------------------------------------------------------------------+");
+    }
+  }
+  if (R.P.compute_band_gap) {  // dos_utils_compute_bandgap (dos_utils.f90:457-750)
+    od_bandgap_result g;
+    RCHECK(R.ck(od_dos_utils_compute_bandgap(R.ctx, R.efermi, R.bi.num_electrons, R.nk, 0, &g)));
+    R.olog(" +----------------------------- Bandgap Analysis -----------------------------+");
+    R.olog(" |%50s%19s       |", "Number of kpoints at       VBM       CBM", "");
+    for (int is = 0; is < ns; ++is) R.olog(" |%25s %3d  :  %5d     %5d%20s       |", " Spin :", is + 1, g.vbm_multiplicity[is], g.cbm_multiplicity[is], "");
+    R.olog(" |%32s%15.10f  eV%18s<- TBg |", "Thermal Bandgap :", g.thermal_bandgap, "");
+    if (!g.thermal_multiplicity) {
+      auto kp = [&](long long k) { return &R.kpoint_r[3 * (size_t)(k - 1)]; };
+      if (g.thermal_vbm_k == g.thermal_cbm_k) {
+        R.olog(" |%32s %10.5f %10.5f %10.5f           |", "At kpoint :", kp(g.thermal_vbm_k)[0], kp(g.thermal_vbm_k)[1], kp(g.thermal_vbm_k)[2]);
+        R.olog(" |             ==> Direct Gap                                                  |");
+      } else {
+        R.olog(" |%32s %10.5f %10.5f %10.5f           |", "Between VBM kpoint :", kp(g.thermal_vbm_k)[0], kp(g.thermal_vbm_k)[1], kp(g.thermal_vbm_k)[2]);
+        R.olog(" |%32s %10.5f %10.5f %10.5f           |", "and CBM kpoint:", kp(g.thermal_cbm_k)[0], kp(g.thermal_cbm_k)[1], kp(g.thermal_cbm_k)[2]);
+        R.olog(" |             ==> Indirect Gap                                               |");
+      }
+    } else {
+      R.olog(" |          ==> Multiple Band Minima and Maxima -- Gap unknown                |");
+    }
+    R.olog(" +----------------------------------------------------------------------------+");
+    R.olog(" |%45s%32s", "Optical Bandgap  ", "|");
+    for (int is = 0; is < ns; ++is) R.olog(" |%25s %3d  : %15.10f  eV%16s<- OBg |", " Spin :", is + 1, g.optical_bandgap[is], "");
+    R.olog(" |%50s%19s       |", "Number of kpoints with this gap         ", "");
+    for (int is = 0; is < ns; ++is) R.olog(" |%25s %3d  :       %5d%25s       |", " Spin :", is + 1, g.optical_multiplicity[is], "");
+    R.olog(" +----------------------------------------------------------------------------+");
+    R.olog(" |%45s%32s", "Average Bandgap  ", "|");
+    for (int is = 0; is < ns; ++is) R.olog(" |%25s %3d  : %15.10f  eV%16s<- ABg |", " Spin :", is + 1, g.average_bandgap[is], "");
+    if (ns > 1) R.olog(" |%33s %15.10f  eV%16s<- wAB |", " Weighted Average : ", g.weighted_average, "");
+    R.olog(" +----------------------------------------------------------------------------+");
+  }
+  if (R.P.compute_band_energy) {  // dos_utils_compute_band_energies (dos_utils.f90:853-924)
+    double be[3], bec;
+    RCHECK(R.ck(od_dos_utils_compute_band_energies(R.ctx, R.efermi, be, &bec)));
+    R.olog(" +--------------------------- Band Energy Analysis ---------------------------+");
+    if (R.P.fixed) R.olog(" |%46s%12.4f eV%8s<- BEF |", " Band energy (Fixed broadening)  : ", be[0], "");
+    if (R.P.adaptive) R.olog(" |%46s%12.4f eV%8s<- BEA |", " Band energy (Adaptive broadening) : ", be[1], "");
+    if (R.P.linear) R.olog(" |%46s%12.4f eV%8s<- BEL |", " Band energy (Linear broadening) : ", be[2], "");
+    R.olog(" |%46s%12.4f eV%8s<- BEC |", " Band energy (From CASTEP) : ", bec, "");
+    R.olog(" +----------------------------------------------------------------------------+");
+  }
+  // write_dos (dos.f90:150-251)
+  const char types[3] = {'f', 'a', 'l'};
+  const char *names[3] = {"fixed", "adaptive", "linear"};
+  const int en[3] = {R.P.fixed, R.P.adaptive, R.P.linear};
+  std::vector<double> dos((size_t)n * ns), idos((size_t)n * ns);
+  for (int t = 0; t < 3; ++t) {
+    if (!en[t]) continue;
+    RCHECK(R.ck(od_dos_get(R.ctx, types[t], dos.data(), idos.data())));
+    FILE *f = fopen((R.base + "." + names[t] + ".dat").c_str(), "w");
+    if (!f) return run_fail(" ERROR: Cannot open output file in dos: write_dos");
+    dat_header(f, "Density of States", names[t], ns, true, R.P.dos_per_volume);
+    for (int i = 0; i < n; ++i) {
+      const double E = R.dosr.emin + (double)i * R.dosr.delta_bins - (R.P.set_efermi_zero ? R.efermi : 0.0);
+      if (ns > 1)
+        fprintf(f, "%s  %s  %s  %s  %s  \n", fE(E, 21, 13).c_str(), fE(dos[i], 21, 13).c_str(), fE(-dos[i + (size_t)n], 21, 13).c_str(),
+                fE(idos[i], 21, 13).c_str(), fE(-idos[i + (size_t)n], 21, 13).c_str());
+      else
+        fprintf(f, "%s  %s  %s  \n", fE(E, 21, 13).c_str(), fE(dos[i], 21, 13).c_str(), fE(idos[i], 21, 13).c_str());
+    }
+    fclose(f);
+  }
+  return OD_OK;
+}
+
+// ---------------------------------------------------------------- task: jdos (jdos.f90:36-145)
+int task_jdos(Run &R) {
+  R.olog("");
+  R.olog(" +============================================================================+");
+  R.olog(" +                           Joint Density of States                          +");
+  R.olog(" +============================================================================+");
+  RCHECK(set_efermi(R));  // jdos_utils_calculate: if (.not. efermi_set) call dos_utils_set_efermi (jdos_utils.f90:88)
+  if (need_grads(R.P)) RCHECK(load_gradients(R));
+  od_jdos_params jp;
+  od_jdos_params_defaults(&jp);
+  jp.fixed = R.P.fixed; jp.adaptive = R.P.adaptive; jp.linear = R.P.linear;
+  jp.br = broadening_of(R.P);
+  jp.jdos_spacing = R.P.jdos_spacing; jp.jdos_max_energy = R.P.jdos_max_energy; jp.scissor_op = R.P.scissor_op;
+  jp.num_exclude_bands = R.P.num_exclude_bands; jp.exclude_bands = R.P.exclude_bands;
+  jp.efermi = R.efermi; jp.dos_per_volume = R.P.dos_per_volume; jp.cell_volume = R.cell_volume;
+  od_jdos_result jr;
+  RCHECK(R.ck(od_jdos_utils_calculate(R.ctx, &jp, nullptr, 0, OD_MEM_HOST, nullptr, OD_MEM_HOST, 0, nullptr, nullptr, 0, &jr)));
+  const int n = jr.nbins, ns = R.ns;
+  const char types[3] = {'f', 'a', 'l'};
+  const char *names[3] = {"fixed", "adaptive", "linear"};
+  const int en[3] = {R.P.fixed, R.P.adaptive, R.P.linear};
+  std::vector<double> jd((size_t)n * ns);
+  for (int t = 0; t < 3; ++t) {
+    if (!en[t]) continue;
+    RCHECK(R.ck(od_jdos_get(R.ctx, types[t], jd.data())));
+    FILE *f = fopen((R.base + ".j" + names[t] + ".dat").c_str(), "w");
+    if (!f) return run_fail(" ERROR: Cannot open output file in dos: write_dos");
+    dat_header(f, "Density of States", names[t], ns, true, R.P.dos_per_volume);
+    for (int i = 0; i < n; ++i) {
+      const double E = (double)i * jr.delta_bins;
+      if (ns > 1) fprintf(f, "%s  %s  %s  \n", fE(E, 21, 13).c_str(), fE(jd[i], 21, 13).c_str(), fE(-jd[i + (size_t)n], 21, 13).c_str());
+      else fprintf(f, "%s  %s  \n", fE(E, 21, 13).c_str(), fE(jd[i], 21, 13).c_str());
+    }
+    fclose(f);
+  }
+  return OD_OK;
+}
+
+// ---------------------------------------------------------------- task: pdos (pdos.F90:48-252, projection_utils.f90)
+// %block positions_frac / positions_abs of <seed>-out.cell (or <seed>.cell): species in order of first appearance
+int read_species(Run &R) {
+  std::string p = R.path("-out.cell");
+  if (!file_exists(p)) p = R.path(".cell");
+  FILE *f = fopen(p.c_str(), "r");
+  if (!f) return run_fail("Error: Problem opening input file %s-out.cell", R.base.c_str());
+  char buf[4096];
+  bool in = false;
+  std::vector<std::string> labels;
+  while (fgets(buf, sizeof(buf), f)) {
+    std::string d = ltrim(rtrim(buf));
+    const std::string dl = lower(d);
+    if (dl.compare(0, 6, "%block") == 0 && dl.find("positions") != std::string::npos) { in = true; continue; }
+    if (dl.compare(0, 9, "%endblock") == 0 && in) break;
+    if (!in || d.empty() || d[0] == '#' || d[0] == '!') continue;
+    if (dl.find("ang") == 0 || dl.find("bohr") == 0) continue;  // optional unit line
+    char lab[64];
+    double x, y, z;
+    if (sscanf(d.c_str(), "%63s %lf %lf %lf", lab, &x, &y, &z) == 4) labels.push_back(lab);
+  }
+  fclose(f);
+  if (labels.empty()) return run_fail("Error: no atoms found in the cell file (%s)", p.c_str());
+  for (const std::string &l : labels) {
+    size_t k = 0;
+    while (k < R.species_label.size() && R.species_label[k] != l) ++k;
+    if (k == R.species_label.size()) { R.species_label.push_back(l); R.species_count.push_back(0); }
+    R.species_count[k]++;
+  }
+  return OD_OK;
+}
+
+int task_pdos(Run &R) {
+  R.olog("");
+  R.olog(" +============================================================================+");
+  R.olog(" +                 Projected Density Of States Calculation                    +");
+  R.olog(" +============================================================================+");
+  // elec_pdos_read (electronic.f90:1122-1276)
+  od_pdos_info pi;
+  std::string pf;
+  char fmt = 'b';
+  if (R.P.legacy_file_format && file_exists(R.path(".pdos_weights"))) { pf = R.path(".pdos_weights"); fmt = 'l'; }
+  else if (file_exists(R.path(".pdos_bin"))) { pf = R.path(".pdos_bin"); fmt = 'b'; }
+  else if (file_exists(R.path(".pdos_fmt"))) { pf = R.path(".pdos_fmt"); fmt = 't'; }
+  else return run_fail("Error: Problem opening pdos_bin file in elec_pdos_read (%s.pdos_bin / .pdos_fmt)", R.base.c_str());
+  if (od_read_pdos_info(pf.c_str(), fmt, &pi) != OD_OK) return run_fail("%s", od_io_last_error());
+  const int norb = pi.norbitals;
+  std::vector<int> sp(norb), rk(norb), am(norb), nocc((size_t)pi.nkpoints * pi.nspins);
+  std::vector<double> pw((size_t)norb * pi.nbands * pi.nkpoints * pi.nspins);
+  if (od_read_pdos(pf.c_str(), fmt, &pi, sp.data(), rk.data(), am.data(), nocc.data(), pw.data()) != OD_OK) return run_fail("%s", od_io_last_error());
+  if (pi.nkpoints != R.nk || pi.nspins != R.ns) return run_fail("pdos file and bands file disagree on k-points / spins");
+  // projection_analyse_orbitals (projection_utils.f90:466-503)
+  RCHECK(read_species(R));
+  const int nspecies_file = *std::max_element(sp.begin(), sp.end());
+  if (nspecies_file > (int)R.species_label.size()) return run_fail("Error: projection_analyse_substring - more species in pdos file than in cell file");
+  constexpr int max_am = 4;
+  std::vector<int> proj_sites(nspecies_file, 0), proj_am((size_t)nspecies_file * max_am, 0);
+  for (int o = 0; o < norb; ++o) {
+    proj_sites[sp[o] - 1] = std::max(proj_sites[sp[o] - 1], rk[o]);
+    if (rk[o] == 1 && am[o] >= 0 && am[o] < max_am) proj_am[(size_t)(sp[o] - 1) * max_am + am[o]] = 1;
+  }
+  std::vector<std::string> proj_symbol;  // species symbols in periodic-table order (:489-499)
+  for (int z = 0; z < 109; ++z)
+    for (const std::string &l : R.species_label) {
+      std::string sym = l.substr(0, 2);
+      if (sym.size() > 1 && !(sym[1] >= 'a' && sym[1] <= 'z')) sym = sym.substr(0, 1);
+      sym[0] = (char)toupper((unsigned char)sym[0]);
+      if (sym == kPeriodic[z]) proj_symbol.push_back(sym);
+    }
+  const int max_sites = *std::max_element(proj_sites.begin(), proj_sites.end());
+  // projection_get_string (:100-262): projection_array(species, site, am, proj) as a list of 3-index masks
+  const int nsp = nspecies_file;
+  std::vector<std::vector<int>> projs;  // each: nsp * max_sites * max_am flags
+  auto blank = [&]() { return std::vector<int>((size_t)nsp * max_sites * max_am, 0); };
+  auto at = [&](std::vector<int> &m, int s, int a, int l) -> int & { return m[(size_t)s + (size_t)nsp * (a + (size_t)max_sites * l)]; };
+  const std::string str = lower(R.P.projectors_string);
+  bool shortcut = true;
+  if (str.find("species_ang") != std::string::npos) {
+    for (int s = 0; s < nsp; ++s)
+      for (int l = 0; l < max_am; ++l) {
+        if (!proj_am[(size_t)s * max_am + l]) continue;
+        auto m = blank();
+        for (int a = 0; a < max_sites; ++a) at(m, s, a, l) = 1;
+        projs.push_back(m);
+      }
+  } else if (str.find("species") != std::string::npos) {
+    for (int s = 0; s < nsp; ++s) {
+      auto m = blank();
+      for (int a = 0; a < max_sites; ++a) for (int l = 0; l < max_am; ++l) at(m, s, a, l) = 1;
+      projs.push_back(m);
+    }
+  } else if (str.find("sites") != std::string::npos) {
+    for (int s = 0; s < nsp; ++s)
+      for (int a = 0; a < proj_sites[s]; ++a) {
+        auto m = blank();
+        for (int l = 0; l < max_am; ++l) at(m, s, a, l) = 1;
+        projs.push_back(m);
+      }
+  } else if (str.find("angular") != std::string::npos) {
+    for (int l = 0; l < max_am; ++l) {
+      auto m = blank();
+      for (int s = 0; s < nsp; ++s) for (int a = 0; a < max_sites; ++a) at(m, s, a, l) = 1;
+      projs.push_back(m);
+    }
+  } else {
+    shortcut = false;
+    std::string c = str;
+    bool sum = false;
+    if (c.compare(0, 4, "sum:") == 0) { sum = true; c = c.substr(4); }
+    size_t pos = 0;
+    while (pos <= c.size()) {  // species sections separated by ':' (projection_analyse_substring :264-459)
+      size_t e = c.find(':', pos);
+      if (e == std::string::npos) e = c.size();
+      std::string sec = c.substr(pos, e - pos);
+      pos = e + 1;
+      if (sec.empty()) { if (e >= c.size()) break; continue; }
+      std::string c_am;
+      const size_t pl = sec.find('(');
+      bool am_sum = true;
+      if (pl != std::string::npos) {
+        const size_t pr = sec.find(')');
+        if (pr == std::string::npos) return run_fail("projection_analyse_substring: found ( but no )");
+        if (pr <= pl) return run_fail("projection_analyse_substring: found ) before (");
+        c_am = sec.substr(pl + 1, pr - pl - 1);
+        sec = sec.substr(0, pl);
+        am_sum = false;
+      }
+      if (sec.empty() || !(sec[0] >= 'a' && sec[0] <= 'z')) return run_fail("projection_analyse_substring: problem reading atomic symbol in pdos string");
+      std::string sym(1, (char)toupper((unsigned char)sec[0]));
+      size_t i = 1;
+      if (sec.size() > 1 && sec[1] >= 'a' && sec[1] <= 'z') { sym += sec[1]; i = 2; }
+      int species = -1;
+      for (int s = 0; s < (int)proj_symbol.size(); ++s) if (proj_symbol[s] == sym) species = s;
+      if (species < 0) return run_fail("projection_analyse_substring: Failed to match atomic symbol in pdos string");
+      std::vector<int> atoms(max_sites, 0), ang(max_am, 0);
+      std::string rest = ltrim(sec.substr(i));
+      bool site_sum = rest.empty();
+      size_t q = 0;
+      while (q < rest.size()) {  // atom numbers: 1,3-5
+        char *endp = nullptr;
+        const long a = strtol(rest.c_str() + q, &endp, 10);
+        if (endp == rest.c_str() + q) return run_fail("projection_analyse_substring Error parsing keyword ");
+        q = endp - rest.c_str();
+        while (q < rest.size() && rest[q] == ' ') ++q;
+        long b = a;
+        if (q < rest.size() && rest[q] == '-') {
+          ++q;
+          b = strtol(rest.c_str() + q, &endp, 10);
+          if (endp == rest.c_str() + q) return run_fail("projection_analyse_substring: Error parsing atoms numbers - incorrect range");
+          q = endp - rest.c_str();
+        }
+        for (long v = std::min(a, b); v <= std::max(a, b); ++v) {
+          if (v < 1 || v > proj_sites[species])
+            return run_fail("projection_analyse_substring: Atom number given in pdos string is greater than number of atoms for given species");
+          atoms[v - 1] = 1;
+        }
+        while (q < rest.size() && (rest[q] == ' ' || rest[q] == ',')) ++q;
+      }
+      if (!am_sum) {
+        std::string d = c_am;
+        for (char &ch : d) if (ch == ',') ch = ' ';
+        size_t k = 0;
+        bool any = false;
+        while (k < d.size()) {
+          while (k < d.size() && d[k] == ' ') ++k;
+          if (k >= d.size()) break;
+          const char ch = d[k++];
+          const int l = ch == 's' ? 0 : ch == 'p' ? 1 : ch == 'd' ? 2 : ch == 'f' ? 3 : -1;
+          if (l < 0) return run_fail("projection_analyse_substring: Problem reading l state ");
+          ang[l] = 1;
+          any = true;
+        }
+        if (!any) am_sum = true;
+      }
+      if (site_sum && am_sum) {
+        auto m = blank();
+        for (int a = 0; a < max_sites; ++a) for (int l = 0; l < max_am; ++l) at(m, species, a, l) = 1;
+        projs.push_back(m);
+      } else if (site_sum) {
+        for (int l = 0; l < max_am; ++l) {
+          if (!ang[l]) continue;
+          auto m = blank();
+          for (int a = 0; a < max_sites; ++a) at(m, species, a, l) = 1;
+          projs.push_back(m);
+        }
+      } else if (am_sum) {
+        for (int a = 0; a < proj_sites[species]; ++a) {
+          if (!atoms[a]) continue;
+          auto m = blank();
+          for (int l = 0; l < max_am; ++l) at(m, species, a, l) = 1;
+          projs.push_back(m);
+        }
+      } else {
+        for (int l = 0; l < max_am; ++l) {
+          if (!ang[l]) continue;
+          for (int a = 0; a < proj_sites[species]; ++a) {
+            if (!atoms[a]) continue;
+            auto m = blank();
+            at(m, species, a, l) = 1;
+            projs.push_back(m);
+          }
+        }
+      }
+      if (e >= c.size()) break;
+    }
+    if (sum && !projs.empty()) {  // :226-254
+      auto m = blank();
+      for (auto &pm : projs) for (size_t k = 0; k < m.size(); ++k) if (pm[k]) m[k] = 1;
+      projs.assign(1, m);
+    }
+  }
+  const int nproj = (int)projs.size();
+  if (nproj < 1) return run_fail("pdos: no projectors");
+  // projection_merge (projection_utils.f90:64-99) on the device: the 4-index lookup flattened to mask(orbital, projector)
+  std::vector<int> mask((size_t)norb * nproj, 0);
+  for (int pj = 0; pj < nproj; ++pj)
+    for (int o = 0; o < norb; ++o) {
+      const int s = sp[o] - 1, a = rk[o] - 1, l = am[o];
+      if (s < nsp && a < max_sites && l >= 0 && l < max_am) mask[o + (size_t)norb * pj] = at(projs[pj], s, a, l);
+    }
+  std::vector<double> mw((size_t)nproj * pi.nbands * R.nk * R.ns);
+  if (pi.nbands != R.nb) return run_fail("pdos file with %d bands for %d bands: not supported by od_projection_merge", pi.nbands, R.nb);
+  RCHECK(R.ck(od_projection_merge(R.ctx, pw.data(), OD_MEM_HOST, mask.data(), norb, nproj, mw.data(), OD_MEM_HOST)));
+  // dos_utils_calculate(matrix_weights, dos_partial)
+  if (need_grads(R.P)) RCHECK(load_gradients(R));
+  od_dos_result dr;
+  RCHECK(R.ck(od_dos_utils_calculate(R.ctx, &R.dosp, mw.data(), nproj, pi.nbands, R.nk, OD_MEM_HOST, &dr)));
+  R.dosr = dr;
+  R.dos_done = true;  // E is allocated from here on (dos_utils.f90:141-147)
+  log_fermi(R, dr);
+  if (R.P.set_efermi_zero && !R.efermi_set) RCHECK(set_efermi(R));  // pdos.F90:88
+  const int n = dr.nbins, ns = R.ns;
+  std::vector<double> wd((size_t)n * ns * nproj);
+  RCHECK(R.ck(od_dos_get_weighted(R.ctx, wd.data())));
+  // pdos_write / write_proj_to_file (pdos.F90:94-252)
+  const char *am_name[4] = {"s", "p", "d", "f"};
+  auto write_file = [&](int p0, int p1, const std::string &name) -> int {
+    FILE *f = fopen(name.c_str(), "w");
+    if (!f) return run_fail(" ERROR: Cannot open output file in pdos: pdos_write");
+    fprintf(f, " ##############################################################################\n #\n");
+    fprintf(f, " #                  O p t a D O S   o u t p u t   f i l e \n #\n #  Generated by optados_b200\n");
+    fprintf(f, " ##############################################################################\n");
+    fprintf(f, "#+----------------------------------------------------------------------------+\n");
+    fprintf(f, "#|                    Partial Density of States -- Projectors                 |\n");
+    fprintf(f, "#+----------------------------------------------------------------------------+\n");
+    for (int spin = 0; spin < ns; ++spin)
+      for (int pj = p0; pj <= p1; ++pj) {
+        fprintf(f, "#|%12s%4d%10s%50s|\n", " Column: ", pj + 1 + spin * nproj, " contains:", "");
+        if (ns > 1) fprintf(f, "#|%16s%10s%14s%5s%15s%16s|\n", " Atom ", "", " AngM Channel ", "", " Spin Channel ", "");
+        else fprintf(f, "#|%16s%10s%14s%36s|\n", " Atom ", "", " AngM Channel ", "");
+        for (int s = 0; s < nsp; ++s)
+          for (int a = 0; a < (s < (int)R.species_count.size() ? R.species_count[s] : max_sites) && a < max_sites; ++a)
+            for (int l = 0; l < max_am; ++l)
+              if (at(projs[pj], s, a, l)) {
+                if (ns > 1) fprintf(f, "#|%13s%3d%18s%16s%4s%24s|\n", proj_symbol[s].c_str(), a + 1, am_name[l], "", spin == 0 ? "Up" : "Down", "");
+                else fprintf(f, "#|%13s%3d%18s%42s|\n", proj_symbol[s].c_str(), a + 1, am_name[l], "");
+              }
+        fprintf(f, "#+----------------------------------------------------------------------------+\n");
+      }
+    for (int i = 0; i < n; ++i) {
+      const double E = dr.emin + (double)i * dr.delta_bins - (R.P.set_efermi_zero ? R.efermi : 0.0);
+      fprintf(f, "%s", fES(E, 14, 7).c_str());
+      for (int spin = 0; spin < ns; ++spin)
+        for (int pj = p0; pj <= p1; ++pj) {
+          const double v = wd[(size_t)i + (size_t)n * (spin + (size_t)ns * pj)];
+          fprintf(f, " %s", fES(spin == 1 ? -v : v, 14, 7).c_str());
+        }
+      fprintf(f, "\n");
+    }
+    fclose(f);
+    return OD_OK;
+  };
+  if (shortcut) return write_file(0, nproj - 1, R.base + ".pdos.dat");
+  const int nfile = nproj / 10 + 1;
+  for (int ifile = 1; ifile <= nfile; ++ifile) {
+    const int s0 = (ifile - 1) * 10 + 1, e0 = ifile == nfile ? nproj : ifile * 10;
+    if (e0 < s0) continue;
+    char nm[64];
+    snprintf(nm, sizeof(nm), ".pdos.proj-%04d-%04d.dat", s0, e0);
+    RCHECK(write_file(s0 - 1, e0 - 1, R.base + nm));
+  }
+  return OD_OK;
+}
+
+// ---------------------------------------------------------------- task: optics (optics.f90:76-155, writers :828-1494)
+int geom_of(const std::string &g) {
+  if (g.find("unpolar") != std::string::npos) return OD_GEOM_UNPOLAR;
+  if (g.find("polar") != std::string::npos) return OD_GEOM_POLAR;
+  if (g.find("tensor") != std::string::npos) return OD_GEOM_TENSOR;
+  return OD_GEOM_POLYCRYS;
+}
+
+int task_optics(Run &R) {
+  R.olog("");
+  R.olog(" +============================================================================+");
+  R.olog(" +                                Optics Calculation                          +");
+  R.olog(" +============================================================================+");
+  RCHECK(set_efermi(R));
+  RCHECK(load_ome(R));
+  if (need_grads(R.P)) RCHECK(load_gradients(R));
+  od_optics_params op;
+  od_optics_params_defaults(&op);
+  op.jdos.fixed = R.P.fixed; op.jdos.adaptive = R.P.adaptive; op.jdos.linear = R.P.linear;
+  op.jdos.br = broadening_of(R.P);
+  op.jdos.jdos_spacing = R.P.jdos_spacing; op.jdos.jdos_max_energy = R.P.jdos_max_energy; op.jdos.scissor_op = R.P.scissor_op;
+  op.jdos.num_exclude_bands = R.P.num_exclude_bands; op.jdos.exclude_bands = R.P.exclude_bands;
+  op.jdos.efermi = R.efermi; op.jdos.cell_volume = R.cell_volume;
+  op.geom = geom_of(R.P.optics_geom);
+  for (int i = 0; i < 3; ++i) op.qdir[i] = R.P.optics_qdir[i];
+  op.lossfn_gaussian = R.P.optics_lossfn_broadening ? R.P.optics_lossfn_gaussian : 0.0;
+  op.intraband = R.P.optics_intraband; op.drude_broadening = R.P.optics_drude_broadening;
+  op.dos_delta_bins = R.dos_done ? R.dosr.delta_bins : 0.0;
+  od_optics_result orr;
+  RCHECK(R.ck(od_optics_calculate(R.ctx, &op, R.ome.data(), OD_MEM_HOST, R.num_symm > 0 ? R.symops.data() : nullptr, R.num_symm, &orr)));
+  const int n = orr.nbins, ng = orr.n_geom, np = orr.n_parts;
+  std::vector<double> E(n), eps((size_t)n * 2 * ng * np), cond, refr, loss, absb, refl;
+  if (orr.have_derived) { cond.resize((size_t)n * 2); refr.resize((size_t)n * 2); loss.resize((size_t)n * orr.n_loss_fn); absb.resize(n); refl.resize(n); }
+  RCHECK(R.ck(od_optics_get(R.ctx, E.data(), eps.data(), orr.have_derived ? cond.data() : nullptr, orr.have_derived ? refr.data() : nullptr,
+                            orr.have_derived ? loss.data() : nullptr, orr.have_derived ? absb.data() : nullptr, orr.have_derived ? refl.data() : nullptr)));
+  auto EP = [&](int i, int c, int g, int t) { return eps[(size_t)i + (size_t)n * (c + 2 * (g + (size_t)ng * t))]; };
+  const double e_charge = 1.602176487E-19;
+  auto header = [&](FILE *f, const char *title) {
+    fprintf(f, " #*********************************************\n #%s\n #*********************************************\n #\n", title);
+    fprintf(f, " # Number of k-points: %12d\n", R.nk);
+    if (R.ns == 1) fprintf(f, " # Number of electrons:%s\n", fL(R.bi.num_electrons[0]).c_str());
+    else fprintf(f, " # Number of electrons:%s%s\n", fL(R.bi.num_electrons[0]).c_str(), fL(R.bi.num_electrons[1]).c_str());
+    fprintf(f, " # Number of bands:%12d\n # Volume of the unit cell (Ang^3):%s\n #\n", R.nb, fL(R.cell_volume).c_str());
+    fprintf(f, " # Dielectric function calculated to%s eV in%s eV steps\n #\n", fF(E[n - 1], 10, 6).c_str(), fF(orr.delta_bins, 10, 6).c_str());
+    fprintf(f, " # optics_geom:  %s\n", R.P.optics_geom);
+    if (std::string(R.P.optics_geom).find("polar") != std::string::npos)
+      fprintf(f, " # q-vector%s%s%s\n", fF(R.P.optics_qdir[0], 10, 3).c_str(), fF(R.P.optics_qdir[1], 10, 3).c_str(), fF(R.P.optics_qdir[2], 10, 3).c_str());
+    if (R.P.scissor_op > 0) fprintf(f, " # Scissor operator:%s\n", fF(R.P.scissor_op, 10, 3).c_str());
+    fprintf(f, " #\n");
+    if (R.P.optics_intraband) fprintf(f, " # Calculation includes intraband term\n");
+  };
+  {  // write_epsilon (optics.f90:828-960)
+    FILE *f = fopen((R.base + "_epsilon.dat").c_str(), "w");
+    if (!f) return run_fail("cannot open %s_epsilon.dat", R.base.c_str());
+    header(f, "            Dielectric function                 ");
+    if (ng == 1) {
+      fprintf(f, " # Result of sum rule: Neff(E) =  %s\n #\n", fL(orr.n_eff).c_str());
+      if (np > 1) fprintf(f, "\n\n");
+      for (int i = 0; i < n; ++i) fprintf(f, "%s%s%s\n", fL(E[i]).c_str(), fL(EP(i, 0, 0, 0)).c_str(), fL(EP(i, 1, 0, 0)).c_str());
+      for (int t = 1; t < np; ++t) {
+        fprintf(f, "\n\n");
+        for (int i = 0; i < n; ++i) fprintf(f, "%s%s%s\n", fL(E[i]).c_str(), fL(EP(i, 0, 0, t)).c_str(), fL(EP(i, 1, 0, t) / (E[i] * e_charge)).c_str());
+      }
+    } else {
+      fprintf(f, "\n\n");
+      for (int g = 0; g < ng; ++g) {
+        fprintf(f, " # Component %12d\n\n\n", g + 1);
+        for (int t = 0; t < np; ++t) {
+          for (int i = 0; i < n; ++i) fprintf(f, "%s%s%s\n", fL(E[i]).c_str(), fL(EP(i, 0, g, t)).c_str(), fL(EP(i, 1, g, t)).c_str());
+          fprintf(f, "\n\n");
+        }
+      }
+    }
+    fclose(f);
+  }
+  if (!orr.have_derived) return OD_OK;
+  {  // write_loss_fn (:962-1070): column 1 unbroadened; with broadening a second block
+    FILE *f = fopen((R.base + "_loss_fn.dat").c_str(), "w");
+    if (!f) return run_fail("cannot open %s_loss_fn.dat", R.base.c_str());
+    header(f, "               Loss function                    ");
+    fprintf(f, " # Result of first sum rule: Neff(E) =  %s\n", fL(orr.n_eff2).c_str());
+    fprintf(f, " # Result of second sum rule (pi/2 = 1.570796327):  %s\n #\n", fL(orr.n_eff3).c_str());
+    if (np == 1) {  // optics.f90:1033-1042
+      for (int i = 0; i < n; ++i) {
+        fprintf(f, "%s%s", fL(E[i]).c_str(), fL(loss[i]).c_str());
+        if (orr.have_loss_fn_broadened) fprintf(f, "%s", fL(loss[(size_t)i + (size_t)n]).c_str());
+        fprintf(f, "\n");
+      }
+    } else {        // :1044-1057: the 3 (4) columns one after the other
+      for (int c = 0; c < orr.n_loss_fn; ++c)
+        for (int i = 0; i < n; ++i) fprintf(f, "%s%s\n", fL(E[i]).c_str(), fL(loss[(size_t)i + (size_t)n * c]).c_str());
+    }
+    fclose(f);
+  }
+  auto two_col = [&](const char *ext, const char *title, const std::vector<double> &v, int ncol) -> int {
+    FILE *f = fopen((R.base + ext).c_str(), "w");
+    if (!f) return run_fail("cannot open %s%s", R.base.c_str(), ext);
+    header(f, title);
+    for (int i = 0; i < n; ++i) {
+      fprintf(f, "%s", fL(E[i]).c_str());
+      for (int c = 0; c < ncol; ++c) fprintf(f, "%s", fL(v[(size_t)i + (size_t)n * c]).c_str());
+      fprintf(f, "\n");
+    }
+    fclose(f);
+    return OD_OK;
+  };
+  RCHECK(two_col("_conductivity.dat", "               Conductivity                     ", cond, 2));
+  RCHECK(two_col("_refractive_index.dat", "             Refractive index                   ", refr, 2));
+  RCHECK(two_col("_absorption.dat", "               Absorption                       ", absb, 1));
+  RCHECK(two_col("_reflection.dat", "               Reflection                       ", refl, 1));
+  return OD_OK;
+}
+
+// ---------------------------------------------------------------- task: core (core.f90:38-83, write_core :170-653)
+int task_core(Run &R) {
+  R.olog("");
+  R.olog(" +============================================================================+");
+  R.olog(" +                            Core Loss Calculation                           +");
+  R.olog(" +============================================================================+");
+  od_elnes_info ei;
+  std::string ef;
+  char fmt = 'b';
+  if (R.P.legacy_file_format && file_exists(R.path(".eels_mat"))) { ef = R.path(".eels_mat"); fmt = 'l'; }
+  else if (file_exists(R.path(".elnes_bin"))) { ef = R.path(".elnes_bin"); fmt = 'b'; }
+  else if (file_exists(R.path(".elnes_fmt"))) { ef = R.path(".elnes_fmt"); fmt = 't'; }
+  else return run_fail("Error: Problem opening elnes_bin file in elec_read_elnes_mat (%s.elnes_bin / .elnes_fmt)", R.base.c_str());
+  if (od_read_elnes_info(ef.c_str(), fmt, &ei) != OD_OK) return run_fail("%s", od_io_last_error());
+  const int norb = ei.norbitals;
+  if (ei.nbands != R.nb || ei.nkpoints != R.nk || ei.nspins != R.ns) return run_fail("elnes file and bands file disagree on the dimensions");
+  std::vector<int> sp(norb), rk(norb), sh(norb), am(norb);
+  std::vector<double> em((size_t)norb * R.nb * 3 * R.nk * R.ns * 2);
+  if (od_read_elnes(ef.c_str(), fmt, &ei, sp.data(), rk.data(), sh.data(), am.data(), em.data()) != OD_OK) return run_fail("%s", od_io_last_error());
+  if (need_grads(R.P)) RCHECK(load_gradients(R));
+  od_core_params cp;
+  od_core_params_defaults(&cp);
+  cp.dos = R.dosp;
+  cp.core_type = !strcmp(R.P.core_type, "emission") ? OD_CORE_EMISSION : (!strcmp(R.P.core_type, "all") ? OD_CORE_ALL : OD_CORE_ABSORPTION);
+  cp.polar = std::string(R.P.core_geom).find("polar") != std::string::npos;
+  for (int i = 0; i < 3; ++i) cp.qdir[i] = R.P.core_qdir[i];
+  cp.lai_broadening = R.P.core_lai_broadening;
+  cp.lai_gaussian_width = R.P.lai_gaussian_width; cp.lai_lorentzian_width = R.P.lai_lorentzian_width;
+  cp.lai_lorentzian_scale = R.P.lai_lorentzian_scale; cp.lai_lorentzian_offset = R.P.lai_lorentzian_offset;
+  cp.set_efermi_zero = R.P.set_efermi_zero; cp.core_chemical_shift = R.P.core_chemical_shift;
+  // if (.not. efermi_set) call dos_utils_set_efermi (core.f90:62): here, so that its Fermi analysis reaches the .odo and
+  // dos_nbins becomes sticky (quirk Q4); od_core_calculate is then handed the level
+  RCHECK(set_efermi(R));
+  cp.dos = R.dosp;
+  cp.dos.efermi_choice = OD_EFERMI_USER;
+  cp.dos.efermi_user = R.efermi;
+  od_core_result cr;
+  RCHECK(R.ck(od_core_calculate(R.ctx, &cp, em.data(), OD_MEM_HOST, norb, R.num_symm > 0 ? R.symops.data() : nullptr, R.num_symm, &cr)));
+  R.dosp.dos_nbins = cp.dos.dos_nbins;
+  R.dos_done = true;
+  R.dosr.nbins = cr.nbins; R.dosr.emin = cr.emin; R.dosr.delta_bins = cr.delta_bins;
+  log_fermi(R, R.dosr);  // the second Fermi analysis, of the weighted pass on the re-gridded energy scale (dos_utils.f90:231-263)
+  const int n = cr.nbins, ns = R.ns;
+  std::vector<double> E(n), wd((size_t)n * ns * norb), wb;
+  if (cr.have_broadened) wb.resize(wd.size());
+  RCHECK(R.ck(od_core_get(R.ctx, E.data(), wd.data(), cr.have_broadened ? wb.data() : nullptr)));
+  // edges: consecutive orbitals with equal (species, rank, shell, l) (core.f90:366-399); channel -> l as
+  // elec_elnes_find_channel_names (electronic.f90:995-1062)
+  auto ch2l = [](int c) { return c == 1 ? 0 : (c <= 4 ? 1 : (c <= 9 ? 2 : 3)); };
+  std::vector<std::vector<int>> edges;
+  for (int o = 0; o < norb; ++o) {
+    if (!edges.empty()) {
+      const int p = edges.back()[0];
+      if (sp[p] == sp[o] && rk[p] == rk[o] && sh[p] == sh[o] && ch2l(am[p]) == ch2l(am[o])) { edges.back().push_back(o); continue; }
+    }
+    edges.push_back({o});
+  }
+  FILE *f = fopen((R.base + "_core_edge.dat").c_str(), "w");
+  if (!f) return run_fail("cannot open %s_core_edge.dat", R.base.c_str());
+  fprintf(f, " #*********************************************\n #            Core loss function               \n #*********************************************\n #\n");
+  if (R.P.core_lai_broadening) {
+    if (R.P.lai_gaussian_width > 1e-14) fprintf(f, " # Gaussian broadening: FWHM%s\n", fL(R.P.lai_gaussian_width).c_str());
+    if (R.P.lai_lorentzian_width > 1e-14) {
+      fprintf(f, " # Lorentzian broadening included\n # Lorentzian scale %s\n # Lorentzian offset %s\n # Lorentzian width %s\n", fL(R.P.lai_lorentzian_scale).c_str(),
+              fL(R.P.lai_lorentzian_offset).c_str(), fL(R.P.lai_lorentzian_width).c_str());
+    }
+  }
+  fprintf(f, " #\n");
+  const char shell_l[4] = {'K', 'L', 'M', 'N'};
+  for (const std::vector<int> &orbs : edges) {
+    const int o0 = orbs[0];
+    fprintf(f, " # species %d site %d    %c%d\n", sp[o0], rk[o0], sh[o0] >= 1 && sh[o0] <= 4 ? shell_l[sh[o0] - 1] : '?', ch2l(am[o0]) == 0 ? 1 : 2 * ch2l(am[o0]));
+    for (int i = 0; i < n; ++i) {
+      double a[2] = {0, 0}, b[2] = {0, 0};
+      for (int is = 0; is < ns; ++is)
+        for (int o : orbs) {
+          a[is] = a[is] + wd[(size_t)i + (size_t)n * (is + (size_t)ns * o)] / (double)orbs.size();
+          if (cr.have_broadened) b[is] = b[is] + wb[(size_t)i + (size_t)n * (is + (size_t)ns * o)] / (double)orbs.size();
+        }
+      if (ns == 1) {
+        if (cr.have_broadened) fprintf(f, "%s%s%s\n", fL(E[i]).c_str(), fL(a[0]).c_str(), fL(b[0]).c_str());
+        else fprintf(f, "%s%s\n", fL(E[i]).c_str(), fL(a[0]).c_str());
+      } else {
+        if (cr.have_broadened)
+          fprintf(f, "%s  %s  %s  %s  %s  %s  %s  \n", fE(E[i], 21, 13).c_str(), fE(a[0], 21, 13).c_str(), fE(a[1], 21, 13).c_str(), fE(a[0] + a[1], 21, 13).c_str(),
+                  fE(b[0], 21, 13).c_str(), fE(b[1], 21, 13).c_str(), fE(b[0] + b[1], 21, 13).c_str());
+        else
+          fprintf(f, "%s  %s  %s  %s  \n", fE(E[i], 21, 13).c_str(), fE(a[0], 21, 13).c_str(), fE(a[1], 21, 13).c_str(), fE(a[0] + a[1], 21, 13).c_str());
+      }
+    }
+    fprintf(f, "\n");
+  }
+  fclose(f);
+  return OD_OK;
+}
+}  // namespace
+
+extern "C" int od_run_seed(od_ctx *ctx, const char *dir, const char *seedname) {
+  if (!ctx || !dir || !seedname) return OD_ERR_ARG;
+  g_run_err.clear();
+  Run R;
+  R.ctx = ctx;
+  R.dir = dir;
+  R.seed = seedname;
+  R.base = R.dir + "/" + R.seed;
+  RCHECK(od_param_read(R.path(".odi").c_str(), &R.P));
+  if (R.P.pdis) return run_fail("task pdispersion is not part of this library (SURVEY.md section 8(f) rank 4 lists it as out of scope)");
+  // elec_read_band_energy (electronic.f90:445-618), cell_calc_lattice, cell_find_MP_grid
+  if (od_read_bands_info(R.path(".bands").c_str(), &R.bi) != OD_OK) return run_fail("%s", od_io_last_error());
+  R.nk = R.bi.nkpoints; R.ns = R.bi.nspins; R.nb = R.bi.nbands;
+  R.band_energy.resize((size_t)R.nb * R.ns * R.nk);
+  R.kpoint_r.resize(3 * (size_t)R.nk);
+  R.kweight.resize(R.nk);
+  if (od_read_bands(R.path(".bands").c_str(), &R.bi, R.band_energy.data(), R.kpoint_r.data(), R.kweight.data()) != OD_OK) return run_fail("%s", od_io_last_error());
+  if (od_cell_calc_lattice(R.bi.real_lattice, R.real_lattice, R.recip, &R.cell_volume) != OD_OK) return run_fail("%s", od_io_last_error());
+  if (od_cell_find_mp_grid(R.kpoint_r.data(), R.nk, R.kgrid) != OD_OK) return run_fail("%s", od_io_last_error());
+  if (R.P.pdos || R.P.core || R.P.optics) {  // cell_read_cell (parameters.f90:397-401 -> cell.f90:405-696)
+    const std::string cf = R.path("-out.cell");
+    int nops = 0;
+    if (file_exists(cf) && od_read_symmetry_ops(cf.c_str(), 0, nullptr, &nops) == OD_OK && nops > 0) {
+      R.symops.resize(9 * (size_t)nops);
+      if (od_read_symmetry_ops(cf.c_str(), nops, R.symops.data(), &nops) != OD_OK) return run_fail("%s", od_io_last_error());
+      R.num_symm = nops;
+    }
+  }
+  RCHECK(R.ck(od_set_system(ctx, R.nk, R.ns, R.nb, R.recip, R.kgrid, R.kweight.data(), R.bi.electrons_per_state)));
+  RCHECK(R.ck(od_set_bands(ctx, R.band_energy.data(), OD_MEM_HOST)));
+  RCHECK(R.ck(od_synchronize(ctx)));
+  fill_dos_params(R);
+  R.odo = fopen(R.path(".odo").c_str(), "w");
+  if (!R.odo) return run_fail("cannot open %s.odo", R.base.c_str());
+  R.olog(" +===========================================================================+");
+  R.olog(" |                    OptaDOS file contract on optados_b200                  |");
+  R.olog(" +===========================================================================+");
+  int rc = OD_OK;
+  // optados.f90:120-222
+  if (rc == OD_OK && R.P.pdos) rc = task_pdos(R);
+  if (rc == OD_OK && R.P.core) rc = task_core(R);
+  if (rc == OD_OK && R.P.dos) rc = task_dos(R);
+  if (rc == OD_OK && R.P.optics) rc = task_optics(R);
+  if (rc == OD_OK && R.P.jdos) rc = task_jdos(R);
+  if (rc != OD_OK) R.olog(" ERROR: %s", g_run_err.c_str());
+  fclose(R.odo);
+  return rc;
+}

@@ -318,6 +318,51 @@ def golden_header_scalars(test, seed):
     return out
 
 
+def copy_testsuite():
+    """the INPUT files of the reference's test-suite (the .odi of every optados test, and the CASTEP-format checkpoint
+    files they link to, still bz2-compressed) -> tests/golden/testsuite/, with index.json = test -> {seed, files, output,
+    parser}.  These are data fixtures for the files-in / files-out tests of od_run_seed (tests/test_run_files.py)."""
+    import configparser
+    import shutil
+    dst = os.path.join(OUT, "testsuite")
+    os.makedirs(os.path.join(dst, "checkpoints"), exist_ok=True)
+    cfg = configparser.ConfigParser()
+    cfg.read(f"{REF}/tests/jobconfig")
+    index = {}
+    for test in sorted(os.listdir(f"{REF}/tests")):
+        d = f"{REF}/tests/{test}"
+        if not (test.startswith("testopt_") and os.path.isdir(d)):
+            continue
+        odis = [f for f in os.listdir(d) if f.endswith(".odi") and not f.startswith("benchmark")]
+        if not odis:
+            continue
+        seed = odis[0][:-4]
+        os.makedirs(os.path.join(dst, "tests", test), exist_ok=True)
+        shutil.copyfile(f"{d}/{odis[0]}", os.path.join(dst, "tests", test, odis[0]))
+        files, complete = {}, True
+        for f in sorted(os.listdir(d)):
+            if f.startswith("benchmark") or f in ("Makefile", ".gitignore") or f.endswith(".odi"):
+                continue
+            src = os.path.realpath(f"{d}/{f}")
+            if not os.path.exists(src):
+                complete = False          # a dangling link (Al4.ome_fmt.bz2 is not in the checkout)
+                continue
+            if "/checkpoints/" in src:
+                rel = src.split("/checkpoints/")[1]
+                os.makedirs(os.path.dirname(os.path.join(dst, "checkpoints", rel)), exist_ok=True)
+                shutil.copyfile(src, os.path.join(dst, "checkpoints", rel))
+                files[f] = "checkpoints/" + rel
+            else:
+                shutil.copyfile(src, os.path.join(dst, "tests", test, f))
+                files[f] = f"tests/{test}/{f}"
+        out = cfg[test]["output"].strip() if cfg.has_section(test) and "output" in cfg[test] else None
+        prog = cfg[test]["program"].strip() if cfg.has_section(test) and "program" in cfg[test] else None
+        index[test] = {"seed": seed, "files": files, "output": out, "program": prog, "complete": complete}
+    with open(os.path.join(dst, "index.json"), "w") as f:
+        json.dump(index, f, indent=1, sort_keys=True)
+    print("testsuite inputs:", len(index), "tests")
+
+
 def save(name, d):
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **{k: np.asarray(v) for k, v in d.items()})
@@ -345,6 +390,8 @@ def main():
         "testopt_core_polarised": "Si2", "testopt_core_emisson": "Si2", "testopt_core_all": "Si2",
         "testopt_core_chemical_shift": "NaGe",
     }
+    # (testopt_pdos_string1 / 4, testopt_jdos_fixed_odo, testopt_optics_poly, testopt_core_absorb are .odo tests:
+    #  their goldens are the tagged numbers of gold_odo.json)
     for t, seed in dat_tests.items():
         blocks = golden_table(t, seed)
         save("gold_" + t, {f"block{i}": b for i, b in enumerate(blocks)})
@@ -357,6 +404,7 @@ def main():
     with open(os.path.join(OUT, "gold_odo.json"), "w") as f:
         json.dump(odo, f, indent=1, sort_keys=True)
     print("gold_odo.json", odo)
+    copy_testsuite()
 
 
 if __name__ == "__main__":
