@@ -344,6 +344,10 @@ def main():
         e2e = {"value": contrib_total / dt, "unit": "contributions/s", "h2d_bytes_per_step": nbe + nbg,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": n_e2e,
                "api": "od_set_bands + od_set_gradients(OD_MEM_HOST_DEFERRED) from pinned host memory + od_dos_utils_calculate + od_dos_get"}
+        # OD_MEM_HOST_DEFERRED leaves the library reading h_bg on every later call: make the gradients resident again
+        # (one plain upload) before the host buffers go away
+        ctx.set_gradients_ptr(h_bg, deferred=False)
+        ctx.synchronize()
         ob.host_free_pinned(h_be)
         ob.host_free_pinned(h_bg)
 

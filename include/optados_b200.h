@@ -57,6 +57,9 @@ enum { OD_EFERMI_OPTADOS = 0, OD_EFERMI_FILE = 1, OD_EFERMI_USER = 2, OD_EFERMI_
 
 /* ---------------------------------------------------------------- context ------------------ */
 const char *od_version(void);
+/* sizeof(struct <name>) for the public structures of this header ("od_dos_params", ...), -1 for an unknown name: lets a
+ * binding in another language (the Fortran shim's derived types, ctypes mirrors) verify its layout at start-up */
+int od_abi_sizeof(const char *struct_name);
 /* single GPU, no communicator (the reference's serial build: comms.F90 stubs) */
 int od_ctx_create(int device, od_ctx **ctx);
 /* one rank per GPU (the reference's MPI build: comms_setup, comms.F90:85).  id128 is the 128-byte
@@ -100,6 +103,10 @@ int od_count_contributions(od_ctx *ctx, char dos_type, double emin, double delta
 /* pinned host memory for the end-to-end path (cudaHostAlloc) */
 int od_host_alloc_pinned(size_t nbytes, void **hptr);
 int od_host_free_pinned(void *hptr);
+/* page-lock / release host memory the caller owns (cudaHostRegister): a Fortran array handed over with OD_MEM_HOST or
+ * OD_MEM_HOST_DEFERRED is then copied at the PCIe rate, asynchronously, instead of through a pageable bounce buffer */
+int od_host_register(void *hptr, size_t nbytes);
+int od_host_unregister(void *hptr);
 
 /* device memory helpers (so weight arrays can stay resident between calls) */
 int od_device_malloc(od_ctx *ctx, size_t nbytes, void **dptr);
@@ -192,8 +199,9 @@ int od_core_prepare_matrix_elements(od_ctx *ctx, const double *elnes_mat, int el
                                     const double qdir[3], const double *symops, int num_sym, int core_type,
                                     double efermi, double *matrix_weights, int out_mem);
 /* projection_merge (projection_utils.f90:64-99) with projection_array flattened by the caller to
- * mask(norb_in, nproj) in {0,1}: pdos_weights(norb_in,nb,nk,ns) -> matrix_weights(nproj,nb,nk,ns) */
-int od_projection_merge(od_ctx *ctx, const double *pdos_weights, int pw_mem, const int *mask, int norb_in,
+ * mask(norb_in, nproj) in {0,1}: pdos_weights(norb_in,pw_nb,nk,ns) -> matrix_weights(nproj,pw_nb,nk,ns), pw_nb =
+ * pdos_mwab%nbands (the bands the .pdos_bin file holds, <= nbands; pass the result on with mw_nb = pw_nb) */
+int od_projection_merge(od_ctx *ctx, const double *pdos_weights, int pw_mem, const int *mask, int norb_in, int pw_nb,
                         int nproj, double *matrix_weights, int out_mem);
 /* calc_epsilon_2 interband part (optics.f90:495-551): epsilon2(nbins, n_geom) */
 int od_calc_epsilon_2(od_ctx *ctx, const double *weighted_jdos, int nbins, int ns, int n_geom,

@@ -155,7 +155,7 @@ EXPORTS = [
     "od_calc_epsilon_1", "od_calc_loss_fn", "od_core_lai_broadening",
     "od_dos_utils_calculate_at_e", "od_optics_params_defaults", "od_optics_calculate", "od_optics_get", "od_core_params_defaults", "od_core_calculate",
     "od_core_get", "od_dos_utils_compute_bandgap", "od_dos_utils_compute_band_energies",
-    "od_odi_defaults", "od_param_read", "od_run_last_error", "od_run_seed",
+    "od_odi_defaults", "od_param_read", "od_run_last_error", "od_run_seed", "od_abi_sizeof", "od_host_register", "od_host_unregister",
     "od_io_last_error", "od_read_bands_info", "od_read_bands", "od_cell_calc_lattice", "od_cell_find_mp_grid",
     "od_read_symmetry_ops", "od_read_ome", "od_read_dome", "od_read_pdos_info", "od_read_pdos", "od_read_elnes_info",
     "od_read_elnes",
@@ -428,9 +428,10 @@ class Context:
         pw = f64(pdos_weights)
         m = np.asfortranarray(mask, dtype=np.int32)
         norb, nproj = m.shape
-        mw = np.zeros((nproj, self.nb, self.nk, self.ns), order="F")
+        pw_nb = pw.shape[1]              # pdos_mwab%nbands: may be smaller than nbands
+        mw = np.zeros((nproj, pw_nb, self.nk, self.ns), order="F")
         self._ck(self.L.od_projection_merge(self.h, _p(pw), C.c_int(OD_MEM_HOST), m.ctypes.data_as(c_ip), C.c_int(norb),
-                                            C.c_int(nproj), _p(mw), C.c_int(OD_MEM_HOST)))
+                                            C.c_int(pw_nb), C.c_int(nproj), _p(mw), C.c_int(OD_MEM_HOST)))
         return mw
 
     def calc_epsilon_2(self, wjdos, cell_volume):

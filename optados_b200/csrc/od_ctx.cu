@@ -95,6 +95,18 @@ bool nccl_load() {
 }
 }  // namespace
 
+// sizeof of the public structures: a binding in another language (the ISO_C_BINDING derived types of the Fortran shim,
+// the ctypes mirrors of the tests) checks its own layout against these at start-up
+extern "C" int od_abi_sizeof(const char *name) {
+  if (!name) return -1;
+#define OD_SZ(T) if (!strcmp(name, #T)) return (int)sizeof(T)
+  OD_SZ(od_broadening); OD_SZ(od_dos_params); OD_SZ(od_dos_result); OD_SZ(od_jdos_params); OD_SZ(od_jdos_result);
+  OD_SZ(od_optics_params); OD_SZ(od_optics_result); OD_SZ(od_core_params); OD_SZ(od_core_result); OD_SZ(od_bandgap_result);
+  OD_SZ(od_odi); OD_SZ(od_bands_info); OD_SZ(od_pdos_info); OD_SZ(od_elnes_info);
+#undef OD_SZ
+  return -1;
+}
+
 extern "C" const char *od_version(void) { return "optados_b200 0.1 (sm_100a, FP64)"; }
 
 extern "C" int od_comm_get_unique_id(void *id128) {
@@ -108,8 +120,23 @@ extern "C" int od_comm_get_unique_id(void *id128) {
   return OD_OK;
 }
 
+// debugging aid (OD_DEBUG_BACKTRACE=1): raw return addresses on SIGSEGV, to be resolved with addr2line against the .so
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void od_segv_handler(int sig) {
+  void *frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "optados_b200: SIGSEGV, backtrace:\n";
+  if (write(2, msg, sizeof(msg) - 1) < 0) {}
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+
 static int ctx_create_common(int device, od_ctx **out) {
   if (!out) return OD_ERR_ARG;
+  if (getenv("OD_DEBUG_BACKTRACE")) signal(SIGSEGV, od_segv_handler);
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);

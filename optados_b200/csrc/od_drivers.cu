@@ -347,6 +347,7 @@ extern "C" int od_jdos_utils_calculate(od_ctx *ctx, od_jdos_params *p, const dou
     double *accum = nullptr;
     OD_CHECK(od_calculate_jdos_device(ctx, types[t], delta, nbins, &p->br, p->efermi, p->scissor_op, p->exclude_bands,
                                       p->num_exclude_bands, mw_dev, ome_dev, ome_dev ? &coef : nullptr, ng, /*merge=*/1, &accum));
+    OD_CHECK(od_merge_status_check(ctx));
     OD_CHECK(pull(ctx, S.dos[t], accum, n1));
     S.have[t] = true;
     if (ng > 0) {  // every enabled scheme recomputes weighted_jdos; the last one survives (jdos_utils.f90:109-136)

@@ -75,6 +75,7 @@ struct od_ctx {
   DevBuf flags;      // int[4]: [0] doslin `stop` conditions met by kernels that are not followed by a host synchronisation
   DevBuf stats_dev;  // unsigned long long[2]: lane-steps / in-window pairs of the narrow engine since the last profile reset
   DevBuf dest_dev;
+  double *merge_status_dev = nullptr;  // status word of the last merged JDOS call (od_merge_status_check)
   void *host_stage = nullptr;  // pinned staging for the results of the task drivers
   size_t host_stage_bytes = 0;
   struct PendingTime { cudaEvent_t e0, e1; int kind; };  // kind 0: prepare, 1: accumulate
@@ -132,6 +133,7 @@ int od_allreduce_device(od_ctx *ctx, double *dbuf, size_t n, char op);
 int od_flags_ready(od_ctx *ctx);
 // after a host synchronisation: report (and clear) what kernels flagged since the last check
 int od_check_deferred(od_ctx *ctx);
+int od_merge_status_check(od_ctx *ctx);
 // device stopwatch without a synchronisation: bracket a region with od_time_begin / od_time_end; the elapsed times are
 // added to ctx->prof when od_profile_get (or od_times_resolve) is called
 int od_time_begin(od_ctx *ctx, int kind, size_t *slot);

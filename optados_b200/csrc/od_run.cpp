@@ -920,8 +920,7 @@ int task_pdos(Run &R) {
       if (s < nsp && a < max_sites && l >= 0 && l < max_am) mask[o + (size_t)norb * pj] = at(projs[pj], s, a, l);
     }
   std::vector<double> mw((size_t)nproj * pi.nbands * R.nk * R.ns);
-  if (pi.nbands != R.nb) return run_fail("pdos file with %d bands for %d bands: not supported by od_projection_merge", pi.nbands, R.nb);
-  RCHECK(R.ck(od_projection_merge(R.ctx, pw.data(), OD_MEM_HOST, mask.data(), norb, nproj, mw.data(), OD_MEM_HOST)));
+  RCHECK(R.ck(od_projection_merge(R.ctx, pw.data(), OD_MEM_HOST, mask.data(), norb, pi.nbands, nproj, mw.data(), OD_MEM_HOST)));
   // dos_utils_calculate(matrix_weights, dos_partial)
   if (need_grads(R.P)) RCHECK(load_gradients(R));
   od_dos_result dr;

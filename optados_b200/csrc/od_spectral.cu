@@ -478,9 +478,13 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
   GridSpec grid{0.0, delta_bins, nbins};  // E(i) = (i-1)*delta_bins (jdos_utils.f90:217)
   const size_t n1 = (size_t)nbins * ns;
   const size_t ntot = n1 + n1 * n_geom;
-  OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * ntot));
+  OD_CHECK(od_buf_ensure(ctx, ctx->accum, sizeof(double) * (ntot + 1)));  // + the status word of the merge
   double *accum = ctx->accum.as<double>();
-  OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * ntot, ctx->stream));
+  OD_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(double) * (ntot + 1), ctx->stream));
+  ctx->merge_status_dev = nullptr;
+  // everything rank-local runs inside this lambda: a failure on one rank travels in the status word of the allreduce and
+  // becomes an error on every rank (od_merge_status_check) instead of a hang in the collective
+  auto local = [&]() -> int {
   const int nacc = 1 + n_geom;
   std::vector<long long> dest((size_t)ns * nacc);
   for (int is = 0; is < ns; ++is) {
@@ -554,8 +558,32 @@ int od_calculate_jdos_device(od_ctx *ctx, char jdos_type, double delta_bins, int
   } else if (n_geom == 0) OD_CHECK((od_run_dense<0, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   else if (n_geom == 1) OD_CHECK((od_run_dense<1, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
   else OD_CHECK((od_run_dense<6, false, JdosProducer>(ctx, p, grid, ns, dest, accum)));
-  if (merge) OD_CHECK(od_allreduce_device(ctx, accum, ntot, 's'));  // jdos_utils_merge (jdos_utils.f90:435-437)
+  return OD_OK;
+  };
+  const int rc_local = local();
+  if (merge && ctx->nranks > 1) {
+    const std::string err_local = ctx->err;
+    if (rc_local != 0) {
+      const double one = 1.0;
+      cudaMemcpyAsync(accum + ntot, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    OD_CHECK(od_allreduce_device(ctx, accum, ntot + 1, 's'));  // jdos_utils_merge (jdos_utils.f90:435-437)
+    ctx->merge_status_dev = accum + ntot;
+    ctx->err = err_local;
+  }
+  if (rc_local != 0) return rc_local;
   *accum_out = accum;
+  return OD_OK;
+}
+
+// after a merge: non-zero if the calculation failed on another rank (synchronises)
+int od_merge_status_check(od_ctx *ctx) {
+  if (!ctx->merge_status_dev) return OD_OK;
+  double status = 0.0;
+  OD_CUDA(ctx, cudaMemcpyAsync(&status, ctx->merge_status_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->merge_status_dev = nullptr;
+  if (status != 0.0) return od_fail(ctx, OD_ERR_STATE, "the calculation failed on %d other rank(s) of the communicator", (int)status);
   return OD_OK;
 }
 
@@ -564,6 +592,7 @@ static int jdos_copy_out(od_ctx *ctx, const double *accum, int nbins, int n_geom
   OD_CUDA(ctx, cudaMemcpyAsync(jdos, accum, sizeof(double) * n1, cudaMemcpyDeviceToHost, ctx->stream));
   if (wjdos && n_geom > 0)
     OD_CUDA(ctx, cudaMemcpyAsync(wjdos, accum + n1, sizeof(double) * n1 * n_geom, cudaMemcpyDeviceToHost, ctx->stream));
+  OD_CHECK(od_merge_status_check(ctx));
   return od_check_deferred(ctx);  // synchronises
 }
 

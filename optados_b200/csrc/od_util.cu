@@ -164,4 +164,11 @@ extern "C" int od_host_alloc_pinned(size_t nbytes, void **hptr) {
   if (!hptr) return OD_ERR_ARG;
   return cudaHostAlloc(hptr, nbytes ? nbytes : 8, cudaHostAllocDefault) == cudaSuccess ? OD_OK : OD_ERR_CUDA;
 }
+// page-lock / release memory the CALLER allocated (a Fortran array): what cudaHostRegister does, so that OD_MEM_HOST /
+// OD_MEM_HOST_DEFERRED uploads from it run at the PCIe rate and overlap with kernels
+extern "C" int od_host_register(void *hptr, size_t nbytes) {
+  if (!hptr || nbytes == 0) return OD_ERR_ARG;
+  return cudaHostRegister(hptr, nbytes, cudaHostRegisterDefault) == cudaSuccess ? OD_OK : OD_ERR_CUDA;
+}
+extern "C" int od_host_unregister(void *hptr) { return cudaHostUnregister(hptr) == cudaSuccess ? OD_OK : OD_ERR_CUDA; }
 extern "C" int od_host_free_pinned(void *hptr) { return cudaFreeHost(hptr) == cudaSuccess ? OD_OK : OD_ERR_CUDA; }

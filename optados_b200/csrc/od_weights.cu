@@ -291,13 +291,15 @@ extern "C" int od_core_prepare_matrix_elements(od_ctx *ctx, const double *elnes_
   return finish_out(ctx, out, matrix_weights, nel, out_mem);
 }
 
-extern "C" int od_projection_merge(od_ctx *ctx, const double *pdos_weights, int pw_mem, const int *mask, int norb_in, int nproj,
-                                   double *matrix_weights, int out_mem) {
+extern "C" int od_projection_merge(od_ctx *ctx, const double *pdos_weights, int pw_mem, const int *mask, int norb_in, int pw_nb,
+                                   int nproj, double *matrix_weights, int out_mem) {
   if (!ctx) return OD_ERR_ARG;
   if (!ctx->have_system) return od_fail(ctx, OD_ERR_STATE, "od_set_system has not been called");
-  if (!pdos_weights || !mask || !matrix_weights || norb_in < 1 || nproj < 1) return od_fail(ctx, OD_ERR_ARG, "bad arguments");
+  if (!pdos_weights || !mask || !matrix_weights || norb_in < 1 || nproj < 1 || pw_nb < 1) return od_fail(ctx, OD_ERR_ARG, "bad arguments");
   OD_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t nstates = (size_t)ctx->nb * ctx->nk * ctx->ns;
+  // pdos_mwab%nbands of the .pdos_bin file, which may be smaller than nbands (projection_utils.f90:84; the result is then
+  // consumed with mw%nbands = pw_nb by calculate_dos, dos_utils.f90:1268)
+  const size_t nstates = (size_t)pw_nb * ctx->nk * ctx->ns;
   const void *d = nullptr;
   OD_CHECK(od_stage_in(ctx, pdos_weights, sizeof(double) * nstates * norb_in, pw_mem, ctx->in_tmp, &d));
   OD_CHECK(od_buf_ensure(ctx, ctx->small, sizeof(int) * (size_t)norb_in * nproj));

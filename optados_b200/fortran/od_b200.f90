@@ -23,7 +23,10 @@ module od_b200
 
   type(c_ptr), save, public :: b200_ctx = c_null_ptr
 
-  integer(c_int), parameter, public :: OD_MEM_HOST = 0, OD_MEM_DEVICE = 1
+  integer(c_int), parameter, public :: OD_MEM_HOST = 0, OD_MEM_DEVICE = 1, OD_MEM_HOST_DEFERRED = 2
+  integer(c_int), parameter, public :: OD_GEOM_POLYCRYS = 0, OD_GEOM_POLAR = 1, OD_GEOM_UNPOLAR = 2, OD_GEOM_TENSOR = 3
+  integer(c_int), parameter, public :: OD_CORE_ABSORPTION = 0, OD_CORE_EMISSION = 1, OD_CORE_ALL = 2
+  integer(c_int), parameter, public :: OD_EFERMI_OPTADOS = 0, OD_EFERMI_FILE = 1, OD_EFERMI_USER = 2, OD_EFERMI_INSULATOR = 3
 
   type, bind(c), public :: od_broadening
     real(c_double) :: adaptive_smearing
@@ -35,7 +38,233 @@ module od_b200
     real(c_double) :: hybrid_linear_grad_tol
   end type od_broadening
 
+  ! ---- the parameter / result structures of the task drivers (include/optados_b200.h, same member order)
+  type, bind(c), public :: od_dos_params
+    integer(c_int) :: fixed, adaptive, linear
+    type(od_broadening) :: br
+    real(c_double) :: dos_spacing
+    integer(c_int) :: dos_nbins
+    integer(c_int) :: have_dos_min_energy, have_dos_max_energy
+    real(c_double) :: dos_min_energy, dos_max_energy
+    integer(c_int) :: efermi_choice
+    real(c_double) :: efermi_user, efermi_castep
+    integer(c_int) :: nspins_electrons
+    real(c_double) :: num_electrons(2)
+    integer(c_int) :: dos_per_volume
+    real(c_double) :: cell_volume
+  end type od_dos_params
+  type, bind(c), public :: od_dos_result
+    integer(c_int) :: nbins
+    real(c_double) :: emin, delta_bins
+    real(c_double) :: efermi_fixed, efermi_adaptive, efermi_linear
+    integer(c_int) :: have_fixed, have_adaptive, have_linear, have_weighted
+    integer(c_int) :: weighted_norb
+  end type od_dos_result
+  type, bind(c), public :: od_jdos_params
+    integer(c_int) :: fixed, adaptive, linear
+    type(od_broadening) :: br
+    real(c_double) :: jdos_spacing, jdos_max_energy, scissor_op
+    integer(c_int) :: num_exclude_bands
+    type(c_ptr) :: exclude_bands          ! c_loc of an integer(c_int) array, or c_null_ptr
+    real(c_double) :: efermi
+    integer(c_int) :: dos_per_volume
+    real(c_double) :: cell_volume
+  end type od_jdos_params
+  type, bind(c), public :: od_jdos_result
+    integer(c_int) :: nbins
+    real(c_double) :: delta_bins
+    integer(c_int) :: have_fixed, have_adaptive, have_linear, have_weighted, n_geom
+  end type od_jdos_result
+  type, bind(c), public :: od_optics_params
+    type(od_jdos_params) :: jdos
+    integer(c_int) :: geom
+    real(c_double) :: qdir(3)
+    real(c_double) :: lossfn_gaussian
+    integer(c_int) :: intraband
+    real(c_double) :: drude_broadening
+    real(c_double) :: dos_delta_bins
+  end type od_optics_params
+  type, bind(c), public :: od_optics_result
+    integer(c_int) :: nbins, n_geom
+    real(c_double) :: delta_bins
+    integer(c_int) :: have_derived, have_loss_fn_broadened
+    real(c_double) :: n_eff, n_eff2, n_eff3
+    integer(c_int) :: n_parts, n_loss_fn
+  end type od_optics_result
+  type, bind(c), public :: od_core_params
+    type(od_dos_params) :: dos
+    integer(c_int) :: core_type, polar
+    real(c_double) :: qdir(3)
+    integer(c_int) :: lai_broadening
+    real(c_double) :: lai_gaussian_width, lai_lorentzian_width, lai_lorentzian_scale, lai_lorentzian_offset
+    integer(c_int) :: set_efermi_zero
+    real(c_double) :: core_chemical_shift
+  end type od_core_params
+  type, bind(c), public :: od_core_result
+    integer(c_int) :: nbins, norb
+    real(c_double) :: emin, delta_bins, efermi
+    integer(c_int) :: have_broadened
+  end type od_core_result
+  type, bind(c), public :: od_bandgap_result
+    real(c_double) :: vbm_energy, cbm_energy, thermal_bandgap
+    integer(c_long_long) :: thermal_vbm_k, thermal_cbm_k
+    integer(c_int) :: vbm_multiplicity(2), cbm_multiplicity(2), optical_multiplicity(2)
+    real(c_double) :: optical_bandgap(2), average_bandgap(2)
+    real(c_double) :: weighted_average
+    integer(c_int) :: thermal_multiplicity
+  end type od_bandgap_result
+
   interface
+    ! ---- the task drivers: one call = one of the reference's public L3 entry points
+    subroutine od_dos_params_defaults(p) bind(c, name='od_dos_params_defaults')
+      import :: od_dos_params
+      type(od_dos_params), intent(out) :: p
+    end subroutine
+    integer(c_int) function od_dos_utils_calculate(ctx, p, mw, mw_norb, mw_nb, mw_nk, mw_mem, res) bind(c, name='od_dos_utils_calculate')
+      import :: c_int, c_ptr, od_dos_params, od_dos_result
+      type(c_ptr), value :: ctx
+      type(od_dos_params), intent(inout) :: p
+      type(c_ptr), value :: mw             ! c_loc(matrix_weights) or c_null_ptr
+      integer(c_int), value :: mw_norb, mw_nb, mw_nk, mw_mem
+      type(od_dos_result), intent(out) :: res
+    end function
+    integer(c_int) function od_dos_get(ctx, dos_type, dos, intdos) bind(c, name='od_dos_get')
+      import :: c_int, c_ptr, c_double, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char), value :: dos_type
+      real(c_double), intent(out) :: dos(*), intdos(*)
+    end function
+    integer(c_int) function od_dos_get_weighted(ctx, weighted_dos) bind(c, name='od_dos_get_weighted')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: weighted_dos(*)
+    end function
+    integer(c_int) function od_dos_utils_set_efermi(ctx, p, efermi) bind(c, name='od_dos_utils_set_efermi')
+      import :: c_int, c_ptr, c_double, od_dos_params
+      type(c_ptr), value :: ctx
+      type(od_dos_params), intent(inout) :: p
+      real(c_double), intent(out) :: efermi
+    end function
+    integer(c_int) function od_dos_utils_calculate_at_e(ctx, p, energy, delta_bins, mw, mw_norb, mw_nb, mw_nk, mw_mem, dos_at_e, &
+                                                        weighted_dos_at_e) bind(c, name='od_dos_utils_calculate_at_e')
+      import :: c_int, c_ptr, c_double, od_dos_params
+      type(c_ptr), value :: ctx
+      type(od_dos_params), intent(in) :: p
+      real(c_double), value :: energy, delta_bins
+      type(c_ptr), value :: mw, weighted_dos_at_e
+      integer(c_int), value :: mw_norb, mw_nb, mw_nk, mw_mem
+      real(c_double), intent(out) :: dos_at_e(3, *)
+    end function
+    integer(c_int) function od_dos_utils_compute_bandgap(ctx, efermi, num_electrons, nk_global, k_first, res) &
+      bind(c, name='od_dos_utils_compute_bandgap')
+      import :: c_int, c_ptr, c_double, c_long_long, od_bandgap_result
+      type(c_ptr), value :: ctx
+      real(c_double), value :: efermi
+      real(c_double), intent(in) :: num_electrons(*)
+      integer(c_long_long), value :: nk_global, k_first
+      type(od_bandgap_result), intent(out) :: res
+    end function
+    integer(c_int) function od_dos_utils_compute_band_energies(ctx, efermi, band_energy_dos, band_energy_castep) &
+      bind(c, name='od_dos_utils_compute_band_energies')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), value :: efermi
+      real(c_double), intent(out) :: band_energy_dos(3), band_energy_castep
+    end function
+    subroutine od_jdos_params_defaults(p) bind(c, name='od_jdos_params_defaults')
+      import :: od_jdos_params
+      type(od_jdos_params), intent(out) :: p
+    end subroutine
+    integer(c_int) function od_jdos_utils_calculate(ctx, p, mw, n_geom, mw_mem, optical_mat, ome_mem, geom, qdir, symops, num_symm, res) &
+      bind(c, name='od_jdos_utils_calculate')
+      import :: c_int, c_ptr, c_double, od_jdos_params, od_jdos_result
+      type(c_ptr), value :: ctx
+      type(od_jdos_params), intent(inout) :: p
+      type(c_ptr), value :: mw, optical_mat, symops   ! exactly one of mw / optical_mat may be non-null
+      integer(c_int), value :: n_geom, mw_mem, ome_mem, geom, num_symm
+      real(c_double), intent(in) :: qdir(3)
+      type(od_jdos_result), intent(out) :: res
+    end function
+    integer(c_int) function od_jdos_get(ctx, jdos_type, jdos) bind(c, name='od_jdos_get')
+      import :: c_int, c_ptr, c_double, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char), value :: jdos_type
+      real(c_double), intent(out) :: jdos(*)
+    end function
+    integer(c_int) function od_jdos_get_weighted(ctx, weighted_jdos) bind(c, name='od_jdos_get_weighted')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: weighted_jdos(*)
+    end function
+    integer(c_int) function od_calculate_jdos_optics(ctx, jdos_type, delta_bins, nbins, br, efermi, scissor_op, exclude_bands, &
+                                                     num_exclude_bands, optical_mat, ome_mem, geom, qdir, symops, num_symm, merge, &
+                                                     jdos, weighted_jdos) bind(c, name='od_calculate_jdos_optics')
+      import :: c_int, c_ptr, c_double, c_char, od_broadening
+      type(c_ptr), value :: ctx
+      character(kind=c_char), value :: jdos_type
+      real(c_double), value :: delta_bins, efermi, scissor_op
+      integer(c_int), value :: nbins, num_exclude_bands, ome_mem, geom, num_symm, merge
+      type(od_broadening), intent(in) :: br
+      integer(c_int), intent(in) :: exclude_bands(*)
+      complex(c_double_complex), intent(in) :: optical_mat(*)
+      real(c_double), intent(in) :: qdir(3)
+      type(c_ptr), value :: symops
+      real(c_double), intent(out) :: jdos(*), weighted_jdos(*)
+    end function
+    subroutine od_optics_params_defaults(p) bind(c, name='od_optics_params_defaults')
+      import :: od_optics_params
+      type(od_optics_params), intent(out) :: p
+    end subroutine
+    integer(c_int) function od_optics_calculate(ctx, p, optical_mat, ome_mem, symops, num_symm, res) bind(c, name='od_optics_calculate')
+      import :: c_int, c_ptr, c_double, od_optics_params, od_optics_result
+      type(c_ptr), value :: ctx
+      type(od_optics_params), intent(inout) :: p
+      complex(c_double_complex), intent(in) :: optical_mat(*)
+      integer(c_int), value :: ome_mem, num_symm
+      type(c_ptr), value :: symops
+      type(od_optics_result), intent(out) :: res
+    end function
+    integer(c_int) function od_optics_get(ctx, E, epsilon, conduct, refract, loss_fn, absorp, reflect) bind(c, name='od_optics_get')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: E, epsilon, conduct, refract, loss_fn, absorp, reflect   ! c_loc(array) or c_null_ptr
+    end function
+    subroutine od_core_params_defaults(p) bind(c, name='od_core_params_defaults')
+      import :: od_core_params
+      type(od_core_params), intent(out) :: p
+    end subroutine
+    integer(c_int) function od_core_calculate(ctx, p, elnes_mat, elnes_mem, norb, symops, num_sym, res) bind(c, name='od_core_calculate')
+      import :: c_int, c_ptr, c_double, od_core_params, od_core_result
+      type(c_ptr), value :: ctx
+      type(od_core_params), intent(inout) :: p
+      complex(c_double_complex), intent(in) :: elnes_mat(*)
+      integer(c_int), value :: elnes_mem, norb, num_sym
+      type(c_ptr), value :: symops
+      type(od_core_result), intent(out) :: res
+    end function
+    integer(c_int) function od_core_get(ctx, E, weighted_dos, weighted_dos_broadened) bind(c, name='od_core_get')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: E, weighted_dos, weighted_dos_broadened
+    end function
+    integer(c_int) function od_host_register(hptr, nbytes) bind(c, name='od_host_register')
+      import :: c_int, c_ptr, c_size_t
+      type(c_ptr), value :: hptr
+      integer(c_size_t), value :: nbytes
+    end function
+    integer(c_int) function od_host_unregister(hptr) bind(c, name='od_host_unregister')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: hptr
+    end function
+    integer(c_int) function od_abi_sizeof(struct_name) bind(c, name='od_abi_sizeof')
+      import :: c_int, c_char
+      character(kind=c_char), intent(in) :: struct_name(*)            ! null-terminated
+    end function
+    integer(c_int) function od_run_seed(ctx, dir, seedname) bind(c, name='od_run_seed')
+      import :: c_int, c_ptr, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char), intent(in) :: dir(*), seedname(*)       ! null-terminated
+    end function
     integer(c_int) function od_ctx_create(device, ctx) bind(c, name='od_ctx_create')
       import :: c_int, c_ptr
       integer(c_int), value :: device
@@ -142,12 +371,12 @@ module od_b200
       real(c_double), value :: efermi
       real(c_double), intent(out) :: mw(*)
     end function
-    integer(c_int) function od_projection_merge(ctx, pdos_weights, pw_mem, mask, norb_in, nproj, mw, out_mem) &
+    integer(c_int) function od_projection_merge(ctx, pdos_weights, pw_mem, mask, norb_in, pw_nb, nproj, mw, out_mem) &
       bind(c, name='od_projection_merge')
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: ctx
       real(c_double), intent(in) :: pdos_weights(*)
-      integer(c_int), value :: pw_mem, norb_in, nproj, out_mem
+      integer(c_int), value :: pw_mem, norb_in, pw_nb, nproj, out_mem
       integer(c_int), intent(in) :: mask(norb_in, nproj)
       real(c_double), intent(out) :: mw(*)
     end function
@@ -185,6 +414,11 @@ module od_b200
   public :: b200_make_weights, b200_core_weights, b200_projection_merge, b200_broadening
   public :: od_allreduce, od_comm_get_unique_id
   public :: od_calc_epsilon_1, od_calc_loss_fn, od_core_lai_broadening
+  public :: od_dos_params_defaults, od_dos_utils_calculate, od_dos_get, od_dos_get_weighted, od_dos_utils_set_efermi
+  public :: od_dos_utils_calculate_at_e, od_dos_utils_compute_bandgap, od_dos_utils_compute_band_energies
+  public :: od_jdos_params_defaults, od_jdos_utils_calculate, od_jdos_get, od_jdos_get_weighted, od_calculate_jdos_optics
+  public :: od_optics_params_defaults, od_optics_calculate, od_optics_get
+  public :: od_core_params_defaults, od_core_calculate, od_core_get, od_run_seed
 
 contains
 
@@ -211,8 +445,21 @@ contains
     use od_comms, only: my_node_id, num_nodes
     use od_cell, only: recip_lattice, kpoint_grid_dim, kpoint_weight, num_kpoints_on_node
     use od_electronic, only: nspins, nbands, electrons_per_state
+    use od_io, only: io_error
     integer, intent(in) :: local_device
     character(kind=c_char), intent(in) :: id128(128)
+    type(od_dos_params) :: chk_dos
+    type(od_jdos_params) :: chk_jdos
+    type(od_optics_params) :: chk_optics
+    type(od_core_params) :: chk_core
+    type(od_bandgap_result) :: chk_gap
+    ! the derived types above must have the layout the library was compiled with
+    if (c_sizeof(chk_dos) /= od_abi_sizeof('od_dos_params'//c_null_char) .or. &
+        c_sizeof(chk_jdos) /= od_abi_sizeof('od_jdos_params'//c_null_char) .or. &
+        c_sizeof(chk_optics) /= od_abi_sizeof('od_optics_params'//c_null_char) .or. &
+        c_sizeof(chk_core) /= od_abi_sizeof('od_core_params'//c_null_char) .or. &
+        c_sizeof(chk_gap) /= od_abi_sizeof('od_bandgap_result'//c_null_char)) &
+      call io_error('optados_b200: od_b200.f90 and liboptados_b200.so disagree on a structure layout (rebuild both)')
     if (num_nodes > 1) then
       call b200_check(od_ctx_create_rank(int(local_device, c_int), int(my_node_id, c_int), int(num_nodes, c_int), id128, b200_ctx))
     else
@@ -235,9 +482,14 @@ contains
   end subroutine b200_upload_bands
 
   !> call once after elec_read_band_gradient (electronic.f90:170)
+  !> band_gradient is the big input (12 GB at BASELINE config 2).  Page-lock the Fortran array once (od_host_register: a
+  !> pageable source is staged through a bounce buffer at a fraction of the PCIe rate) and hand the library the HOST
+  !> pointer: with OD_MEM_HOST_DEFERRED it is uploaded slab by slab inside calculate_dos, under the kernels.
   subroutine b200_upload_gradients()
     use od_electronic, only: band_gradient
-    call b200_check(od_set_gradients(b200_ctx, band_gradient, OD_MEM_HOST))
+    integer(c_int) :: ierr
+    ierr = od_host_register(c_loc(band_gradient), int(size(band_gradient), c_size_t)*8_c_size_t)   ! (failure = stay pageable)
+    call b200_check(od_set_gradients(b200_ctx, band_gradient, OD_MEM_HOST_DEFERRED))
   end subroutine b200_upload_gradients
 
   function b200_broadening() result(br)
@@ -372,7 +624,7 @@ contains
       end do
     end do
     call b200_check(od_projection_merge(b200_ctx, pdos_weights, OD_MEM_HOST, mask, int(pdos_mwab%norbitals, c_int), &
-                                        int(num_proj, c_int), matrix_weights, OD_MEM_HOST))
+                                        int(pdos_mwab%nbands, c_int), int(num_proj, c_int), matrix_weights, OD_MEM_HOST))
   end subroutine b200_projection_merge
 
 end module od_b200

@@ -112,6 +112,23 @@ def test_compare_dos_and_options(ob, odo):
     ctx.close()
 
 
+def test_pdos_file_with_fewer_bands_than_the_bands_file(ob, odo):
+    """projection_merge loops over pdos_mwab%nbands (projection_utils.f90:84), which a .pdos_bin written with
+    fewer bands than the .bands file makes smaller than nbands; the result is consumed with mw%nbands (dos_utils.f90:1268)"""
+    fx = fixture("si2_dos")
+    ctx, s = gpu_ctx(ob, fx, odo)
+    pw = np.asfortranarray(fx["pdos_weights"][:, : s.nb - 3, :, :])
+    mask = pdos_mask(fx, [dict(am=0), dict(am=1), dict(species=1, rank=2)])
+    mw = ctx.projection_merge(pw, mask)
+    ref_mw = odo.projection_merge(pw, mask)
+    assert mw.shape == ref_mw.shape == (3, s.nb - 3, s.nk, s.ns) and np.array_equal(mw, ref_mw)
+    E, delta, n = odo.dos_energy_scale(s, 0.05)
+    ref = odo.calculate_dos("a", s, odo.make_broadening(), E, delta, ref_mw)
+    dos, intdos, wdos = ctx.calculate_dos("a", E[0], delta, n, mw=mw)
+    assert rel_to_peak(wdos, ref[2]) < TOL_SPEC and rel_to_peak(dos, ref[0]) < TOL_SPEC
+    ctx.close()
+
+
 @pytest.mark.parametrize("test,fxname,projectors", [
     ("testopt_pdos_angular", "si2_optics", [dict(am=l) for l in range(4)]),
     ("testopt_pdos_string2", "si2_dos", [dict(species=1, rank=1, am=1)]),
