@@ -141,11 +141,14 @@ __device__ __forceinline__ void od_sub_cell_corners_fast(const double grad[3], c
   if (B < C) { t = B; B = C; C = t; }
   if (A < B) { t = A; A = B; B = t; }
   const double ab = A + B, amb = A - B;
+  // (A - B) + C <= (A + B) - C exactly, but not after rounding when B == C: keep EV[3] <= EV[2] (doslin `stop`s on
+  // unordered corners, dos_utils.f90:1430)
+  const double x2 = amb + C, x3 = fmax(ab - C, x2);
   EV[0] = energy;
   EV[1] = energy + fmin(C - amb, amb - C);
-  EV[2] = energy - (amb + C);
-  EV[3] = energy - (ab - C);
-  EV[4] = energy - (ab + C);
+  EV[2] = energy - x2;
+  EV[3] = energy - x3;
+  EV[4] = energy - fmax(ab + C, x3);
 }
 
 __device__ __forceinline__ void od_sub_cell_corners(const double grad[3], const double step[3], const double *rs,

@@ -368,6 +368,8 @@ struct NarrowArgs {
   double *out_dos, *out_int, *out_step;  // [ns * bpad + NR_T]; JD mode: out_dos / out_int are the two channels
   double *out_dos_em, *out_corr;         // Gaussian DOS, Euler-Maclaurin groups: their DOS and the correction sums
   int no_em;                             // OD_NO_EM=1: rational erfc for every group (tests)
+  int debug;                             // OD_NARROW_DEBUG bit 0: every group through the record-by-record path
+  int *flags;                            // ctx->flags: [0] |= doslin `stop` conditions (reported by od_check_deferred)
   // JD (JDOS / optics) mode: channel pass `chan` accumulates K*m0 and K*m1 with (m0, m1) =
   // (1, wt[0]) for chan 0 and (wt[2 chan - 1], wt[2 chan]) after that; wts[rec * ng + a]
   const double *wts;
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       // exp underflows.  Gaussian only; del <= 8 by construction, so this only trips on sparse data.
       bool irregular = Wc + 1 > NR_T - A.cell;  // (+1: the step of a centre just above the window)
       if (!LINEAR) irregular = irregular || (valid[0] && (double)a[0] * delta > 25.0 * p1[0]) || (valid[1] && (double)a[1] * delta > 25.0 * p1[1]);
-      irregular = __any_sync(FULL, irregular);
+      irregular = __any_sync(FULL, irregular) || (A.debug & 1);
 
       if (irregular) {
         // sparse data, a group that straddles the two spin channels, ...: record by record, lanes over
@@ -638,6 +640,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
                 double cum; int bad = 0;
                 d = od_doslin(a0, a1, a2, a3, a4, Ej, &cum, &bad) * ao;
                 sv = ((r < c_l) ? cum : cum - 1.0) * ao;
+                if (bad) atomicOr(&A.flags[0], bad);
               } else {
                 gauss_direct(a0, a1, ao, Ej, r, c_l, A.cf, d, sv);
               }
@@ -1234,6 +1237,8 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, int col0, int col1
   A.out_dos_em = JD ? nullptr : S.chan + 2 * S.nout;  // DOS: chan = [dos | int | dos_em | corr]
   A.out_corr = JD ? nullptr : S.chan + 3 * S.nout;
   A.no_em = getenv("OD_NO_EM") ? 1 : 0;
+  A.debug = getenv("OD_NARROW_DEBUG") ? atoi(getenv("OD_NARROW_DEBUG")) : 0;
+  A.flags = ctx->flags.as<int>();
   A.wts = S.ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
   A.ng = S.ps.ng;
   A.col0 = col0;

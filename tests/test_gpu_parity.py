@@ -1221,3 +1221,47 @@ def test_nonsymmetric_lattice_jdos_and_optics(ob, odo, jtype):
         mw_g = ctx.make_weights(om, geom, ef, qdir=q, symops=symops)
         assert np.abs(mw_g - mw).max() <= 1e-12 * np.abs(mw).max()
     ctx.close()
+
+
+@pytest.mark.parametrize("dos_type", ["l", "a"])
+def test_record_by_record_path_on_a_symmetric_mesh(ob, odo, dos_type, monkeypatch):
+    """The narrow engine's record-by-record path (groups that straddle the spin channels or are too sparse for a tile) is
+    taken by a handful of groups per call, so a bug there shows up as a few missing states at sizes no oracle test reaches
+    (found in round 2 through bench.py's multi_gpu_parity: 1e-5 of peak on the linear DOS).  OD_NARROW_DEBUG=1 sends EVERY group
+    through it.  The cubic synthetic mesh has k-points with two gradient components of equal magnitude, where the closed-form
+    sub-cell corners (A - B) + C and (A + B) - C must stay ordered after rounding (doslin stops on unordered corners,
+    dos_utils.f90:1430)."""
+    ctx = ob.Context(0)
+    grid, ns, nb = (20, 20, 20), 2, 24
+    nk = 3000
+    ctx.synth_bands(grid, 0, nk, ns, nb, seed=2)
+    be, bg, kw = ctx.get_bands(), ctx.get_gradients(), ctx.get_kweights()
+    s = odo.Sys(be, kw, np.eye(3) * (2 * np.pi / 5.43), grid, bg, electrons_per_state=1.0)
+    E, delta, n = odo.dos_energy_scale(s, 0.0, dos_nbins=6000)
+    ref = odo.calculate_dos(dos_type, s, odo.make_broadening(), E, delta, nthreads=8)
+    for dbg in ("0", "1"):
+        monkeypatch.setenv("OD_NARROW_DEBUG", dbg)
+        dos, intdos, _ = ctx.calculate_dos(dos_type, E[0], delta, n)
+        assert rel_to_peak(dos, ref[0]) < 1e-11, dbg
+        assert np.abs(intdos - ref[1]).max() < 1e-12 * np.abs(ref[1]).max(), dbg
+    ctx.close()
+
+
+def test_result_does_not_depend_on_the_kpoint_slabs(ob, monkeypatch):
+    """the spectra of one call must not depend on how the k-points are cut into slabs (different slab sizes put different
+    records into the sparse / straddling groups)"""
+    ctx = ob.Context(0)
+    grid, ns, nb, nbins = (100, 100, 100), 2, 64, 12000
+    ctx.synth_bands(grid, 240000, 4000, ns, nb, seed=2)
+    emin, delta = -14.9, 44.5 / (nbins - 1)
+    for t in ("l", "a"):
+        monkeypatch.delenv("OD_SLAB_UNITS", raising=False)
+        monkeypatch.delenv("OD_LINEAR_SLAB_UNITS", raising=False)
+        d0, i0, _ = ctx.calculate_dos(t, emin, delta, nbins)
+        for su in ("40000", "130000"):
+            monkeypatch.setenv("OD_SLAB_UNITS", su)
+            monkeypatch.setenv("OD_LINEAR_SLAB_UNITS", su)
+            d, i, _ = ctx.calculate_dos(t, emin, delta, nbins)
+            assert rel_to_peak(d, d0) < 1e-12, (t, su)
+            assert np.abs(i - i0).max() < 1e-12 * np.abs(i0).max(), (t, su)
+    ctx.close()
