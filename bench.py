@@ -213,11 +213,14 @@ def main():
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     args = parse()
-    rank, world, local, dist = dist_setup(args)
     if args.impl == "reference":
-        run_reference(args, rank, world, local, dist)
-        barrier(dist)
+        # rank 0 alone runs the CPU arm; the other ranks leave at once WITHOUT joining a process group (ranks spinning in a
+        # barrier would take host cores away from the loop being timed)
+        rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+        if rank == 0:
+            run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")), local, None)
         return
+    rank, world, local, dist = dist_setup(args)
     import optados_b200 as ob
 
     nk_named = args.nk if args.nk else GRID[0] * GRID[1] * GRID[2]
@@ -227,15 +230,19 @@ def main():
         grid_total, nk_total = GRID, nk_named
     per = ob.dist_array(nk_total, world)            # algor_dist_array (algorithms.f90:309)
     nk_gpu, k_first = per[rank], sum(per[:rank])
-    uid = None
-    if world > 1:
+    def new_ctx():
+        """one context per rank; a communicator id serves ONE ncclCommInitRank round, so every new set of rank contexts gets
+        a fresh id from rank 0 (collective: every rank calls this)"""
+        if world == 1:
+            return ob.Context(local)
         import torch
         buf = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", local))
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(ob.get_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
-    ctx = ob.Context(local, rank, world, uid)
+        return ob.Context(local, rank, world, bytes(buf.cpu().numpy().tobytes()))
+
+    ctx = new_ctx()
     if args.partition == "cyclic":     # same counts as algor_dist_array, k = rank + i * world
         ctx.synth_bands(grid_total, rank, nk_gpu, NS, NB, lattice_a=LATTICE_A, seed=SEED, k_stride=world)
     else:
@@ -395,7 +402,7 @@ def main():
         bc = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(bc)
         env = bc.Env(local=local, rank=rank, world=world,
-                     make_ctx=lambda: ob.Context(local, rank, world, uid) if world > 1 else ob.Context(local),
+                     make_ctx=new_ctx,
                      max_over_ranks=lambda x: max_over_ranks(dist, x, local), sum_over_ranks=lambda x: sum_over_ranks(dist, x, local),
                      barrier=lambda: barrier(dist), fp64_peak=fp64_peak, hbm_peak=hbm_peak, reps=2, parity=True)
         configs = {}
