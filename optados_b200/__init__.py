@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liboptados_b200.so")
+LIB_PATH = os.environ.get("OD_B200_LIB") or os.path.join(_HERE, "lib", "liboptados_b200.so")   # (override: kernel-variant experiments only)
 
 OD_MEM_HOST, OD_MEM_DEVICE, OD_MEM_HOST_DEFERRED = 0, 1, 2
 GEOM = {"polycrys": 0, "polar": 1, "unpolar": 2, "tensor": 3}

@@ -43,6 +43,7 @@
 //     reproducible to rounding (~1e-16 relative), not bit for bit.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <type_traits>
 
@@ -58,7 +59,10 @@ constexpr int NR_WARPS = 8;      // warps per CTA
 constexpr int NR_CTAS_PER_SM = 2; // accumulate kernels: 2 x 8 warps per SM (registers and shared memory both allow no more)
 constexpr int NR_NCLS = 10;      // width classes
 constexpr int NR_MAXBUCKETS = 52224;  // x 4 B = 204 KB of shared memory in the prepare passes
-constexpr int NR_PREP_THREADS = 1024;
+#ifndef OD_PREP_THREADS
+#define OD_PREP_THREADS 512
+#endif
+constexpr int NR_PREP_THREADS = OD_PREP_THREADS;   // x PREP_U units per thread in flight (the 204 KB bucket table allows one CTA per SM)
 constexpr unsigned KEY_WIDE = 0xFFFFFFFEu, KEY_DROP = 0xFFFFFFFFu;
 
 struct __align__(32) GRec {  // Gaussian record
@@ -73,10 +77,13 @@ struct __align__(64) LRec {  // linear record
   double pad;
 };
 
+static_assert(sizeof(GRec) == 32 && offsetof(GRec, klo) == 24 && sizeof(LRec) == 64 && offsetof(LRec, klo) == 48, "record layouts the 32-byte stores of the scatter pass write");
+
 struct PrepSpec {
   GridSpec grid;
   int bpad;      // padded bins per spin (>= nbins + NR_T)
   int cell;      // bins per position cell (power of two)
+  int cshift;    // log2(cell)
   int ncells;    // ns * bpad / cell
   int nbuckets;  // NR_NCLS * ncells; bucket = class * ncells + cell
   double gwin;      // half-width of a Gaussian window in units of w (erf window for DOS, cut-off for JDOS)
@@ -140,35 +147,52 @@ __device__ __forceinline__ Cls classify(const RecOut &r, const PrepSpec &ps) {
 }
 
 // ---------------------------------------------------------------- pass A: keys + per-CTA histogram row
+// Both prepare passes walk the units in tiles of NR_PREP_THREADS * U consecutive units per CTA (pass A and pass B MUST use the
+// same unit -> CTA mapping: the write cursors of pass B are per CTA).  A thread issues the loads of its U units of a tile
+// before it touches the first of them: the passes are bound by memory latency (ncu, round 1: long-scoreboard stalls, 30 % of
+// the DRAM bandwidth with one unit per thread in flight), not by bandwidth or arithmetic.
 template <class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
 prep_hist_kernel(Producer prod, PrepSpec ps, unsigned *__restrict__ keys, unsigned *__restrict__ table /* [gridDim.x][nbuckets] */,
                  unsigned long long *__restrict__ wide_count /* [ns] */) {
   extern __shared__ unsigned sh_hist[];
+  constexpr int U = Producer::PREP_U;
   for (int i = threadIdx.x; i < ps.nbuckets; i += blockDim.x) sh_hist[i] = 0;
   __syncthreads();
   unsigned long long wide0 = 0, wide1 = 0;
-  const unsigned upz = (unsigned)prod.units_per_z, stride = gridDim.x * blockDim.x;
+  const unsigned upz = (unsigned)prod.units_per_z, tile = NR_PREP_THREADS * U;
   for (int is = 0; is < prod.ns; ++is)
-  for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < upz; u += stride) {
-    const size_t t = (size_t)is * upz + u;
-    RecOut r;
-    r.mode = -1;
-    prod(u, is, r);
-    Cls c;
-    c.kind = 2;
-    if (r.mode >= 0) c = classify(r, ps);
-    unsigned key;
-    if (c.kind == 0) {
-      key = (unsigned)(width_class(c.wlen) * ps.ncells + (is * ps.bpad + c.klo) / ps.cell);
-      atomicAdd(&sh_hist[key], 1u);
-    } else if (c.kind == 1) {
-      key = KEY_WIDE;
-      if (is == 0) wide0++; else wide1++;
-    } else {
-      key = KEY_DROP;
+  for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < upz; t0 += (unsigned long long)gridDim.x * tile) {
+    typename Producer::Raw raw[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const unsigned long long u = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
+      if (u < upz) prod.template load<false>((unsigned)u, is, raw[j]);
     }
-    keys[t] = key;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const unsigned long long u = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
+      if (u >= upz) continue;
+      RecOut r;
+      r.mode = -1;
+      prod.template make<false>((unsigned)u, is, raw[j], r);
+      Cls c;
+      c.kind = 2;
+      if (r.mode >= 0) c = classify(r, ps);
+      unsigned key;
+      if (c.kind == 0) {
+        // key = cell index * 16 + width class (bucket = class * ncells + cell index: no division in either pass)
+        const unsigned cls = (unsigned)width_class(c.wlen), ci = (unsigned)(is * ps.bpad + c.klo) >> ps.cshift;
+        key = ci * 16u + cls;
+        atomicAdd(&sh_hist[cls * (unsigned)ps.ncells + ci], 1u);
+      } else if (c.kind == 1) {
+        key = KEY_WIDE;
+        if (is == 0) wide0++; else wide1++;
+      } else {
+        key = KEY_DROP;
+      }
+      keys[(size_t)is * upz + u] = key;
+    }
   }
   __syncthreads();
   unsigned *row = table + (size_t)blockIdx.x * ps.nbuckets;
@@ -239,16 +263,15 @@ __global__ void __launch_bounds__(1024) scan_kernel(const unsigned *__restrict__
   }
 }
 
-// a record leaves as 16-byte stores (2 / 4 per record instead of one store per field: the LSU queue is what the
-// scatter pass runs out of)
-template <int N16>
-__device__ __forceinline__ void store_rec16(void *dst, const void *src) {
-  const uint4 *s = reinterpret_cast<const uint4 *>(src);
-  uint4 v[N16];
-#pragma unroll
-  for (int i = 0; i < N16; ++i) v[i] = s[i];
-#pragma unroll
-  for (int i = 0; i < N16; ++i) reinterpret_cast<uint4 *>(dst)[i] = v[i];
+// A record leaves as 32-byte stores (st.global.v4.f64 = STG.E.ENL2.256, sm_100): the scatter pass is bound by the number of
+// store transactions in flight per SM -- every record lands in a different line -- so 8-byte stores (4 / 8 per record),
+// 16-byte stores (2 / 4) and 32-byte stores (1 / 2) differ in proportion.
+__device__ __forceinline__ void st256(void *dst, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+// (klo, cpos, wlen) as the last 8 bytes of a record: int klo | unsigned short cpos | unsigned short wlen
+__device__ __forceinline__ double rec_tail(int klo, int cpos, int wlen) {
+  return __hiloint2double((int)((unsigned)cpos | ((unsigned)wlen << 16)), klo);
 }
 
 // ---------------------------------------------------------------- pass B: scatter (shared-memory cursors)
@@ -259,48 +282,74 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
                     double *__restrict__ stephist,
                     unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor, long long wide_stride) {
   extern __shared__ unsigned sh_cur[];
+  constexpr int U = Producer::PREP_U;
   const unsigned *row = table + (size_t)blockIdx.x * ps.nbuckets;
   for (int i = threadIdx.x; i < ps.nbuckets; i += blockDim.x) sh_cur[i] = base[i] + row[i];
   __syncthreads();
-  const unsigned upz = (unsigned)prod.units_per_z, stride = gridDim.x * blockDim.x;
-  for (int is = 0; is < prod.ns; ++is)
-  for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < upz; u += stride) {
-    const size_t t = (size_t)is * upz + u;
-    const unsigned key = keys[t];
-    if (key == KEY_WIDE) {
-      const unsigned long long pos = atomicAdd(&wide_cursor[is], 1ull);
-      widelist[(size_t)is * wide_stride + pos] = (unsigned)u;
-      continue;
+  const unsigned upz = (unsigned)prod.units_per_z, tile = NR_PREP_THREADS * U;
+  const unsigned long long tstep = (unsigned long long)gridDim.x * tile;
+  for (int is = 0; is < prod.ns; ++is) {
+  unsigned key_next[U];
+  auto load_keys = [&](unsigned long long t0) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const unsigned long long u = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
+      key_next[j] = (u < upz) ? keys[(size_t)is * upz + u] : KEY_WIDE;  // (KEY_WIDE: nothing to load; the slot is skipped below)
     }
-    if (key == KEY_DROP && !ps.with_int) continue;  // null pair / off-grid unit without a step
-    RecOut r;
-    r.mode = -1;
-    prod(u, is, r);
-    if (r.mode < 0) continue;
-    const Cls c = classify(r, ps);
-    if (key == KEY_DROP) {  // off the grid: only its step (rare)
-      if (c.cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + c.cstep], r.omega);
-      continue;
+  };
+  load_keys((unsigned long long)blockIdx.x * tile);
+  for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < upz; t0 += tstep) {
+    typename Producer::Raw raw[U];
+    unsigned key[U];
+    // the keys of this tile were loaded one iteration ago; issue every input load of the tile, then the keys of the
+    // next tile, before the first use: two levels of loads in flight per thread
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const unsigned long long u = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
+      key[j] = key_next[j];
+      if (key[j] != KEY_WIDE && (key[j] != KEY_DROP || ps.with_int)) prod.template load<true>((unsigned)u, is, raw[j]);
     }
-    const unsigned pos = atomicAdd(&sh_cur[key], 1u);
-    // keep the record inside the cell pass A counted it in, whatever this pass recomputed
-    const int cell_lo = (int)(key % (unsigned)ps.ncells) * ps.cell - is * ps.bpad;
-    int klo = min(max(c.klo, cell_lo), cell_lo + ps.cell - 1);
-    const int wlen = min(max(c.wlen - (klo - c.klo), 1), NR_WMAX);
-    const int cpos = min(max(c.cstep - klo, 0), wlen);
-    if (LINEAR) {
-      LRec o;
-      o.e0 = r.e0; o.e1 = r.p1; o.e2 = r.p2; o.e3 = r.p3; o.e4 = r.p4; o.om = r.omega;
-      o.klo = is * ps.bpad + klo; o.cpos = (unsigned short)cpos; o.wlen = (unsigned short)wlen; o.pad = 0.0;
-      reinterpret_cast<LRec *>(recs_v)[pos] = o;  // (16-byte stores measured slower here: register pressure)
-    } else {
-      GRec o;
-      o.e = r.e0; o.w = r.p1; o.om = r.omega;
-      o.klo = is * ps.bpad + klo; o.cpos = (unsigned short)cpos; o.wlen = (unsigned short)wlen;
-      store_rec16<sizeof(GRec) / 16>(reinterpret_cast<GRec *>(recs_v) + pos, &o);
+    load_keys(t0 + tstep);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const unsigned long long ul = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
+      if (ul >= upz) continue;
+      const unsigned u = (unsigned)ul;
+      if (key[j] == KEY_WIDE) {
+        const unsigned long long pos = atomicAdd(&wide_cursor[is], 1ull);
+        widelist[(size_t)is * wide_stride + pos] = u;
+        continue;
+      }
+      if (key[j] == KEY_DROP && !ps.with_int) continue;  // null pair / off-grid unit without a step
+      RecOut r;
+      r.mode = -1;
+      prod.template make<true>(u, is, raw[j], r);
+      if (r.mode < 0) continue;
+      const Cls c = classify(r, ps);
+      if (key[j] == KEY_DROP) {  // off the grid: only its step (rare)
+        if (c.cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + c.cstep], r.omega);
+        continue;
+      }
+      const unsigned ci = key[j] >> 4;
+      const unsigned pos = atomicAdd(&sh_cur[(key[j] & 15u) * (unsigned)ps.ncells + ci], 1u);
+      // keep the record inside the cell pass A counted it in, whatever this pass recomputed
+      const int cell_lo = (int)(ci << ps.cshift) - is * ps.bpad;
+      int klo = min(max(c.klo, cell_lo), cell_lo + ps.cell - 1);
+      const int wlen = min(max(c.wlen - (klo - c.klo), 1), NR_WMAX);
+      const int cpos = min(max(c.cstep - klo, 0), wlen);
+      if (LINEAR) {
+        LRec *o = reinterpret_cast<LRec *>(recs_v) + pos;
+        st256(o, r.e0, r.p1, r.p2, r.p3);
+        st256(reinterpret_cast<char *>(o) + 32, r.p4, r.omega, rec_tail(is * ps.bpad + klo, cpos, wlen), 0.0);
+      } else {
+        st256(reinterpret_cast<GRec *>(recs_v) + pos, r.e0, r.p1, r.omega, rec_tail(is * ps.bpad + klo, cpos, wlen));
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a)  // (static indices: a loop over ps.ng would put the whole record into local memory)
+        if (a < ps.ng) wts[(size_t)pos * ps.ng + a] = r.wt[a];
+      if (ps.want_unit) runit[pos] = u;
     }
-    for (int a = 0; a < ps.ng; ++a) wts[(size_t)pos * ps.ng + a] = r.wt[a];
-    if (ps.want_unit) runit[pos] = u;
+  }
   }
 }
 
@@ -1200,15 +1249,14 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   OD_LAUNCH_CHECK(ctx);
   double *wts = ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
   unsigned *runit = ps.want_unit ? ctx->scratch_e.as<unsigned>() : nullptr;
-  if (linear) {
-    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<true, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-    prep_scatter_kernel<true, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(
-        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride);
-  } else {
-    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<false, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-    prep_scatter_kernel<false, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(
-        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride);
-  }
+#define SC_LAUNCH(LIN)                                                                                                               \
+  do {                                                                                                                               \
+    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<LIN, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem)); \
+    prep_scatter_kernel<LIN, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(                                         \
+        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride); \
+  } while (0)
+  if (linear) SC_LAUNCH(true); else SC_LAUNCH(false);
+#undef SC_LAUNCH
   OD_LAUNCH_CHECK(ctx);
   return OD_OK;
 }
@@ -1279,6 +1327,8 @@ int narrow_scratch(od_ctx *ctx, const GridSpec &grid, int ns, long long total_un
   ps.grid = grid;
   ps.cell = narrow_cell_for(grid.nbins, ns);
   if (ps.cell == 0) return od_fail(ctx, OD_ERR_ARG, "narrow engine: energy grid too large (%d bins)", grid.nbins);
+  ps.cshift = 0;
+  while ((1 << ps.cshift) < ps.cell) ++ps.cshift;
   ps.bpad = ((grid.nbins + NR_T + ps.cell - 1) / ps.cell) * ps.cell;
   ps.ncells = ns * ps.bpad / ps.cell;
   ps.nbuckets = NR_NCLS * ps.ncells;

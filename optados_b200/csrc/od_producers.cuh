@@ -2,6 +2,28 @@
 #pragma once
 #include "od_accum.cuh"
 
+// n / d for 32-bit n by multiplication (Granlund-Montgomery round-up method, exact for every n < 2^32): the prepare passes
+// of the narrow engine split a unit index into (k-point, band) once per unit, and an integer division is ~20 instructions
+struct FastDiv {
+  unsigned d = 1, m = 1, s1 = 0, s2 = 0;
+  FastDiv() = default;
+  explicit FastDiv(unsigned div) : d(div) {
+    unsigned l = 0;
+    while ((1ull << l) < div) ++l;  // ceil(log2 d)
+    m = (unsigned)(((1ull << 32) * ((1ull << l) - div)) / div + 1);
+    s1 = l < 1 ? l : 1;
+    s2 = l > 1 ? l - 1 : 0;
+  }
+  __host__ __device__ __forceinline__ unsigned div(unsigned n) const {
+#ifdef __CUDA_ARCH__
+    const unsigned t = __umulhi(m, n);
+#else
+    const unsigned t = (unsigned)(((unsigned long long)m * n) >> 32);
+#endif
+    return (t + ((n - t) >> s1)) >> s2;
+  }
+};
+
 // Broadening set-up common to calculate_dos / calculate_dos_at_e / calculate_jdos
 // (dos_utils.f90:1208-1218, jdos_utils.f90:324-334)
 struct BroadSpec {
@@ -55,6 +77,37 @@ struct DosProducer {
   const double *mw;  // matrix_weights(norb, mw_nb, mw_nk, ns) or null
   int norb, mw_nb, mw_nk;
   int og;  // orbitals per z-slice group (== NW of the kernel)
+  FastDiv nb_div;  // / nb (set by dos_producer)
+
+  // The prepare passes of the narrow engine split a unit into its loads and the arithmetic on them, so that a thread can
+  // have the loads of several units in flight at once (PREP_U units per thread and iteration; the passes are bound by
+  // memory latency, not by bandwidth).  No weights here: those passes run with mw == nullptr.
+  struct Raw {
+    double e, g0, g1, g2, kw;
+  };
+#ifndef OD_PREP_U_DOS
+#define OD_PREP_U_DOS 4
+#endif
+  static constexpr int PREP_U = OD_PREP_U_DOS;
+  template <bool WT>
+  __device__ __forceinline__ void load(unsigned u, int is, Raw &w) const {
+    const unsigned ikl = nb_div.div(u), ib = u - ikl * (unsigned)nb;
+    const long long ik = k_first + ikl;
+    w.e = bands[ib + (size_t)nb * (is + (size_t)ns * ik)];
+    w.g0 = w.g1 = w.g2 = 0.0;
+    if (b.type != 0) {
+      const size_t gi = ib + (size_t)nb * (3 * (ikl + (size_t)nk_g * is));
+      w.g0 = grads[gi];
+      w.g1 = grads[gi + nb];
+      w.g2 = grads[gi + 2 * (size_t)nb];
+    }
+    w.kw = kw[ik];
+  }
+  template <bool WT>
+  __device__ __forceinline__ void make(unsigned, int, const Raw &w, RecOut &r) const {
+    const double g[3] = {w.g0, w.g1, w.g2};
+    od_make_record(b, w.e, g, eps * w.kw, r);
+  }
 
   __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
     const int is = z % ns, grp = z / ns;
@@ -127,6 +180,93 @@ struct JdosProducer {
   const double *ome;   // optical_mat(nb,nb,3,nk,ns) complex or null (fused make_weights)
   int n_geom;
   OpticsCoef coef;
+
+  // load / make split for the prepare passes of the narrow engine (see DosProducer): every load of a slot is issued
+  // before the first test; WT = also the weight columns (scatter pass).  Slabs hold < 2^30 pair slots.
+  struct Raw {
+    double ei, ej, g0, g1, g2, kw;
+    double2 m0, m1, m2;
+    double wt[6];
+    int ib, jb;
+  };
+  static constexpr int PREP_U = 2;
+  __device__ __forceinline__ void slot(unsigned uu, int &ib, int &jb, long long &ik) const {
+    if (occ_list) {
+      const unsigned t = uu / (unsigned)n_occ, tj = t / (unsigned)n_unocc;
+      ib = occ_list[uu - t * (unsigned)n_occ];
+      jb = unocc_list[t - tj * (unsigned)n_unocc];
+      ik = k_first + tj;
+    } else {
+      const unsigned t = uu / (unsigned)nb, tj = t / (unsigned)nb;
+      ib = (int)(uu - t * (unsigned)nb);
+      jb = (int)(t - tj * (unsigned)nb);
+      ik = k_first + tj;
+    }
+  }
+  template <bool WT>
+  __device__ __forceinline__ void load(unsigned uu, int is, Raw &w) const {
+    int ib, jb;
+    long long ik;
+    slot(uu, ib, jb, ik);
+    w.ib = ib; w.jb = jb;
+    const size_t eb = (size_t)nb * (is + (size_t)ns * ik);
+    w.ei = bands[eb + ib]; w.ej = bands[eb + jb];
+    w.g0 = w.g1 = w.g2 = 0.0;
+    if (b.type != 0) {
+      const size_t gi = (size_t)nb * (3 * (ik + (size_t)nk * is));
+      const double a0 = grads[gi + jb], a1 = grads[gi + ib], b0 = grads[gi + nb + jb], b1 = grads[gi + nb + ib];
+      const double c0 = grads[gi + 2 * (size_t)nb + jb], c1 = grads[gi + 2 * (size_t)nb + ib];
+      w.g0 = a0 - a1; w.g1 = b0 - b1; w.g2 = c0 - c1;
+    }
+    w.kw = kw[ik];
+    if (WT) {
+      const size_t nb2 = (size_t)nb * nb;
+      if (ome) {
+        const size_t oi = ib + (size_t)nb * jb + nb2 * 3 * (ik + (size_t)nk * is);
+        w.m0 = reinterpret_cast<const double2 *>(ome)[oi];
+        w.m1 = reinterpret_cast<const double2 *>(ome)[oi + nb2];
+        w.m2 = reinterpret_cast<const double2 *>(ome)[oi + 2 * nb2];
+      } else if (mw) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+          if (a < n_geom) w.wt[a] = mw[ib + (size_t)nb * (jb + (size_t)nb * (ik + (size_t)nk * (is + (size_t)ns * a)))];
+      }
+    }
+  }
+  template <bool WT>
+  __device__ __forceinline__ void make(unsigned, int, const Raw &w, RecOut &r) const {
+    r.mode = -1;
+    const int ib = w.ib, jb = w.jb;
+    for (int x = 0; x < n_exclude; ++x)
+      if (exclude[x] == ib + 1) return;                         // jdos_utils.f90:355-357
+    const double ei = w.ei, ej = w.ej;
+    if (ei >= efermi) return;                                   // :358
+    if (ej < efermi) return;                                    // :360
+    const double g[3] = {w.g0, w.g1, w.g2};
+    od_make_record(b, ej - ei + scissor, g, eps * w.kw, r);   // :366-372, :383
+    if (!WT) return;
+    if (mw) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) r.wt[a] = a < n_geom ? w.wt[a] : 0.0;
+    } else if (ome) {
+      // make_weights fused (optics.f90:259-269): only n2 >= n1 is ever filled; strict >/< tests
+      double wt[6] = {0, 0, 0, 0, 0, 0};
+      if (jb >= ib && !(ei > efermi && ib != jb) && !(ej < efermi && ib != jb)) {
+        double factor = 0.0;
+        if (jb == ib) factor = 1.0;
+        else if (ej > efermi) factor = 1.0 / ((ej - ei + scissor) * (ej - ei + scissor));
+        double P[6];
+        od_ome_products(w.m0, w.m1, w.m2, P);
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+          if (a < n_geom)
+            wt[a] = factor * (coef.c[a][0] * P[0] + coef.c[a][1] * P[1] + coef.c[a][2] * P[2] + coef.c[a][3] * P[3] +
+                              coef.c[a][4] * P[4] + coef.c[a][5] * P[5]);
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) r.wt[a] = wt[a];
+    }
+  }
 
   __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
     const int is = z;

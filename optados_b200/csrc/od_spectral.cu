@@ -71,11 +71,14 @@ __global__ void linear_smear_kernel(const double *__restrict__ dos, double *__re
 
 // ------------------------------------------------------------------ calculate_dos
 // k-point slabs (measured on B200, config 2, see profiles/r02_summary.md): the accumulation kernels like long record
-// arrays (fewer launch tails, fuller buckets: 62.8 / 58.4 / 57.2 ms per step at 16M / 32M / 48M units), the scatter of
-// the 64-byte linear records likes short ones (its write frontier has to stay mergeable in the L2: 25.4 / 30.7 / 42.5 ms).
-// So a slab is 48M units and the linear scheme walks it in sub-slabs of 24M.
-#define OD_SLAB_UNITS_DEFAULT (48ll << 20)
-#define OD_LINEAR_SLAB_UNITS_DEFAULT (24ll << 20)
+// arrays (fewer launch tails, fuller buckets: adaptive 83.6 / 77.8 / 76.2 / 75.0 ms per pass at 16M / 32M / 48M / 96M units), the
+// scatter of the 64-byte linear records likes short ones (its write frontier has to stay mergeable in the L2: prepare 24.7 /
+// 26.4 / 28.6 / 32.1 ms, against accumulate 63.5 / 58.3 / 57.3 / 55.4).  So a slab is 96M units and the linear scheme walks
+// it in sub-slabs of 32M.
+#define OD_SLAB_UNITS_DEFAULT (96ll << 20)
+#define OD_LINEAR_SLAB_UNITS_DEFAULT (32ll << 20)
+// streamed (host) gradients: the copy of the first slab and the kernels of the last one are not overlapped -- short slabs
+#define OD_STREAM_SLAB_UNITS (32ll << 20)
 // one k-point slab of one broadening scheme, ADDED into accum = [dos | intdos | weighted_dos]
 static int dos_producer(od_ctx *ctx, char dos_type, const od_broadening *br, const GridSpec &grid, const double *mw_dev, int norb,
                         int mw_nb, int mw_nk, long long k_first, int nk_slab, const double *grads_dev, int nk_g, DosProducer *out) {
@@ -87,6 +90,7 @@ static int dos_producer(od_ctx *ctx, char dos_type, const od_broadening *br, con
   p.eps = ctx->eps;
   OD_CHECK(od_make_broadspec(ctx, dos_type, br, grid.delta, /*honor_hybrid=*/false, &p.b));
   p.mw = mw_dev; p.norb = norb; p.mw_nb = mw_nb; p.mw_nk = mw_nk; p.og = OD_MAXW;
+  p.nb_div = FastDiv((unsigned)ctx->nb);
   *out = p;
   return OD_OK;
 }
@@ -199,7 +203,7 @@ int od_dos_accumulate(od_ctx *ctx, int ntypes, const char *types, const bool *we
       }
     }
     const long long units = (long long)nb * ns * nk;
-    const int nslabs = (int)std::max<long long>(1, std::min<long long>({64, (units + OD_SLAB_UNITS_DEFAULT - 1) / OD_SLAB_UNITS_DEFAULT,
+    const int nslabs = (int)std::max<long long>(1, std::min<long long>({64, (units + OD_STREAM_SLAB_UNITS - 1) / OD_STREAM_SLAB_UNITS,
                                                                       (long long)nk / 1024}));
     const int slab_nk = (nk + nslabs - 1) / nslabs;
     const size_t slab_elems = (size_t)nb * 3 * slab_nk * ns;
