@@ -52,6 +52,10 @@
 
 namespace {
 
+#ifndef OD_MAIN_UNROLL
+#define OD_MAIN_UNROLL 2
+#endif
+constexpr int NR_MAIN_UNROLL = OD_MAIN_UNROLL;  // main (wrap-free) walks
 constexpr int NR_T = 512;        // bins per warp tile
 constexpr int NR_WMAX = OD_NARROW_WMAX;     // widest window (bins) the narrow engine takes (Wc + 1 <= NR_T - cell)
 constexpr int NR_CHUNK = 256;   // records per work item (512: +1 %, 1024: +3 % on config 2)
@@ -789,7 +793,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
               *qp = acc;
               __syncwarp();
             };
-#pragma unroll 1
+#pragma unroll NR_MAIN_UNROLL
             for (int t = 0; t < nmain; ++t) step(std::false_type{});
 #pragma unroll 1
             for (int t = 0; t < 31; ++t) step(std::true_type{});
@@ -824,7 +828,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           *qp = acc;
           __syncwarp();
         };
-#pragma unroll 1
+#pragma unroll NR_MAIN_UNROLL
         for (int t = 0; t < nmain; ++t) step(std::false_type{});
 #pragma unroll 1
         for (int t = 0; t < 31; ++t) step(std::true_type{});
@@ -896,7 +900,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           ++r; --dA; --dB;
           __syncwarp();
         };
-#pragma unroll 1
+#pragma unroll NR_MAIN_UNROLL
         for (int t = 0; t < nmain; ++t) step(std::false_type{});
 #pragma unroll 1
         for (int t = 0; t < 31; ++t) step(std::true_type{});
