@@ -95,6 +95,7 @@ struct PrepSpec {
   int linear_pass;  // a linear pass sends Gaussian records (hybrid_linear fall-back) to the dense engine
   int ng;           // weight columns carried beside each record (JDOS / optics)
   int want_unit;    // also record each record's unit index (PDOS / core: weights are gathered from matrix_weights)
+  int wmax;         // widest window the tiles take with this cell: min(NR_WMAX, NR_T - 2 * cell)
 };
 
 struct Cls {
@@ -143,7 +144,7 @@ __device__ __forceinline__ Cls classify(const RecOut &r, const PrepSpec &ps) {
   c.klo = (int)a;
   const int khi = (int)b;
   c.wlen = khi - c.klo + 1;
-  c.kind = (c.wlen <= NR_WMAX && !degenerate) ? 0 : 1;
+  c.kind = (c.wlen <= ps.wmax && !degenerate) ? 0 : 1;
   int cp = c.cstep - c.klo;
   cp = cp < 0 ? 0 : (cp > c.wlen ? c.wlen : cp);
   c.cpos = cp;
@@ -339,7 +340,7 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
       // keep the record inside the cell pass A counted it in, whatever this pass recomputed
       const int cell_lo = (int)(ci << ps.cshift) - is * ps.bpad;
       int klo = min(max(c.klo, cell_lo), cell_lo + ps.cell - 1);
-      const int wlen = min(max(c.wlen - (klo - c.klo), 1), NR_WMAX);
+      const int wlen = min(max(c.wlen - (klo - c.klo), 1), ps.wmax);
       const int cpos = min(max(c.cstep - klo, 0), wlen);
       if (LINEAR) {
         LRec *o = reinterpret_cast<LRec *>(recs_v) + pos;
@@ -605,7 +606,13 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       __syncwarp();
     }
 
-    for (int g0 = 0; g0 < n; g0 += 64) {
+    // A group whose records do not fit one tile together (a chunk that straddles two width classes or the two spin channels,
+    // sparse buckets of a small job) is walked in several passes over the SAME g0: every pass takes the records that fit a
+    // tile with the lowest pending one and defers the others (`defer`, `adv` = 0).  The record-by-record path below is
+    // ~100x slower per record, and a single such group used to be the tail of every launch (0.5 ms).
+    bool defer[2] = {false, false};
+    int adv = 64, npass = 0;
+    for (int g0 = 0; g0 < n; g0 += adv) {
       // ---- my two records (and a prefetch of the two this lane takes in the next group)
       bool valid[2];
       long long idx[2];
@@ -614,7 +621,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const int pos = g0 + 32 * s + lane;
-        valid[s] = pos < n;
+        valid[s] = pos < n && (adv != 0 || defer[s]);
         idx[s] = c0 + (valid[s] ? (int)order[pos] : 0);
         if (pos + 64 < n) {
           const char *nx = reinterpret_cast<const char *>(A.recs) + (size_t)(c0 + order[pos + 64]) * RECB;
@@ -631,6 +638,29 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
             e0[s] = r.e; p1[s] = r.w; om[s] = r.om; klo[s] = r.klo; wlen[s] = r.wlen; cpos[s] = r.cpos;
           }
         }
+      }
+      // ---- which of the pending records go together in this pass: those whose window ends inside a tile that starts at the
+      //      lowest pending window, and (Gaussian) whose recurrence may start that far below their own window
+      const int gl = __reduce_min_sync(FULL, min(klo[0], klo[1]));
+      {
+        ++npass;
+        bool any_defer = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          bool sel = valid[s] && (klo[s] + wlen[s] - gl <= NR_T - A.cell - 1);
+          if (!LINEAR) sel = sel && ((double)(klo[s] - gl) * delta <= 25.0 * p1[s]);
+          if (npass > 80) sel = valid[s];  // (cannot happen: the lowest record is always taken; then the record-by-record path)
+          defer[s] = valid[s] && !sel;
+          if (defer[s]) {
+            valid[s] = false;
+            e0[s] = 0; p1[s] = 1; p2[s] = p3[s] = p4[s] = 0; om[s] = 0;
+            klo[s] = 0x3fffffff; wlen[s] = 0; cpos[s] = 0;
+          }
+          any_defer = any_defer || defer[s];
+        }
+        any_defer = __any_sync(FULL, any_defer);
+        adv = any_defer ? 0 : 64;
+        if (!any_defer) npass = 0;
       }
       double m0[2] = {1.0, 1.0}, m1[2] = {0.0, 0.0};  // JD channel multipliers
       if (JD) {
@@ -652,8 +682,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           m1[s] = A.col1 == -1 ? 1.0 : ((A.col1 >= 0 && w) ? w[A.col1] : 0.0);
         }
       }
-      // ---- the group's common window [gl, gl + Wc)
-      const int gl = __reduce_min_sync(FULL, min(klo[0], klo[1]));
+      // ---- the common window [gl, gl + Wc) of this pass
       const int gh = __reduce_max_sync(FULL, max(valid[0] ? klo[0] + wlen[0] - 1 : -0x3fffffff, valid[1] ? klo[1] + wlen[1] - 1 : -0x3fffffff));
       int Wc = gh - gl + 1;
       if (Wc < 32) Wc = 32;
@@ -672,6 +701,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       if (!LINEAR) irregular = irregular || (valid[0] && (double)a[0] * delta > 25.0 * p1[0]) || (valid[1] && (double)a[1] * delta > 25.0 * p1[1]);
       irregular = __any_sync(FULL, irregular) || (A.debug & 1);
 
+      if (irregular && (A.debug & 4)) continue;  // (timing experiment: drop the record-by-record groups)
       if (irregular) {
         // sparse data, a group that straddles the two spin channels, ...: record by record, lanes over
         // bins, straight to HBM.
@@ -1172,30 +1202,40 @@ __global__ void __launch_bounds__(1024) combine_kernel(const double *__restrict_
                                                        const double *__restrict__ stephist, const double *__restrict__ n_dos_em,
                                                        const double *__restrict__ n_corr, double delta, int nbins, int bpad,
                                                        double *__restrict__ dos, double *__restrict__ intdos) {
-  __shared__ double sh[1024];
-  __shared__ double carry;
-  const int is = blockIdx.x;
-  if (threadIdx.x == 0) carry = 0.0;
+  // grid (blocks of 1024 bins, spin channels).  A CTA first sums the prefix terms of all bins below its block (independent,
+  // coalesced loads: at most 20 per thread on a 20 000-bin grid), then scans its own 1024 bins with shuffles.
+  __shared__ double warp_tot[32], below_w[32];
+  __shared__ double below_s;
+  const int is = blockIdx.y, b0 = blockIdx.x * 1024, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double *dem_p = n_dos_em + (size_t)is * bpad, *step_p = stephist + (size_t)is * bpad;
+  double below = 0.0;
+  for (int i = threadIdx.x; i < b0; i += 1024) below += fma(delta, dem_p[i], step_p[i]);
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+  const int j = b0 + threadIdx.x;
+  const double dem = (j < nbins) ? dem_p[j] : 0.0;
+  double v = (j < nbins) ? fma(delta, dem, step_p[j]) : 0.0;
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  if (lane == 0) below_w[warp] = below;
   __syncthreads();
-  for (int b0 = 0; b0 < nbins; b0 += 1024) {
-    const int j = b0 + threadIdx.x;
-    const double dem = (j < nbins) ? n_dos_em[(size_t)is * bpad + j] : 0.0;
-    const double v = (j < nbins) ? fma(delta, dem, stephist[(size_t)is * bpad + j]) : 0.0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const double t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0.0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
+  if (warp == 0) {
+    double w = warp_tot[lane], bsum = below_w[lane];
+    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
     }
-    if (j < nbins) {
-      dos[(size_t)is * nbins + j] += n_dos[(size_t)is * bpad + j] + dem;
-      intdos[(size_t)is * nbins + j] += n_int[(size_t)is * bpad + j] - n_corr[(size_t)is * bpad + j] - 0.5 * delta * dem + (carry + sh[threadIdx.x]);
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
-    __syncthreads();
+    warp_tot[lane] = w;  // inclusive over the warps of this block
+    if (lane == 0) below_s = bsum;
+  }
+  __syncthreads();
+  if (j < nbins) {
+    const double before = below_s + (warp > 0 ? warp_tot[warp - 1] : 0.0);
+    dos[(size_t)is * nbins + j] += n_dos[(size_t)is * bpad + j] + dem;
+    intdos[(size_t)is * nbins + j] += n_int[(size_t)is * bpad + j] - n_corr[(size_t)is * bpad + j] - 0.5 * delta * dem + (before + v);
   }
 }
 
@@ -1234,7 +1274,10 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   strip_weights(prod_keys);
   set_eager(prod);            // pass B only runs on slots pass A accepted: loads first, tests after
   const PrepSpec &ps = S.ps;
-  const int prows = ctx->sm_count;  // one prepare CTA per SM; pass A and pass B MUST use the same grid
+  // one prepare CTA per SM, fewer for small jobs (every CTA zeroes, dumps and re-reads a row of the bucket table); pass A and
+  // pass B MUST use the same grid
+  const long long per_cta = (long long)NR_PREP_THREADS * Producer::PREP_U;  // at least one tile per CTA
+  const int prows = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count, ((long long)prod.units_per_z + per_cta - 1) / per_cta));
   const size_t hist_smem = sizeof(unsigned) * ps.nbuckets;
   const size_t units = (size_t)prod.units_per_z * prod.ns;
   *wide_stride = prod.units_per_z;
@@ -1315,12 +1358,20 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, int col0, int col1
   return OD_OK;
 }
 
-// bins per position cell for a grid: the smallest power of two >= 8 whose bucket table fits the prepare passes'
-// shared memory; 0 = the grid is too large for the narrow engine (the callers then use the dense engine)
-int narrow_cell_for(int nbins, int ns) {
+// bins per position cell: the smallest power of two >= 8 whose bucket table fits the prepare passes' shared memory -- and,
+// for small jobs, large enough that a bucket holds of the order of a chunk of records (a chunk of 256 consecutive records
+// that spans a dozen sparse buckets walks the union of their windows: a 1M-unit job on a 20 000-bin grid ran 6x slower per
+// record than a 500M-unit one); 0 = the grid is too large for the narrow engine (the callers then use the dense engine).
+// total_units < 0: the grid test alone.
+int narrow_cell_for(int nbins, int ns, long long total_units = -1) {
   for (int cell = 8; cell <= 128; cell *= 2) {
     const int bpad = ((nbins + NR_T + cell - 1) / cell) * cell;
-    if ((long long)NR_NCLS * ns * (bpad / cell) <= NR_MAXBUCKETS) return cell;
+    const long long nbuckets = (long long)NR_NCLS * ns * (bpad / cell);
+    if (nbuckets > NR_MAXBUCKETS) continue;
+    // (units spread over about a third of the buckets: the band structure does not cover the padded grid, and a width
+    // class holds a part of the units)
+    if (total_units >= 0 && cell < 64 && total_units < 64 * nbuckets) continue;
+    return cell;
   }
   return 0;
 }
@@ -1329,8 +1380,9 @@ int narrow_cell_for(int nbins, int ns) {
 int narrow_scratch(od_ctx *ctx, const GridSpec &grid, int ns, long long total_units, int nchan_arrays, Scratch &S) {
   PrepSpec &ps = S.ps;
   ps.grid = grid;
-  ps.cell = narrow_cell_for(grid.nbins, ns);
+  ps.cell = narrow_cell_for(grid.nbins, ns, total_units);
   if (ps.cell == 0) return od_fail(ctx, OD_ERR_ARG, "narrow engine: energy grid too large (%d bins)", grid.nbins);
+  ps.wmax = std::min(NR_WMAX, NR_T - 2 * ps.cell);
   ps.cshift = 0;
   while ((1 << ps.cshift) < ps.cell) ++ps.cshift;
   ps.bpad = ((grid.nbins + NR_T + ps.cell - 1) / ps.cell) * ps.cell;
@@ -1393,7 +1445,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   OD_CHECK(od_time_begin(ctx, 1, &ta));
   OD_CHECK(narrow_launch<false>(ctx, S, linear, -2, -2, ndos, nint, nullptr));
   const size_t n1 = (size_t)nbins * ns;
-  combine_kernel<<<ns, 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, S.chan + 2 * S.nout, S.chan + 3 * S.nout, grid.delta, nbins, S.ps.bpad,
+  combine_kernel<<<dim3((nbins + 1023) / 1024, ns), 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, S.chan + 2 * S.nout, S.chan + 3 * S.nout, grid.delta, nbins, S.ps.bpad,
                                                 accum, accum + n1);
   OD_LAUNCH_CHECK(ctx);
   int wpasses = 0;
