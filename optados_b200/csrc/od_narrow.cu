@@ -981,7 +981,7 @@ constexpr int PG_KS = PG_KC + 4;
 template <int BN>
 constexpr size_t pg_smem_bytes() {
   return sizeof(double) * (2 * PG_BM * PG_KS + 2 * PG_KC * (BN + 4) + 2 * PG_KC * 12) + sizeof(long long) * 2 * PG_KC +
-         sizeof(int) * 4 * PG_KC;
+         sizeof(int) * 4 * PG_KC + sizeof(unsigned) * 2 * (PG_BM / 8);
 }
 
 // D(16x8) += A(16x8) B(8x8) in FP64 on the tensor cores.  Fragments (g = lane / 4, t = lane % 4):
@@ -1014,6 +1014,7 @@ __global__ void __launch_bounds__(256, 2) pdos_gemm_kernel(PgArgs A) {
   double *sP = sW + 2 * PG_KC * WS;                            // [2][KC][12]
   long long *sRow = reinterpret_cast<long long *>(sP + 2 * PG_KC * 12);  // [2][KC]
   int *sI = reinterpret_cast<int *>(sRow + 2 * PG_KC);         // [2][KC][2]
+  unsigned *sMask = reinterpret_cast<unsigned *>(sI + 4 * PG_KC);  // [2][BM / 8]: records with a non-zero entry in each 8-bin run
   __shared__ int s_item;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int fg = lane >> 2, ft = lane & 3;      // fragment coordinates
@@ -1127,6 +1128,10 @@ __global__ void __launch_bounds__(256, 2) pdos_gemm_kernel(PgArgs A) {
       double *dst = sG + ((size_t)buf * PG_BM + run * 8) * PG_KS + k;
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[i * PG_KS] = v[i];
+      // which records reach this run of 8 bins: the MMA loop skips the (16 bins x 8 records) blocks that are all zero --
+      // the records of a chunk are neighbours in (class, window start), so the zeros of a tile are whole bands of it
+      const unsigned m = __ballot_sync(0xffffffffu, lo <= hi);
+      if (lane == 0) sMask[buf * (PG_BM / 8) + run] = m;
     };
 
     double acc[NB][4];
@@ -1155,8 +1160,10 @@ __global__ void __launch_bounds__(256, 2) pdos_gemm_kernel(PgArgs A) {
       if (more) fill_g(nxt);
       const double *gp = sG + ((size_t)cur * PG_BM + wm * 16 + fg) * PG_KS + ft;
       const double *wp = sW + ((size_t)cur * PG_KC + ft) * WS + wn * 8 * NB + fg;
+      const unsigned blk = sMask[cur * (PG_BM / 8) + 2 * wm] | sMask[cur * (PG_BM / 8) + 2 * wm + 1];  // my 16 bins
 #pragma unroll
       for (int kk = 0; kk < PG_KC; kk += 8) {
+        if (((blk >> kk) & 0xffu) == 0) continue;  // (warp-uniform)
         const double a0 = gp[kk], a1 = gp[8 * PG_KS + kk], a2 = gp[kk + 4], a3 = gp[8 * PG_KS + kk + 4];
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
