@@ -352,11 +352,38 @@ def main():
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": n_e2e,
                "api": "od_set_bands + od_set_gradients(OD_MEM_HOST_DEFERRED) from pinned host memory + od_dos_utils_calculate + od_dos_get"}
         # OD_MEM_HOST_DEFERRED leaves the library reading h_bg on every later call: make the gradients resident again
-        # (one plain upload) before the host buffers go away
+        # (one plain upload) before the host buffers go away.  That upload doubles as the measurement of what the box can
+        # deliver: all N ranks copy their 12.3 GB / N of pinned memory at the same time and nothing else runs -- the
+        # concurrent host-to-device ceiling the end-to-end number is to be read against.
+        ctx.synchronize()
+        barrier(dist)
+        t0 = time.perf_counter()
         ctx.set_gradients_ptr(h_bg, deferred=False)
         ctx.synchronize()
+        dt_copy = time.perf_counter() - t0
+        barrier(dist)
+        dt_copy_max = max_over_ranks(dist, dt_copy, local)
+        e2e["h2d_ceiling_gbs"] = sum_over_ranks(dist, float(nbg), local) / dt_copy_max / 1e9      # all ranks together
+        e2e["h2d_ceiling_gbs_per_gpu"] = nbg / dt_copy / 1e9
+        e2e["h2d_floor_ms_per_step"] = sum_over_ranks(dist, float(nbe + nbg), local) / (e2e["h2d_ceiling_gbs"] * 1e9) * 1e3
         ob.host_free_pinned(h_be)
         ob.host_free_pinned(h_bg)
+
+    # ---- the reference's own decomposition beside the cyclic deal: contiguous k-point blocks (algor_dist_array), which on the
+    #      k1-ordered synthetic mesh carry unequal work (the windows follow sin(2 pi k1))
+    block = None
+    if world > 1 and args.partition == "cyclic":
+        ctx.synth_bands(grid_total, k_first, nk_gpu, NS, NB, lattice_a=LATTICE_A, seed=SEED)
+        step()
+        ctx.synchronize()
+        barrier(dist)
+        ctx.timer_start()
+        for _ in range(args.steps):
+            step()
+        ms_blk = max_over_ranks(dist, ctx.timer_stop() / args.steps, local)
+        barrier(dist)
+        block = {"partition": "contiguous blocks (algor_dist_array)", "ms_per_step": ms_blk, "value": contrib_total / (ms_blk * 1e-3)}
+        ctx.synth_bands(grid_total, rank, nk_gpu, NS, NB, lattice_a=LATTICE_A, seed=SEED, k_stride=world)
 
     # ---- multi-rank parity of the LIBRARY (not the oracle): rank 0 runs the whole mesh on one communicator-less ctx and
     #      compares the spectra the N ranks produced through od_dos_utils_calculate + the NCCL merge with it
@@ -424,7 +451,7 @@ def main():
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, world, nk_total), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "configs": configs,
-                "multi_gpu_parity": parity, "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "multi_gpu_parity": parity, "block_partition": block, "gpu_launches": int(launches), "clocks": sampler.summary(),
                 "dense_equivalent_evaluations_per_s": 2.0 * float(nk_total) * NB * NS * NBINS / (ms_step * 1e-3),
                 "contributions_per_step": contrib_total, "wall_ms_per_step": wall / args.steps * 1e3,
                 "efermi_adaptive": r.get("efermi_adaptive"), "efermi_linear": r.get("efermi_linear")}

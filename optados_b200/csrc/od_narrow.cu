@@ -94,6 +94,7 @@ struct PrepSpec {
   int with_int;     // integrated spectrum wanted (DOS): off-grid units still contribute their step
   int linear_pass;  // a linear pass sends Gaussian records (hybrid_linear fall-back) to the dense engine
   int ng;           // weight columns carried beside each record (JDOS / optics)
+  int wstride;      // doubles per weight row: 0 (none), 1, 4 or 8
   int want_unit;    // also record each record's unit index (PDOS / core: weights are gathered from matrix_weights)
   int wmax;         // widest window the tiles take with this cell: min(NR_WMAX, NR_T - 2 * cell)
 };
@@ -349,9 +350,14 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
       } else {
         st256(reinterpret_cast<GRec *>(recs_v) + pos, r.e0, r.p1, r.omega, rec_tail(is * ps.bpad + klo, cpos, wlen));
       }
-#pragma unroll
-      for (int a = 0; a < 6; ++a)  // (static indices: a loop over ps.ng would put the whole record into local memory)
-        if (a < ps.ng) wts[(size_t)pos * ps.ng + a] = r.wt[a];
+      // weight columns ride beside the record in rows of 1, 4 or 8 doubles: one / two 32-byte stores instead of ng 8-byte ones
+      // (static indices: a loop over ps.ng would put the whole record into local memory)
+      if (ps.wstride == 1) wts[pos] = r.wt[0];
+      else if (ps.wstride == 4) st256(wts + (size_t)pos * 4, r.wt[0], r.wt[1], r.wt[2], r.wt[3]);
+      else if (ps.wstride == 8) {
+        st256(wts + (size_t)pos * 8, r.wt[0], r.wt[1], r.wt[2], r.wt[3]);
+        st256(wts + (size_t)pos * 8 + 4, r.wt[4], r.wt[5], 0.0, 0.0);
+      }
       if (ps.want_unit) runit[pos] = u;
     }
   }
@@ -427,7 +433,7 @@ struct NarrowArgs {
   // JD (JDOS / optics) mode: channel pass `chan` accumulates K*m0 and K*m1 with (m0, m1) =
   // (1, wt[0]) for chan 0 and (wt[2 chan - 1], wt[2 chan]) after that; wts[rec * ng + a]
   const double *wts;
-  int ng;
+  int ng, wstride;
   int col0, col1;  // weight column feeding m0 / m1; -1 = the constant 1, -2 = zero
   // PDOS / core: weights gathered from matrix_weights(norb, mw_nb, mw_nk, ns) by unit index
   const unsigned *runit;
@@ -676,7 +682,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
             if (ik < A.mw_nk && (int)ib < A.mw_nb)  // dos_utils.f90:1268-1269
               w = A.mw + (size_t)A.norb * (ib + (size_t)A.mw_nb * (ik + (size_t)A.mw_nk * is));
           } else if (A.wts) {
-            w = A.wts + (size_t)idx[s] * A.ng;
+            w = A.wts + (size_t)idx[s] * A.wstride;
           }
           m0[s] = A.col0 == -1 ? 1.0 : ((A.col0 >= 0 && w) ? w[A.col0] : 0.0);
           m1[s] = A.col1 == -1 ? 1.0 : ((A.col1 >= 0 && w) ? w[A.col1] : 0.0);
@@ -1291,7 +1297,7 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   const size_t rec_bytes = linear ? sizeof(LRec) : sizeof(GRec);
   OD_CHECK(od_buf_ensure(ctx, ctx->recs, rec_bytes * units + 256));
   OD_CHECK(od_buf_ensure(ctx, ctx->scratch_b, sizeof(unsigned) * units + 256));
-  if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * units * ps.ng + 256));
+  if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * units * ps.wstride + 256));
   if (ps.want_unit) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_e, sizeof(unsigned) * units + 256));
   OD_CUDA(ctx, cudaMemsetAsync(S.wide, 0, sizeof(unsigned long long) * 5, ctx->stream));
   OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
@@ -1343,6 +1349,7 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, int col0, int col1
   A.flags = ctx->flags.as<int>();
   A.wts = S.ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
   A.ng = S.ps.ng;
+  A.wstride = S.ps.wstride;
   A.col0 = col0;
   A.col1 = col1;
   A.runit = nullptr; A.mw = nullptr; A.norb = A.mw_nb = A.mw_nk = A.nb = A.mw_ns = 0; A.k_first = 0;
@@ -1441,6 +1448,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   S.ps.with_int = 1;
   S.ps.linear_pass = 0;  // calculate_dos ignores hybrid_linear (quirk Q8): a linear pass has no Gaussian records
   S.ps.ng = 0;
+  S.ps.wstride = 0;
   S.ps.want_unit = norb > 0;
   double *ndos = S.chan, *nint = S.chan + S.nout;
 
@@ -1578,6 +1586,7 @@ int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &gri
   S.ps.with_int = 0;
   S.ps.linear_pass = linear ? 1 : 0;  // hybrid_linear fall-back records (jdos_utils.f90:365) -> dense engine
   S.ps.ng = n_geom;
+  S.ps.wstride = n_geom <= 0 ? 0 : (n_geom == 1 ? 1 : (n_geom <= 4 ? 4 : 8));
   S.ps.want_unit = 0;
   const size_t n1 = (size_t)nbins * ns;
   for (long long k0 = 0; k0 < nk; k0 += slab_k) {

@@ -182,9 +182,12 @@ def cfg4(env, k_per_gpu=25000):
         ms, wall, prof, out = _timed(ctx, lambda: ctx.calculate_jdos_optics_ptr("a", delta, nbins, ef, ome.data_ptr(), geom, merge=merge),
                                      env.reps, env.barrier)
         ms = env.max_over_ranks(ms)
-        contrib = env.sum_over_ranks(prof["contributions"])     # in-window (pair, bin) evaluations of the engine
+        evals = env.sum_over_ranks(prof["contributions"])       # in-window (pair, bin) evaluations of the engine, ALL channel passes
         lane = env.sum_over_ranks(prof["lane_steps"])
-        res[geom] = {"ms": ms, "contributions": contrib, "contributions_per_s": contrib / (ms * 1e-3), "lane_efficiency": contrib / max(lane, 1.0),
+        npass = 1 + ng // 2                                     # (jdos, w1) (w2, w3) (w4, w5) (w6, -): every pass re-walks the records
+        contrib = evals / npass                                 # the metric's unit: one in-window (pair, bin) contribution, counted once
+        res[geom] = {"ms": ms, "contributions": contrib, "contributions_per_s": contrib / (ms * 1e-3), "lane_efficiency": evals / max(lane, 1.0),
+                     "channel_passes": npass, "engine_evaluations": evals,
                      "roofline": _roof(contrib * (38.0 + 2.0 * ng), pairs * 48.0, ms, env.fp64_peak * env.world, env.hbm_peak * env.world),
                      "device_ms": {"prepare": prof["prepare_ms"], "accumulate": prof["accumulate_ms"]}}
     del ome

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Turn gpurun_out/*.ncu-rep (+ the launch-list csv) into the small tracked summaries under profiles/.
-usage: tools/ncu_summary.py <report.ncu-rep> <launches.csv> <out_prefix>"""
+usage: tools/ncu_summary.py <report.ncu-rep> <launches.csv> <out_prefix> [units of the captured slab]"""
 import csv
 import subprocess
 import sys
@@ -30,6 +30,30 @@ def main():
         w.writerow([units[c] for c in cols])
         for r in data:
             w.writerow([r[c].split("(")[0] if c == cols[0] else r[c] for c in cols])
+    # per-kernel figures of the captured slab for bench.py (roofline.traffic, roofline.kernels_ncu): kernels of the same
+    # name (template arguments kept) are summed over the capture
+    if len(sys.argv) > 4:
+        import json
+        import re
+        units_slab = float(sys.argv[4])
+        g = lambda r, m: float(r[hdr.index(m)].replace(",", "")) if m in hdr and r[hdr.index(m)] else 0.0
+        ub = lambda m: {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(units[hdr.index(m)], 1.0)
+        ut = {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")], 1.0)
+        ks = OrderedDict()
+        for r in data:
+            name = re.sub(r"^void |<unnamed>::|\(.*$", "", r[hdr.index("Kernel Name")])
+            k = ks.setdefault(name, {"launches": 0, "ms": 0.0, "dram_bytes": 0.0, "fp64_pipe_pct": 0.0, "units": units_slab})
+            ms = g(r, "gpu__time_duration.sum") * ut
+            k["launches"] += 1
+            k["fp64_pipe_pct"] += g(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") * ms   # time-weighted
+            k["ms"] += ms
+            k["dram_bytes"] += g(r, "dram__bytes_read.sum") * ub("dram__bytes_read.sum") + g(r, "dram__bytes_write.sum") * ub("dram__bytes_write.sum")
+        for k in ks.values():
+            k["fp64_pipe_pct"] = k["fp64_pipe_pct"] / k["ms"] if k["ms"] > 0 else 0.0
+        json.dump({"source": rep, "units_of_the_captured_slab": units_slab,
+                   "note": "ncu --set full --clock-control none of one mid-mesh k-point slab (tools/ncu_slab.py), both schemes once; ms and "
+                           "dram_bytes are sums over the launches of a kernel in that capture (cold-cache, serialised)", "kernels": ks},
+                  open(out + "_kernels.json", "w"), indent=1)
     rows = list(csv.reader(open(launches)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, data = rows[hi], rows[hi + 1:]
