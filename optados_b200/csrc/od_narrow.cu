@@ -97,12 +97,37 @@ struct PrepSpec {
   int wstride;      // doubles per weight row: 0 (none), 1, 4 or 8
   int want_unit;    // also record each record's unit index (PDOS / core: weights are gathered from matrix_weights)
   int wmax;         // widest window the tiles take with this cell: min(NR_WMAX, NR_T - 2 * cell)
+  double inv_delta; // 1 / grid.delta (IEEE, host): a per-thread division is ~30 instructions of a 200-instruction pass
 };
 
 struct Cls {
   int klo, wlen, cpos, cstep;  // cstep: absolute step bin in [0, nbins]
   int kind;                    // 0 narrow, 1 wide, 2 off the grid (step only)
 };
+
+// unit -> (CTA, step, thread) mapping of the prepare passes (pass A and pass B MUST share it: the write cursors of pass B are
+// per CTA).  The lanes of a warp take 32 CONSECUTIVE units of ONE k-point (consecutive bands / pair slots: 256 B per input
+// array and load), a "row"; rows are numbered band-group-major, row = group * nk + k, and a CTA takes one contiguous range of
+// rows: it walks the k-points of (mostly) one group of 32 bands.  A band lives in a small part of the energy grid, so a CTA
+// then fills a few hundred buckets instead of all of them, and along a regular k-mesh consecutive records of a lane fall
+// into the same bucket: the 32-byte records of pass B complete their 128-byte lines in L2 within microseconds.  With the
+// k-major mapping of round 1 (a CTA = consecutive units = all bands of a few k-points) every CTA had every bucket open
+// (148 x 17 000 half-written lines = 320 MB against 126 MB of L2) and the scatter ran at the rate of random 32-byte DRAM
+// writes (40-50 G sectors/s, a quarter of the bandwidth: the row-activation limit).
+struct PrepMap {
+  unsigned W, nk;            // units per k-point, k-points of the slab
+  FastDiv nk_div;
+  unsigned long long nrows;  // ceil(W / 32) * nk
+  unsigned long long per;    // rows per CTA
+};
+constexpr unsigned NR_PREP_ROWS = NR_PREP_THREADS / 32;  // rows a CTA takes per step and unit slot
+
+__device__ __forceinline__ bool prep_unit(const PrepMap &pm, unsigned long long row, unsigned long long row_end, unsigned lane, unsigned &u) {
+  if (row >= row_end) return false;
+  const unsigned g = pm.nk_div.div((unsigned)row), k = (unsigned)row - g * pm.nk, w = g * 32u + lane;
+  u = k * pm.W + w;
+  return w < pm.W;
+}
 
 #define NR_ERFWIN (OD_ERF_CUT * OD_SQRT_TWO)  // 8.2024...: |z| beyond which the NSWC erf saturates
 
@@ -114,7 +139,7 @@ __device__ __forceinline__ Cls classify(const RecOut &r, const PrepSpec &ps) {
   const GridSpec &g = ps.grid;
   Cls c;
   double lo, hi, centre;
-  const double inv = 1.0 / g.delta;
+  const double inv = ps.inv_delta;
   bool degenerate = false;
   if (r.mode == 0) {
     lo = r.e0 - ps.gwin * r.p1;
@@ -155,49 +180,76 @@ __device__ __forceinline__ Cls classify(const RecOut &r, const PrepSpec &ps) {
 // ---------------------------------------------------------------- pass A: keys + per-CTA histogram row
 // Both prepare passes walk the units in tiles of NR_PREP_THREADS * U consecutive units per CTA (pass A and pass B MUST use the
 // same unit -> CTA mapping: the write cursors of pass B are per CTA).  A thread issues the loads of its U units of a tile
-// before it touches the first of them: the passes are bound by memory latency (ncu, round 1: long-scoreboard stalls, 30 % of
-// the DRAM bandwidth with one unit per thread in flight), not by bandwidth or arithmetic.
-template <class Producer>
+// before it touches the first of them, and prefetches the lines of its units of the NEXT tile into L2 (prefetch.global.L2:
+// no registers held): the passes are bound by memory latency and by the length of their dependent instruction chains at 16
+// warps per SM (ncu, round 2: half of the stall samples on the first use of a load, issue slots 25-55 % busy), not by
+// DRAM bandwidth (30-40 %).
+//
+// STAGE = what pass A hands to pass B beside the 4-byte key, so that pass B does not repeat pass A's arithmetic:
+//   0  nothing: pass B rebuilds and re-classifies the record (JDOS: its weights come from the matrix elements anyway);
+//   1  the record's tail (klo | cpos | wlen, 8 B per unit, unit order): pass B rebuilds the corners but does not classify
+//      (linear DOS: the 64-byte record itself would cost more traffic than its 3 dot products);
+//   2  the whole 32-byte Gaussian record in unit order (coalesced): pass B is a pure permutation -- one 32-byte load, one
+//      shared-memory cursor, one 32-byte store per unit (Gaussian DOS; +28 B of traffic per unit for -150 instructions).
+// An off-grid unit (key KEY_DROP) carries its step bin in the klo field.
+__device__ __forceinline__ double rec_tail(int klo, int cpos, int wlen);
+__device__ __forceinline__ void st256(void *dst, double a, double b, double c, double d);
+
+template <class Producer, int STAGE>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
 prep_hist_kernel(Producer prod, PrepSpec ps, unsigned *__restrict__ keys, unsigned *__restrict__ table /* [gridDim.x][nbuckets] */,
-                 unsigned long long *__restrict__ wide_count /* [ns] */) {
+                 unsigned long long *__restrict__ wide_count /* [ns] */, void *__restrict__ stage, PrepMap pm) {
   extern __shared__ unsigned sh_hist[];
+  __shared__ unsigned char s_cls[512];  // width class of a window length (9 compares + adds per unit otherwise)
   constexpr int U = Producer::PREP_U;
+  static_assert(NR_WMAX < 512, "class table");
   for (int i = threadIdx.x; i < ps.nbuckets; i += blockDim.x) sh_hist[i] = 0;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_cls[i] = (unsigned char)width_class(i);
   __syncthreads();
   unsigned long long wide0 = 0, wide1 = 0;
-  const unsigned upz = (unsigned)prod.units_per_z, tile = NR_PREP_THREADS * U;
+  const unsigned upz = (unsigned)prod.units_per_z, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long r_begin = (unsigned long long)blockIdx.x * pm.per, r_end = min(pm.nrows, r_begin + pm.per);
   for (int is = 0; is < prod.ns; ++is)
-  for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < upz; t0 += (unsigned long long)gridDim.x * tile) {
+  for (unsigned long long t0 = r_begin; t0 < r_end; t0 += NR_PREP_ROWS * U) {
     typename Producer::Raw raw[U];
+    unsigned uu[U];
+    bool ok[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      const unsigned long long u = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
-      if (u < upz) prod.template load<false>((unsigned)u, is, raw[j]);
+      ok[j] = prep_unit(pm, t0 + (unsigned)j * NR_PREP_ROWS + warp, r_end, lane, uu[j]);
+      if (ok[j]) prod.template load<false>(uu[j], is, raw[j]);
     }
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      const unsigned long long u = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
-      if (u >= upz) continue;
+      if (!ok[j]) continue;
+      const unsigned u = uu[j];
       RecOut r;
       r.mode = -1;
       prod.template make<false>((unsigned)u, is, raw[j], r);
       Cls c;
-      c.kind = 2;
+      c.kind = 2; c.klo = 0; c.wlen = 0; c.cpos = 0; c.cstep = ps.grid.nbins;
       if (r.mode >= 0) c = classify(r, ps);
       unsigned key;
+      int tk = c.cstep, tc = 0, tw = 0;
       if (c.kind == 0) {
         // key = cell index * 16 + width class (bucket = class * ncells + cell index: no division in either pass)
-        const unsigned cls = (unsigned)width_class(c.wlen), ci = (unsigned)(is * ps.bpad + c.klo) >> ps.cshift;
+        const unsigned cls = s_cls[c.wlen], ci = (unsigned)(is * ps.bpad + c.klo) >> ps.cshift;
         key = ci * 16u + cls;
         atomicAdd(&sh_hist[cls * (unsigned)ps.ncells + ci], 1u);
+        tk = is * ps.bpad + c.klo; tc = c.cpos; tw = c.wlen;
       } else if (c.kind == 1) {
         key = KEY_WIDE;
         if (is == 0) wide0++; else wide1++;
       } else {
         key = KEY_DROP;
       }
-      keys[(size_t)is * upz + u] = key;
+      const size_t su = (size_t)is * upz + u;
+      keys[su] = key;
+      if (STAGE == 2) {
+        if (c.kind != 1) st256(reinterpret_cast<GRec *>(stage) + su, r.e0, r.p1, r.omega, rec_tail(tk, tc, tw));
+      } else if (STAGE == 1) {
+        if (c.kind != 1) reinterpret_cast<double *>(stage)[su] = rec_tail(tk, tc, tw);
+      }
     }
   }
   __syncthreads();
@@ -280,50 +332,74 @@ __device__ __forceinline__ double rec_tail(int klo, int cpos, int wlen) {
   return __hiloint2double((int)((unsigned)cpos | ((unsigned)wlen << 16)), klo);
 }
 
+__device__ __forceinline__ void ld256(const void *src, double &a, double &b, double &c, double &d) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(src));
+}
+__device__ __forceinline__ void tail_unpack(double tail, int &klo, int &cpos, int &wlen) {
+  klo = __double2loint(tail);  // (rec_tail: int klo | unsigned short cpos | unsigned short wlen, little endian)
+  const unsigned hi = (unsigned)__double2hiint(tail);
+  cpos = (int)(hi & 0xffffu);
+  wlen = (int)(hi >> 16);
+}
+
 // ---------------------------------------------------------------- pass B: scatter (shared-memory cursors)
-template <bool LINEAR, class Producer>
+// The cursors of a tile's units are taken (shared-memory atomics with return, ~100 cycles) right after its keys are known,
+// before the records are built: a store that waits for its own cursor was 16 % of this pass's stall samples.
+// TAILS: pass A left every unit's tail (STAGE 1) -- no classification here.
+template <bool LINEAR, class Producer, bool TAILS>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
 prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,
                     const unsigned *__restrict__ base, void *__restrict__ recs_v, double *__restrict__ wts, unsigned *__restrict__ runit,
                     double *__restrict__ stephist,
-                    unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor, long long wide_stride) {
+                    unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor, long long wide_stride,
+                    const double *__restrict__ tails, PrepMap pm) {
   extern __shared__ unsigned sh_cur[];
   constexpr int U = Producer::PREP_U;
   const unsigned *row = table + (size_t)blockIdx.x * ps.nbuckets;
   for (int i = threadIdx.x; i < ps.nbuckets; i += blockDim.x) sh_cur[i] = base[i] + row[i];
   __syncthreads();
-  const unsigned upz = (unsigned)prod.units_per_z, tile = NR_PREP_THREADS * U;
-  const unsigned long long tstep = (unsigned long long)gridDim.x * tile;
+  const unsigned upz = (unsigned)prod.units_per_z, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long r_begin = (unsigned long long)blockIdx.x * pm.per, r_end = min(pm.nrows, r_begin + pm.per);
   for (int is = 0; is < prod.ns; ++is) {
-  unsigned key_next[U];
+  unsigned key_next[U], u_next[U];
+  bool ok_next[U];
   auto load_keys = [&](unsigned long long t0) {
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      const unsigned long long u = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
-      key_next[j] = (u < upz) ? keys[(size_t)is * upz + u] : KEY_WIDE;  // (KEY_WIDE: nothing to load; the slot is skipped below)
+      ok_next[j] = prep_unit(pm, t0 + (unsigned)j * NR_PREP_ROWS + warp, r_end, lane, u_next[j]);
+      key_next[j] = ok_next[j] ? keys[(size_t)is * upz + u_next[j]] : KEY_WIDE;  // (KEY_WIDE: nothing to load; the slot is skipped below)
     }
   };
-  load_keys((unsigned long long)blockIdx.x * tile);
-  for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < upz; t0 += tstep) {
+  load_keys(r_begin);
+  for (unsigned long long t0 = r_begin; t0 < r_end; t0 += NR_PREP_ROWS * U) {
     typename Producer::Raw raw[U];
-    unsigned key[U];
+    unsigned key[U], pos[U], uu[U];
+    bool ok[U];
+    double tl[U];
     // the keys of this tile were loaded one iteration ago; issue every input load of the tile, then the keys of the
     // next tile, before the first use: two levels of loads in flight per thread
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      const unsigned long long u = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
-      key[j] = key_next[j];
-      if (key[j] != KEY_WIDE && (key[j] != KEY_DROP || ps.with_int)) prod.template load<true>((unsigned)u, is, raw[j]);
+      key[j] = key_next[j]; uu[j] = u_next[j]; ok[j] = ok_next[j];
+      tl[j] = 0.0;
+      if (key[j] != KEY_WIDE && (key[j] != KEY_DROP || ps.with_int)) {
+        prod.template load<true>(uu[j], is, raw[j]);
+        if (TAILS) tl[j] = tails[(size_t)is * upz + uu[j]];
+      }
     }
-    load_keys(t0 + tstep);
+    load_keys(t0 + NR_PREP_ROWS * U);
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      const unsigned long long ul = t0 + (unsigned)j * NR_PREP_THREADS + threadIdx.x;
-      if (ul >= upz) continue;
-      const unsigned u = (unsigned)ul;
+      pos[j] = 0;
+      if (key[j] < KEY_WIDE) pos[j] = atomicAdd(&sh_cur[(key[j] & 15u) * (unsigned)ps.ncells + (key[j] >> 4)], 1u);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (!ok[j]) continue;
+      const unsigned u = uu[j];
       if (key[j] == KEY_WIDE) {
-        const unsigned long long pos = atomicAdd(&wide_cursor[is], 1ull);
-        widelist[(size_t)is * wide_stride + pos] = u;
+        const unsigned long long wp = atomicAdd(&wide_cursor[is], 1ull);
+        widelist[(size_t)is * wide_stride + wp] = u;
         continue;
       }
       if (key[j] == KEY_DROP && !ps.with_int) continue;  // null pair / off-grid unit without a step
@@ -331,36 +407,120 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
       r.mode = -1;
       prod.template make<true>(u, is, raw[j], r);
       if (r.mode < 0) continue;
-      const Cls c = classify(r, ps);
-      if (key[j] == KEY_DROP) {  // off the grid: only its step (rare)
-        if (c.cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + c.cstep], r.omega);
-        continue;
-      }
-      const unsigned ci = key[j] >> 4;
-      const unsigned pos = atomicAdd(&sh_cur[(key[j] & 15u) * (unsigned)ps.ncells + ci], 1u);
-      // keep the record inside the cell pass A counted it in, whatever this pass recomputed
-      const int cell_lo = (int)(ci << ps.cshift) - is * ps.bpad;
-      int klo = min(max(c.klo, cell_lo), cell_lo + ps.cell - 1);
-      const int wlen = min(max(c.wlen - (klo - c.klo), 1), ps.wmax);
-      const int cpos = min(max(c.cstep - klo, 0), wlen);
-      if (LINEAR) {
-        LRec *o = reinterpret_cast<LRec *>(recs_v) + pos;
-        st256(o, r.e0, r.p1, r.p2, r.p3);
-        st256(reinterpret_cast<char *>(o) + 32, r.p4, r.omega, rec_tail(is * ps.bpad + klo, cpos, wlen), 0.0);
+      int klo, wlen, cpos;  // klo in global numbering (spin * bpad + bin)
+      if (TAILS) {
+        tail_unpack(tl[j], klo, cpos, wlen);
+        if (key[j] == KEY_DROP) {  // off the grid: only its step (rare); the klo field carries the step bin
+          if (klo < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + klo], r.omega);
+          continue;
+        }
       } else {
-        st256(reinterpret_cast<GRec *>(recs_v) + pos, r.e0, r.p1, r.omega, rec_tail(is * ps.bpad + klo, cpos, wlen));
+        const Cls c = classify(r, ps);
+        if (key[j] == KEY_DROP) {
+          if (c.cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + c.cstep], r.omega);
+          continue;
+        }
+        // keep the record inside the cell pass A counted it in, whatever this pass recomputed
+        const unsigned ci = key[j] >> 4;
+        const int cell_lo = (int)(ci << ps.cshift) - is * ps.bpad;
+        const int kl = min(max(c.klo, cell_lo), cell_lo + ps.cell - 1);
+        wlen = min(max(c.wlen - (kl - c.klo), 1), ps.wmax);
+        cpos = min(max(c.cstep - kl, 0), wlen);
+        klo = is * ps.bpad + kl;
+      }
+      const unsigned p = pos[j];
+      if (LINEAR) {
+        LRec *o = reinterpret_cast<LRec *>(recs_v) + p;
+        st256(o, r.e0, r.p1, r.p2, r.p3);
+        st256(reinterpret_cast<char *>(o) + 32, r.p4, r.omega, rec_tail(klo, cpos, wlen), 0.0);
+      } else {
+        st256(reinterpret_cast<GRec *>(recs_v) + p, r.e0, r.p1, r.omega, rec_tail(klo, cpos, wlen));
       }
       // weight columns ride beside the record in rows of 1, 4 or 8 doubles: one / two 32-byte stores instead of ng 8-byte ones
       // (static indices: a loop over ps.ng would put the whole record into local memory)
-      if (ps.wstride == 1) wts[pos] = r.wt[0];
-      else if (ps.wstride == 4) st256(wts + (size_t)pos * 4, r.wt[0], r.wt[1], r.wt[2], r.wt[3]);
+      if (ps.wstride == 1) wts[p] = r.wt[0];
+      else if (ps.wstride == 4) st256(wts + (size_t)p * 4, r.wt[0], r.wt[1], r.wt[2], r.wt[3]);
       else if (ps.wstride == 8) {
-        st256(wts + (size_t)pos * 8, r.wt[0], r.wt[1], r.wt[2], r.wt[3]);
-        st256(wts + (size_t)pos * 8 + 4, r.wt[4], r.wt[5], 0.0, 0.0);
+        st256(wts + (size_t)p * 8, r.wt[0], r.wt[1], r.wt[2], r.wt[3]);
+        st256(wts + (size_t)p * 8 + 4, r.wt[4], r.wt[5], 0.0, 0.0);
       }
-      if (ps.want_unit) runit[pos] = u;
+      if (ps.want_unit) runit[p] = u;
     }
   }
+  }
+}
+
+// ---------------------------------------------------------------- pass B of staged Gaussian records (STAGE 2): a permutation
+// Same unit -> CTA mapping and tiles as pass A.  Keys and staged records of tile t+1 are loaded (coalesced: 4 B and 32 B per
+// thread and unit) before tile t is processed; per unit one shared-memory cursor and one 32-byte store.
+template <int U>
+__global__ void __launch_bounds__(NR_PREP_THREADS)
+prep_permute_kernel(PrepSpec ps, unsigned upz, int ns, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,
+                    const unsigned *__restrict__ base, const GRec *__restrict__ stage, GRec *__restrict__ recs, unsigned *__restrict__ runit,
+                    double *__restrict__ stephist, unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor,
+                    long long wide_stride, PrepMap pm) {
+  extern __shared__ unsigned sh_cur[];
+  const unsigned *row = table + (size_t)blockIdx.x * ps.nbuckets;
+  for (int i = threadIdx.x; i < ps.nbuckets; i += blockDim.x) sh_cur[i] = base[i] + row[i];
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long r_begin = (unsigned long long)blockIdx.x * pm.per, r_end = min(pm.nrows, r_begin + pm.per);
+  constexpr unsigned tstep = NR_PREP_ROWS * U;
+  struct Tile {
+    double a[U], b[U], c[U], d[U];
+    unsigned key[U], u[U];
+    bool ok[U];
+  };
+  for (int is = 0; is < ns; ++is) {
+    const size_t s0 = (size_t)is * upz;
+    auto fetch = [&](Tile &T, unsigned long long t0) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        T.ok[j] = prep_unit(pm, t0 + (unsigned)j * NR_PREP_ROWS + warp, r_end, lane, T.u[j]);
+        T.key[j] = KEY_WIDE;
+        T.a[j] = T.b[j] = T.c[j] = T.d[j] = 0.0;
+        if (T.ok[j]) {
+          T.key[j] = keys[s0 + T.u[j]];
+          ld256(stage + s0 + T.u[j], T.a[j], T.b[j], T.c[j], T.d[j]);  // (wide units: never written by pass A, never used here)
+        }
+      }
+    };
+    auto process = [&](const Tile &T) {
+      unsigned pos[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        pos[j] = 0;
+        if (T.key[j] < KEY_WIDE) pos[j] = atomicAdd(&sh_cur[(T.key[j] & 15u) * (unsigned)ps.ncells + (T.key[j] >> 4)], 1u);
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (!T.ok[j]) continue;
+        if (T.key[j] < KEY_WIDE) {
+          st256(recs + pos[j], T.a[j], T.b[j], T.c[j], T.d[j]);
+          if (ps.want_unit) runit[pos[j]] = T.u[j];
+        } else if (T.key[j] == KEY_WIDE) {
+          const unsigned long long wp = atomicAdd(&wide_cursor[is], 1ull);
+          widelist[(size_t)is * wide_stride + wp] = T.u[j];
+        } else if (ps.with_int) {  // off the grid: only its step (rare); the klo field carries the step bin
+          const int cstep = __double2loint(T.d[j]);
+          if (cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + cstep], T.c[j]);
+        }
+      }
+    };
+    Tile A, B;
+    unsigned long long t0 = r_begin;
+    if (t0 >= r_end) continue;
+    fetch(A, t0);
+    for (;;) {
+      fetch(B, t0 + tstep);
+      process(A);
+      t0 += tstep;
+      if (t0 >= r_end) break;
+      fetch(A, t0 + tstep);
+      process(B);
+      t0 += tstep;
+      if (t0 >= r_end) break;
+    }
   }
 }
 
@@ -426,7 +586,7 @@ struct NarrowArgs {
   unsigned long long *stats;             // [0] lane-steps spent, [1] in-window (record, bin) pairs
   ErfcxCoef cf;
   double *out_dos, *out_int, *out_step;  // [ns * bpad + NR_T]; JD mode: out_dos / out_int are the two channels
-  double *out_dos_em, *out_corr;         // Gaussian DOS, Euler-Maclaurin groups: their DOS and the correction sums
+  double *out_dos_em;                    // Gaussian DOS, Euler-Maclaurin groups: their DOS (the integral follows from it, c_em_fir)
   int no_em;                             // OD_NO_EM=1: rational erfc for every group (tests)
   int debug;                             // OD_NARROW_DEBUG bit 0: every group through the record-by-record path
   int *flags;                            // ctx->flags: [0] |= doslin `stop` conditions (reported by od_check_deferred)
@@ -442,20 +602,27 @@ struct NarrowArgs {
   long long k_first;
 };
 
-// tile -> HBM.  mode 0: (dos, local part of the integrated DOS, steps) / the two JD channels; mode 1: the
-// Euler-Maclaurin pair (dos_em, corr)
+// tile -> HBM.  mode 0: (dos, local part of the integrated DOS, steps) / the two JD channels; mode 1: the DOS of the
+// Euler-Maclaurin groups alone, the tile then being an array of NR_T doubles
 __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, int mode, const NarrowArgs &A, int lane) {
-  double *o0 = mode ? A.out_dos_em : A.out_dos, *o1 = mode ? A.out_corr : A.out_int;
+  if (mode) {
+    double *t1 = reinterpret_cast<double *>(tile);
+    for (int i = lane; i < used; i += 32) {
+      const double v = t1[i];
+      if (v != 0.0) atomicAdd(&A.out_dos_em[base + i], v);
+      t1[i] = 0.0;
+    }
+    __syncwarp();
+    return;
+  }
   for (int i = lane; i < used; i += 32) {
     const double2 v = tile[i];
-    if (v.x != 0.0) atomicAdd(&o0[base + i], v.x);
-    if (v.y != 0.0) atomicAdd(&o1[base + i], v.y);
+    if (v.x != 0.0) atomicAdd(&A.out_dos[base + i], v.x);
+    if (v.y != 0.0) atomicAdd(&A.out_int[base + i], v.y);
     tile[i] = make_double2(0.0, 0.0);
-    if (!mode) {
-      const double s = stile[i];
-      if (s != 0.0) atomicAdd(&A.out_step[base + i], s);
-      stile[i] = 0.0;
-    }
+    const double s = stile[i];
+    if (s != 0.0) atomicAdd(&A.out_step[base + i], s);
+    stile[i] = 0.0;
   }
   __syncwarp();
 }
@@ -470,49 +637,30 @@ __device__ __forceinline__ void gauss_direct(double e, double w, double om, doub
   s = (j < cabs) ? h : -h;
 }
 
-// Euler-Maclaurin form of the integrated Gaussian (tools/em_table.py prints the table and the del thresholds):
-//   omega Phi(z_j) = dE S_j - g_j [dE/2 + w z_j W(z_j^2)],   z W(z^2) = - sum_{k=1..NT} B_2k/(2k)! del^2k He_{2k-1}(z)
-// with S_j the inclusive sum of the record's Gaussian values from the bottom of its window.  Summed over records the
-// first term is a prefix sum of the DOS these records produce, so the kernel only accumulates g and g z w W(z^2) per bin
-// (10 FP64 operations for NT = 4, 13 for NT = 7, against 21 + a reciprocal for the rational erfc) and combine_kernel
-// does the prefix sum once per call.  Truncation: <= 3e-12 of omega for del <= 0.2568 (NT = 4) / 0.5348 (NT = 7).
-constexpr double EM_DEL4 = 0.2568, EM_DEL7 = 0.5348;
-__constant__ double c_emT[7][7] = {
-    {-8.33333333333333287e-02, 0, 0, 0, 0, 0, 0},
-    {-4.16666666666666661e-03, 1.38888888888888894e-03, 0, 0, 0, 0, 0},
-    {-4.96031746031746004e-04, 3.30687830687830669e-04, -3.30687830687830710e-05, 0, 0, 0, 0},
-    {-8.68055555555555589e-05, 8.68055555555555589e-05, -1.73611111111111111e-05, 8.26719576719576754e-07, 0, 0, 0},
-    {-1.97285353535353552e-05, 2.63047138047138036e-05, -7.89141414141414141e-06, 7.51563251563251527e-07, -2.08767569878681002e-08, 0, 0},
-    {-5.49291564916564902e-06, 9.15485941527608198e-06, -3.66194376611043296e-06, 5.23134823730061852e-07, -2.90630457627812118e-08,
-     5.28419013868749322e-10, 0},
-    {-1.80844907407407414e-06, 3.61689814814814829e-06, -1.80844907407407414e-06, 3.44466490299823656e-07, -2.87055408583186369e-08,
-     1.04383784939340501e-09, -1.33825365306846789e-11}};
-
-// c[m] = w * sum_{k > m} T[k][m] del^(2k+2): coefficient of z^(2m+1) in w z W(z^2)
-template <int NT>
-__device__ __forceinline__ void em_coeffs(double del, double w, double (&c)[NT]) {
-  const double d2 = del * del;
-  double pw[NT];
-  pw[0] = d2 * w;
-#pragma unroll
-  for (int k = 1; k < NT; ++k) pw[k] = pw[k - 1] * d2;
-#pragma unroll
-  for (int m = 0; m < NT; ++m) {
-    double a = 0.0;
-#pragma unroll
-    for (int k = NT - 1; k >= m; --k) a = fma(c_emT[k][m], pw[k], a);
-    c[m] = a;
-  }
-}
-
-template <int NT>
-__device__ __forceinline__ double em_zw(double z, const double (&c)[NT]) {
-  const double u = z * z;
-  double w = c[NT - 1];
-#pragma unroll
-  for (int m = NT - 2; m >= 0; --m) w = fma(w, u, c[m]);
-  return z * w;
-}
+// Integrated DOS of the wide Gaussians without any per-bin work (tools/em_fir.py).  Euler-Maclaurin: for f sampled with
+// spacing dE,   dE sum_{n<=j} f_n = F(E_j) + dE [ f_j / 2 + sum_k B_2k dE^(2k-1)/(2k)! f^(2k-1)(E_j) ],  F the running integral.
+// On f = exp(i k E) the bracket is 1/2 + i phi(theta), phi = 1/theta - cot(theta/2)/2, theta = k dE.  A sum of Gaussians of
+// width w >= dE / 0.4, each deposited over at least +-8 w, has the spectrum exp(-(theta w/dE)^2/2): 4e-14 at the Nyquist
+// frequency, so the sampled DOS of those records determines its own integral, and the derivative series can be applied to the
+// SUMMED spectrum as one antisymmetric 40-tap filter,  sum_k ... = sum_n a_n (f_{j+n} - f_{j-n})  (least-squares fit of
+// 2 sum_n a_n sin(n theta) to phi under the weight of the widest spectrum; 1.3e-15 of a record's weight over all widths and
+// grid offsets).  The accumulation kernel therefore deposits only g (two multiplies and an add per record and bin) for groups
+// with dE/w <= EM_DELMAX whose windows are not clipped by the grid, and combine_kernel forms
+//   intdos_j += dE (prefix(dos_em)_j - dos_em_j / 2 - sum_n a_n (dos_em_{j+n} - dos_em_{j-n}))
+// once per call.  (Round 2 first evaluated the series per record and bin as a polynomial in z: 10-13 FP64 operations.)
+constexpr double EM_DELMAX = 0.40;
+constexpr int EM_NTAPS = 40;
+__constant__ double c_em_fir[EM_NTAPS] = {
+    8.91334410894595863e-02, -4.78780582194980112e-02, 3.20342800797231569e-02, -2.36303978263413123e-02,
+    1.83764680682251304e-02, -1.47459748485493179e-02, 1.20640884105840951e-02, -9.98802551019282656e-03,
+    8.32593542078903688e-03, -6.96245923776002765e-03, 5.82427128159195874e-03, -4.86261777000064187e-03,
+    4.04381183373205087e-03, -3.34374882732787777e-03, 2.74458465447531335e-03, -2.23264161192572412e-03,
+    1.79704460262508072e-03, -1.42881152412623579e-03, 1.12023855146349289e-03, -8.64485364005221487e-04,
+    6.55301778524417411e-04, -4.86858148529509716e-04, 3.53653802422202303e-04, -2.50484339417797615e-04,
+    1.72451929225559677e-04, -1.15004265215845567e-04, 7.39885074993904500e-05, -4.57072027603903677e-05,
+    2.69643832116552231e-05, -1.50922236765937371e-05, 7.95190288326125929e-06, -3.90647835159152347e-06,
+    1.76811678738557096e-06, -7.26140962748321804e-07, 2.65201468100874104e-07, -8.37836256336142419e-08,
+    2.19918392195048603e-08, -4.49858390838473364e-09, 6.37782080464529024e-10, -4.70258149603027033e-11};
 
 constexpr int NR_NLV = 64;                                    // levels of the in-chunk counting sort
 constexpr int NR_SORT_INTS = 72;                              // per warp: 65 counters (+ padding) ...
@@ -750,7 +898,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
 
       // ---- Gaussian DOS: which form of the integrated spectrum does this group take?
       double invw[2] = {1.0, 1.0}, del[2] = {0.0, 0.0}, zB[2] = {0.0, 0.0};
-      int emode = 0;  // 0: rational erfc (bracket + steps); 4 / 7: Euler-Maclaurin with that many terms
+      int emode = 0;  // 0: rational erfc (bracket + steps); 1: Euler-Maclaurin group -- only the DOS is deposited (c_em_fir)
       if (!LINEAR) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -759,13 +907,18 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           zB[s] = (E0[s] - e0[s]) * invw[s];
         }
         if (!JD && !A.no_em) {
-          // every record must start its walk where Phi is still ~0 (a window clipped by the bottom of the grid does
-          // not) and sit inside the series' range of validity
+          // every record must deposit its whole Gaussian: the walk starts at or below -8 w (a window clipped by the bottom
+          // of the grid does not), the record's own window ends at or above +8 w (one clipped by the top does not), and the
+          // widths stay inside the filter's band
           const double dl = fmax(valid[0] ? del[0] : 0.0, valid[1] ? del[1] : 0.0);
           const double dmax = __hiloint2double((int)__reduce_max_sync(FULL, (unsigned)__double2hiint(dl)), 0);
-          const bool ok = __all_sync(FULL, (!valid[0] || zB[0] <= -8.0) && (!valid[1] || zB[1] <= -8.0));
-          // dmax is del rounded DOWN to its high word: compare against thresholds lowered by one part in 10^6
-          if (ok && dmax <= EM_DEL7 * (1.0 - 1e-6)) emode = dmax <= EM_DEL4 * (1.0 - 1e-6) ? 4 : 7;
+          bool ok = true;
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            ok = ok && (!valid[s] || (zB[s] <= -8.0 && fma((double)(a[s] + wlen[s] - 1), del[s], zB[s]) >= 8.0));
+          ok = __all_sync(FULL, ok);
+          // dmax is del rounded DOWN to its high word: compare against a threshold lowered by one part in 10^6
+          if (ok && dmax <= EM_DELMAX * (1.0 - 1e-6)) emode = 1;
         }
       }
       const int want_mode = emode ? 1 : 0;
@@ -808,34 +961,24 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         // doubles; as predicated moves inside one loop they were 13 of 47 instructions of EVERY step.
         const int nmain = Wc - 31;
         if (!JD && emode) {
-          auto em_run = [&](auto NTc) {
-            constexpr int NT = decltype(NTc)::value;
-            double cA[NT], cB[NT];
-            em_coeffs<NT>(del[0], p1[0], cA);
-            em_coeffs<NT>(del[1], p1[1], cB);
-            auto step = [&](auto WRAP) {
-              if (decltype(WRAP)::value) {
-                if (r == Wc) { r = 0; g[0] = gB[0]; rr[0] = rB[0]; z[0] = zB[0]; g[1] = gB[1]; rr[1] = rB[1]; z[1] = zB[1]; }
-              }
-              const double gA = g[0], gb = g[1];
-              const double tA = em_zw<NT>(z[0], cA), tb = em_zw<NT>(z[1], cB);
-              double2 *qp = tw + r;
-              g[0] *= rr[0]; rr[0] *= q[0]; z[0] += del[0];
-              g[1] *= rr[1]; rr[1] *= q[1]; z[1] += del[1];
-              ++r;
-              double2 acc = *qp;
-              acc.x += gA + gb;
-              acc.y += fma(gA, tA, gb * tb);
-              *qp = acc;
-              __syncwarp();
-            };
-#pragma unroll NR_MAIN_UNROLL
-            for (int t = 0; t < nmain; ++t) step(std::false_type{});
-#pragma unroll 1
-            for (int t = 0; t < 31; ++t) step(std::true_type{});
+          // Euler-Maclaurin group: the tile is an array of doubles, 6 FP64 operations per step for two records
+          double *tw1 = reinterpret_cast<double *>(tile) + off;
+          auto step = [&](auto WRAP) {
+            if (decltype(WRAP)::value) {
+              if (r == Wc) { r = 0; g[0] = gB[0]; rr[0] = rB[0]; g[1] = gB[1]; rr[1] = rB[1]; }
+            }
+            const double sum = g[0] + g[1];
+            double *qp = tw1 + r;
+            g[0] *= rr[0]; rr[0] *= q[0];
+            g[1] *= rr[1]; rr[1] *= q[1];
+            ++r;
+            *qp += sum;
+            __syncwarp();
           };
-          if (emode == 4) em_run(std::integral_constant<int, 4>{});
-          else em_run(std::integral_constant<int, 7>{});
+#pragma unroll 4
+          for (int t = 0; t < nmain; ++t) step(std::false_type{});
+#pragma unroll 1
+          for (int t = 0; t < 31; ++t) step(std::true_type{});
           continue;
         }
         const double clA = p1[0] * 1.2533141373155002512, clB = p1[1] * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
@@ -1210,10 +1353,10 @@ struct WideListProducer {
 };
 
 // out(j, is): dos += narrow dos (both families of groups); intdos += the local part of the rational-erfc groups + the
-// inclusive prefix sum of their step histogram + the Euler-Maclaurin groups' dE (prefix(dos_em)_j - dos_em_j / 2) - corr_j
+// inclusive prefix sum of their step histogram + the Euler-Maclaurin groups' dE (prefix(dos_em)_j - dos_em_j / 2 - fir_j)
 __global__ void __launch_bounds__(1024) combine_kernel(const double *__restrict__ n_dos, const double *__restrict__ n_int,
                                                        const double *__restrict__ stephist, const double *__restrict__ n_dos_em,
-                                                       const double *__restrict__ n_corr, double delta, int nbins, int bpad,
+                                                       double delta, int nbins, int bpad,
                                                        double *__restrict__ dos, double *__restrict__ intdos) {
   // grid (blocks of 1024 bins, spin channels).  A CTA first sums the prefix terms of all bins below its block (independent,
   // coalesced loads: at most 20 per thread on a 20 000-bin grid), then scans its own 1024 bins with shuffles.
@@ -1248,7 +1391,14 @@ __global__ void __launch_bounds__(1024) combine_kernel(const double *__restrict_
   if (j < nbins) {
     const double before = below_s + (warp > 0 ? warp_tot[warp - 1] : 0.0);
     dos[(size_t)is * nbins + j] += n_dos[(size_t)is * bpad + j] + dem;
-    intdos[(size_t)is * nbins + j] += n_int[(size_t)is * bpad + j] - n_corr[(size_t)is * bpad + j] - 0.5 * delta * dem + (before + v);
+    // end correction of the Euler-Maclaurin groups (their Gaussians lie wholly inside the grid: zero beyond its ends)
+    double fir = 0.0;
+#pragma unroll 8
+    for (int n = 1; n <= EM_NTAPS; ++n) {
+      const double up = (j + n < nbins) ? dem_p[j + n] : 0.0, dn = (j - n >= 0) ? dem_p[j - n] : 0.0;
+      fir = fma(c_em_fir[n - 1], up - dn, fir);
+    }
+    intdos[(size_t)is * nbins + j] += n_int[(size_t)is * bpad + j] - delta * (0.5 * dem + fir) + (before + v);
   }
 }
 
@@ -1289,8 +1439,14 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   const PrepSpec &ps = S.ps;
   // one prepare CTA per SM, fewer for small jobs (every CTA zeroes, dumps and re-reads a row of the bucket table); pass A and
   // pass B MUST use the same grid
-  const long long per_cta = (long long)NR_PREP_THREADS * Producer::PREP_U;  // at least one tile per CTA
-  const int prows = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count, ((long long)prod.units_per_z + per_cta - 1) / per_cta));
+  PrepMap pm;
+  pm.W = (unsigned)prod.inner();
+  pm.nk = (unsigned)(prod.units_per_z / prod.inner());
+  pm.nk_div = FastDiv(pm.nk);
+  pm.nrows = (unsigned long long)((pm.W + 31) / 32) * pm.nk;
+  const long long per_cta = (long long)NR_PREP_ROWS * Producer::PREP_U;  // at least one tile of rows per CTA
+  const int prows = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count, ((long long)pm.nrows + per_cta - 1) / per_cta));
+  pm.per = (pm.nrows + prows - 1) / prows;
   const size_t hist_smem = sizeof(unsigned) * ps.nbuckets;
   const size_t units = (size_t)prod.units_per_z * prod.ns;
   *wide_stride = prod.units_per_z;
@@ -1300,23 +1456,45 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * units * ps.wstride + 256));
   if (ps.want_unit) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_e, sizeof(unsigned) * units + 256));
   OD_CUDA(ctx, cudaMemsetAsync(S.wide, 0, sizeof(unsigned long long) * 5, ctx->stream));
-  OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-  prep_hist_kernel<Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod_keys, ps, S.keys, S.table, S.wide);
+  // what pass A hands to pass B (see prep_hist_kernel): whole Gaussian records, the tails of linear ones, or nothing
+  constexpr bool STAGED = Producer::PREP_STAGED;
+  const int stage = !STAGED ? 0 : (linear ? 1 : 2);
+  if (stage) OD_CHECK(od_buf_ensure(ctx, ctx->stage, (stage == 2 ? sizeof(GRec) : sizeof(double)) * units + 256));
+  double *wts = ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
+  unsigned *runit = ps.want_unit ? ctx->scratch_e.as<unsigned>() : nullptr;
+#define HIST_LAUNCH(ST)                                                                                                              \
+  do {                                                                                                                               \
+    OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem)); \
+    prep_hist_kernel<Producer, ST><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod_keys, ps, S.keys, S.table, S.wide, ctx->stage.p, pm); \
+  } while (0)
+#define SC_LAUNCH(LIN, TL)                                                                                                           \
+  do {                                                                                                                               \
+    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<LIN, Producer, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem)); \
+    prep_scatter_kernel<LIN, Producer, TL><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(                                     \
+        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride, \
+        ctx->stage.as<double>(), pm);                                                                                                \
+  } while (0)
+  if (STAGED && stage == 2) HIST_LAUNCH(2); else if (STAGED && stage == 1) HIST_LAUNCH(1); else HIST_LAUNCH(0);
   OD_LAUNCH_CHECK(ctx);
   prep_colscan_kernel<<<(ps.nbuckets + 255) / 256, 256, 0, ctx->stream>>>(S.table, prows, ps.nbuckets, S.colsum);
   OD_LAUNCH_CHECK(ctx);
   scan_kernel<<<1, 1024, 0, ctx->stream>>>(S.colsum, ps.nbuckets, S.base);
   OD_LAUNCH_CHECK(ctx);
-  double *wts = ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
-  unsigned *runit = ps.want_unit ? ctx->scratch_e.as<unsigned>() : nullptr;
-#define SC_LAUNCH(LIN)                                                                                                               \
-  do {                                                                                                                               \
-    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<LIN, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem)); \
-    prep_scatter_kernel<LIN, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(                                         \
-        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride); \
-  } while (0)
-  if (linear) SC_LAUNCH(true); else SC_LAUNCH(false);
+  if (STAGED && stage == 2) {
+    constexpr int U = Producer::PREP_U;
+    OD_CUDA(ctx, cudaFuncSetAttribute(prep_permute_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+    prep_permute_kernel<U><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(
+        ps, (unsigned)prod.units_per_z, prod.ns, S.keys, S.table, S.base, ctx->stage.as<GRec>(), ctx->recs.as<GRec>(), runit, S.stephist,
+        ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride, pm);
+  } else if (STAGED && stage == 1) {
+    SC_LAUNCH(true, true);
+  } else if (linear) {
+    SC_LAUNCH(true, false);
+  } else {
+    SC_LAUNCH(false, false);
+  }
 #undef SC_LAUNCH
+#undef HIST_LAUNCH
   OD_LAUNCH_CHECK(ctx);
   return OD_OK;
 }
@@ -1342,8 +1520,7 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, int col0, int col1
   A.out_dos = out0;
   A.out_int = out1;
   A.out_step = S.stephist;
-  A.out_dos_em = JD ? nullptr : S.chan + 2 * S.nout;  // DOS: chan = [dos | int | dos_em | corr]
-  A.out_corr = JD ? nullptr : S.chan + 3 * S.nout;
+  A.out_dos_em = JD ? nullptr : S.chan + 2 * S.nout;  // DOS: chan = [dos | int | dos_em]
   A.no_em = getenv("OD_NO_EM") ? 1 : 0;
   A.debug = getenv("OD_NARROW_DEBUG") ? atoi(getenv("OD_NARROW_DEBUG")) : 0;
   A.flags = ctx->flags.as<int>();
@@ -1394,6 +1571,7 @@ int narrow_cell_for(int nbins, int ns, long long total_units = -1) {
 int narrow_scratch(od_ctx *ctx, const GridSpec &grid, int ns, long long total_units, int nchan_arrays, Scratch &S) {
   PrepSpec &ps = S.ps;
   ps.grid = grid;
+  ps.inv_delta = 1.0 / grid.delta;
   ps.cell = narrow_cell_for(grid.nbins, ns, total_units);
   if (ps.cell == 0) return od_fail(ctx, OD_ERR_ARG, "narrow engine: energy grid too large (%d bins)", grid.nbins);
   ps.wmax = std::min(NR_WMAX, NR_T - 2 * ps.cell);
@@ -1443,7 +1621,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   if (total >= (1ll << 32) || prod.units_per_z >= (1ll << 31))
     return od_fail(ctx, OD_ERR_ARG, "narrow engine: more than 2^31 units per spin channel in one call");
   Scratch S;
-  OD_CHECK(narrow_scratch(ctx, grid, ns, total, 4, S));  // [dos | local intdos | dos of the Euler-Maclaurin groups | their corrections]
+  OD_CHECK(narrow_scratch(ctx, grid, ns, total, 3, S));  // [dos | local intdos | dos of the Euler-Maclaurin groups]
   S.ps.gwin = NR_ERFWIN;
   S.ps.with_int = 1;
   S.ps.linear_pass = 0;  // calculate_dos ignores hybrid_linear (quirk Q8): a linear pass has no Gaussian records
@@ -1460,7 +1638,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   OD_CHECK(od_time_begin(ctx, 1, &ta));
   OD_CHECK(narrow_launch<false>(ctx, S, linear, -2, -2, ndos, nint, nullptr));
   const size_t n1 = (size_t)nbins * ns;
-  combine_kernel<<<dim3((nbins + 1023) / 1024, ns), 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, S.chan + 2 * S.nout, S.chan + 3 * S.nout, grid.delta, nbins, S.ps.bpad,
+  combine_kernel<<<dim3((nbins + 1023) / 1024, ns), 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, S.chan + 2 * S.nout, grid.delta, nbins, S.ps.bpad,
                                                 accum, accum + n1);
   OD_LAUNCH_CHECK(ctx);
   int wpasses = 0;

@@ -4,6 +4,8 @@
 
 // n / d for 32-bit n by multiplication (Granlund-Montgomery round-up method, exact for every n < 2^32): the prepare passes
 // of the narrow engine split a unit index into (k-point, band) once per unit, and an integer division is ~20 instructions
+__device__ __forceinline__ void od_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct FastDiv {
   unsigned d = 1, m = 1, s1 = 0, s2 = 0;
   FastDiv() = default;
@@ -23,6 +25,23 @@ struct FastDiv {
     return (t + ((n - t) >> s1)) >> s2;
   }
 };
+
+// sqrt(x) to ~1 ulp for finite x >= 0 (rsqrt.approx.ftz.f64 carries ~22 bits; two Goldschmidt steps and one residual
+// correction); tiny and huge arguments take the IEEE path
+__device__ __forceinline__ double od_fast_sqrt(double x) {
+  if (!(x > 1e-280 && x < 1e280)) return sqrt(x);
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double g = x * r, h = 0.5 * r;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  const double d = fma(-g, g, x);
+  return fma(d, h, g);
+}
 
 // Broadening set-up common to calculate_dos / calculate_dos_at_e / calculate_jdos
 // (dos_utils.f90:1208-1218, jdos_utils.f90:324-334)
@@ -45,7 +64,13 @@ __device__ __forceinline__ void od_make_record(const BroadSpec &b, double centre
   double width = 0.0;
   bool force_adaptive = false;
   double gnorm = 0.0;
-  if (b.type != 0) gnorm = sqrt(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);  // sqrt(dot_product(grad,grad))
+  // sqrt(dot_product(grad,grad)): only the adaptive width and the hybrid_linear test use it (an IEEE square root is ~30
+  // instructions, a seventh of the narrow engine's key pass); the narrow engine (fast_corners) takes it to ~1 ulp by
+  // MUFU.RSQ64H + Goldschmidt, the exact engines keep the IEEE one
+  if (b.type == 1 || (b.type == 2 && b.honor_hybrid && b.hybrid)) {
+    const double g2 = grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2];
+    gnorm = b.fast_corners ? od_fast_sqrt(g2) : sqrt(g2);
+  }
   // hybrid_linear only changes anything for the linear scheme (for 'f' the reference tests an
   // unset gradient); dos_utils.f90:1758, jdos_utils.f90:365
   if (b.type == 2 && b.honor_hybrid && b.hybrid && (b.hybrid_tol > gnorm)) force_adaptive = true;
@@ -89,6 +114,8 @@ struct DosProducer {
 #define OD_PREP_U_DOS 4
 #endif
   static constexpr int PREP_U = OD_PREP_U_DOS;
+  static constexpr bool PREP_STAGED = true;   // pass A hands its records / windows to pass B (see prep_hist_kernel)
+  __host__ __device__ long long inner() const { return nb; }  // units per k-point
   template <bool WT>
   __device__ __forceinline__ void load(unsigned u, int is, Raw &w) const {
     const unsigned ikl = nb_div.div(u), ib = u - ikl * (unsigned)nb;
@@ -107,6 +134,17 @@ struct DosProducer {
   __device__ __forceinline__ void make(unsigned, int, const Raw &w, RecOut &r) const {
     const double g[3] = {w.g0, w.g1, w.g2};
     od_make_record(b, w.e, g, eps * w.kw, r);
+  }
+  // the lines load() will touch, into L2 (issued a tile or two ahead by the prepare passes: no registers held)
+  __device__ __forceinline__ void prefetch(unsigned u, int is) const {
+    const unsigned ikl = nb_div.div(u), ib = u - ikl * (unsigned)nb;
+    od_prefetch_l2(bands + ib + (size_t)nb * (is + (size_t)ns * (k_first + ikl)));
+    if (b.type != 0) {
+      const double *gp = grads + ib + (size_t)nb * (3 * (ikl + (size_t)nk_g * is));
+      od_prefetch_l2(gp);
+      od_prefetch_l2(gp + nb);
+      od_prefetch_l2(gp + 2 * (size_t)nb);
+    }
   }
 
   __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
@@ -190,6 +228,9 @@ struct JdosProducer {
     int ib, jb;
   };
   static constexpr int PREP_U = 2;
+  static constexpr bool PREP_STAGED = false;  // pass B rebuilds the record (the weights come from the matrix elements anyway)
+  __device__ __forceinline__ void prefetch(unsigned, int) const {}  // (band data of a k-point is re-used by all its pairs: cached)
+  __host__ __device__ long long inner() const { return pairs_per_k(); }  // units (pair slots) per k-point
   __device__ __forceinline__ void slot(unsigned uu, int &ib, int &jb, long long &ik) const {
     if (occ_list) {
       const unsigned t = uu / (unsigned)n_occ, tj = t / (unsigned)n_unocc;
