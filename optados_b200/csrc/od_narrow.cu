@@ -191,6 +191,10 @@ __device__ __forceinline__ Cls classify(const RecOut &r, const PrepSpec &ps) {
 //      (linear DOS: the 64-byte record itself would cost more traffic than its 3 dot products);
 //   2  the whole 32-byte Gaussian record in unit order (coalesced): pass B is a pure permutation -- one 32-byte load, one
 //      shared-memory cursor, one 32-byte store per unit (Gaussian DOS; +28 B of traffic per unit for -150 instructions).
+// (Measured and dropped, profiles/r02_summary.md: pass B sorting only 4-byte indices, the accumulation kernel gathering staged
+// records through them.  Pass B is bound by the NUMBER of scattered store requests (~94 G/s for 4-byte, ~56 G/s for 32-byte
+// ones), not by their bytes, so the index form only wins for the 64-byte records, and the gathers cost the accumulation
+// kernel as much as pass B saved.)
 // An off-grid unit (key KEY_DROP) carries its step bin in the klo field.
 __device__ __forceinline__ double rec_tail(int klo, int cpos, int wlen);
 __device__ __forceinline__ void st256(void *dst, double a, double b, double c, double d);
@@ -343,8 +347,10 @@ __device__ __forceinline__ void tail_unpack(double tail, int &klo, int &cpos, in
 }
 
 // ---------------------------------------------------------------- pass B: scatter (shared-memory cursors)
-// The cursors of a tile's units are taken (shared-memory atomics with return, ~100 cycles) right after its keys are known,
-// before the records are built: a store that waits for its own cursor was 16 % of this pass's stall samples.
+// The cursors of a tile's units are taken (shared-memory atomics with return) right after its keys are known, before the
+// records are built: a store that waits for its own cursor was 16 % of this pass's stall samples.  (Handing every unit's
+// rank inside its CTA's share of the bucket from pass A to pass B, which then needs no atomics, was measured: +4 B of
+// traffic per unit and pass, 8 % slower -- pass B is bound by the memory system, not by its shared-memory atomics.)
 // TAILS: pass A left every unit's tail (STAGE 1) -- no classification here.
 template <bool LINEAR, class Producer, bool TAILS>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
@@ -465,7 +471,7 @@ prep_permute_kernel(PrepSpec ps, unsigned upz, int ns, const unsigned *__restric
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned long long r_begin = (unsigned long long)blockIdx.x * pm.per, r_end = min(pm.nrows, r_begin + pm.per);
-  constexpr unsigned tstep = NR_PREP_ROWS * U;
+  constexpr unsigned ROWS = NR_PREP_THREADS / 32, tstep = ROWS * U;
   struct Tile {
     double a[U], b[U], c[U], d[U];
     unsigned key[U], u[U];
@@ -476,7 +482,7 @@ prep_permute_kernel(PrepSpec ps, unsigned upz, int ns, const unsigned *__restric
     auto fetch = [&](Tile &T, unsigned long long t0) {
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        T.ok[j] = prep_unit(pm, t0 + (unsigned)j * NR_PREP_ROWS + warp, r_end, lane, T.u[j]);
+        T.ok[j] = prep_unit(pm, t0 + (unsigned)j * ROWS + warp, r_end, lane, T.u[j]);
         T.key[j] = KEY_WIDE;
         T.a[j] = T.b[j] = T.c[j] = T.d[j] = 0.0;
         if (T.ok[j]) {
@@ -795,7 +801,8 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       }
       // ---- which of the pending records go together in this pass: those whose window ends inside a tile that starts at the
       //      lowest pending window, and (Gaussian) whose recurrence may start that far below their own window
-      const int gl = __reduce_min_sync(FULL, min(klo[0], klo[1]));
+      int gl = __reduce_min_sync(FULL, min(klo[0], klo[1]));
+      if (!LINEAR && !JD) gl &= ~1;  // (the two-bin walk of the Euler-Maclaurin groups addresses the tile in aligned pairs)
       {
         ++npass;
         bool any_defer = false;
@@ -840,6 +847,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       const int gh = __reduce_max_sync(FULL, max(valid[0] ? klo[0] + wlen[0] - 1 : -0x3fffffff, valid[1] ? klo[1] + wlen[1] - 1 : -0x3fffffff));
       int Wc = gh - gl + 1;
       if (Wc < 32) Wc = 32;
+      if (!LINEAR && !JD) Wc += Wc & 1;
       int jb[2], a[2], cabs[2];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -942,7 +950,10 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       }
       __syncwarp();
 
-      int r = lane;
+      // Euler-Maclaurin groups of >= 64 bins walk two bins per step (lane l starts at bin 2 l): one LDS.128 / STS.128 and one
+      // warp synchronisation per four (record, bin) pairs -- the one-bin walk was bound by the shared-memory round trip
+      const bool pairwalk = !LINEAR && !JD && emode && Wc >= 64;
+      int r = pairwalk ? 2 * lane : lane;
       if (!LINEAR) {
         double amp[2], q[2], gB[2], rB[2], z[2], g[2], rr[2];
 #pragma unroll
@@ -952,7 +963,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           q[s] = exp(-del[s] * del[s]);
           gB[s] = amp[s] * exp(-0.5 * zB[s] * zB[s]);
           rB[s] = exp(-fma(zB[s], del[s], hd2));
-          z[s] = zB[s] + (double)lane * del[s];
+          z[s] = zB[s] + (double)r * del[s];
           g[s] = amp[s] * exp(-0.5 * z[s] * z[s]);
           rr[s] = exp(-fma(z[s], del[s], hd2));
         }
@@ -960,6 +971,33 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         // at bin l), then 31 steps in which exactly one lane per step wraps round to bin 0.  The restart values are 6
         // doubles; as predicated moves inside one loop they were 13 of 47 instructions of EVERY step.
         const int nmain = Wc - 31;
+        if (pairwalk) {
+          // (same multiplications in the same order as the one-bin walk: g_{j+1} = g_j r_j, r_{j+1} = r_j q)
+          double2 *tw2 = reinterpret_cast<double2 *>(reinterpret_cast<double *>(tile) + off);  // off is even
+          auto step2 = [&](auto WRAP) {
+            if (decltype(WRAP)::value) {
+              if (r == Wc) { r = 0; g[0] = gB[0]; rr[0] = rB[0]; g[1] = gB[1]; rr[1] = rB[1]; }
+            }
+            const double a0 = g[0], b0 = g[1];
+            const double a1 = a0 * rr[0], b1 = b0 * rr[1];
+            const double ra = rr[0] * q[0], rb = rr[1] * q[1];
+            double2 *qp = tw2 + (r >> 1);
+            g[0] = a1 * ra; g[1] = b1 * rb;
+            rr[0] = ra * q[0]; rr[1] = rb * q[1];
+            r += 2;
+            double2 acc = *qp;
+            acc.x += a0 + b0;
+            acc.y += a1 + b1;
+            *qp = acc;
+            __syncwarp();
+          };
+          const int nmain2 = (Wc >> 1) - 31;
+#pragma unroll 2
+          for (int t = 0; t < nmain2; ++t) step2(std::false_type{});
+#pragma unroll 1
+          for (int t = 0; t < 31; ++t) step2(std::true_type{});
+          continue;
+        }
         if (!JD && emode) {
           // Euler-Maclaurin group: the tile is an array of doubles, 6 FP64 operations per step for two records
           double *tw1 = reinterpret_cast<double *>(tile) + off;
