@@ -299,16 +299,25 @@ def main():
     step_tf = sum_over_ranks(dist, flops_step, local) / (ms_step * 1e-3) / 1e12 / world     # per GPU
     states = float(nk_gpu) * NB * NS
     hbm_gbs = 2.0 * states * BYTES_PER_STATE / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
-    traffic, kernels = None, None
+    traffic, kernels, pipe_pct = None, None, None
     try:   # per-kernel ncu figures of one k-point slab (tools/ncu_summary.py -> profiles/r02_kernels.json), scaled to this step's units
         kj = json.load(open(os.path.join(ROOT, "profiles", "r02_kernels.json")))
-        kernels = {k: {"fp64_pipe_pct": v["fp64_pipe_pct"], "ms_per_launch": v["ms"], "dram_bytes_per_unit": v["dram_bytes"] / v["units"]}
+        kernels = {k: {"fp64_pipe_pct": v["fp64_pipe_pct"], "ms_per_launch": v["ms"] / max(1, v["launches"]),
+                       "dram_bytes_per_unit": v["dram_bytes"] / v["launches"] / v["units"]}
                    for k, v in kj["kernels"].items()}
-        traffic = sum(v["dram_bytes"] / v["units"] for v in kj["kernels"].values()) * states
+        # every kernel of the capture runs once per scheme and unit (prep_hist twice: once per scheme)
+        traffic = sum(v["dram_bytes"] / v["units"] for v in kj["kernels"].values()) / kj.get("repeats", 1) * states
+        acc = [v for k, v in kj["kernels"].items() if k.startswith("narrow_kernel")]
+        pipe_pct = sum(v["fp64_pipe_pct"] * v["ms"] for v in acc) / sum(v["ms"] for v in acc)
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
+                "frac_note": "ALGORITHMIC flops (SURVEY.md 8(d): 76 per adaptive contribution with its integrated DOS, 30 per linear one) / "
+                             "duration / peak.  It exceeds 1 since round 2: the integrated DOS of the wide Gaussians is no longer evaluated per "
+                             "(state, bin) -- it follows from the summed DOS through a 40-tap Euler-Maclaurin filter (tools/em_fir.py) -- so the "
+                             "kernels execute about a third of the reference's arithmetic.  Hardware utilisation: fp64_pipe_pct.",
+                "fp64_pipe_pct": pipe_pct,
                 "frac_step": step_tf / fp64_peak if fp64_peak > 0 else None, "achieved_step": step_tf,
                 "traffic": traffic,
                 "traffic_note": "DRAM bytes per step of ALL kernels of the step, prepare passes included (ncu dram__bytes_read+write per unit, "

@@ -116,17 +116,35 @@ struct Cls {
 // writes (40-50 G sectors/s, a quarter of the bandwidth: the row-activation limit).
 struct PrepMap {
   unsigned W, nk;            // units per k-point, k-points of the slab
-  FastDiv nk_div;
+  unsigned ngroups;          // ceil(W / 32)
+  int kmajor;                // rows numbered k-major, row = k * ngroups + group (JDOS: the 4096 pair slots of a k-point share its
+                             // band energies and gradients, which stay in L1 while a CTA walks them; group-major rows cost
+                             // config 4 a quarter more in both passes)
+  FastDiv nk_div;            // / nk (group-major) or / ngroups (k-major)
   unsigned long long nrows;  // ceil(W / 32) * nk
   unsigned long long per;    // rows per CTA
 };
 constexpr unsigned NR_PREP_ROWS = NR_PREP_THREADS / 32;  // rows a CTA takes per step and unit slot
 
-__device__ __forceinline__ bool prep_unit(const PrepMap &pm, unsigned long long row, unsigned long long row_end, unsigned lane, unsigned &u) {
+__device__ __forceinline__ bool prep_unit(const PrepMap &pm, unsigned long long row, unsigned long long row_end, unsigned lane, unsigned &u);
+__device__ __forceinline__ bool prep_unit(const PrepMap &pm, unsigned long long row, unsigned long long row_end, unsigned lane, unsigned &u,
+                                          unsigned &k, unsigned &w) {
   if (row >= row_end) return false;
-  const unsigned g = pm.nk_div.div((unsigned)row), k = (unsigned)row - g * pm.nk, w = g * 32u + lane;
+  unsigned g;
+  if (pm.kmajor) {
+    k = pm.nk_div.div((unsigned)row);
+    g = (unsigned)row - k * pm.ngroups;
+  } else {
+    g = pm.nk_div.div((unsigned)row);
+    k = (unsigned)row - g * pm.nk;
+  }
+  w = g * 32u + lane;
   u = k * pm.W + w;
   return w < pm.W;
+}
+__device__ __forceinline__ bool prep_unit(const PrepMap &pm, unsigned long long row, unsigned long long row_end, unsigned lane, unsigned &u) {
+  unsigned k, w;
+  return prep_unit(pm, row, row_end, lane, u, k, w);
 }
 
 #define NR_ERFWIN (OD_ERF_CUT * OD_SQRT_TWO)  // 8.2024...: |z| beyond which the NSWC erf saturates
@@ -220,8 +238,9 @@ prep_hist_kernel(Producer prod, PrepSpec ps, unsigned *__restrict__ keys, unsign
     bool ok[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      ok[j] = prep_unit(pm, t0 + (unsigned)j * NR_PREP_ROWS + warp, r_end, lane, uu[j]);
-      if (ok[j]) prod.template load<false>(uu[j], is, raw[j]);
+      unsigned kk, ww;
+      ok[j] = prep_unit(pm, t0 + (unsigned)j * NR_PREP_ROWS + warp, r_end, lane, uu[j], kk, ww);
+      if (ok[j]) prod.template load_kw<false>(kk, ww, is, raw[j]);
     }
 #pragma unroll
     for (int j = 0; j < U; ++j) {
@@ -367,13 +386,14 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
   const unsigned upz = (unsigned)prod.units_per_z, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned long long r_begin = (unsigned long long)blockIdx.x * pm.per, r_end = min(pm.nrows, r_begin + pm.per);
   for (int is = 0; is < prod.ns; ++is) {
-  unsigned key_next[U], u_next[U];
+  unsigned key_next[U], k_next[U], w_next[U];  // (the unit index is k * W + w)
   bool ok_next[U];
   auto load_keys = [&](unsigned long long t0) {
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      ok_next[j] = prep_unit(pm, t0 + (unsigned)j * NR_PREP_ROWS + warp, r_end, lane, u_next[j]);
-      key_next[j] = ok_next[j] ? keys[(size_t)is * upz + u_next[j]] : KEY_WIDE;  // (KEY_WIDE: nothing to load; the slot is skipped below)
+      unsigned un;
+      ok_next[j] = prep_unit(pm, t0 + (unsigned)j * NR_PREP_ROWS + warp, r_end, lane, un, k_next[j], w_next[j]);
+      key_next[j] = ok_next[j] ? keys[(size_t)is * upz + un] : KEY_WIDE;  // (KEY_WIDE: nothing to load; the slot is skipped below)
     }
   };
   load_keys(r_begin);
@@ -386,10 +406,10 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
     // next tile, before the first use: two levels of loads in flight per thread
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      key[j] = key_next[j]; uu[j] = u_next[j]; ok[j] = ok_next[j];
+      key[j] = key_next[j]; uu[j] = k_next[j] * pm.W + w_next[j]; ok[j] = ok_next[j];
       tl[j] = 0.0;
       if (key[j] != KEY_WIDE && (key[j] != KEY_DROP || ps.with_int)) {
-        prod.template load<true>(uu[j], is, raw[j]);
+        prod.template load_kw<true>(k_next[j], w_next[j], is, raw[j]);
         if (TAILS) tl[j] = tails[(size_t)is * upz + uu[j]];
       }
     }
@@ -1464,6 +1484,8 @@ inline void strip_weights(DosProducer &p) { p.mw = nullptr; }
 inline void strip_weights(JdosProducer &p) { p.mw = nullptr; p.ome = nullptr; }
 inline void set_eager(DosProducer &) {}
 inline void set_eager(JdosProducer &p) { p.eager = 1; }
+inline void set_divs(DosProducer &) {}
+inline void set_divs(JdosProducer &p) { p.nocc_div = FastDiv((unsigned)(p.occ_list ? p.n_occ : p.nb)); }
 
 // Both prepare passes, without a host synchronisation: the number of records (S.base[nbuckets]) and of wide units
 // (S.wide[0..1]) stay on the device, the record buffers are sized for the worst case (every unit narrow / every unit wide).
@@ -1471,6 +1493,7 @@ template <class Producer>
 int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear, long long *wide_stride) {
   Producer prod = prod_in;
   prod.b.fast_corners = 1;  // both passes; wide units are re-made by the dense engine with the reference's arithmetic
+  set_divs(prod);
   Producer prod_keys = prod;  // pass A only needs the windows: no weight columns, no optical matrix elements
   strip_weights(prod_keys);
   set_eager(prod);            // pass B only runs on slots pass A accepted: loads first, tests after
@@ -1480,8 +1503,10 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   PrepMap pm;
   pm.W = (unsigned)prod.inner();
   pm.nk = (unsigned)(prod.units_per_z / prod.inner());
-  pm.nk_div = FastDiv(pm.nk);
-  pm.nrows = (unsigned long long)((pm.W + 31) / 32) * pm.nk;
+  pm.ngroups = (pm.W + 31) / 32;
+  pm.kmajor = Producer::PREP_KMAJOR ? 1 : 0;
+  pm.nk_div = FastDiv(pm.kmajor ? pm.ngroups : pm.nk);
+  pm.nrows = (unsigned long long)pm.ngroups * pm.nk;
   const long long per_cta = (long long)NR_PREP_ROWS * Producer::PREP_U;  // at least one tile of rows per CTA
   const int prows = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count, ((long long)pm.nrows + per_cta - 1) / per_cta));
   pm.per = (pm.nrows + prows - 1) / prows;

@@ -115,10 +115,16 @@ struct DosProducer {
 #endif
   static constexpr int PREP_U = OD_PREP_U_DOS;
   static constexpr bool PREP_STAGED = true;   // pass A hands its records / windows to pass B (see prep_hist_kernel)
+  static constexpr bool PREP_KMAJOR = false;  // band-group-major rows: a CTA fills few buckets (see PrepMap, od_narrow.cu)
   __host__ __device__ long long inner() const { return nb; }  // units per k-point
   template <bool WT>
   __device__ __forceinline__ void load(unsigned u, int is, Raw &w) const {
-    const unsigned ikl = nb_div.div(u), ib = u - ikl * (unsigned)nb;
+    const unsigned ikl = nb_div.div(u);
+    load_kw<WT>(ikl, u - ikl * (unsigned)nb, is, w);
+  }
+  // (k-point of the slab, band): the prepare passes know both, no division
+  template <bool WT>
+  __device__ __forceinline__ void load_kw(unsigned ikl, unsigned ib, int is, Raw &w) const {
     const long long ik = k_first + ikl;
     w.e = bands[ib + (size_t)nb * (is + (size_t)ns * ik)];
     w.g0 = w.g1 = w.g2 = 0.0;
@@ -207,6 +213,7 @@ struct JdosProducer {
   // pair, only bands that are unoccupied somewhere the upper one; null = all nb x nb slots
   const int *occ_list, *unocc_list;
   int n_occ, n_unocc;
+  FastDiv nocc_div;  // / n_occ (candidate lists) or / nb (all slots); set by the narrow engine before its prepare passes
   int eager;  // issue all loads of a slot before testing it (scatter pass of the narrow engine)
   __host__ __device__ long long pairs_per_k() const { return occ_list ? (long long)n_occ * n_unocc : (long long)nb * nb; }
   const double *bands, *grads, *kw;
@@ -229,6 +236,7 @@ struct JdosProducer {
   };
   static constexpr int PREP_U = 2;
   static constexpr bool PREP_STAGED = false;  // pass B rebuilds the record (the weights come from the matrix elements anyway)
+  static constexpr bool PREP_KMAJOR = true;   // see PrepMap (od_narrow.cu)
   __device__ __forceinline__ void prefetch(unsigned, int) const {}  // (band data of a k-point is re-used by all its pairs: cached)
   __host__ __device__ long long inner() const { return pairs_per_k(); }  // units (pair slots) per k-point
   __device__ __forceinline__ void slot(unsigned uu, int &ib, int &jb, long long &ik) const {
@@ -249,6 +257,25 @@ struct JdosProducer {
     int ib, jb;
     long long ik;
     slot(uu, ib, jb, ik);
+    load_at<WT>(ib, jb, ik, is, w);
+  }
+  // (k-point of the slab, pair slot of that k-point): one multiply-shift division instead of two hardware ones
+  template <bool WT>
+  __device__ __forceinline__ void load_kw(unsigned ikl, unsigned wslot, int is, Raw &w) const {
+    int ib, jb;
+    if (occ_list) {
+      const unsigned t = nocc_div.div(wslot);
+      ib = occ_list[wslot - t * (unsigned)n_occ];
+      jb = unocc_list[t];
+    } else {
+      const unsigned t = nocc_div.div(wslot);  // (set to / nb without candidate lists)
+      ib = (int)(wslot - t * (unsigned)nb);
+      jb = (int)t;
+    }
+    load_at<WT>(ib, jb, k_first + ikl, is, w);
+  }
+  template <bool WT>
+  __device__ __forceinline__ void load_at(int ib, int jb, long long ik, int is, Raw &w) const {
     w.ib = ib; w.jb = jb;
     const size_t eb = (size_t)nb * (is + (size_t)ns * ik);
     w.ei = bands[eb + ib]; w.ej = bands[eb + jb];
