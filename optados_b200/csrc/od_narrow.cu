@@ -629,14 +629,15 @@ struct NarrowArgs {
 };
 
 // tile -> HBM.  mode 0: (dos, local part of the integrated DOS, steps) / the two JD channels; mode 1: the DOS of the
-// Euler-Maclaurin groups alone, the tile then being an array of NR_T doubles
+// Euler-Maclaurin groups alone, the tile then being two arrays of NR_T doubles (one per half-warp, summed here)
 __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, int mode, const NarrowArgs &A, int lane) {
-  if (mode) {
+  if (mode) {  // two copies of NR_T doubles, one per half-warp
     double *t1 = reinterpret_cast<double *>(tile);
     for (int i = lane; i < used; i += 32) {
-      const double v = t1[i];
+      const double v = t1[i] + t1[i + NR_T];
       if (v != 0.0) atomicAdd(&A.out_dos_em[base + i], v);
       t1[i] = 0.0;
+      t1[i + NR_T] = 0.0;
     }
     __syncwarp();
     return;
@@ -970,10 +971,13 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       }
       __syncwarp();
 
-      // Euler-Maclaurin groups of >= 64 bins walk two bins per step (lane l starts at bin 2 l): one LDS.128 / STS.128 and one
-      // warp synchronisation per four (record, bin) pairs -- the one-bin walk was bound by the shared-memory round trip
-      const bool pairwalk = !LINEAR && !JD && emode && Wc >= 64;
-      int r = pairwalk ? 2 * lane : lane;
+      // Euler-Maclaurin groups walk two bins per step: one LDS.128 / STS.128 and one warp synchronisation per four (record, bin)
+      // pairs -- the one-bin walk was bound by the shared-memory round trip.  The two half-warps deposit into their own copies
+      // of the tile (it holds 8 bytes per bin in this mode, so there is room for two), lane l starting at bin 2 (l mod 16): the
+      // staggered starts then span 30 bins instead of 62 and only 15 steps of a walk carry the wrap test and its 8 selects
+      // (with one copy the 31 wrap steps were 83 % of the instructions of an 84-bin walk).
+      const bool pairwalk = !LINEAR && !JD && emode;  // (Wc is even and >= 32)
+      int r = pairwalk ? 2 * (lane & 15) : lane;
       if (!LINEAR) {
         double amp[2], q[2], gB[2], rB[2], z[2], g[2], rr[2];
 #pragma unroll
@@ -993,7 +997,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         const int nmain = Wc - 31;
         if (pairwalk) {
           // (same multiplications in the same order as the one-bin walk: g_{j+1} = g_j r_j, r_{j+1} = r_j q)
-          double2 *tw2 = reinterpret_cast<double2 *>(reinterpret_cast<double *>(tile) + off);  // off is even
+          double2 *tw2 = reinterpret_cast<double2 *>(reinterpret_cast<double *>(tile) + (lane >> 4) * NR_T + off);  // off is even
           auto step2 = [&](auto WRAP) {
             if (decltype(WRAP)::value) {
               if (r == Wc) { r = 0; g[0] = gB[0]; rr[0] = rB[0]; g[1] = gB[1]; rr[1] = rB[1]; }
@@ -1011,32 +1015,11 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
             *qp = acc;
             __syncwarp();
           };
-          const int nmain2 = (Wc >> 1) - 31;
+          const int nmain2 = (Wc >> 1) - 15;
 #pragma unroll 2
           for (int t = 0; t < nmain2; ++t) step2(std::false_type{});
 #pragma unroll 1
-          for (int t = 0; t < 31; ++t) step2(std::true_type{});
-          continue;
-        }
-        if (!JD && emode) {
-          // Euler-Maclaurin group: the tile is an array of doubles, 6 FP64 operations per step for two records
-          double *tw1 = reinterpret_cast<double *>(tile) + off;
-          auto step = [&](auto WRAP) {
-            if (decltype(WRAP)::value) {
-              if (r == Wc) { r = 0; g[0] = gB[0]; rr[0] = rB[0]; g[1] = gB[1]; rr[1] = rB[1]; }
-            }
-            const double sum = g[0] + g[1];
-            double *qp = tw1 + r;
-            g[0] *= rr[0]; rr[0] *= q[0];
-            g[1] *= rr[1]; rr[1] *= q[1];
-            ++r;
-            *qp += sum;
-            __syncwarp();
-          };
-#pragma unroll 4
-          for (int t = 0; t < nmain; ++t) step(std::false_type{});
-#pragma unroll 1
-          for (int t = 0; t < 31; ++t) step(std::true_type{});
+          for (int t = 0; t < 15; ++t) step2(std::true_type{});
           continue;
         }
         const double clA = p1[0] * 1.2533141373155002512, clB = p1[1] * 1.2533141373155002512;  // w sqrt(pi/2):  (omega/2) g' = g cl
