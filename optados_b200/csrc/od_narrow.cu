@@ -289,59 +289,79 @@ prep_hist_kernel(Producer prod, PrepSpec ps, unsigned *__restrict__ keys, unsign
 }
 
 // column scan: table[c][b] <- sum_{c' < c} table[c'][b];  colsum[b] <- sum_c table[c][b]
-// (16 independent loads in flight per thread: the column is short, the round trips are what costs)
+// Four threads share a column (a quarter of the rows each, 16 independent loads in flight per thread): the column is
+// short, the round trips are what costs -- this kernel and the scan below run once per slab and scheme, between the two
+// prepare passes, and were 84 us of fixed cost each time (0.25 of the 0.68 ms a config-2 step does not scale by at N = 8).
 __global__ void __launch_bounds__(256) prep_colscan_kernel(unsigned *__restrict__ table, int nrows, int nbuckets,
                                                           unsigned *__restrict__ colsum) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbuckets) return;
-  unsigned run = 0;
-  for (int c0 = 0; c0 < nrows; c0 += 16) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = tid >> 2, part = tid & 3;  // (the four threads of a column are neighbours in a warp)
+  const bool on = b < nbuckets;
+  const int per = (nrows + 3) / 4, r0 = min(part * per, nrows), r1 = min(r0 + per, nrows);
+  unsigned sum = 0;
+  if (on)
+    for (int c0 = r0; c0 < r1; c0 += 16) {
+      unsigned v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = (c0 + i < r1) ? table[(size_t)(c0 + i) * nbuckets + b] : 0u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sum += v[i];
+    }
+  // exclusive prefix over the four parts of the column
+  const unsigned s1 = __shfl_up_sync(0xffffffffu, sum, 1), s2 = __shfl_up_sync(0xffffffffu, sum, 2), s3 = __shfl_up_sync(0xffffffffu, sum, 3);
+  unsigned run = (part >= 1 ? s1 : 0u) + (part >= 2 ? s2 : 0u) + (part >= 3 ? s3 : 0u);
+  if (on && part == 3) colsum[b] = run + sum;
+  if (!on) return;
+  for (int c0 = r0; c0 < r1; c0 += 16) {
     unsigned v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = (c0 + i < nrows) ? table[(size_t)(c0 + i) * nbuckets + b] : 0u;
+    for (int i = 0; i < 16; ++i) v[i] = (c0 + i < r1) ? table[(size_t)(c0 + i) * nbuckets + b] : 0u;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      if (c0 + i < nrows) {
+      if (c0 + i < r1) {
         table[(size_t)(c0 + i) * nbuckets + b] = run;
         run += v[i];
       }
   }
-  colsum[b] = run;
 }
 
-// exclusive scan of the bucket totals (single CTA, one contiguous segment per thread); base[n] = number of
-// narrow records
+// exclusive scan of the bucket totals (single CTA; tiles of 1024 consecutive totals, the next tile's load in flight while
+// the current one is scanned with shuffles); base[n] = number of narrow records
 __global__ void __launch_bounds__(1024) scan_kernel(const unsigned *__restrict__ hist, int n, unsigned *__restrict__ base) {
   __shared__ unsigned warp_tot[32];
-  const int seg = (n + 1023) / 1024;
-  const int i0 = min(threadIdx.x * seg, n), i1 = min(i0 + seg, n);
-  unsigned sum = 0;
-  for (int i = i0; i < i1; ++i) sum += hist[i];
+  __shared__ unsigned carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned incl = sum;
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warp_tot[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    const unsigned w = warp_tot[lane];
-    unsigned wi = w;
+  unsigned carry = 0;
+  unsigned next = threadIdx.x < n ? hist[threadIdx.x] : 0u;
+  for (int t0 = 0; t0 < n; t0 += 1024) {
+    const int i = t0 + threadIdx.x;
+    const unsigned v = next;
+    next = (i + 1024 < n) ? hist[i + 1024] : 0u;
+    unsigned incl = v;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += t;
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    warp_tot[lane] = wi - w;  // exclusive
-    if (lane == 31) base[n] = wi;
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned w = warp_tot[lane];
+      unsigned wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;  // exclusive over the warps
+      if (lane == 31) carry_s = wi;
+    }
+    __syncthreads();
+    if (i < n) base[i] = carry + warp_tot[warp] + incl - v;
+    carry += carry_s;
+    __syncthreads();
   }
-  __syncthreads();
-  unsigned run = warp_tot[warp] + incl - sum;
-  for (int i = i0; i < i1; ++i) {
-    const unsigned v = hist[i];
-    base[i] = run;
-    run += v;
-  }
+  if (threadIdx.x == 0) base[n] = carry;
 }
 
 // A record leaves as 32-byte stores (st.global.v4.f64 = STG.E.ENL2.256, sm_100): the scatter pass is bound by the number of
@@ -718,6 +738,12 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
   const double delta = A.grid.delta, emin = A.grid.emin;
   const long long nrec = (long long)*A.nrec_dev;
   const long long nchunks = (nrec + NR_CHUNK - 1) / NR_CHUNK;
+  // Small jobs (fewer than two chunks per warp of the grid: 600k records) are bound by the time ONE warp needs for its
+  // chunk, not by throughput (a 2000-k-point step spent 0.76 of its 0.94 ms of kernels in the two accumulation launches at a
+  // quarter of their large-job rate): four warps then share a chunk -- each regroups all of it (4 % of the work) and walks
+  // one of its four groups of 64 records.
+  const int split = nchunks < 2ll * gridDim.x * NR_WARPS ? 4 : 1;
+  const long long nitems = nchunks * split;
   constexpr size_t RECB = LINEAR ? sizeof(LRec) : sizeof(GRec);
   constexpr size_t TAILB = LINEAR ? 48 : 24;  // byte offset of (klo, cpos | wlen << 16) in a record
   constexpr unsigned FULL = 0xffffffffu;
@@ -726,8 +752,9 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
     unsigned long long ch = 0;
     if (lane == 0) ch = atomicAdd(A.next_chunk, 1ull);
     ch = __shfl_sync(FULL, ch, 0);
-    if ((long long)ch >= nchunks) break;
-    const long long c0 = (long long)ch * NR_CHUNK;
+    if ((long long)ch >= nitems) break;
+    const int quarter = split == 1 ? 0 : (int)(ch & 3ull);
+    const long long c0 = (long long)(split == 1 ? ch : ch >> 2) * NR_CHUNK;
     const int n = (int)min((long long)NR_CHUNK, nrec - c0);
     unsigned long long st_steps = 0, st_useful = 0;
 
@@ -793,7 +820,8 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
     // ~100x slower per record, and a single such group used to be the tail of every launch (0.5 ms).
     bool defer[2] = {false, false};
     int adv = 64, npass = 0;
-    for (int g0 = 0; g0 < n; g0 += adv) {
+    const int g_end = split == 1 ? n : min(n, 64 * quarter + 64);
+    for (int g0 = 64 * quarter; g0 < g_end; g0 += adv) {
       // ---- my two records (and a prefetch of the two this lane takes in the next group)
       bool valid[2];
       long long idx[2];
@@ -1522,7 +1550,7 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   } while (0)
   if (STAGED && stage == 2) HIST_LAUNCH(2); else if (STAGED && stage == 1) HIST_LAUNCH(1); else HIST_LAUNCH(0);
   OD_LAUNCH_CHECK(ctx);
-  prep_colscan_kernel<<<(ps.nbuckets + 255) / 256, 256, 0, ctx->stream>>>(S.table, prows, ps.nbuckets, S.colsum);
+  prep_colscan_kernel<<<(4 * ps.nbuckets + 255) / 256, 256, 0, ctx->stream>>>(S.table, prows, ps.nbuckets, S.colsum);
   OD_LAUNCH_CHECK(ctx);
   scan_kernel<<<1, 1024, 0, ctx->stream>>>(S.colsum, ps.nbuckets, S.base);
   OD_LAUNCH_CHECK(ctx);
