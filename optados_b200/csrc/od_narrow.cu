@@ -1172,6 +1172,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
 // gathered (coalesced, 8 * BN bytes per record) into W[32][BN], and the product runs on the FP64 tensor cores
 // (DMMA m16n8k8, see pdos_gemm_kernel below).
 constexpr int PG_BM = 64, PG_KC = 32, PG_SEG = 2048;
+constexpr int PG_THREADS = 288;  // 8 DMMA warps + 1 producer warp (record parameters of the chunk after next)
 
 
 struct PgItem {
@@ -1216,13 +1217,14 @@ __device__ __forceinline__ void dmma_16x8x8(double (&c)[4], double a0, double a1
 // utilisation, profiles/), a DMMA needs 12 operand loads for 128 FMAs per thread instead of 64.  Measured DMMA peak
 // on B200: 37.1 TFLOP/s (the same pipe as DFMA).
 // The chunk loop is software-pipelined over three chunks with one barrier per chunk:
-//   chunk c+2: its 32 records (+ unit indices) are loaded by warp 0 before the MMA loop and turned into
-//              parameters after it;
+//   chunk c+2: its 32 records (+ unit indices) are loaded and turned into parameters (one exp, two reciprocals, one
+//              division per record) by a ninth, producer warp -- as a side job of warp 0 that chain ended every chunk
+//              after the other warps had reached the barrier (34 % of the kernel's stall samples);
 //   chunk c+1: weight rows are loaded (coalesced) into registers before the MMA loop and parked in shared memory
 //              after it; its G tile is expanded before the MMA loop;
 //   chunk c  : 4 k-steps of NB DMMAs per warp (warp tile 16 bins x 8 NB orbitals).
 template <int BN, bool LINEAR>
-__global__ void __launch_bounds__(256, 2) pdos_gemm_kernel(PgArgs A) {
+__global__ void __launch_bounds__(PG_THREADS, 2) pdos_gemm_kernel(PgArgs A) {
   constexpr int WS = BN + 4;             // row stride of the W tile
   constexpr int NB = BN / 16;            // 8-orbital blocks per warp (8 warps = 4 bin blocks x 2 orbital halves)
   constexpr int EPT = PG_KC * BN / 256;  // weight elements per thread and chunk
@@ -1362,19 +1364,27 @@ __global__ void __launch_bounds__(256, 2) pdos_gemm_kernel(PgArgs A) {
     RecRegs R;
     R.ok = false;
     double wr[EPT];
-    if (warp == 0) { load_rec(0, R); store_params(0, R); load_rec(1, R); }
+    if (warp == 8) { load_rec(0, R); store_params(0, R); load_rec(1, R); }
     __syncthreads();
-    load_w(0, wr);
-    fill_g(0);
-    store_w(0, wr);
-    if (warp == 0) store_params(1, R);
+    if (warp < 8) {
+      load_w(0, wr);
+      fill_g(0);
+      store_w(0, wr);
+    } else {
+      store_params(1, R);
+    }
     __syncthreads();
 
     for (int c = 0; c < nch; ++c) {
       const int cur = c & 1, nxt = cur ^ 1;
       const bool more = c + 1 < nch;
+      if (warp == 8) {  // cur's parameters were last read before the previous barrier
+        load_rec(c + 2, R);
+        if (c + 2 < nch) store_params(cur, R);
+        __syncthreads();
+        continue;
+      }
       if (more) load_w(nxt, wr);
-      if (warp == 0) load_rec(c + 2, R);
       if (more) fill_g(nxt);
       const double *gp = sG + ((size_t)cur * PG_BM + wm * 16 + fg) * PG_KS + ft;
       const double *wp = sW + ((size_t)cur * PG_KC + ft) * WS + wn * 8 * NB + fg;
@@ -1390,9 +1400,9 @@ __global__ void __launch_bounds__(256, 2) pdos_gemm_kernel(PgArgs A) {
         }
       }
       if (more) store_w(nxt, wr);
-      if (warp == 0 && c + 2 < nch) store_params(cur, R);  // cur's parameters were last read before the previous barrier
       __syncthreads();
     }
+    if (warp < 8)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -1750,10 +1760,10 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
     const int smem = (int)pg_smem_bytes<BNV>();                                                                          \
     if (linear) {                                                                                                        \
       OD_CUDA(ctx, cudaFuncSetAttribute(pdos_gemm_kernel<BNV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      pdos_gemm_kernel<BNV, true><<<blocks, 256, smem, ctx->stream>>>(A);                                                 \
+      pdos_gemm_kernel<BNV, true><<<blocks, PG_THREADS, smem, ctx->stream>>>(A);                                                 \
     } else {                                                                                                             \
       OD_CUDA(ctx, cudaFuncSetAttribute(pdos_gemm_kernel<BNV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      pdos_gemm_kernel<BNV, false><<<blocks, 256, smem, ctx->stream>>>(A);                                                \
+      pdos_gemm_kernel<BNV, false><<<blocks, PG_THREADS, smem, ctx->stream>>>(A);                                                \
     }                                                                                                                    \
   } while (0)
       if (BN == 64) PG_LAUNCH(64); else if (BN == 32) PG_LAUNCH(32); else PG_LAUNCH(16);
