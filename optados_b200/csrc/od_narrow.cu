@@ -1180,11 +1180,42 @@ struct PgItem {
   unsigned rec0, rec1;
 };
 
+// The work items are enumerated on the device: a "triple" (spin, 64-bin tile, width class) owns the contiguous range of sorted
+// records whose windows can reach the tile, cut into segments of PG_SEG records x orbital tiles; pg_count_kernel counts the
+// items of every triple from the bucket bases, scan_kernel turns the counts into offsets, and a CTA maps an item number back
+// to its triple by bisection.  (Round 1 built the list on the host: a copy of the bucket table and two stream
+// synchronisations per slab.)
+struct PgPlan {
+  const unsigned *base;   // bucket bases of the prepare passes (S.base)
+  const unsigned *offs;   // [ntriples + 1] exclusive scan of the item counts; offs[ntriples] = number of items
+  int ntriples, ntiles, otiles, nbins, bpad, cell, ncells;
+  int wmax[NR_NCLS];
+};
+
+__device__ __forceinline__ void pg_triple_range(const PgPlan &P, int tr, int &is, int &b0, unsigned &r0, unsigned &r1) {
+  const int c = tr % NR_NCLS, tt = tr / NR_NCLS;
+  const int tile = tt % P.ntiles;
+  is = tt / P.ntiles;
+  b0 = tile * PG_BM;
+  const int g0 = is * P.bpad + b0;
+  const int glo = max(is * P.bpad, g0 - P.wmax[c] + 1), ghi = min(is * P.bpad + P.nbins - 1, g0 + PG_BM - 1);
+  r0 = P.base[(size_t)c * P.ncells + glo / P.cell];
+  r1 = P.base[(size_t)c * P.ncells + ghi / P.cell + 1];
+}
+
+__global__ void pg_count_kernel(PgPlan P, unsigned *__restrict__ counts) {
+  const int tr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tr >= P.ntriples) return;
+  int is, b0;
+  unsigned r0, r1;
+  pg_triple_range(P, tr, is, b0, r0, r1);
+  counts[tr] = r1 > r0 ? ((r1 - r0 + PG_SEG - 1) / PG_SEG) * (unsigned)P.otiles : 0u;
+}
+
 struct PgArgs {
   const void *recs;
   const unsigned *runit;
-  const PgItem *items;
-  int nitems;
+  PgPlan plan;
   unsigned long long *next_item;
   GridSpec grid;
   int bpad, ns;
@@ -1235,7 +1266,8 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pdos_gemm_kernel(PgArgs A) {
   long long *sRow = reinterpret_cast<long long *>(sP + 2 * PG_KC * 12);  // [2][KC]
   int *sI = reinterpret_cast<int *>(sRow + 2 * PG_KC);         // [2][KC][2]
   unsigned *sMask = reinterpret_cast<unsigned *>(sI + 4 * PG_KC);  // [2][BM / 8]: records with a non-zero entry in each 8-bin run
-  __shared__ int s_item;
+  __shared__ PgItem s_item;
+  __shared__ int s_more;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int fg = lane >> 2, ft = lane & 3;      // fragment coordinates
   const int wm = warp >> 1, wn = warp & 1;      // warp tile: bins wm*16 .. +15, orbitals wn*8*NB .. +8*NB-1
@@ -1250,11 +1282,30 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pdos_gemm_kernel(PgArgs A) {
 
   for (;;) {
     __syncthreads();
-    if (t == 0) s_item = (int)atomicAdd(A.next_item, 1ull);
+    if (t == 0) {
+      const PgPlan &P = A.plan;
+      const unsigned it = (unsigned)atomicAdd(A.next_item, 1ull);
+      s_more = it < P.offs[P.ntriples];
+      if (s_more) {
+        int lo = 0, hi = P.ntriples;  // the last triple with offs[tr] <= it (empty triples repeat an offset: skipped by "<=")
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (P.offs[mid] <= it) lo = mid; else hi = mid;
+        }
+        int is, b0;
+        unsigned r0, r1;
+        pg_triple_range(P, lo, is, b0, r0, r1);
+        const unsigned local = it - P.offs[lo], seg = local / (unsigned)P.otiles;
+        PgItem q;
+        q.is = is; q.b0 = b0; q.otile = (int)(local - seg * (unsigned)P.otiles);
+        q.rec0 = r0 + seg * PG_SEG;
+        q.rec1 = min(r1, q.rec0 + (unsigned)PG_SEG);
+        s_item = q;
+      }
+    }
     __syncthreads();
-    const int it = s_item;
-    if (it >= A.nitems) break;
-    const PgItem item = A.items[it];
+    if (!s_more) break;
+    const PgItem item = s_item;
     const int b0 = item.b0, is = item.is, obase = item.otile * BN;
     const int nch = (int)((item.rec1 - item.rec0 + PG_KC - 1) / PG_KC);
 
@@ -1727,51 +1778,45 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   OD_LAUNCH_CHECK(ctx);
   int wpasses = 0;
   if (norb >= 8) {
-    // many projectors: banded GEMM over (bin tile, orbital tile, record segment) work items
+    // many projectors: banded GEMM over (bin tile, orbital tile, record segment) work items, enumerated on the device
     const PrepSpec &ps = S.ps;
-    std::vector<unsigned> hbase((size_t)ps.nbuckets + 1);
-    OD_CUDA(ctx, cudaMemcpyAsync(hbase.data(), S.base, sizeof(unsigned) * hbase.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     static const int wmax[NR_NCLS] = {24, 32, 44, 60, 84, 116, 160, 224, 320, NR_WMAX};
     const int BN = norb > 32 ? 64 : (norb > 16 ? 32 : 16);
-    const int otiles = (norb + BN - 1) / BN;
-    std::vector<PgItem> items;
-    for (int is = 0; is < ns; ++is)
-      for (int b0 = 0; b0 < nbins; b0 += PG_BM)
-        for (int c = 0; c < NR_NCLS; ++c) {
-          const int g0 = is * ps.bpad + b0;
-          const int glo = std::max(is * ps.bpad, g0 - wmax[c] + 1), ghi = std::min(is * ps.bpad + nbins - 1, g0 + PG_BM - 1);
-          const unsigned r0 = hbase[(size_t)c * ps.ncells + glo / ps.cell], r1 = hbase[(size_t)c * ps.ncells + ghi / ps.cell + 1];
-          for (unsigned r = r0; r < r1; r += PG_SEG)
-            for (int ot = 0; ot < otiles; ++ot) items.push_back(PgItem{is, b0, ot, r, std::min(r1, r + (unsigned)PG_SEG)});
-        }
-    if (!items.empty()) {
-      OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(PgItem) * items.size() + 64));
-      OD_CUDA(ctx, cudaMemcpyAsync(ctx->scratch_d.p, items.data(), sizeof(PgItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
-      OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
-      PgArgs A;
-      A.recs = ctx->recs.p; A.runit = ctx->scratch_e.as<unsigned>(); A.items = ctx->scratch_d.as<PgItem>(); A.nitems = (int)items.size();
-      A.next_item = S.wide + 4; A.grid = grid; A.bpad = ps.bpad; A.ns = ns;
-      A.mw = prod_in.mw; A.norb = norb; A.mw_nb = prod_in.mw_nb; A.mw_nk = prod_in.mw_nk; A.nb = prod_in.nb; A.k_first = prod_in.k_first;
-      A.wdos = accum + 2 * n1;
-      const int blocks = (int)std::min<size_t>(items.size(), (size_t)ctx->sm_count * 2);
+    PgArgs A;
+    PgPlan &P = A.plan;
+    P.ntiles = (nbins + PG_BM - 1) / PG_BM;
+    P.ntriples = ns * P.ntiles * NR_NCLS;
+    P.otiles = (norb + BN - 1) / BN;
+    P.nbins = nbins; P.bpad = ps.bpad; P.cell = ps.cell; P.ncells = ps.ncells;
+    for (int c = 0; c < NR_NCLS; ++c) P.wmax[c] = wmax[c];
+    OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(unsigned) * (2 * (size_t)P.ntriples + 2) + 64));
+    unsigned *counts = ctx->scratch_d.as<unsigned>(), *offs = counts + P.ntriples;
+    P.base = S.base; P.offs = offs;
+    pg_count_kernel<<<(P.ntriples + 255) / 256, 256, 0, ctx->stream>>>(P, counts);
+    OD_LAUNCH_CHECK(ctx);
+    scan_kernel<<<1, 1024, 0, ctx->stream>>>(counts, P.ntriples, offs);
+    OD_LAUNCH_CHECK(ctx);
+    OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
+    A.recs = ctx->recs.p; A.runit = ctx->scratch_e.as<unsigned>();
+    A.next_item = S.wide + 4; A.grid = grid; A.bpad = ps.bpad; A.ns = ns;
+    A.mw = prod_in.mw; A.norb = norb; A.mw_nb = prod_in.mw_nb; A.mw_nk = prod_in.mw_nk; A.nb = prod_in.nb; A.k_first = prod_in.k_first;
+    A.wdos = accum + 2 * n1;
+    const int blocks = ctx->sm_count * 2;  // persistent; the number of items is read on the device
 #define PG_LAUNCH(BNV)                                                                                                   \
   do {                                                                                                                   \
     const int smem = (int)pg_smem_bytes<BNV>();                                                                          \
     if (linear) {                                                                                                        \
       OD_CUDA(ctx, cudaFuncSetAttribute(pdos_gemm_kernel<BNV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      pdos_gemm_kernel<BNV, true><<<blocks, PG_THREADS, smem, ctx->stream>>>(A);                                                 \
+      pdos_gemm_kernel<BNV, true><<<blocks, PG_THREADS, smem, ctx->stream>>>(A);                                          \
     } else {                                                                                                             \
       OD_CUDA(ctx, cudaFuncSetAttribute(pdos_gemm_kernel<BNV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      pdos_gemm_kernel<BNV, false><<<blocks, PG_THREADS, smem, ctx->stream>>>(A);                                                \
+      pdos_gemm_kernel<BNV, false><<<blocks, PG_THREADS, smem, ctx->stream>>>(A);                                         \
     }                                                                                                                    \
   } while (0)
-      if (BN == 64) PG_LAUNCH(64); else if (BN == 32) PG_LAUNCH(32); else PG_LAUNCH(16);
+    if (BN == 64) PG_LAUNCH(64); else if (BN == 32) PG_LAUNCH(32); else PG_LAUNCH(16);
 #undef PG_LAUNCH
-      OD_LAUNCH_CHECK(ctx);
-      OD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // items is a host vector
-      wpasses = 1;
-    }
+    OD_LAUNCH_CHECK(ctx);
+    wpasses = 1;
   } else if (norb > 0) {
     // weighted spectrum: columns (2c, 2c+1) per pass, K * matrix_weights(o, ib, ik, is) (dos_utils.f90:1271)
     MwGather gth;
