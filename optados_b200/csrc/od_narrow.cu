@@ -648,10 +648,11 @@ struct NarrowArgs {
   long long k_first;
 };
 
-// tile -> HBM.  mode 0: (dos, local part of the integrated DOS, steps) / the two JD channels; mode 1: the DOS of the
-// Euler-Maclaurin groups alone, the tile then being two arrays of NR_T doubles (one per half-warp, summed here)
+// tile -> HBM.  mode 0: (dos, local part of the integrated DOS, steps) / the two JD channels; mode 2: the same in two copies
+// of NR_T / 2 bins (one per half-warp, summed here); mode 1: the DOS of the Euler-Maclaurin groups alone, the tile then
+// being two arrays of NR_T doubles (one per half-warp)
 __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, int mode, const NarrowArgs &A, int lane) {
-  if (mode) {  // two copies of NR_T doubles, one per half-warp
+  if (mode == 1) {  // two copies of NR_T doubles, one per half-warp
     double *t1 = reinterpret_cast<double *>(tile);
     for (int i = lane; i < used; i += 32) {
       const double v = t1[i] + t1[i + NR_T];
@@ -663,7 +664,12 @@ __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int bas
     return;
   }
   for (int i = lane; i < used; i += 32) {
-    const double2 v = tile[i];
+    double2 v = tile[i];
+    if (mode == 2) {  // two copies of NR_T / 2 bins, one per half-warp
+      const double2 v2 = tile[i + NR_T / 2];
+      v.x += v2.x; v.y += v2.y;
+      tile[i + NR_T / 2] = make_double2(0.0, 0.0);
+    }
     if (v.x != 0.0) atomicAdd(&A.out_dos[base + i], v.x);
     if (v.y != 0.0) atomicAdd(&A.out_int[base + i], v.y);
     tile[i] = make_double2(0.0, 0.0);
@@ -895,7 +901,13 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       // ---- the common window [gl, gl + Wc) of this pass
       const int gh = __reduce_max_sync(FULL, max(valid[0] ? klo[0] + wlen[0] - 1 : -0x3fffffff, valid[1] ? klo[1] + wlen[1] - 1 : -0x3fffffff));
       int Wc = gh - gl + 1;
-      if (Wc < 32) Wc = 32;
+      // A window that fits half a tile is walked on TWO copies of the tile, one per half-warp (summed at the flush): the
+      // lanes' starts are then staggered over 16 bins instead of 32, so the shortest walk is 16 steps instead of 32 (a third
+      // of the linear and JDOS groups of the BASELINE configurations have windows under 32 bins) and 15 steps of a walk
+      // carry the wrap test instead of 31.
+      const bool half = Wc + 2 <= NR_T / 2 - A.cell;
+      const int wfloor = half ? 16 : 32;
+      if (Wc < wfloor) Wc = wfloor;
       if (!LINEAR && !JD) Wc += Wc & 1;
       int jb[2], a[2], cabs[2];
 #pragma unroll
@@ -978,8 +990,9 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           if (ok && dmax <= EM_DELMAX * (1.0 - 1e-6)) emode = 1;
         }
       }
-      const int want_mode = emode ? 1 : 0;
-      if (gl < base || gl + Wc + 1 > base + NR_T || want_mode != tmode) {
+      if (emode && Wc < 32) Wc = 32;  // (cannot happen: dE/w <= 0.4 means windows of >= 41 bins)
+      const int want_mode = emode ? 1 : (half ? 2 : 0);
+      if (gl < base || gl + Wc + 1 > base + (want_mode == 2 ? NR_T / 2 : NR_T) || want_mode != tmode) {
         flush_tile(tile, stile, base, used, tmode, A, lane);
         base = gl & ~(A.cell - 1);
         used = 0;
@@ -989,7 +1002,8 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       used = max(used, off + Wc + 1);
       st_steps += (unsigned)Wc * ((valid[0] ? 1u : 0u) + (valid[1] ? 1u : 0u));
       st_useful += (unsigned)(wlen[0] + wlen[1]);
-      double2 *tw = tile + off;
+      double2 *tw = tile + off + (want_mode == 2 ? (lane >> 4) * (NR_T / 2) : 0);
+      const int ntail = want_mode == 2 ? 15 : 31;  // wrap steps of the one-bin walks
 
       // ---- the steps H: one add per record into the warp-private step tile.  Several records of a
       //      group usually share their centre bin, so this one place uses shared-memory atomics.
@@ -1005,7 +1019,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       // staggered starts then span 30 bins instead of 62 and only 15 steps of a walk carry the wrap test and its 8 selects
       // (with one copy the 31 wrap steps were 83 % of the instructions of an 84-bin walk).
       const bool pairwalk = !LINEAR && !JD && emode;  // (Wc is even and >= 32)
-      int r = pairwalk ? 2 * (lane & 15) : lane;
+      int r = pairwalk ? 2 * (lane & 15) : (want_mode == 2 ? (lane & 15) : lane);
       if (!LINEAR) {
         double amp[2], q[2], gB[2], rB[2], z[2], g[2], rr[2];
 #pragma unroll
@@ -1022,7 +1036,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         // Every walk below is split in two: Wc - 31 steps in which no lane can reach the end of the window (lane l starts
         // at bin l), then 31 steps in which exactly one lane per step wraps round to bin 0.  The restart values are 6
         // doubles; as predicated moves inside one loop they were 13 of 47 instructions of EVERY step.
-        const int nmain = Wc - 31;
+        const int nmain = Wc - ntail;
         if (pairwalk) {
           // (same multiplications in the same order as the one-bin walk: g_{j+1} = g_j r_j, r_{j+1} = r_j q)
           double2 *tw2 = reinterpret_cast<double2 *>(reinterpret_cast<double *>(tile) + (lane >> 4) * NR_T + off);  // off is even
@@ -1079,7 +1093,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
 #pragma unroll NR_MAIN_UNROLL
         for (int t = 0; t < nmain; ++t) step(std::false_type{});
 #pragma unroll 1
-        for (int t = 0; t < 31; ++t) step(std::true_type{});
+        for (int t = 0; t < ntail; ++t) step(std::true_type{});
       } else {
         // doslin (dos_utils.f90:1391-1528) in x = e_use - e4 = dd - |E_j - e0| (the mirror of :1469), with
         // aa = e3-e4 <= bb = e2-e4 <= cc = e1-e4 <= dd = e0-e4.  The five branches collapse into two smooth
@@ -1102,7 +1116,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           a2_6[s] = aa[s] * aa[s] * sixth;
           k30[s] = 0.5 * (aa[s] * aa[s] * third - cc[s] * bb[s]) - cb * cb * sixth;
           tB[s] = E0[s] - e0[s];  // E_j - e0 at relative bin 0
-          tt[s] = tB[s] + (double)lane * delta;
+          tt[s] = tB[s] + (double)r * delta;
         }
         auto clamp0 = [](double v) {  // max(v, +0) on the sign / exponent word: negative -> < 2^-1022
           return __hiloint2double(max(__double2hiint(v), 0), __double2loint(v));
@@ -1124,7 +1138,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         // the sign of the local part flips where the walk passes the record's centre: d = cabs - 1 - r goes negative there,
         // so the flip is the sign bit of a counter (one add and one logic operation per record and step)
         int dA = cabs[0] - 1 - r, dB = cabs[1] - 1 - r;
-        const int nmain = Wc - 31;
+        const int nmain = Wc - ntail;
         auto step = [&](auto WRAP) {
           if (decltype(WRAP)::value) {
             if (r == Wc) { r = 0; tt[0] = tB[0]; tt[1] = tB[1]; dA = cabs[0] - 1; dB = cabs[1] - 1; }
@@ -1151,7 +1165,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
 #pragma unroll NR_MAIN_UNROLL
         for (int t = 0; t < nmain; ++t) step(std::false_type{});
 #pragma unroll 1
-        for (int t = 0; t < 31; ++t) step(std::true_type{});
+        for (int t = 0; t < ntail; ++t) step(std::true_type{});
       }
     }
     for (int o = 16; o > 0; o >>= 1) st_useful += __shfl_xor_sync(FULL, st_useful, o);
