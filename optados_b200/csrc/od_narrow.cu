@@ -196,31 +196,21 @@ __device__ __forceinline__ Cls classify(const RecOut &r, const PrepSpec &ps) {
 }
 
 // ---------------------------------------------------------------- pass A: keys + per-CTA histogram row
-// Both prepare passes walk the units in tiles of NR_PREP_THREADS * U consecutive units per CTA (pass A and pass B MUST use the
-// same unit -> CTA mapping: the write cursors of pass B are per CTA).  A thread issues the loads of its U units of a tile
-// before it touches the first of them, and prefetches the lines of its units of the NEXT tile into L2 (prefetch.global.L2:
-// no registers held): the passes are bound by memory latency and by the length of their dependent instruction chains at 16
-// warps per SM (ncu, round 2: half of the stall samples on the first use of a load, issue slots 25-55 % busy), not by
-// DRAM bandwidth (30-40 %).
+// Both prepare passes walk the units in tiles of 16 rows x U (PrepMap; pass A and pass B MUST use the same unit -> CTA
+// mapping: the write cursors of pass B are per CTA).  A thread issues the loads of its U units of a tile before it touches
+// the first of them.  Pass A is bound by its issue slots (8 warp-instructions per unit at 52-57 % issue utilisation, 16 warps
+// per SM next to a 204 KB bucket table), pass B by the number of scattered store requests (see below), neither by DRAM
+// bandwidth (40-45 %).
 //
-// STAGE = what pass A hands to pass B beside the 4-byte key, so that pass B does not repeat pass A's arithmetic:
-//   0  nothing: pass B rebuilds and re-classifies the record (JDOS: its weights come from the matrix elements anyway);
-//   1  the record's tail (klo | cpos | wlen, 8 B per unit, unit order): pass B rebuilds the corners but does not classify
-//      (linear DOS: the 64-byte record itself would cost more traffic than its 3 dot products);
-//   2  the whole 32-byte Gaussian record in unit order (coalesced): pass B is a pure permutation -- one 32-byte load, one
-//      shared-memory cursor, one 32-byte store per unit (Gaussian DOS; +28 B of traffic per unit for -150 instructions).
-// (Measured and dropped, profiles/r02_summary.md: pass B sorting only 4-byte indices, the accumulation kernel gathering staged
-// records through them.  Pass B is bound by the NUMBER of scattered store requests (~94 G/s for 4-byte, ~56 G/s for 32-byte
-// ones), not by their bytes, so the index form only wins for the 64-byte records, and the gathers cost the accumulation
-// kernel as much as pass B saved.)
-// An off-grid unit (key KEY_DROP) carries its step bin in the klo field.
-__device__ __forceinline__ double rec_tail(int klo, int cpos, int wlen);
-__device__ __forceinline__ void st256(void *dst, double a, double b, double c, double d);
-
-template <class Producer, int STAGE>
+// (Measured and dropped, profiles/r02_summary.md: pass A handing its records (32-byte Gaussian ones, staged in unit order) or
+// their tails to pass B so that pass B need not rebuild them -- once the band-group-major rows had made pass B a matter of
+// scattered store REQUESTS (~56 G/s for 32-byte ones) its instruction count no longer mattered, and the staged traffic cost
+// more than the arithmetic it saved (config 2: 119.7 -> 117.7 ms without staging); pass B sorting only 4-byte indices with the
+// accumulation kernel gathering staged records; ranks from pass A's atomics instead of cursor atomics in pass B.)
+template <class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
 prep_hist_kernel(Producer prod, PrepSpec ps, unsigned *__restrict__ keys, unsigned *__restrict__ table /* [gridDim.x][nbuckets] */,
-                 unsigned long long *__restrict__ wide_count /* [ns] */, void *__restrict__ stage, PrepMap pm) {
+                 unsigned long long *__restrict__ wide_count /* [ns] */, PrepMap pm) {
   extern __shared__ unsigned sh_hist[];
   __shared__ unsigned char s_cls[512];  // width class of a window length (9 compares + adds per unit otherwise)
   constexpr int U = Producer::PREP_U;
@@ -253,26 +243,18 @@ prep_hist_kernel(Producer prod, PrepSpec ps, unsigned *__restrict__ keys, unsign
       c.kind = 2; c.klo = 0; c.wlen = 0; c.cpos = 0; c.cstep = ps.grid.nbins;
       if (r.mode >= 0) c = classify(r, ps);
       unsigned key;
-      int tk = c.cstep, tc = 0, tw = 0;
       if (c.kind == 0) {
         // key = cell index * 16 + width class (bucket = class * ncells + cell index: no division in either pass)
         const unsigned cls = s_cls[c.wlen], ci = (unsigned)(is * ps.bpad + c.klo) >> ps.cshift;
         key = ci * 16u + cls;
         atomicAdd(&sh_hist[cls * (unsigned)ps.ncells + ci], 1u);
-        tk = is * ps.bpad + c.klo; tc = c.cpos; tw = c.wlen;
       } else if (c.kind == 1) {
         key = KEY_WIDE;
         if (is == 0) wide0++; else wide1++;
       } else {
         key = KEY_DROP;
       }
-      const size_t su = (size_t)is * upz + u;
-      keys[su] = key;
-      if (STAGE == 2) {
-        if (c.kind != 1) st256(reinterpret_cast<GRec *>(stage) + su, r.e0, r.p1, r.omega, rec_tail(tk, tc, tw));
-      } else if (STAGE == 1) {
-        if (c.kind != 1) reinterpret_cast<double *>(stage)[su] = rec_tail(tk, tc, tw);
-      }
+      keys[(size_t)is * upz + u] = key;
     }
   }
   __syncthreads();
@@ -375,29 +357,19 @@ __device__ __forceinline__ double rec_tail(int klo, int cpos, int wlen) {
   return __hiloint2double((int)((unsigned)cpos | ((unsigned)wlen << 16)), klo);
 }
 
-__device__ __forceinline__ void ld256(const void *src, double &a, double &b, double &c, double &d) {
-  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(src));
-}
-__device__ __forceinline__ void tail_unpack(double tail, int &klo, int &cpos, int &wlen) {
-  klo = __double2loint(tail);  // (rec_tail: int klo | unsigned short cpos | unsigned short wlen, little endian)
-  const unsigned hi = (unsigned)__double2hiint(tail);
-  cpos = (int)(hi & 0xffffu);
-  wlen = (int)(hi >> 16);
-}
-
 // ---------------------------------------------------------------- pass B: scatter (shared-memory cursors)
 // The cursors of a tile's units are taken (shared-memory atomics with return) right after its keys are known, before the
-// records are built: a store that waits for its own cursor was 16 % of this pass's stall samples.  (Handing every unit's
-// rank inside its CTA's share of the bucket from pass A to pass B, which then needs no atomics, was measured: +4 B of
-// traffic per unit and pass, 8 % slower -- pass B is bound by the memory system, not by its shared-memory atomics.)
-// TAILS: pass A left every unit's tail (STAGE 1) -- no classification here.
-template <bool LINEAR, class Producer, bool TAILS>
+// records are built: a store that waits for its own cursor was 16 % of this pass's stall samples.  What bounds the pass is
+// the NUMBER of scattered store requests it issues -- one per 32 bytes of record, ~56 G/s chip-wide whatever else the kernel
+// does (a pass that only permutes staged records: 0.57 ms per 32M Gaussian records; this one, which rebuilds them: 0.59 ms;
+// one that scatters 4-byte indices: 0.36 ms with or without cursor atomics, at 512 or 1024 threads).
+template <bool LINEAR, class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
 prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,
                     const unsigned *__restrict__ base, void *__restrict__ recs_v, double *__restrict__ wts, unsigned *__restrict__ runit,
                     double *__restrict__ stephist,
                     unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor, long long wide_stride,
-                    const double *__restrict__ tails, PrepMap pm) {
+                    PrepMap pm) {
   extern __shared__ unsigned sh_cur[];
   constexpr int U = Producer::PREP_U;
   const unsigned *row = table + (size_t)blockIdx.x * ps.nbuckets;
@@ -421,17 +393,12 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
     typename Producer::Raw raw[U];
     unsigned key[U], pos[U], uu[U];
     bool ok[U];
-    double tl[U];
     // the keys of this tile were loaded one iteration ago; issue every input load of the tile, then the keys of the
     // next tile, before the first use: two levels of loads in flight per thread
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       key[j] = key_next[j]; uu[j] = k_next[j] * pm.W + w_next[j]; ok[j] = ok_next[j];
-      tl[j] = 0.0;
-      if (key[j] != KEY_WIDE && (key[j] != KEY_DROP || ps.with_int)) {
-        prod.template load_kw<true>(k_next[j], w_next[j], is, raw[j]);
-        if (TAILS) tl[j] = tails[(size_t)is * upz + uu[j]];
-      }
+      if (key[j] != KEY_WIDE && (key[j] != KEY_DROP || ps.with_int)) prod.template load_kw<true>(k_next[j], w_next[j], is, raw[j]);
     }
     load_keys(t0 + NR_PREP_ROWS * U);
 #pragma unroll
@@ -453,27 +420,18 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
       r.mode = -1;
       prod.template make<true>(u, is, raw[j], r);
       if (r.mode < 0) continue;
-      int klo, wlen, cpos;  // klo in global numbering (spin * bpad + bin)
-      if (TAILS) {
-        tail_unpack(tl[j], klo, cpos, wlen);
-        if (key[j] == KEY_DROP) {  // off the grid: only its step (rare); the klo field carries the step bin
-          if (klo < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + klo], r.omega);
-          continue;
-        }
-      } else {
-        const Cls c = classify(r, ps);
-        if (key[j] == KEY_DROP) {
-          if (c.cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + c.cstep], r.omega);
-          continue;
-        }
-        // keep the record inside the cell pass A counted it in, whatever this pass recomputed
-        const unsigned ci = key[j] >> 4;
-        const int cell_lo = (int)(ci << ps.cshift) - is * ps.bpad;
-        const int kl = min(max(c.klo, cell_lo), cell_lo + ps.cell - 1);
-        wlen = min(max(c.wlen - (kl - c.klo), 1), ps.wmax);
-        cpos = min(max(c.cstep - kl, 0), wlen);
-        klo = is * ps.bpad + kl;
+      const Cls c = classify(r, ps);
+      if (key[j] == KEY_DROP) {  // off the grid: only its step (rare)
+        if (c.cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + c.cstep], r.omega);
+        continue;
       }
+      // keep the record inside the cell pass A counted it in, whatever this pass recomputed
+      const unsigned ci = key[j] >> 4;
+      const int cell_lo = (int)(ci << ps.cshift) - is * ps.bpad;
+      const int kl = min(max(c.klo, cell_lo), cell_lo + ps.cell - 1);
+      const int wlen = min(max(c.wlen - (kl - c.klo), 1), ps.wmax);
+      const int cpos = min(max(c.cstep - kl, 0), wlen);
+      const int klo = is * ps.bpad + kl;  // global numbering (spin * bpad + bin)
       const unsigned p = pos[j];
       if (LINEAR) {
         LRec *o = reinterpret_cast<LRec *>(recs_v) + p;
@@ -493,80 +451,6 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
       if (ps.want_unit) runit[p] = u;
     }
   }
-  }
-}
-
-// ---------------------------------------------------------------- pass B of staged Gaussian records (STAGE 2): a permutation
-// Same unit -> CTA mapping and tiles as pass A.  Keys and staged records of tile t+1 are loaded (coalesced: 4 B and 32 B per
-// thread and unit) before tile t is processed; per unit one shared-memory cursor and one 32-byte store.
-template <int U>
-__global__ void __launch_bounds__(NR_PREP_THREADS)
-prep_permute_kernel(PrepSpec ps, unsigned upz, int ns, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,
-                    const unsigned *__restrict__ base, const GRec *__restrict__ stage, GRec *__restrict__ recs, unsigned *__restrict__ runit,
-                    double *__restrict__ stephist, unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor,
-                    long long wide_stride, PrepMap pm) {
-  extern __shared__ unsigned sh_cur[];
-  const unsigned *row = table + (size_t)blockIdx.x * ps.nbuckets;
-  for (int i = threadIdx.x; i < ps.nbuckets; i += blockDim.x) sh_cur[i] = base[i] + row[i];
-  __syncthreads();
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const unsigned long long r_begin = (unsigned long long)blockIdx.x * pm.per, r_end = min(pm.nrows, r_begin + pm.per);
-  constexpr unsigned ROWS = NR_PREP_THREADS / 32, tstep = ROWS * U;
-  struct Tile {
-    double a[U], b[U], c[U], d[U];
-    unsigned key[U], u[U];
-    bool ok[U];
-  };
-  for (int is = 0; is < ns; ++is) {
-    const size_t s0 = (size_t)is * upz;
-    auto fetch = [&](Tile &T, unsigned long long t0) {
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        T.ok[j] = prep_unit(pm, t0 + (unsigned)j * ROWS + warp, r_end, lane, T.u[j]);
-        T.key[j] = KEY_WIDE;
-        T.a[j] = T.b[j] = T.c[j] = T.d[j] = 0.0;
-        if (T.ok[j]) {
-          T.key[j] = keys[s0 + T.u[j]];
-          ld256(stage + s0 + T.u[j], T.a[j], T.b[j], T.c[j], T.d[j]);  // (wide units: never written by pass A, never used here)
-        }
-      }
-    };
-    auto process = [&](const Tile &T) {
-      unsigned pos[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        pos[j] = 0;
-        if (T.key[j] < KEY_WIDE) pos[j] = atomicAdd(&sh_cur[(T.key[j] & 15u) * (unsigned)ps.ncells + (T.key[j] >> 4)], 1u);
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        if (!T.ok[j]) continue;
-        if (T.key[j] < KEY_WIDE) {
-          st256(recs + pos[j], T.a[j], T.b[j], T.c[j], T.d[j]);
-          if (ps.want_unit) runit[pos[j]] = T.u[j];
-        } else if (T.key[j] == KEY_WIDE) {
-          const unsigned long long wp = atomicAdd(&wide_cursor[is], 1ull);
-          widelist[(size_t)is * wide_stride + wp] = T.u[j];
-        } else if (ps.with_int) {  // off the grid: only its step (rare); the klo field carries the step bin
-          const int cstep = __double2loint(T.d[j]);
-          if (cstep < ps.grid.nbins) atomicAdd(&stephist[(size_t)is * ps.bpad + cstep], T.c[j]);
-        }
-      }
-    };
-    Tile A, B;
-    unsigned long long t0 = r_begin;
-    if (t0 >= r_end) continue;
-    fetch(A, t0);
-    for (;;) {
-      fetch(B, t0 + tstep);
-      process(A);
-      t0 += tstep;
-      if (t0 >= r_end) break;
-      fetch(A, t0 + tstep);
-      process(B);
-      t0 += tstep;
-      if (t0 >= r_end) break;
-    }
   }
 }
 
@@ -1605,45 +1489,23 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * units * ps.wstride + 256));
   if (ps.want_unit) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_e, sizeof(unsigned) * units + 256));
   OD_CUDA(ctx, cudaMemsetAsync(S.wide, 0, sizeof(unsigned long long) * 5, ctx->stream));
-  // what pass A hands to pass B (see prep_hist_kernel): whole Gaussian records, the tails of linear ones, or nothing
-  constexpr bool STAGED = Producer::PREP_STAGED;
-  const int stage = !STAGED ? 0 : (linear ? 1 : 2);
-  if (stage) OD_CHECK(od_buf_ensure(ctx, ctx->stage, (stage == 2 ? sizeof(GRec) : sizeof(double)) * units + 256));
   double *wts = ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
   unsigned *runit = ps.want_unit ? ctx->scratch_e.as<unsigned>() : nullptr;
-#define HIST_LAUNCH(ST)                                                                                                              \
-  do {                                                                                                                               \
-    OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem)); \
-    prep_hist_kernel<Producer, ST><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod_keys, ps, S.keys, S.table, S.wide, ctx->stage.p, pm); \
-  } while (0)
-#define SC_LAUNCH(LIN, TL)                                                                                                           \
-  do {                                                                                                                               \
-    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<LIN, Producer, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem)); \
-    prep_scatter_kernel<LIN, Producer, TL><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(                                     \
-        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride, \
-        ctx->stage.as<double>(), pm);                                                                                                \
-  } while (0)
-  if (STAGED && stage == 2) HIST_LAUNCH(2); else if (STAGED && stage == 1) HIST_LAUNCH(1); else HIST_LAUNCH(0);
+  OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+  prep_hist_kernel<Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod_keys, ps, S.keys, S.table, S.wide, pm);
   OD_LAUNCH_CHECK(ctx);
   prep_colscan_kernel<<<(4 * ps.nbuckets + 255) / 256, 256, 0, ctx->stream>>>(S.table, prows, ps.nbuckets, S.colsum);
   OD_LAUNCH_CHECK(ctx);
   scan_kernel<<<1, 1024, 0, ctx->stream>>>(S.colsum, ps.nbuckets, S.base);
   OD_LAUNCH_CHECK(ctx);
-  if (STAGED && stage == 2) {
-    constexpr int U = Producer::PREP_U;
-    OD_CUDA(ctx, cudaFuncSetAttribute(prep_permute_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-    prep_permute_kernel<U><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(
-        ps, (unsigned)prod.units_per_z, prod.ns, S.keys, S.table, S.base, ctx->stage.as<GRec>(), ctx->recs.as<GRec>(), runit, S.stephist,
-        ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride, pm);
-  } else if (STAGED && stage == 1) {
-    SC_LAUNCH(true, true);
-  } else if (linear) {
-    SC_LAUNCH(true, false);
-  } else {
-    SC_LAUNCH(false, false);
-  }
+#define SC_LAUNCH(LIN)                                                                                                               \
+  do {                                                                                                                               \
+    OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<LIN, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem)); \
+    prep_scatter_kernel<LIN, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(                                         \
+        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride, pm); \
+  } while (0)
+  if (linear) SC_LAUNCH(true); else SC_LAUNCH(false);
 #undef SC_LAUNCH
-#undef HIST_LAUNCH
   OD_LAUNCH_CHECK(ctx);
   return OD_OK;
 }

@@ -4,8 +4,6 @@
 
 // n / d for 32-bit n by multiplication (Granlund-Montgomery round-up method, exact for every n < 2^32): the prepare passes
 // of the narrow engine split a unit index into (k-point, band) once per unit, and an integer division is ~20 instructions
-__device__ __forceinline__ void od_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 struct FastDiv {
   unsigned d = 1, m = 1, s1 = 0, s2 = 0;
   FastDiv() = default;
@@ -114,7 +112,6 @@ struct DosProducer {
 #define OD_PREP_U_DOS 4
 #endif
   static constexpr int PREP_U = OD_PREP_U_DOS;
-  static constexpr bool PREP_STAGED = true;   // pass A hands its records / windows to pass B (see prep_hist_kernel)
   static constexpr bool PREP_KMAJOR = false;  // band-group-major rows: a CTA fills few buckets (see PrepMap, od_narrow.cu)
   __host__ __device__ long long inner() const { return nb; }  // units per k-point
   template <bool WT>
@@ -140,17 +137,6 @@ struct DosProducer {
   __device__ __forceinline__ void make(unsigned, int, const Raw &w, RecOut &r) const {
     const double g[3] = {w.g0, w.g1, w.g2};
     od_make_record(b, w.e, g, eps * w.kw, r);
-  }
-  // the lines load() will touch, into L2 (issued a tile or two ahead by the prepare passes: no registers held)
-  __device__ __forceinline__ void prefetch(unsigned u, int is) const {
-    const unsigned ikl = nb_div.div(u), ib = u - ikl * (unsigned)nb;
-    od_prefetch_l2(bands + ib + (size_t)nb * (is + (size_t)ns * (k_first + ikl)));
-    if (b.type != 0) {
-      const double *gp = grads + ib + (size_t)nb * (3 * (ikl + (size_t)nk_g * is));
-      od_prefetch_l2(gp);
-      od_prefetch_l2(gp + nb);
-      od_prefetch_l2(gp + 2 * (size_t)nb);
-    }
   }
 
   __device__ __forceinline__ void operator()(long long u, int z, RecOut &r) const {
@@ -235,9 +221,7 @@ struct JdosProducer {
     int ib, jb;
   };
   static constexpr int PREP_U = 2;
-  static constexpr bool PREP_STAGED = false;  // pass B rebuilds the record (the weights come from the matrix elements anyway)
   static constexpr bool PREP_KMAJOR = true;   // see PrepMap (od_narrow.cu)
-  __device__ __forceinline__ void prefetch(unsigned, int) const {}  // (band data of a k-point is re-used by all its pairs: cached)
   __host__ __device__ long long inner() const { return pairs_per_k(); }  // units (pair slots) per k-point
   __device__ __forceinline__ void slot(unsigned uu, int &ib, int &jb, long long &ik) const {
     if (occ_list) {
