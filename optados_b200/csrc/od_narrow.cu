@@ -362,7 +362,9 @@ __device__ __forceinline__ double rec_tail(int klo, int cpos, int wlen) {
 // records are built: a store that waits for its own cursor was 16 % of this pass's stall samples.  What bounds the pass is
 // the NUMBER of scattered store requests it issues -- one per 32 bytes of record, ~56 G/s chip-wide whatever else the kernel
 // does (a pass that only permutes staged records: 0.57 ms per 32M Gaussian records; this one, which rebuilds them: 0.59 ms;
-// one that scatters 4-byte indices: 0.36 ms with or without cursor atomics, at 512 or 1024 threads).
+// one that scatters 4-byte indices: 0.36 ms with or without cursor atomics, at 512 or 1024 threads; neighbouring lanes swapping
+// halves so that every store instruction writes whole 64-byte linear records: 0.87 -> 0.90 ms, so the unit is the 32-byte
+// sector, not the instruction).
 template <bool LINEAR, class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
 prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,

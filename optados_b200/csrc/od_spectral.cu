@@ -71,11 +71,11 @@ __global__ void linear_smear_kernel(const double *__restrict__ dos, double *__re
 
 // ------------------------------------------------------------------ calculate_dos
 // k-point slabs (measured on B200, config 2, see profiles/r02_summary.md): the accumulation kernels like long record
-// arrays (fewer launch tails, fuller buckets: adaptive 83.6 / 77.8 / 76.2 / 75.0 ms per pass at 16M / 32M / 48M / 96M units), the
-// scatter of the 64-byte linear records likes short ones (its write frontier has to stay mergeable in the L2: prepare 24.7 /
-// 26.4 / 28.6 / 32.1 ms, against accumulate 63.5 / 58.3 / 57.3 / 55.4).  So a slab is 96M units and the linear scheme walks
-// it in sub-slabs of 32M.
-#define OD_SLAB_UNITS_DEFAULT (96ll << 20)
+// arrays (fewer launch tails, fuller buckets), the scatter of the records likes short ones (its frontier of half-written
+// lines has to stay mergeable in the L2), the 64-byte linear records more so than the 32-byte Gaussian ones.  Step time with
+// the final kernels, (slab, linear sub-slab) in units: (48M, 24M) 117.8 ms, (64M, 32M) 116.0, (96M, 32M) 117.4, (128M, 32M)
+// 118.7, (96M, 16M) 121.8, (96M, 48M) 120.6, (96M, 96M) 127.1 (prepare 47.5 instead of 34.8 ms).
+#define OD_SLAB_UNITS_DEFAULT (64ll << 20)
 #define OD_LINEAR_SLAB_UNITS_DEFAULT (32ll << 20)
 // streamed (host) gradients: the copy of the first slab and the kernels of the last one are not overlapped -- short slabs
 #define OD_STREAM_SLAB_UNITS (32ll << 20)
