@@ -991,22 +991,19 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         // they come and flips the sign of I with an XOR -- 2 FP64 operations less per dual step, 3.91 -> 3.78 ms per 32M units,
         // but the golden linear DOS of the reference's test-suite then differs by 4e-12 of peak instead of < 2e-12.)
         constexpr double third = 1.0 / 3.0, sixth = 1.0 / 6.0, tiny = 1e-280;
-        // (every coefficient below carries the record's weight sc = alpha * omega: the walk then adds D and I as they come,
-        // and the sign flip of the local part is an XOR on I instead of a multiplication by +-sc)
-        double aa[2], bb[2], cc[2], dd[2], hh[2], haa[2], inv2a[2], inv2cb[2], i6a[2], i6cb[2], a2_6[2], k30[2], sc[2], hsc[2], tB[2], tt[2];
+        double aa[2], bb[2], cc[2], dd[2], hh[2], haa[2], inv2a[2], inv2cb[2], i6a[2], i6cb[2], a2_6[2], k30[2], sc[2], tB[2], tt[2];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           aa[s] = p3[s] - p4[s]; bb[s] = p2[s] - p4[s]; cc[s] = p1[s] - p4[s]; dd[s] = e0[s] - p4[s];
+          hh[s] = 0.5 * (cc[s] + bb[s] - aa[s]); haa[s] = 0.5 * aa[s];
           const double cb = cc[s] - bb[s];
           const double full = (cc[s] - aa[s]) * cc[s] + (aa[s] * aa[s] - cb * cb) * third;
           sc[s] = valid[s] ? om[s] * fast_rcp(full + (cc[s] + bb[s] - aa[s]) * (dd[s] - cc[s])) : 0.0;  // alpha * omega
-          hsc[s] = 0.5 * sc[s];
-          hh[s] = hsc[s] * (cc[s] + bb[s] - aa[s]); haa[s] = hsc[s] * aa[s];
-          inv2a[s] = aa[s] > tiny ? hsc[s] * fast_rcp(aa[s]) : 0.0;
-          inv2cb[s] = cb > tiny ? hsc[s] * fast_rcp(cb) : 0.0;
+          inv2a[s] = aa[s] > tiny ? 0.5 * fast_rcp(aa[s]) : 0.0;
+          inv2cb[s] = cb > tiny ? 0.5 * fast_rcp(cb) : 0.0;
           i6a[s] = inv2a[s] * third; i6cb[s] = inv2cb[s] * third;
-          a2_6[s] = sc[s] * (aa[s] * aa[s] * sixth);
-          k30[s] = sc[s] * (0.5 * (aa[s] * aa[s] * third - cc[s] * bb[s]) - cb * cb * sixth);
+          a2_6[s] = aa[s] * aa[s] * sixth;
+          k30[s] = 0.5 * (aa[s] * aa[s] * third - cc[s] * bb[s]) - cb * cb * sixth;
           tB[s] = E0[s] - e0[s];  // E_j - e0 at relative bin 0
           tt[s] = tB[s] + (double)r * delta;
         }
@@ -1017,15 +1014,16 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           const double x = clamp0(dd[s] - fabs(t));  // bins outside (e4, 2 e0 - e4): x -> +0, D = I = 0
           const double p = clamp0(aa[s] - x), y = clamp0(cc[s] - x);
           const double pp = p * p, yy = y * y;
-          const double Dlo = fma(pp, inv2a[s], fma(x, sc[s], -haa[s])), Dhi = fma(-yy, inv2cb[s], hh[s]);
+          const double Dlo = fma(pp, inv2a[s], x - haa[s]), Dhi = fma(-yy, inv2cb[s], hh[s]);
           const bool lo = x < bb[s];
           D = lo ? Dlo : Dhi;
           if (!JD) {
-            const double Ilo = fma(-(pp * p), i6a[s], fma(x, fma(x, hsc[s], -haa[s]), a2_6[s]));
+            const double Ilo = fma(-(pp * p), i6a[s], fma(x, fma(x, 0.5, -haa[s]), a2_6[s]));
             const double Ihi = fma(yy * y, i6cb[s], fma(hh[s], x, k30[s]));
             I = lo ? Ilo : Ihi;
           }
         };
+        const double scm0A = sc[0] * m0[0], scm1A = sc[0] * m1[0], scm0B = sc[1] * m0[1], scm1B = sc[1] * m1[1];
         // the sign of the local part flips where the walk passes the record's centre: d = cabs - 1 - r goes negative there,
         // so the flip is the sign bit of a counter (one add and one logic operation per record and step)
         int dA = cabs[0] - 1 - r, dB = cabs[1] - 1 - r;
@@ -1040,13 +1038,13 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           lin_eval(0, tt[0], DA, IA);
           lin_eval(1, tt[1], DB, IB);
           if (JD) {
-            acc.x += fma(DA, m0[0], DB * m0[1]);
-            acc.y += fma(DA, m1[0], DB * m1[1]);
+            acc.x += fma(DA, scm0A, DB * scm0B);
+            acc.y += fma(DA, scm1A, DB * scm1B);
           } else {
-            const double fA = __hiloint2double(__double2hiint(IA) ^ (dA & 0x80000000), __double2loint(IA));
-            const double fB = __hiloint2double(__double2hiint(IB) ^ (dB & 0x80000000), __double2loint(IB));
-            acc.x += DA + DB;
-            acc.y += fA + fB;
+            const double sA = __hiloint2double(__double2hiint(sc[0]) ^ (dA & 0x80000000), __double2loint(sc[0]));
+            const double sB = __hiloint2double(__double2hiint(sc[1]) ^ (dB & 0x80000000), __double2loint(sc[1]));
+            acc.x += fma(DA, sc[0], DB * sc[1]);
+            acc.y += fma(IA, sA, IB * sB);
           }
           *qp = acc;
           tt[0] += delta; tt[1] += delta;
