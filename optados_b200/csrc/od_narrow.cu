@@ -1250,20 +1250,44 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pdos_gemm_kernel(PgArgs A) {
       sI[(buf * PG_KC + lane) * 2] = klo; sI[(buf * PG_KC + lane) * 2 + 1] = wlen;
       sRow[buf * PG_KC + lane] = row;
     };
+    // weight rows of a chunk, global -> registers -> shared.  With an even number of orbitals (rows then start on 16-byte
+    // boundaries) a thread moves pairs: half the row look-ups, bounds tests, loads and stores (they were 30 % of the kernel's
+    // instructions element by element).
+    const bool wpairs = BN == 64 && !LINEAR && (A.norb & 1) == 0 && (reinterpret_cast<size_t>(A.mw) & 15) == 0;  // (no gain at 16 / 32 orbitals per tile; spills in the linear variant)
     auto load_w = [&](int buf, double (&wr)[EPT]) {  // rows of the chunk whose parameters sit in `buf`
+      if (wpairs) {
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        const int e = i * 256 + t, k = e / BN, oo = e % BN;
-        const long long row = sRow[buf * PG_KC + k];
-        const int o = obase + oo;
-        wr[i] = (row >= 0 && o < A.norb) ? A.mw[row + o] : 0.0;
+        for (int i = 0; i < EPT / 2; ++i) {
+          const int e = i * 256 + t, k = e / (BN / 2), oo = 2 * (e % (BN / 2));
+          const long long row = sRow[buf * PG_KC + k];
+          const int o = obase + oo;
+          double2 v = make_double2(0.0, 0.0);
+          if (row >= 0 && o < A.norb) v = *reinterpret_cast<const double2 *>(A.mw + row + o);  // (o + 1 < norb: both even)
+          wr[2 * i] = v.x; wr[2 * i + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          const int e = i * 256 + t, k = e / BN, oo = e % BN;
+          const long long row = sRow[buf * PG_KC + k];
+          const int o = obase + oo;
+          wr[i] = (row >= 0 && o < A.norb) ? A.mw[row + o] : 0.0;
+        }
       }
     };
     auto store_w = [&](int buf, const double (&wr)[EPT]) {
+      if (wpairs) {
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        const int e = i * 256 + t, k = e / BN, oo = e % BN;
-        sW[((size_t)buf * PG_KC + k) * WS + oo] = wr[i];
+        for (int i = 0; i < EPT / 2; ++i) {
+          const int e = i * 256 + t, k = e / (BN / 2), oo = 2 * (e % (BN / 2));
+          *reinterpret_cast<double2 *>(sW + ((size_t)buf * PG_KC + k) * WS + oo) = make_double2(wr[2 * i], wr[2 * i + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          const int e = i * 256 + t, k = e / BN, oo = e % BN;
+          sW[((size_t)buf * PG_KC + k) * WS + oo] = wr[i];
+        }
       }
     };
     auto fill_g = [&](int buf) {  // thread -> record k = lane, run of 8 bins = warp
