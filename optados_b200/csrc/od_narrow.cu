@@ -9,27 +9,30 @@
 //      (width class, first cell of the window); each CTA writes its histogram as one row of a
 //      [CTA][bucket] table.  A column scan turns the table into per-CTA write cursors, and pass B
 //      (same unit -> CTA mapping) scatters 32-byte (Gaussian) / 64-byte (linear) records into
-//      bucket order using shared-memory cursors only.  Sorting by width class as well as by
-//      position makes the 32 records of a warp-group nearly congruent, which is what lets one
-//      lane = one record run without idle lanes.
-//   2. ACCUMULATES: warps pull chunks of 256 consecutive records.  Within a group of 32 records
-//      LANE = RECORD: every lane walks all bins of the group's common window, lane l starting l
-//      bins in and wrapping round, so that in any one step the 32 lanes touch 32 DIFFERENT bins
-//      of a warp-private shared-memory tile -- plain LDS/STS read-modify-write, no atomics, no
-//      reductions; windows of >= 64 bins run as two interleaved half-window streams per lane.
-//      Walking consecutive bins lets a lane advance its Gaussian by the recurrence
-//      g(j+1) = g(j) r(j), r(j+1) = r(j) q  (q = exp(-dE^2/w^2)): two multiplies per bin instead
-//      of an exp.  The integrated spectrum is split as Phi(z) = H(z >= 0) + [Phi(z) - H]: the
-//      bracket is as local as the DOS and shares its Gaussian; the steps H go to a warp-private
-//      step tile once per record and become a prefix sum at the very end.  The bracket is
-//        - for windows up to 84 bins: -+ (1/2) g' R(|z|), R = P5/Q6 ~ erfcx(|z|/sqrt 2)
-//          (tools/fit_erfcx.py, 5.4e-15), one reciprocal per bin;
-//        - for wider windows (dE/w <= 0.2): the Euler-Maclaurin relation between the lane's running
-//          sum of its own Gaussian values and the integral (see narrow_kernel<.., EM>).
+//      bucket order using shared-memory cursors only.  A CTA walks the k-points of one group of 32
+//      bands (PrepMap): it then fills few buckets, and its scattered records complete their lines
+//      in L2.  Sorting by width class as well as by position makes the records of a warp-group
+//      nearly congruent, which is what lets a lane run a record without idle lanes.
+//   2. ACCUMULATES: warps pull chunks of 256 consecutive records and regroup them by a counting
+//      sort on (window start, length).  Within a group of 64 records LANE = TWO RECORDS: every
+//      lane walks all bins of the group's common window, the lanes starting at staggered bins and
+//      wrapping round, so that in any one step they touch DIFFERENT bins of a warp-private
+//      shared-memory tile -- plain LDS/STS read-modify-write, no atomics, no reductions.  Windows
+//      that fit half a tile run on two copies of it (one per half-warp: starts staggered over 16
+//      bins, shortest walk 16 steps).  Walking consecutive bins lets a lane advance its Gaussian by
+//      the recurrence g(j+1) = g(j) r(j), r(j+1) = r(j) q  (q = exp(-dE^2/w^2)): two multiplies
+//      per bin instead of an exp.  The integrated spectrum:
+//        - windows under 41 bins (dE/w > 0.4): Phi(z) = H(z >= 0) + [Phi(z) - H]; the bracket is as
+//          local as the DOS and shares its Gaussian, -+ (1/2) g' R(|z|), R = P5/Q6 ~ erfcx(|z|/sqrt 2)
+//          (tools/fit_erfcx.py, 5.4e-15), one reciprocal per bin; the steps H go to a warp-private
+//          step tile once per record and become a prefix sum at the very end;
+//        - wider windows (nearly all of a fine grid): NO per-bin work -- the kernel deposits only the
+//          DOS of those groups (two bins per step), and their integral follows from the summed DOS by
+//          a prefix sum and one 40-tap Euler-Maclaurin filter on the grid (c_em_fir, combine_kernel).
 //      The linear scheme evaluates doslin as two smooth forms with clamped arguments and one select.
 //      JDOS / optics / weighted DOS run the same loops in channel passes (JD), many projectors through
 //      a banded GEMM on the FP64 tensor cores (pdos_gemm_kernel).  Tiles are flushed to HBM with FP64
-//      reductions only when a warp's window slides off its 512-bin tile or its chunk ends.
+//      reductions only when a warp's window slides off its tile or its chunk ends.
 //   3. Units whose window is wider than 480 bins (and degenerate ones) go to the dense bin-owner
 //      engine (od_accum.cuh) through a compacted list; the partial spectra are then combined.
 //
