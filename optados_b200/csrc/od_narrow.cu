@@ -530,6 +530,9 @@ struct NarrowArgs {
   const double *wts;
   int ng, wstride;
   int col0, col1;  // weight column feeding m0 / m1; -1 = the constant 1, -2 = zero
+  // four-channel passes (JD == 2: the tile holds 32 bytes per bin over NR_T / 2 bins): two more columns and outputs
+  int col2, col3;
+  double *out2, *out3;
   // PDOS / core: weights gathered from matrix_weights(norb, mw_nb, mw_nk, ns) by unit index
   const unsigned *runit;
   const double *mw;
@@ -539,7 +542,7 @@ struct NarrowArgs {
 
 // tile -> HBM.  mode 0: (dos, local part of the integrated DOS, steps) / the two JD channels; mode 2: the same in two copies
 // of NR_T / 2 bins (one per half-warp, summed here); mode 1: the DOS of the Euler-Maclaurin groups alone, the tile then
-// being two arrays of NR_T doubles (one per half-warp)
+// being two arrays of NR_T doubles (one per half-warp); mode 3: four JD channels per bin in two copies of NR_T / 4 bins
 __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int base, int used, int mode, const NarrowArgs &A, int lane) {
   if (mode == 1) {  // two copies of NR_T doubles, one per half-warp
     double *t1 = reinterpret_cast<double *>(tile);
@@ -548,6 +551,23 @@ __device__ __forceinline__ void flush_tile(double2 *tile, double *stile, int bas
       if (v != 0.0) atomicAdd(&A.out_dos_em[base + i], v);
       t1[i] = 0.0;
       t1[i + NR_T] = 0.0;
+    }
+    __syncwarp();
+    return;
+  }
+  if (mode == 3) {  // four JD channels per bin, two copies of NR_T / 4 bins (one per half-warp)
+    for (int i = lane; i < used; i += 32) {
+      double2 a = tile[2 * i], b = tile[2 * i + 1];
+      const double2 a2 = tile[NR_T / 2 + 2 * i], b2 = tile[NR_T / 2 + 2 * i + 1];
+      a.x += a2.x; a.y += a2.y; b.x += b2.x; b.y += b2.y;
+      tile[NR_T / 2 + 2 * i] = make_double2(0.0, 0.0);
+      tile[NR_T / 2 + 2 * i + 1] = make_double2(0.0, 0.0);
+      if (a.x != 0.0) atomicAdd(&A.out_dos[base + i], a.x);
+      if (a.y != 0.0) atomicAdd(&A.out_int[base + i], a.y);
+      if (b.x != 0.0) atomicAdd(&A.out2[base + i], b.x);
+      if (b.y != 0.0) atomicAdd(&A.out3[base + i], b.y);
+      tile[2 * i] = make_double2(0.0, 0.0);
+      tile[2 * i + 1] = make_double2(0.0, 0.0);
     }
     __syncwarp();
     return;
@@ -617,8 +637,13 @@ static_assert(NR_CHUNK == 256, "the in-chunk sort keeps 8 records per lane and o
 // contribution: with the integrated spectrum down to 10 FP64 operations per bin the kernel then ran at 72 % of the
 // shared-memory wavefront peak and 53 % of the FP64 pipe; two records per lane halve the wavefronts and give every lane
 // two independent recurrences, which is also what the short windows of the linear scheme were missing.)
-template <bool LINEAR, bool JD>
+// JD: 0 = DOS + integrated DOS; 1 = two weight channels per pass (K m0, K m1); 2 = four channels per pass on two copies
+// (one per half-warp) of a tile of NR_T / 4 bins -- the optics tensor (JDOS + 6 components) then walks its records twice
+// instead of four times.
+template <bool LINEAR, int JD>
 __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(NarrowArgs A) {
+  constexpr bool JD4 = JD == 2;
+  constexpr int CAP = JD4 ? NR_T / 4 : NR_T;  // bins of the tile (of one copy)
   extern __shared__ double2 sh_tiles[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2 *tile = sh_tiles + (size_t)warp * NR_T;
@@ -752,7 +777,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         bool any_defer = false;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          bool sel = valid[s] && (klo[s] + wlen[s] - gl <= NR_T - A.cell - 1);
+          bool sel = valid[s] && (klo[s] + wlen[s] - gl <= CAP - A.cell - 1);
           if (!LINEAR) sel = sel && ((double)(klo[s] - gl) * delta <= 25.0 * p1[s]);
           if (npass > 80) sel = valid[s];  // (cannot happen: the lowest record is always taken; then the record-by-record path)
           defer[s] = valid[s] && !sel;
@@ -767,7 +792,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         adv = any_defer ? 0 : 64;
         if (!any_defer) npass = 0;
       }
-      double m0[2] = {1.0, 1.0}, m1[2] = {0.0, 0.0};  // JD channel multipliers
+      double m0[2] = {1.0, 1.0}, m1[2] = {0.0, 0.0}, m2[2] = {0.0, 0.0}, m3[2] = {0.0, 0.0};  // JD channel multipliers
       if (JD) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -785,6 +810,10 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           }
           m0[s] = A.col0 == -1 ? 1.0 : ((A.col0 >= 0 && w) ? w[A.col0] : 0.0);
           m1[s] = A.col1 == -1 ? 1.0 : ((A.col1 >= 0 && w) ? w[A.col1] : 0.0);
+          if (JD4) {
+            m2[s] = (A.col2 >= 0 && w) ? w[A.col2] : 0.0;
+            m3[s] = (A.col3 >= 0 && w) ? w[A.col3] : 0.0;
+          }
         }
       }
       // ---- the common window [gl, gl + Wc) of this pass
@@ -794,7 +823,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       // lanes' starts are then staggered over 16 bins instead of 32, so the shortest walk is 16 steps instead of 32 (a third
       // of the linear and JDOS groups of the BASELINE configurations have windows under 32 bins) and 15 steps of a walk
       // carry the wrap test instead of 31.
-      const bool half = Wc + 2 <= NR_T / 2 - A.cell;
+      const bool half = JD4 || Wc + 2 <= NR_T / 2 - A.cell;
       const int wfloor = half ? 16 : 32;
       if (Wc < wfloor) Wc = wfloor;
       if (!LINEAR && !JD) Wc += Wc & 1;
@@ -809,7 +838,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       // The fast loop starts every lane's recurrence a few bins BELOW its own window (relative bin
       // `lane`, and bin 0 after the wrap): harmless while that start is not so deep in the tail that
       // exp underflows.  Gaussian only; del <= 8 by construction, so this only trips on sparse data.
-      bool irregular = Wc + 1 > NR_T - A.cell;  // (+1: the step of a centre just above the window)
+      bool irregular = Wc + 1 > CAP - A.cell;  // (+1: the step of a centre just above the window)
       if (!LINEAR) irregular = irregular || (valid[0] && (double)a[0] * delta > 25.0 * p1[0]) || (valid[1] && (double)a[1] * delta > 25.0 * p1[1]);
       irregular = __any_sync(FULL, irregular) || (A.debug & 1);
 
@@ -826,6 +855,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
             const double a0 = __shfl_sync(FULL, e0[s], l), a1 = __shfl_sync(FULL, p1[s], l), a2 = __shfl_sync(FULL, p2[s], l);
             const double a3 = __shfl_sync(FULL, p3[s], l), a4 = __shfl_sync(FULL, p4[s], l), ao = __shfl_sync(FULL, om[s], l);
             const double b0 = __shfl_sync(FULL, m0[s], l), b1 = __shfl_sync(FULL, m1[s], l);
+            const double b2 = JD4 ? __shfl_sync(FULL, m2[s], l) : 0.0, b3 = JD4 ? __shfl_sync(FULL, m3[s], l) : 0.0;
             if (w_l == 0) continue;
             if (!JD && lane == 0 && jb_l + c_l < A.grid.nbins) atomicAdd(&A.out_step[k_l + c_l], ao);
             for (int r = lane; r < w_l; r += 32) {
@@ -838,6 +868,10 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
                 if (bad) atomicOr(&A.flags[0], bad);
               } else {
                 gauss_direct(a0, a1, ao, Ej, r, c_l, A.cf, d, sv);
+              }
+              if (JD4) {
+                if (d * b2 != 0.0) atomicAdd(&A.out2[k_l + r], d * b2);
+                if (d * b3 != 0.0) atomicAdd(&A.out3[k_l + r], d * b3);
               }
               if (JD) { sv = d * b1; d = d * b0; }
               if (d != 0.0) atomicAdd(&A.out_dos[k_l + r], d);
@@ -880,8 +914,8 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         }
       }
       if (emode && Wc < 32) Wc = 32;  // (cannot happen: dE/w <= 0.4 means windows of >= 41 bins)
-      const int want_mode = emode ? 1 : (half ? 2 : 0);
-      if (gl < base || gl + Wc + 1 > base + (want_mode == 2 ? NR_T / 2 : NR_T) || want_mode != tmode) {
+      const int want_mode = JD4 ? 3 : (emode ? 1 : (half ? 2 : 0));
+      if (gl < base || gl + Wc + 1 > base + (want_mode == 3 ? NR_T / 4 : want_mode == 2 ? NR_T / 2 : NR_T) || want_mode != tmode) {
         flush_tile(tile, stile, base, used, tmode, A, lane);
         base = gl & ~(A.cell - 1);
         used = 0;
@@ -891,8 +925,8 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       used = max(used, off + Wc + 1);
       st_steps += (unsigned)Wc * ((valid[0] ? 1u : 0u) + (valid[1] ? 1u : 0u));
       st_useful += (unsigned)(wlen[0] + wlen[1]);
-      double2 *tw = tile + off + (want_mode == 2 ? (lane >> 4) * (NR_T / 2) : 0);
-      const int ntail = want_mode == 2 ? 15 : 31;  // wrap steps of the one-bin walks
+      double2 *tw = JD4 ? tile + (lane >> 4) * (NR_T / 2) + 2 * off : tile + off + (want_mode == 2 ? (lane >> 4) * (NR_T / 2) : 0);
+      const int ntail = want_mode >= 2 ? 15 : 31;  // wrap steps of the one-bin walks
 
       // ---- the steps H: one add per record into the warp-private step tile.  Several records of a
       //      group usually share their centre bin, so this one place uses shared-memory atomics.
@@ -908,7 +942,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       // staggered starts then span 30 bins instead of 62 and only 15 steps of a walk carry the wrap test and its 8 selects
       // (with one copy the 31 wrap steps were 83 % of the instructions of an 84-bin walk).
       const bool pairwalk = !LINEAR && !JD && emode;  // (Wc is even and >= 32)
-      int r = pairwalk ? 2 * (lane & 15) : (want_mode == 2 ? (lane & 15) : lane);
+      int r = pairwalk ? 2 * (lane & 15) : (want_mode >= 2 ? (lane & 15) : lane);
       if (!LINEAR) {
         double amp[2], q[2], gB[2], rB[2], z[2], g[2], rr[2];
 #pragma unroll
@@ -961,12 +995,18 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           // capture this step's inputs, then advance the recurrences at once so that the next step's
           // operands are ready long before the rational chains below have drained
           const double uA = fabs(z[0]), uB = fabs(z[1]), gA = g[0], gb = g[1];
-          double2 *qp = tw + r;
+          double2 *qp = JD4 ? tw + 2 * r : tw + r;
           const bool fA = r >= cabs[0], fB = r >= cabs[1];
           g[0] *= rr[0]; rr[0] *= q[0]; z[0] += del[0];
           g[1] *= rr[1]; rr[1] *= q[1]; z[1] += del[1];
           ++r;
           double2 acc = *qp;
+          if (JD4) {
+            double2 acc2 = qp[1];
+            acc2.x += fma(gA, m2[0], gb * m2[1]);
+            acc2.y += fma(gA, m3[0], gb * m3[1]);
+            qp[1] = acc2;
+          }
           if (JD) {
             acc.x += fma(gA, m0[0], gb * m0[1]);
             acc.y += fma(gA, m1[0], gb * m1[1]);
@@ -1035,11 +1075,17 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           if (decltype(WRAP)::value) {
             if (r == Wc) { r = 0; tt[0] = tB[0]; tt[1] = tB[1]; dA = cabs[0] - 1; dB = cabs[1] - 1; }
           }
-          double2 *qp = tw + r;
+          double2 *qp = JD4 ? tw + 2 * r : tw + r;
           double2 acc = *qp;
           double DA, IA = 0, DB, IB = 0;
           lin_eval(0, tt[0], DA, IA);
           lin_eval(1, tt[1], DB, IB);
+          if (JD4) {
+            double2 acc2 = qp[1];
+            acc2.x += fma(DA, sc[0] * m2[0], DB * (sc[1] * m2[1]));
+            acc2.y += fma(DA, sc[0] * m3[0], DB * (sc[1] * m3[1]));
+            qp[1] = acc2;
+          }
           if (JD) {
             acc.x += fma(DA, scm0A, DB * scm0B);
             acc.y += fma(DA, scm1A, DB * scm1B);
@@ -1548,9 +1594,9 @@ struct MwGather {
   long long k_first = 0;
 };
 
-template <bool JD>
+template <int JD>
 int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, int col0, int col1, double *out0, double *out1,
-                  const MwGather *gather = nullptr) {
+                  const MwGather *gather = nullptr, int col2 = -2, int col3 = -2, double *out2 = nullptr, double *out3 = nullptr) {
   NarrowArgs A;
   A.recs = ctx->recs.p;
   A.nrec_dev = S.base + S.ps.nbuckets;
@@ -1572,6 +1618,7 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, int col0, int col1
   A.wstride = S.ps.wstride;
   A.col0 = col0;
   A.col1 = col1;
+  A.col2 = col2; A.col3 = col3; A.out2 = out2; A.out3 = out3;
   A.runit = nullptr; A.mw = nullptr; A.norb = A.mw_nb = A.mw_nk = A.nb = A.mw_ns = 0; A.k_first = 0;
   if (gather) {
     A.runit = ctx->scratch_e.as<unsigned>();
@@ -1679,7 +1726,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
   OD_CHECK(narrow_prepare(ctx, prod, S, linear, &wide_stride));
   OD_CHECK(od_time_end(ctx, tp));
   OD_CHECK(od_time_begin(ctx, 1, &ta));
-  OD_CHECK(narrow_launch<false>(ctx, S, linear, -2, -2, ndos, nint, nullptr));
+  OD_CHECK(narrow_launch<0>(ctx, S, linear, -2, -2, ndos, nint, nullptr));
   const size_t n1 = (size_t)nbins * ns;
   combine_kernel<<<dim3((nbins + 1023) / 1024, ns), 1024, 0, ctx->stream>>>(ndos, nint, S.stephist, S.chan + 2 * S.nout, grid.delta, nbins, S.ps.bpad,
                                                 accum, accum + n1);
@@ -1732,7 +1779,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
     gth.k_first = prod_in.k_first;
     for (int c = 0; 2 * c < norb; ++c, ++wpasses) {
       OD_CUDA(ctx, cudaMemsetAsync(S.chan, 0, sizeof(double) * 2 * S.nout, ctx->stream));
-      OD_CHECK(narrow_launch<true>(ctx, S, linear, 2 * c, 2 * c + 1 < norb ? 2 * c + 1 : -2, ndos, nint, &gth));
+      OD_CHECK(narrow_launch<1>(ctx, S, linear, 2 * c, 2 * c + 1 < norb ? 2 * c + 1 : -2, ndos, nint, &gth));
       ChanDest dest;
       for (long long &d : dest.d) d = -1;
       dest.d[0] = (long long)(2 * n1 + n1 * (size_t)(2 * c));
@@ -1794,9 +1841,14 @@ int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &gri
   // slabs in od_spectral.cu), and < 2^30 for the 32-bit unit arithmetic; OD_JDOS_SLAB_SLOTS overrides for experiments
   const long long slab_slots = std::min<long long>(1ll << 30, getenv("OD_JDOS_SLAB_SLOTS") ? atoll(getenv("OD_JDOS_SLAB_SLOTS")) : (16ll << 20));
   const long long slab_k = std::max<long long>(1, slab_slots / ppk);
-  const int npass = 1 + n_geom / 2;  // channel pairs: (jdos, w1) (w2, w3) (w4, w5) (w6, -)
+  // channels: 0 = JDOS, a >= 1 = geometry component a.  Two per pass (the tile in two copies: short walks), or -- from three
+  // channels on -- four per pass on a tile of half the bins: the tensor's 7 channels take 2 passes over the records, not 4
+  const bool quad = n_geom >= 2 && narrow_cell_for(grid.nbins, ns, std::min(nk, slab_k) * ppk * ns) <= 16;  // (room for windows of 96 bins)
+  const int cpp = quad ? 4 : 2;                  // channels per pass
+  const int npass = (1 + n_geom + cpp - 1) / cpp;
   Scratch S;
-  OD_CHECK(narrow_scratch(ctx, grid, ns, std::min(nk, slab_k) * ppk * ns, 2 * npass, S));
+  OD_CHECK(narrow_scratch(ctx, grid, ns, std::min(nk, slab_k) * ppk * ns, cpp * npass, S));
+  if (quad) S.ps.wmax = std::min(S.ps.wmax, NR_T / 4 - 2 * S.ps.cell);  // (wider windows: dense engine)
   S.ps.gwin = OD_SQRT60;   // the Gaussian cut-off (algorithms.f90:83); no erf window in JDOS
   S.ps.with_int = 0;
   S.ps.linear_pass = linear ? 1 : 0;  // hybrid_linear fall-back records (jdos_utils.f90:365) -> dense engine
@@ -1814,9 +1866,14 @@ int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &gri
     OD_CHECK(narrow_prepare(ctx, prod, S, linear, &wide_stride));
     OD_CHECK(od_time_end(ctx, tp));
     OD_CHECK(od_time_begin(ctx, 1, &ta));
-    for (int c = 0; c < npass; ++c) {  // (jdos, w1) (w2, w3) (w4, w5) (w6, -)
-      const int col0 = c == 0 ? -1 : 2 * c - 1, col1 = 2 * c < n_geom ? 2 * c : -2;
-      OD_CHECK(narrow_launch<true>(ctx, S, linear, col0, col1, S.chan + (size_t)(2 * c) * S.nout, S.chan + (size_t)(2 * c + 1) * S.nout));
+    for (int c = 0; c < npass; ++c) {
+      auto col = [&](int ch) { return ch == 0 ? -1 : (ch <= n_geom ? ch - 1 : -2); };  // weight column of channel ch
+      double *o = S.chan + (size_t)(cpp * c) * S.nout;
+      if (quad)
+        OD_CHECK(narrow_launch<2>(ctx, S, linear, col(4 * c), col(4 * c + 1), o, o + S.nout, nullptr, col(4 * c + 2), col(4 * c + 3),
+                                  o + 2 * S.nout, o + 3 * S.nout));
+      else
+        OD_CHECK(narrow_launch<1>(ctx, S, linear, col(2 * c), col(2 * c + 1), o, o + S.nout));
     }
     OD_CHECK(od_time_end(ctx, ta));
     {
@@ -1844,8 +1901,8 @@ int od_narrow_jdos(od_ctx *ctx, const JdosProducer &prod_in, const GridSpec &gri
   for (long long &d : dest.d) d = -1;
   dest.d[0] = 0;
   for (int a = 1; a <= n_geom; ++a) dest.d[a] = (long long)(n1 + (size_t)nbins * ns * (a - 1));
-  dim3 g((nbins + 255) / 256, 2 * npass * ns);
-  combine_channels_kernel<<<g, 256, 0, ctx->stream>>>(S.chan, S.nout, 2 * npass, nbins, S.ps.bpad, ns, dest, accum);
+  dim3 g((nbins + 255) / 256, cpp * npass * ns);
+  combine_channels_kernel<<<g, 256, 0, ctx->stream>>>(S.chan, S.nout, cpp * npass, nbins, S.ps.bpad, ns, dest, accum);
   OD_LAUNCH_CHECK(ctx);
   if (ctx->pending_times.size() > 4096) OD_CHECK(od_times_resolve(ctx));
   return OD_OK;

@@ -184,7 +184,7 @@ def cfg4(env, k_per_gpu=25000):
         ms = env.max_over_ranks(ms)
         evals = env.sum_over_ranks(prof["contributions"])       # in-window (pair, bin) evaluations of the engine, ALL channel passes
         lane = env.sum_over_ranks(prof["lane_steps"])
-        npass = 1 + ng // 2                                     # (jdos, w1) (w2, w3) (w4, w5) (w6, -): every pass re-walks the records
+        npass = (1 + ng + 3) // 4 if ng >= 2 else 1 + ng // 2   # channels per pass: 4 from three channels on (tensor: 2 passes), else 2
         contrib = evals / npass                                 # the metric's unit: one in-window (pair, bin) contribution, counted once
         res[geom] = {"ms": ms, "contributions": contrib, "contributions_per_s": contrib / (ms * 1e-3), "lane_efficiency": evals / max(lane, 1.0),
                      "channel_passes": npass, "engine_evaluations": evals,
