@@ -1123,7 +1123,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
 // same two-multiply recurrence along bins, linear by the branch-free doslin pieces), their weight rows are
 // gathered (coalesced, 8 * BN bytes per record) into W[32][BN], and the product runs on the FP64 tensor cores
 // (DMMA m16n8k8, see pdos_gemm_kernel below).
-constexpr int PG_BM = 64, PG_KC = 32, PG_SEG = 2048;
+constexpr int PG_BM = 64, PG_KC = 32, PG_SEG = 4096;
 constexpr int PG_THREADS = 288;  // 8 DMMA warps + 1 producer warp (record parameters of the chunk after next)
 
 
