@@ -72,6 +72,10 @@ constexpr int NR_MAXBUCKETS = 52224;  // x 4 B = 204 KB of shared memory in the 
 constexpr int NR_PREP_THREADS = OD_PREP_THREADS;   // x PREP_U units per thread in flight (the 204 KB bucket table allows one CTA per SM)
 constexpr unsigned KEY_WIDE = 0xFFFFFFFEu, KEY_DROP = 0xFFFFFFFFu;
 
+// With PrepSpec.want_unit (PDOS / core: the weights are gathered from matrix_weights by unit index) a record carries its
+// unit index instead of a separate sorted index array (one scattered store request less per unit): a linear record in its
+// padding, a Gaussian one in the high word of its tail, whose low word then packs klo (23 bits) | wlen << 23 -- the step
+// position cpos is recomputed from e by the one consumer that needs it.
 struct __align__(32) GRec {  // Gaussian record
   double e, w, om;
   int klo;                    // first bin of the window, global numbering (spin * bpad + bin)
@@ -371,7 +375,7 @@ __device__ __forceinline__ double rec_tail(int klo, int cpos, int wlen) {
 template <bool LINEAR, class Producer>
 __global__ void __launch_bounds__(NR_PREP_THREADS)
 prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ keys, const unsigned *__restrict__ table,
-                    const unsigned *__restrict__ base, void *__restrict__ recs_v, double *__restrict__ wts, unsigned *__restrict__ runit,
+                    const unsigned *__restrict__ base, void *__restrict__ recs_v, double *__restrict__ wts,
                     double *__restrict__ stephist,
                     unsigned *__restrict__ widelist, unsigned long long *__restrict__ wide_cursor, long long wide_stride,
                     PrepMap pm) {
@@ -441,9 +445,10 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
       if (LINEAR) {
         LRec *o = reinterpret_cast<LRec *>(recs_v) + p;
         st256(o, r.e0, r.p1, r.p2, r.p3);
-        st256(reinterpret_cast<char *>(o) + 32, r.p4, r.omega, rec_tail(klo, cpos, wlen), 0.0);
+        st256(reinterpret_cast<char *>(o) + 32, r.p4, r.omega, rec_tail(klo, cpos, wlen), ps.want_unit ? __hiloint2double(0, (int)u) : 0.0);
       } else {
-        st256(reinterpret_cast<GRec *>(recs_v) + p, r.e0, r.p1, r.omega, rec_tail(klo, cpos, wlen));
+        const double tail = ps.want_unit ? __hiloint2double((int)u, klo | (wlen << 23)) : rec_tail(klo, cpos, wlen);
+        st256(reinterpret_cast<GRec *>(recs_v) + p, r.e0, r.p1, r.omega, tail);
       }
       // weight columns ride beside the record in rows of 1, 4 or 8 doubles: one / two 32-byte stores instead of ng 8-byte ones
       // (static indices: a loop over ps.ng would put the whole record into local memory)
@@ -453,7 +458,6 @@ prep_scatter_kernel(Producer prod, PrepSpec ps, const unsigned *__restrict__ key
         st256(wts + (size_t)p * 8, r.wt[0], r.wt[1], r.wt[2], r.wt[3]);
         st256(wts + (size_t)p * 8 + 4, r.wt[4], r.wt[5], 0.0, 0.0);
       }
-      if (ps.want_unit) runit[p] = u;
     }
   }
   }
@@ -533,8 +537,8 @@ struct NarrowArgs {
   // four-channel passes (JD == 2: the tile holds 32 bytes per bin over NR_T / 2 bins): two more columns and outputs
   int col2, col3;
   double *out2, *out3;
-  // PDOS / core: weights gathered from matrix_weights(norb, mw_nb, mw_nk, ns) by unit index
-  const unsigned *runit;
+  // PDOS / core: weights gathered from matrix_weights(norb, mw_nb, mw_nk, ns) by the unit index the records carry
+  int unit_in_rec;       // records were built with want_unit (see GRec)
   const double *mw;
   int norb, mw_nb, mw_nk, nb, mw_ns;
   long long k_first;
@@ -692,9 +696,10 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         const int li = j * 32 + lane;
         int2 t = make_int2(0, 0);
         if (li < n) t = *reinterpret_cast<const int2 *>(rb + (size_t)li * RECB);
-        klo_j[j] = t.x;
-        wl_j[j] = (int)((unsigned)t.y >> 16);
-        if (li < n) { kmin = min(kmin, t.x); kmax = max(kmax, t.x); wmin = min(wmin, wl_j[j]); wmax = max(wmax, wl_j[j]); }
+        const bool packed = !LINEAR && A.unit_in_rec;  // tail = klo | wlen << 23, unit
+        klo_j[j] = packed ? (t.x & 0x7fffff) : t.x;
+        wl_j[j] = packed ? (int)((unsigned)t.x >> 23) : (int)((unsigned)t.y >> 16);
+        if (li < n) { kmin = min(kmin, klo_j[j]); kmax = max(kmax, klo_j[j]); wmin = min(wmin, wl_j[j]); wmax = max(wmax, wl_j[j]); }
       }
       kmin = __reduce_min_sync(FULL, kmin); kmax = __reduce_max_sync(FULL, kmax);
       wmin = __reduce_min_sync(FULL, wmin); wmax = __reduce_max_sync(FULL, wmax);
@@ -747,6 +752,7 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
       long long idx[2];
       double e0[2], p1[2], p2[2], p3[2], p4[2], om[2];
       int klo[2], wlen[2], cpos[2];
+      unsigned unit[2] = {0u, 0u};
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const int pos = g0 + 32 * s + lane;
@@ -762,9 +768,18 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
           if (LINEAR) {
             const LRec r = reinterpret_cast<const LRec *>(A.recs)[idx[s]];
             e0[s] = r.e0; p1[s] = r.e1; p2[s] = r.e2; p3[s] = r.e3; p4[s] = r.e4; om[s] = r.om; klo[s] = r.klo; wlen[s] = r.wlen; cpos[s] = r.cpos;
+            unit[s] = (unsigned)__double2loint(r.pad);
           } else {
             const GRec r = reinterpret_cast<const GRec *>(A.recs)[idx[s]];
             e0[s] = r.e; p1[s] = r.w; om[s] = r.om; klo[s] = r.klo; wlen[s] = r.wlen; cpos[s] = r.cpos;
+            if (A.unit_in_rec) {  // packed tail (see GRec): the step position follows from e as in classify()
+              unit[s] = (unsigned)r.cpos | ((unsigned)r.wlen << 16);
+              wlen[s] = (int)((unsigned)r.klo >> 23);
+              klo[s] = r.klo & 0x7fffff;
+              const int kl = klo[s] - (klo[s] >= A.bpad ? A.bpad : 0);
+              const int cstep = (int)fmin(fmax(ceil((r.e - emin) * (1.0 / delta)), 0.0), (double)A.grid.nbins);
+              cpos[s] = min(max(cstep - kl, 0), wlen[s]);
+            }
           }
         }
       }
@@ -798,8 +813,8 @@ __global__ void __launch_bounds__(NR_WARPS * 32, NR_CTAS_PER_SM) narrow_kernel(N
         for (int s = 0; s < 2; ++s) {
           if (!valid[s]) continue;
           const double *w = nullptr;
-          if (A.runit) {
-            const unsigned u = A.runit[idx[s]];
+          if (A.mw) {
+            const unsigned u = unit[s];
             const unsigned ikl = u / (unsigned)A.nb, ib = u - ikl * (unsigned)A.nb;
             const long long ik = A.k_first + ikl;
             const int is = klo[s] >= A.bpad ? 1 : 0;
@@ -1166,7 +1181,6 @@ __global__ void pg_count_kernel(PgPlan P, unsigned *__restrict__ counts) {
 
 struct PgArgs {
   const void *recs;
-  const unsigned *runit;
   PgPlan plan;
   unsigned long long *next_item;
   GridSpec grid;
@@ -1268,11 +1282,12 @@ __global__ void __launch_bounds__(PG_THREADS, 2) pdos_gemm_kernel(PgArgs A) {
       if (LINEAR) {
         const LRec r = reinterpret_cast<const LRec *>(A.recs)[idx];
         R.e0 = r.e0; R.p1 = r.e1; R.p2 = r.e2; R.p3 = r.e3; R.p4 = r.e4; R.om = r.om; R.klo = r.klo; R.wlen = r.wlen;
-      } else {
+        R.unit = (unsigned)__double2loint(r.pad);
+      } else {  // packed tail (see GRec)
         const GRec r = reinterpret_cast<const GRec *>(A.recs)[idx];
-        R.e0 = r.e; R.p1 = r.w; R.om = r.om; R.klo = r.klo; R.wlen = r.wlen;
+        R.e0 = r.e; R.p1 = r.w; R.om = r.om; R.klo = r.klo & 0x7fffff; R.wlen = (int)((unsigned)r.klo >> 23);
+        R.unit = (unsigned)r.cpos | ((unsigned)r.wlen << 16);
       }
-      R.unit = A.runit[idx];
     };
     auto store_params = [&](int buf, const RecRegs &R) {  // warp 0
       double *P = sP + ((size_t)buf * PG_KC + lane) * 12;
@@ -1565,10 +1580,8 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   OD_CHECK(od_buf_ensure(ctx, ctx->recs, rec_bytes * units + 256));
   OD_CHECK(od_buf_ensure(ctx, ctx->scratch_b, sizeof(unsigned) * units + 256));
   if (ps.ng > 0) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_d, sizeof(double) * units * ps.wstride + 256));
-  if (ps.want_unit) OD_CHECK(od_buf_ensure(ctx, ctx->scratch_e, sizeof(unsigned) * units + 256));
   OD_CUDA(ctx, cudaMemsetAsync(S.wide, 0, sizeof(unsigned long long) * 5, ctx->stream));
   double *wts = ps.ng > 0 ? ctx->scratch_d.as<double>() : nullptr;
-  unsigned *runit = ps.want_unit ? ctx->scratch_e.as<unsigned>() : nullptr;
   OD_CUDA(ctx, cudaFuncSetAttribute(prep_hist_kernel<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
   prep_hist_kernel<Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(prod_keys, ps, S.keys, S.table, S.wide, pm);
   OD_LAUNCH_CHECK(ctx);
@@ -1580,7 +1593,7 @@ int narrow_prepare(od_ctx *ctx, const Producer &prod_in, Scratch &S, bool linear
   do {                                                                                                                               \
     OD_CUDA(ctx, cudaFuncSetAttribute(prep_scatter_kernel<LIN, Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem)); \
     prep_scatter_kernel<LIN, Producer><<<prows, NR_PREP_THREADS, hist_smem, ctx->stream>>>(                                         \
-        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, runit, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride, pm); \
+        prod, ps, S.keys, S.table, S.base, ctx->recs.p, wts, S.stephist, ctx->scratch_b.as<unsigned>(), S.wide + 2, *wide_stride, pm); \
   } while (0)
   if (linear) SC_LAUNCH(true); else SC_LAUNCH(false);
 #undef SC_LAUNCH
@@ -1619,9 +1632,9 @@ int narrow_launch(od_ctx *ctx, const Scratch &S, bool linear, int col0, int col1
   A.col0 = col0;
   A.col1 = col1;
   A.col2 = col2; A.col3 = col3; A.out2 = out2; A.out3 = out3;
-  A.runit = nullptr; A.mw = nullptr; A.norb = A.mw_nb = A.mw_nk = A.nb = A.mw_ns = 0; A.k_first = 0;
+  A.mw = nullptr; A.norb = A.mw_nb = A.mw_nk = A.nb = A.mw_ns = 0; A.k_first = 0;
+  A.unit_in_rec = S.ps.want_unit;
   if (gather) {
-    A.runit = ctx->scratch_e.as<unsigned>();
     A.mw = gather->mw; A.norb = gather->norb; A.mw_nb = gather->mw_nb; A.mw_nk = gather->mw_nk; A.nb = gather->nb;
     A.k_first = gather->k_first;
   }
@@ -1752,7 +1765,7 @@ int od_narrow_dos(od_ctx *ctx, const DosProducer &prod_in, const GridSpec &grid,
     scan_kernel<<<1, 1024, 0, ctx->stream>>>(counts, P.ntriples, offs);
     OD_LAUNCH_CHECK(ctx);
     OD_CUDA(ctx, cudaMemsetAsync(S.wide + 4, 0, sizeof(unsigned long long), ctx->stream));
-    A.recs = ctx->recs.p; A.runit = ctx->scratch_e.as<unsigned>();
+    A.recs = ctx->recs.p;
     A.next_item = S.wide + 4; A.grid = grid; A.bpad = ps.bpad; A.ns = ns;
     A.mw = prod_in.mw; A.norb = norb; A.mw_nb = prod_in.mw_nb; A.mw_nk = prod_in.mw_nk; A.nb = prod_in.nb; A.k_first = prod_in.k_first;
     A.wdos = accum + 2 * n1;
