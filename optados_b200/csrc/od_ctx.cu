@@ -184,7 +184,7 @@ extern "C" int od_ctx_destroy(od_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(ctx->comm));
   DevBuf *bufs[] = {&ctx->kweight, &ctx->bands, &ctx->grads, &ctx->partial, &ctx->accum, &ctx->small, &ctx->recs,
-                    &ctx->keys, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->scratch_d, &ctx->scratch_e, &ctx->mw_tmp, &ctx->in_tmp, &ctx->in_tmp2, &ctx->moments, &ctx->task_mw, &ctx->flags, &ctx->stats_dev, &ctx->dest_dev};
+                    &ctx->keys, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->scratch_d, &ctx->mw_tmp, &ctx->in_tmp, &ctx->in_tmp2, &ctx->moments, &ctx->task_mw, &ctx->flags, &ctx->stats_dev, &ctx->dest_dev};
   for (DevBuf *b : bufs) od_buf_release(*b);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);

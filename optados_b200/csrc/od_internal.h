@@ -81,7 +81,7 @@ struct od_ctx {
   struct PendingTime { cudaEvent_t e0, e1; int kind; };  // kind 0: prepare, 1: accumulate
   std::vector<PendingTime> pending_times;
   std::vector<cudaEvent_t> event_pool;
-  DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, scratch_e, mw_tmp, in_tmp, in_tmp2, moments, task_mw;
+  DevBuf partial, accum, small, recs, keys, scratch_a, scratch_b, scratch_c, scratch_d, mw_tmp, in_tmp, in_tmp2, moments, task_mw;
 
   Spectra dos_res, jdos_res;
   double vbm_energy = 0.0, cbm_energy = 0.0;  // od_dos_utils module variables set by compute_bandgap (dos_utils.f90:55-56)

@@ -102,7 +102,7 @@ struct PrepSpec {
   int linear_pass;  // a linear pass sends Gaussian records (hybrid_linear fall-back) to the dense engine
   int ng;           // weight columns carried beside each record (JDOS / optics)
   int wstride;      // doubles per weight row: 0 (none), 1, 4 or 8
-  int want_unit;    // also record each record's unit index (PDOS / core: weights are gathered from matrix_weights)
+  int want_unit;    // the records carry their unit index (PDOS / core: weights are gathered from matrix_weights by it; see GRec)
   int wmax;         // widest window the tiles take with this cell: min(NR_WMAX, NR_T - 2 * cell)
   double inv_delta; // 1 / grid.delta (IEEE, host): a per-thread division is ~30 instructions of a 200-instruction pass
 };
